@@ -1,0 +1,76 @@
+"""ORACLE (test infrastructure) — plugs the CPU restatement behind the ``World`` API.
+
+``use_oracle()`` is a context manager that swaps ``World``'s backend factory so worlds created
+inside it (on ``device="cpu"``) step through :mod:`oracle.world_step` instead of the CUDA
+kernels.  It exists so the host-side object model / ``Environment`` can be checked against the
+reference on CPU, and so ``bench.py --impl reference`` can time a CPU baseline.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+
+from vectorizedmultiagentsimulator_b200.backend import PlanRuntime
+from vectorizedmultiagentsimulator_b200.simulator.core import World
+
+from . import queries, world_step
+
+
+class OracleBackend(PlanRuntime):
+    def __init__(self, world):
+        super().__init__(world)
+        assert torch.device(world.device).type == "cpu", "the oracle is a CPU checker"
+
+    def _state(self):
+        slab = self.world.slab
+        return dict(
+            pos=slab.pos, vel=slab.vel, rot=slab.rot, ang_vel=slab.ang_vel, force=slab.force, torque=slab.torque
+        )
+
+    def step(self):
+        self.refresh()
+        world_step.world_step(
+            self.tables,
+            self._state(),
+            fixed_rot=self.per_env_fixed_rotations(),
+            exact_broad_phase=self.world.exact_broad_phase,
+        )
+
+    def cast_rays(self, entity, angles, max_range, entity_filter):
+        src = self.index_of(entity)
+        targets = self.ray_targets(entity, entity_filter)
+        slab = self.world.slab
+        return queries.cast_rays(self.tables, slab.pos, slab.rot, src, targets, angles, max_range)
+
+    def lidar_measure(self, sensor):
+        return self.cast_rays(
+            sensor.agent, sensor._angles + sensor.agent.state.rot, sensor._max_range, sensor.entity_filter
+        )
+
+    def pair_distance(self, a, b):
+        slab = self.world.slab
+        return queries.pair_distance(self.tables, slab.pos, slab.rot, self.index_of(a), self.index_of(b))
+
+    def pair_overlap(self, a, b):
+        slab = self.world.slab
+        return queries.pair_overlap(self.tables, slab.pos, slab.rot, self.index_of(a), self.index_of(b))
+
+    def distance_from_point(self, entity, point):
+        slab = self.world.slab
+        return queries.distance_from_point(self.tables, slab.pos, slab.rot, self.index_of(entity), point)
+
+    def any_within_broad_phase(self, a, b):
+        thr = a.shape.circumscribed_radius() + b.shape.circumscribed_radius()
+        d = torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1)
+        return bool((d <= thr).any())
+
+
+@contextlib.contextmanager
+def use_oracle():
+    previous = World._backend_factory
+    World._backend_factory = OracleBackend
+    try:
+        yield
+    finally:
+        World._backend_factory = previous

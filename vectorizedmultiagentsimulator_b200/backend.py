@@ -1,0 +1,229 @@
+"""Execution backends behind ``World.step`` / ``cast_rays`` / the distance queries.
+
+``PlanRuntime`` holds the host logic every backend shares: compiling the world into
+:class:`~.simulator.plan.PlanTables` when its static structure changed, resolving LIDAR
+target lists from ``entity_filter`` callables, and tracking per-env joint rotations.
+
+``CudaBackend`` is the product: it uploads the tables once and turns each API call into one
+call of the C-ABI library (``include/vmas_b200.h``) on torch's current CUDA stream.  It
+refuses to run anywhere else — there is deliberately no CPU or torch-eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .simulator import plan as P
+
+
+class PlanRuntime:
+    def __init__(self, world):
+        self.world = world
+        self.tables: Optional[P.PlanTables] = None
+        self._plan_version = -1
+        self._targets_cache: Dict[Tuple[int, Callable], List[int]] = {}
+        self._entity_index: Dict[int, int] = {}
+        self._joint_constraints = []  # (item index, JointConstraint) for per-env fixed rotations
+
+    # -- plan ----------------------------------------------------------------------------
+    def refresh(self) -> bool:
+        """Recompile if the world's static structure changed.  Returns True if it did."""
+        w = self.world
+        w._ensure_slab()
+        if self.tables is not None and self._plan_version == w._plan_version:
+            return False
+        desc = P.describe_world(w)
+        self.tables = P.build_tables(desc)
+        self._plan_version = w._plan_version
+        self._targets_cache.clear()
+        ents = w.entities
+        self._entity_index = {id(e): i for i, e in enumerate(ents)}
+        # joint constraints in item order (items 0..J-1 are the joints)
+        by_pair = {}
+        for c in w._joints.values():
+            by_pair[(self._entity_index[id(c.entity_a)], self._entity_index[id(c.entity_b)])] = c
+        self._joint_constraints = []
+        for k, it in enumerate(desc.items):
+            if it["kind"] != P.K_JOINT:
+                break
+            self._joint_constraints.append((k, by_pair[(it["a"], it["b"])]))
+        self.on_new_tables()
+        return True
+
+    def on_new_tables(self):
+        pass
+
+    def index_of(self, entity) -> int:
+        self.refresh()
+        try:
+            return self._entity_index[id(entity)]
+        except KeyError:
+            raise RuntimeError(f"Entity '{entity.name}' does not belong to this world") from None
+
+    def per_env_fixed_rotations(self) -> Dict[int, Tensor]:
+        """item index → ``[B, 1]`` fixed rotation, for the joints whose value is a tensor."""
+        out = {}
+        for k, c in self._joint_constraints:
+            if not c.rotate and not isinstance(c.fixed_rotation, (int, float)):
+                out[k] = c.fixed_rotation
+        return out
+
+    # -- LIDAR target lists ----------------------------------------------------------------
+    def ray_targets(self, entity, entity_filter: Callable) -> List[int]:
+        """Entities a ray from ``entity`` can hit (ref core.py:1678-1691)."""
+        self.refresh()
+        key = (id(entity), entity_filter)  # holding the callable keeps its identity unique
+        cached = self._targets_cache.get(key)
+        if cached is not None:
+            return cached
+        if len(self._targets_cache) > 512:
+            self._targets_cache.clear()
+        targets = []
+        for i, e in enumerate(self.world.entities):
+            if entity is e or not entity_filter(e):
+                continue
+            assert e.collides(entity) and entity.collides(e), "Rays are only casted among collidables"
+            P._shape_kind(e.shape)  # raises for unsupported shapes
+            targets.append(i)
+        self._targets_cache[key] = targets
+        return targets
+
+
+def _require_cuda(world):
+    dev = torch.device(world.device)
+    if dev.type != "cuda":
+        raise RuntimeError(
+            f"vectorizedmultiagentsimulator_b200 runs its physics only on CUDA (sm_100a); world device is "
+            f"'{dev}'. There is no CPU fallback."
+        )
+    return dev
+
+
+class CudaBackend(PlanRuntime):
+    """One process-local driver of the sm_100a kernels for one world (one GPU)."""
+
+    def __init__(self, world):
+        super().__init__(world)
+        self.device = _require_cuda(world)
+        from . import _native
+
+        self.lib = _native.load()  # raises if the extension is not built
+        self._native = _native
+        self._dev_tables = None
+        self._fixed_rot = None
+        self._fixed_rot_versions = {}
+        self._mask = None
+        self._ray_cache: Dict[Tuple[int, Callable], Tensor] = {}
+        self.launches = 0
+
+    # -- tables ----------------------------------------------------------------------------
+    def on_new_tables(self):
+        self._dev_tables = self._native.DeviceTables(self.tables, self.world, self.device)
+        self._fixed_rot_versions = {}
+        self._ray_cache.clear()
+
+    def _sync_fixed_rotations(self):
+        dt = self._dev_tables
+        if dt.joint_rot is None:
+            return
+        for k, c in self._joint_constraints:
+            if c.rotate:
+                continue
+            ver = c._fixed_rotation_version
+            if self._fixed_rot_versions.get(k) == ver:
+                continue
+            value = c.fixed_rotation
+            if isinstance(value, (int, float)):
+                dt.joint_rot[:, k].fill_(float(value))
+            else:
+                dt.joint_rot[:, k].copy_(value.reshape(-1))
+            self._fixed_rot_versions[k] = ver
+
+    # -- hot path ---------------------------------------------------------------------------
+    def step(self):
+        self.refresh()
+        self._sync_fixed_rotations()
+        slab = self.world.slab
+        self.launches += self._native.world_step(
+            self.lib, self._dev_tables, slab, exact_broad_phase=self.world.exact_broad_phase
+        )
+
+    def _targets_tensor(self, entity, entity_filter) -> Tuple[int, Tensor]:
+        src = self.index_of(entity)
+        key = (id(entity), entity_filter)
+        t = self._ray_cache.get(key)
+        if t is None:
+            if len(self._ray_cache) > 512:
+                self._ray_cache.clear()
+            idx = self.ray_targets(entity, entity_filter)
+            t = torch.tensor(idx if idx else [0], dtype=torch.int32, device=self.device)
+            t._n_valid = len(idx)
+            self._ray_cache[key] = t
+        return src, t
+
+    def cast_rays(self, entity, angles: Tensor, max_range: float, entity_filter) -> Tensor:
+        src, targets = self._targets_tensor(entity, entity_filter)
+        slab = self.world.slab
+        angles = angles.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(angles)
+        self._native.cast_rays(
+            self.lib, self._dev_tables, slab, src, targets, targets._n_valid, angles, None, float(max_range), out
+        )
+        self.launches += 1
+        return out
+
+    def lidar_measure(self, sensor) -> Tensor:
+        """``sensor._angles + agent.rot`` is folded into the kernel (ref sensors.py:116-121)."""
+        src, targets = self._targets_tensor(sensor.agent, sensor.entity_filter)
+        slab = self.world.slab
+        out = torch.empty_like(sensor._angles)
+        self._native.cast_rays(
+            self.lib,
+            self._dev_tables,
+            slab,
+            src,
+            targets,
+            targets._n_valid,
+            sensor._angles,
+            src,
+            float(sensor._max_range),
+            out,
+        )
+        self.launches += 1
+        return out
+
+    # -- queries -----------------------------------------------------------------------------
+    def pair_distance(self, a, b) -> Tensor:
+        ia, ib = self.index_of(a), self.index_of(b)
+        out = torch.empty(self.world.batch_dim, dtype=torch.float32, device=self.device)
+        self._native.pair_query(self.lib, self._dev_tables, self.world.slab, ia, ib, 0, out)
+        self.launches += 1
+        return out
+
+    def pair_overlap(self, a, b) -> Tensor:
+        ia, ib = self.index_of(a), self.index_of(b)
+        out = torch.empty(self.world.batch_dim, dtype=torch.bool, device=self.device)
+        self._native.pair_query(self.lib, self._dev_tables, self.world.slab, ia, ib, 1, out)
+        self.launches += 1
+        return out
+
+    def distance_from_point(self, entity, point: Tensor) -> Tensor:
+        ie = self.index_of(entity)
+        point = point.to(device=self.device, dtype=torch.float32)
+        if point.dim() == 1:
+            point = point.unsqueeze(0)
+        point = point.expand(self.world.batch_dim, 2).contiguous()
+        out = torch.empty(self.world.batch_dim, dtype=torch.float32, device=self.device)
+        self._native.point_query(self.lib, self._dev_tables, self.world.slab, ie, point, out)
+        self.launches += 1
+        return out
+
+    def any_within_broad_phase(self, a, b) -> bool:
+        ia, ib = self.index_of(a), self.index_of(b)
+        thr = a.shape.circumscribed_radius() + b.shape.circumscribed_radius()
+        pos = self.world.slab.pos
+        d = torch.linalg.vector_norm(pos[:, ia] - pos[:, ib], dim=-1)
+        return bool((d <= thr).any())

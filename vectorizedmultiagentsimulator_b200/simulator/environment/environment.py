@@ -1,0 +1,528 @@
+"""``Environment``: the vectorised env users step (ref vmas/simulator/environment/environment.py).
+
+Same public surface and return layout as the reference (``step`` → ``obs, rews, dones, infos``
+with one ``[num_envs, ...]`` tensor per policy agent).  What differs is underneath:
+
+* ``world.step()`` is the CUDA physics kernel, not python;
+* action validation can be *deferred* (``action_checks="deferred"``): the nan / range tests
+  are evaluated on the device into a flag that is read back asynchronously and raised on the
+  next call, instead of forcing two host syncs per agent per step (ref environment.py:621,
+  651-653).  ``"sync"`` reproduces the reference timing of the asserts, ``"off"`` skips them;
+* ``grad_enabled=True`` is rejected: the kernels are forward-only.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+import random
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from ..core import Agent, TorchVectorizedObject
+from ..scenario import BaseScenario
+from ..utils import AGENT_OBS_TYPE, DEVICE_TYPING, TorchUtils
+from . import spaces
+
+
+@contextlib.contextmanager
+def local_seed(vmas_random_state):
+    """Runs the body on the environment's private (torch-CPU, numpy, python) RNG streams."""
+    outer = (torch.random.get_rng_state(), np.random.get_state(), random.getstate())
+    torch.random.set_rng_state(vmas_random_state[0])
+    np.random.set_state(vmas_random_state[1])
+    random.setstate(vmas_random_state[2])
+    try:
+        yield
+    finally:
+        vmas_random_state[0] = torch.random.get_rng_state()
+        vmas_random_state[1] = np.random.get_state()
+        vmas_random_state[2] = random.getstate()
+        torch.random.set_rng_state(outer[0])
+        np.random.set_state(outer[1])
+        random.setstate(outer[2])
+
+
+def _seeded(method):
+    def wrapper(self, *args, **kwargs):
+        with local_seed(Environment.vmas_random_state):
+            return method(self, *args, **kwargs)
+
+    wrapper.__name__ = method.__name__
+    wrapper.__doc__ = method.__doc__
+    return wrapper
+
+
+class Environment(TorchVectorizedObject):
+    metadata = {"render.modes": ["human", "rgb_array"], "runtime.vectorized": True}
+    vmas_random_state = [torch.random.get_rng_state(), np.random.get_state(), random.getstate()]
+
+    def __init__(
+        self,
+        scenario: BaseScenario,
+        num_envs: int = 32,
+        device: DEVICE_TYPING = "cpu",
+        max_steps: Optional[int] = None,
+        continuous_actions: bool = True,
+        seed: Optional[int] = None,
+        dict_spaces: bool = False,
+        multidiscrete_actions: bool = False,
+        clamp_actions: bool = False,
+        grad_enabled: bool = False,
+        terminated_truncated: bool = False,
+        action_checks: Optional[str] = None,
+        **kwargs,
+    ):
+        if multidiscrete_actions:
+            assert (
+                not continuous_actions
+            ), "When asking for multidiscrete_actions, make sure continuous_actions=False"
+        if grad_enabled:
+            raise NotImplementedError(
+                "grad_enabled=True is not supported: the B200 physics kernels are forward-only"
+            )
+        with local_seed(Environment.vmas_random_state):
+            self.scenario = scenario
+            self.num_envs = num_envs
+            TorchVectorizedObject.__init__(self, num_envs, torch.device(device))
+            self.world = self.scenario.env_make_world(self.num_envs, self.device, **kwargs)
+
+            self.agents = self.world.policy_agents
+            self.n_agents = len(self.agents)
+            self.max_steps = max_steps
+            self.continuous_actions = continuous_actions
+            self.dict_spaces = dict_spaces
+            self.clamp_action = clamp_actions
+            self.grad_enabled = grad_enabled
+            self.terminated_truncated = terminated_truncated
+            if action_checks is None:
+                action_checks = "deferred" if self.device.type == "cuda" else "sync"
+            assert action_checks in ("sync", "deferred", "off")
+            self.action_checks = action_checks
+            self._bad_action_flag = None  # device uint8 [1], set by deferred checks
+            self._bad_action_host = None
+            self._bad_action_event = None
+
+            observations = self._reset(seed=seed)
+
+            self.multidiscrete_actions = multidiscrete_actions
+            self.action_space = self.get_action_space()
+            self.observation_space = self.get_observation_space(observations)
+
+            self.viewer = None
+            self.headless = None
+            self.visible_display = None
+            self.text_lines = None
+
+    # ------------------------------------------------------------------------------------
+    # public API (each runs on the env's private RNG streams)
+    # ------------------------------------------------------------------------------------
+    @_seeded
+    def reset(
+        self,
+        seed: Optional[int] = None,
+        return_observations: bool = True,
+        return_info: bool = False,
+        return_dones: bool = False,
+    ):
+        """Resets all envs; returns observations for all envs and agents."""
+        return self._reset(seed, return_observations, return_info, return_dones)
+
+    @_seeded
+    def reset_at(
+        self,
+        index: int,
+        return_observations: bool = True,
+        return_info: bool = False,
+        return_dones: bool = False,
+    ):
+        """Resets env ``index``; returns observations for all agents (all envs)."""
+        return self._reset_at(index, return_observations, return_info, return_dones)
+
+    @_seeded
+    def get_from_scenario(
+        self,
+        get_observations: bool,
+        get_rewards: bool,
+        get_infos: bool,
+        get_dones: bool,
+        dict_agent_names: Optional[bool] = None,
+    ):
+        return self._get_from_scenario(
+            get_observations, get_rewards, get_infos, get_dones, dict_agent_names
+        )
+
+    @_seeded
+    def seed(self, seed=None):
+        return self._seed(seed)
+
+    @_seeded
+    def done(self):
+        return self._done()
+
+    @_seeded
+    def step(self, actions: Union[List, Dict]):
+        """One vectorised step.
+
+        Args:
+            actions: list (or dict by agent name) with one ``[num_envs, action_size]`` tensor
+                per policy agent.
+        Returns:
+            ``obs, rewards, dones, infos`` (or ``obs, rewards, terminated, truncated, infos``),
+            lists (or dicts) with one entry per policy agent.
+        """
+        return self._step(actions)
+
+    # ------------------------------------------------------------------------------------
+    def _reset(self, seed=None, return_observations=True, return_info=False, return_dones=False):
+        if seed is not None:
+            self._seed(seed)
+        self.scenario.env_reset_world_at(env_index=None)
+        self.steps = torch.zeros(self.num_envs, device=self.device)
+        result = self._get_from_scenario(
+            get_observations=return_observations,
+            get_infos=return_info,
+            get_rewards=False,
+            get_dones=return_dones,
+        )
+        return result[0] if result and len(result) == 1 else result
+
+    def _reset_at(self, index, return_observations=True, return_info=False, return_dones=False):
+        self._check_batch_index(index)
+        self.scenario.env_reset_world_at(index)
+        self.steps[index] = 0
+        result = self._get_from_scenario(
+            get_observations=return_observations,
+            get_infos=return_info,
+            get_rewards=False,
+            get_dones=return_dones,
+        )
+        return result[0] if result and len(result) == 1 else result
+
+    def _get_from_scenario(
+        self, get_observations, get_rewards, get_infos, get_dones, dict_agent_names=None
+    ):
+        if not (get_infos or get_dones or get_rewards or get_observations):
+            return
+        by_name = self.dict_spaces if dict_agent_names is None else dict_agent_names
+
+        def collect(fn):
+            out = {} if by_name else []
+            for agent in self.agents:
+                value = fn(agent)
+                if by_name:
+                    out[agent.name] = value
+                else:
+                    out.append(value)
+            return out
+
+        # order matters: scenarios cache shared terms while computing agent 0's reward
+        rewards = collect(lambda a: self.scenario.reward(a).clone()) if get_rewards else None
+        obs = (
+            collect(lambda a: TorchUtils.recursive_clone(self.scenario.observation(a)))
+            if get_observations
+            else None
+        )
+        infos = (
+            collect(lambda a: TorchUtils.recursive_clone(self.scenario.info(a))) if get_infos else None
+        )
+        if self.terminated_truncated:
+            terminated = truncated = None
+            if get_dones:
+                terminated, truncated = self._done()
+            result = [obs, rewards, terminated, truncated, infos]
+        else:
+            dones = self._done() if get_dones else None
+            result = [obs, rewards, dones, infos]
+        return [data for data in result if data is not None]
+
+    def _seed(self, seed=None):
+        if seed is None:
+            seed = 0
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        random.seed(seed)
+        return [seed]
+
+    def _step(self, actions):
+        self._raise_deferred_action_errors()
+        if isinstance(actions, Dict):
+            by_name = actions
+            actions = []
+            for agent in self.agents:
+                if agent.name not in by_name:
+                    raise AssertionError(f"Agent '{agent.name}' not contained in action dict")
+                actions.append(by_name[agent.name])
+            assert (
+                len(by_name) == self.n_agents
+            ), f"Expecting actions for {self.n_agents}, got {len(by_name)} actions"
+        assert (
+            len(actions) == self.n_agents
+        ), f"Expecting actions for {self.n_agents}, got {len(actions)} actions"
+        actions = list(actions)
+        for i, agent in enumerate(self.agents):
+            a = actions[i]
+            if not isinstance(a, Tensor):
+                a = torch.tensor(a, dtype=torch.float32, device=self.device)
+            if a.dim() == 1:
+                a = a.unsqueeze(-1)
+            assert (
+                a.shape[0] == self.num_envs
+            ), f"Actions used in input of env must be of len {self.num_envs}, got {a.shape[0]}"
+            expected = self.get_agent_action_size(agent)
+            assert a.shape[1] == expected, (
+                f"Action for agent {agent.name} has shape {a.shape[1]},"
+                f" but should have shape {expected}"
+            )
+            actions[i] = a
+
+        for action, agent in zip(actions, self.agents):
+            self._set_action(action, agent)
+        # scripted agents + scenario-specific processing + dynamics (action -> force/torque)
+        for agent in self.world.agents:
+            self.scenario.env_process_action(agent)
+
+        self.scenario.pre_step()
+        self.world.step()
+        self.scenario.post_step()
+        self.steps += 1
+
+        self._launch_deferred_action_readback()
+        return self._get_from_scenario(
+            get_observations=True, get_infos=True, get_rewards=True, get_dones=True
+        )
+
+    def _done(self):
+        terminated = self.scenario.done().clone()
+        truncated = self.steps >= self.max_steps if self.max_steps is not None else None
+        if self.terminated_truncated:
+            if truncated is None:
+                truncated = torch.zeros_like(terminated)
+            return terminated, truncated
+        if truncated is None:
+            return terminated
+        return terminated + truncated
+
+    # ------------------------------------------------------------------------------------
+    # spaces
+    # ------------------------------------------------------------------------------------
+    def get_action_space(self):
+        if self.dict_spaces:
+            return spaces.Dict({a.name: self.get_agent_action_space(a) for a in self.agents})
+        return spaces.Tuple([self.get_agent_action_space(a) for a in self.agents])
+
+    def get_observation_space(self, observations: Union[List, Dict]):
+        if self.dict_spaces:
+            return spaces.Dict(
+                {
+                    a.name: self.get_agent_observation_space(a, observations[a.name])
+                    for a in self.agents
+                }
+            )
+        return spaces.Tuple(
+            [self.get_agent_observation_space(a, observations[i]) for i, a in enumerate(self.agents)]
+        )
+
+    def _comm_dims(self, agent: Agent) -> int:
+        return self.world.dim_c if not agent.silent else 0
+
+    def get_agent_action_size(self, agent: Agent):
+        if self.continuous_actions:
+            return agent.action.action_size + self._comm_dims(agent)
+        if self.multidiscrete_actions:
+            return agent.action_size + (1 if self._comm_dims(agent) != 0 else 0)
+        return 1
+
+    def get_agent_action_space(self, agent: Agent):
+        comm = self._comm_dims(agent)
+        if self.continuous_actions:
+            u_range = agent.action.u_range_tensor.tolist()
+            return spaces.Box(
+                low=np.array([-r for r in u_range] + [0] * comm, dtype=np.float32),
+                high=np.array(u_range + [1] * comm, dtype=np.float32),
+                shape=(self.get_agent_action_size(agent),),
+                dtype=np.float32,
+            )
+        if self.multidiscrete_actions:
+            return spaces.MultiDiscrete(list(agent.discrete_action_nvec) + ([comm] if comm != 0 else []))
+        return spaces.Discrete(math.prod(agent.discrete_action_nvec) * (comm if comm != 0 else 1))
+
+    def get_agent_observation_space(self, agent: Agent, obs: AGENT_OBS_TYPE):
+        if isinstance(obs, Tensor):
+            return spaces.Box(
+                low=-np.float32("inf"), high=np.float32("inf"), shape=obs.shape[1:], dtype=np.float32
+            )
+        if isinstance(obs, Dict):
+            return spaces.Dict(
+                {k: self.get_agent_observation_space(agent, v) for k, v in obs.items()}
+            )
+        raise NotImplementedError(f"Invalid type of observation {obs} for agent {agent.name}")
+
+    # ------------------------------------------------------------------------------------
+    # random actions (ref environment.py:525-607)
+    # ------------------------------------------------------------------------------------
+    @_seeded
+    def get_random_action(self, agent: Agent) -> Tensor:
+        """A uniformly random valid action ``[batch_dim, action_size]`` for ``agent``."""
+        kw = dict(device=agent.device, dtype=torch.float32)
+        if self.continuous_actions:
+            cols = []
+            for k in range(agent.action_size):
+                r = agent.action.u_range_tensor[k]
+                cols.append(torch.zeros(agent.batch_dim, **kw).uniform_(-r, r))
+            for _ in range(self._comm_dims(agent)):
+                cols.append(torch.zeros(agent.batch_dim, **kw).uniform_(0, 1))
+            return torch.stack(cols, dim=-1)
+        space = self.get_agent_action_space(agent)
+        if self.multidiscrete_actions:
+            cols = [
+                torch.randint(low=0, high=int(n), size=(agent.batch_dim,), device=agent.device)
+                for n in space.nvec
+            ]
+            return torch.stack(cols, dim=-1)
+        return torch.randint(low=0, high=int(space.n), size=(agent.batch_dim,), device=agent.device)
+
+    def get_random_actions(self) -> Sequence[Tensor]:
+        """Random actions for all policy agents, ready for :meth:`step`."""
+        return [self.get_random_action(agent) for agent in self.agents]
+
+    # ------------------------------------------------------------------------------------
+    # action decoding (ref environment.py:609-749)
+    # ------------------------------------------------------------------------------------
+    def _flag_if(self, condition: Tensor, message: str):
+        """``assert not condition.any()`` — immediately, deferred to the next call, or never."""
+        if self.action_checks == "off":
+            return
+        if self.action_checks == "sync":
+            assert not bool(condition.any()), message
+            return
+        if self._bad_action_flag is None:
+            self._bad_action_flag = torch.zeros(1, dtype=torch.bool, device=self.device)
+            self._bad_action_messages = []
+        self._bad_action_flag |= condition.any()
+        if message not in self._bad_action_messages:
+            self._bad_action_messages.append(message)
+
+    def _launch_deferred_action_readback(self):
+        if self.action_checks != "deferred" or self._bad_action_flag is None:
+            return
+        if self._bad_action_host is None:
+            pin = self.device.type == "cuda"
+            self._bad_action_host = torch.zeros(1, dtype=torch.bool, pin_memory=pin)
+        self._bad_action_host.copy_(self._bad_action_flag, non_blocking=True)
+        if self.device.type == "cuda":
+            self._bad_action_event = torch.cuda.Event()
+            self._bad_action_event.record()
+
+    def _raise_deferred_action_errors(self):
+        if self._bad_action_host is None:
+            return
+        if self._bad_action_event is not None:
+            self._bad_action_event.synchronize()
+        if bool(self._bad_action_host.item()):
+            self._bad_action_flag.zero_()
+            self._bad_action_host.zero_()
+            raise AssertionError(
+                "Invalid action in the previous step: " + "; ".join(self._bad_action_messages)
+            )
+
+    def check_actions_now(self):
+        """Force the deferred action checks to be read back and raised (one host sync)."""
+        self._launch_deferred_action_readback()
+        self._raise_deferred_action_errors()
+
+    def _check_discrete_action(self, action: Tensor, low: int, high: int, type: str):
+        self._flag_if(
+            (action < low) | (action >= high),
+            f"Discrete {type} actions are out of bounds, allowed int range [{low},{high})",
+        )
+
+    def _set_action(self, action: Tensor, agent: Agent):
+        action = action.detach().to(self.device)
+        self._flag_if(action.isnan(), f"Action of agent {agent.name} contains NaN")
+        assert action.shape[1] == self.get_agent_action_size(agent), (
+            f"Agent {agent.name} has wrong action size, got {action.shape[1]}, "
+            f"expected {self.get_agent_action_size(agent)}"
+        )
+        n_phys = agent.action_size
+        comm = self._comm_dims(agent)
+        u_range = agent.action.u_range_tensor
+
+        if self.clamp_action and self.continuous_actions:
+            physical = action[..., :n_phys].clamp(-u_range, u_range)
+            if comm > 0:
+                action = torch.cat([physical, action[..., n_phys:].clamp(0, 1)], dim=-1)
+            else:
+                action = physical
+
+        column = 0
+        if self.continuous_actions:
+            physical = action[:, :n_phys]
+            column += self.world.dim_p
+            self._flag_if(
+                torch.abs(physical) > u_range,
+                f"Physical actions of agent {agent.name} are out of its range {agent.u_range}",
+            )
+            u = physical.to(torch.float32).clone()
+        else:
+            action = action.clone()
+            if not self.multidiscrete_actions:
+                # unravel the flat index of the cartesian product into one index per component
+                flat = action.squeeze(-1)
+                nvec = list(agent.discrete_action_nvec) + ([self.world.dim_c] if comm != 0 else [])
+                parts = []
+                for i in range(len(nvec)):
+                    stride = math.prod(nvec[i + 1 :])
+                    parts.append(flat // stride)
+                    flat = flat % stride
+                action = torch.stack(parts, dim=-1)
+            u = torch.zeros(self.batch_dim, n_phys, device=self.device, dtype=torch.float32)
+            for n in agent.discrete_action_nvec:
+                idx = action[:, column]
+                self._check_discrete_action(idx.unsqueeze(-1), low=0, high=n, type="physical")
+                u_max = u_range[column]
+                if n % 2 != 0:
+                    # odd n: index 0 means "no force"; indices 1..n//2 shift down by one
+                    stay = idx == 0
+                    lower_half = (idx > 0) & (idx <= n // 2)
+                    idx = torch.where(stay, torch.full_like(idx, n // 2), idx)
+                    idx = torch.where(lower_half, idx - 1, idx)
+                u[:, column] = (idx / (n - 1)) * (2 * u_max) - u_max
+                column += 1
+
+        u = u * agent.action.u_multiplier_tensor
+        noise_level = agent.action.u_noise
+        if (max(noise_level) if isinstance(noise_level, Sequence) else noise_level) > 0:
+            u = u + torch.randn(*u.shape, device=self.device, dtype=torch.float32) * agent.action.u_noise_tensor
+        agent.action.u = u
+
+        if comm > 0:
+            comm_action = action[:, column:]
+            if not self.continuous_actions:
+                self._check_discrete_action(comm_action, 0, self.world.dim_c, "communication")
+                one_hot = torch.zeros(
+                    self.num_envs, self.world.dim_c, device=self.device, dtype=torch.float32
+                )
+                one_hot.scatter_(1, comm_action.long(), 1)
+                c = one_hot
+            else:
+                self._flag_if(
+                    (comm_action > 1) | (comm_action < 0), "Comm actions are out of range [0,1]"
+                )
+                c = comm_action.clone()
+            if agent.c_noise > 0:
+                c = c + torch.randn(*c.shape, device=self.device, dtype=torch.float32) * agent.c_noise
+            agent.action.c = c
+
+    # ------------------------------------------------------------------------------------
+    def render(self, *args, **kwargs):
+        raise NotImplementedError(
+            "Rendering (pyglet viewer) is outside the scope of the B200 hot-path build"
+        )
+
+    def to(self, device: DEVICE_TYPING):
+        device = torch.device(device)
+        self.scenario.to(device)
+        super().to(device)
