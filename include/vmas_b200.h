@@ -1,0 +1,144 @@
+/*
+ * vmas_b200.h — C ABI of the B200 (sm_100a) physics hot path of VMAS.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * replaces one piece of the reference's pure-Python/PyTorch hot path
+ * (/root/reference/vmas/simulator/core.py); the Python host (ctypes, see
+ * vectorizedmultiagentsimulator_b200/_native.py and INTEGRATION.md) passes device pointers of
+ * tensors it owns plus the CUDA stream to launch on.  Nothing here allocates device memory or
+ * synchronises the device.
+ *
+ * State layout (all fp32, contiguous, one CUDA device):
+ *   pos     [B, E, 2]   vel     [B, E, 2]   rot   [B, E]   ang_vel [B, E]
+ *   force   [B, A, 2]   torque  [B, A]      (A = agents; E follows world.entities order)
+ *
+ * Return convention: >= 0 on success (for launch functions: the number of kernels launched),
+ * < 0 on error; vmas_b200_last_error() then returns a message for the calling thread.
+ */
+#ifndef VMAS_B200_H
+#define VMAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMAS_B200_ABI_VERSION 1
+
+/* shape kinds (ent_i32[:,0]) */
+enum { VMAS_SHAPE_SPHERE = 0, VMAS_SHAPE_BOX = 1, VMAS_SHAPE_LINE = 2 };
+/* work-item kinds (item_i32[:,0]), in force-accumulation order (ref core.py:2175-2189) */
+enum { VMAS_K_JOINT = 0, VMAS_K_SS = 1, VMAS_K_LS = 2, VMAS_K_LL = 3, VMAS_K_BS = 4, VMAS_K_BL = 5, VMAS_K_BB = 6 };
+
+/* entity flag bits (ent_i32[:,1]) */
+enum {
+  VMAS_F_MOVABLE = 1 << 0, VMAS_F_ROTATABLE = 1 << 1, VMAS_F_HOLLOW = 1 << 2, VMAS_F_AGENT = 1 << 3,
+  VMAS_F_LIN_FRIC = 1 << 4, VMAS_F_ANG_FRIC = 1 << 5, VMAS_F_GRAVITY = 1 << 6, VMAS_F_MAX_SPEED = 1 << 7,
+  VMAS_F_V_RANGE = 1 << 8, VMAS_F_MAX_F = 1 << 9, VMAS_F_F_RANGE = 1 << 10, VMAS_F_MAX_T = 1 << 11,
+  VMAS_F_T_RANGE = 1 << 12, VMAS_F_TRIG = 1 << 13
+};
+/* columns of ent_f32 [E, 20] */
+enum {
+  VMAS_EF_D0 = 0, VMAS_EF_D1, VMAS_EF_MASS, VMAS_EF_INERTIA, VMAS_EF_DRAG_MULT, VMAS_EF_LIN_FRIC,
+  VMAS_EF_ANG_FRIC, VMAS_EF_GRAV_X, VMAS_EF_GRAV_Y, VMAS_EF_MAX_SPEED, VMAS_EF_V_RANGE, VMAS_EF_MAX_F,
+  VMAS_EF_F_RANGE, VMAS_EF_MAX_T, VMAS_EF_T_RANGE, VMAS_EF_CIRC_R, VMAS_EF_R_PLUS_LMD,
+  VMAS_EF_COLS = 20
+};
+/* columns of item_f32 [NI, 8] */
+enum {
+  VMAS_IF_BROAD_THR = 0, VMAS_IF_DMIN_BASE, VMAS_IF_AX, VMAS_IF_AY, VMAS_IF_BX, VMAS_IF_BY, VMAS_IF_DIST,
+  VMAS_IF_FIXED_ROT, VMAS_IF_COLS
+};
+/* item flag bits (item_i32[:,3] low byte); bits 8.. hold (mask bit index + 1), 0 = never masked */
+enum { VMAS_IFLAG_JOINT_ROTATE = 1, VMAS_IFLAG_JOINT_ROT_PER_ENV = 2, VMAS_IFLAG_ALWAYS_ACTIVE = 4 };
+
+/* World scalars (ref World.__init__, core.py:1091-1150).  Host memory, passed by pointer. */
+typedef struct VmasWorldConfig {
+  int32_t batch_dim;      /* B */
+  int32_t n_entities;     /* E */
+  int32_t n_agents;       /* A */
+  int32_t n_items;        /* joints + candidate collision pairs */
+  int32_t n_joints;       /* items [0, n_joints) are joint constraints */
+  int32_t n_masked;       /* items that obey the batch-wide broad-phase mask (line/box pairs) */
+  int32_t substeps;       /* S */
+  int32_t has_x_semidim, has_y_semidim, has_world_gravity;
+  float sub_dt;           /* fp32(dt / S) */
+  float x_semidim, y_semidim;
+  float collision_force, joint_force, torque_constraint_force, contact_margin;
+  float gravity_x, gravity_y;
+} VmasWorldConfig;
+
+/* Plan tables compiled on the host from the world's static structure.  DEVICE pointers. */
+typedef struct VmasPlanTables {
+  const float*   ent_f32;     /* [E, VMAS_EF_COLS] */
+  const int32_t* ent_i32;     /* [E, 4]: shape, flags, agent index, - */
+  const float*   item_f32;    /* [NI, VMAS_IF_COLS] */
+  const int32_t* item_i32;    /* [NI, 4]: kind, a, b, flags | (mask bit + 1) << 8 */
+  const int32_t* inc_off;     /* [E + 1] CSR offsets: items incident to each entity */
+  const int32_t* inc;         /* item * 2 + side, ascending item order */
+  const int32_t* sched;       /* [n_rounds, group] item per lane, -1 = idle; rounds are kind-uniform */
+  const int32_t* masked_items;/* [n_masked] item index of each mask bit */
+  const float*   joint_rot;   /* [B, n_joints] per-env fixed rotations, or NULL */
+  int32_t n_rounds;
+  int32_t group;              /* lanes per env: 8, 16 or 32 */
+  int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */
+  int32_t reserved;
+} VmasPlanTables;
+
+/* The state slab.  DEVICE pointers. */
+typedef struct VmasState {
+  float* pos; float* vel; float* rot; float* ang_vel; float* force; float* torque;
+} VmasState;
+
+int vmas_b200_abi_version(void);
+const char* vmas_b200_last_error(void);
+
+/*
+ * One World.step(): S substeps of force accumulation -> contact/joint resolution ->
+ * semi-implicit Euler, in place on `st`.  Replaces ref core.py:1972-2015 (and everything it
+ * calls: :2018-2908, physics.py, joints.py:186-216).
+ *   mask        device scratch, uint32[(n_masked + 31) / 32 + 1], zero before the first call; only
+ *               used when the world has line/box pairs and exact_broad_phase != 0
+ *               (batch-wide pair activation, ref core.py:2797-2801).
+ * Sphere-only worlds run all S substeps in ONE launch; otherwise 2 launches per substep.
+ */
+int vmas_b200_world_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                         uint32_t* mask, int exact_broad_phase, void* cuda_stream);
+
+/* Same, for a sub-range of substeps [first_substep, first_substep + n_substeps) (testing). */
+int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                             uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
+                             void* cuda_stream);
+
+/*
+ * World.cast_rays() (ref core.py:1662-1786) for one source entity.
+ *   targets      device int32[n_targets]: entity indices the rays may hit
+ *   angles       device fp32 [B, n_rays]
+ *   add_rot_of   >= 0: add rot[:, add_rot_of] to every angle (Lidar.measure, ref sensors.py:116-121)
+ *   out          device fp32 [B, n_rays]
+ */
+int vmas_b200_cast_rays(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                        int32_t src_entity, const int32_t* targets, int32_t n_targets,
+                        const float* angles, int32_t n_rays, int32_t add_rot_of, float max_range,
+                        float* out, void* cuda_stream);
+
+/*
+ * World.get_distance (mode 0 -> fp32 out[B]) / World.is_overlapping (mode 1 -> uint8 out[B]) for
+ * the entity pair (a, b).  Replaces ref core.py:1822-1969.
+ */
+int vmas_b200_pair_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                         int32_t a, int32_t b, int32_t mode, void* out, void* cuda_stream);
+
+/* World.get_distance_from_point (ref core.py:1788-1820): point fp32 [B, 2] -> out fp32 [B]. */
+int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                          int32_t entity, const float* point, float* out, void* cuda_stream);
+
+/* The broad-phase pass alone: ORs bit i of `mask` if masked item i is within range in any env. */
+int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                          uint32_t* mask, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMAS_B200_H */

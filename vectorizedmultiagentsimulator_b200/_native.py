@@ -1,0 +1,344 @@
+"""ctypes binding of the C-ABI library ``libvmas_b200.so`` (``include/vmas_b200.h``).
+
+The library is built in-tree by :func:`build` (``nvcc -gencode arch=compute_100a,code=sm_100a``)
+and loaded by :func:`load`, which fails loudly if it is missing: there is no fallback path.
+PyTorch only provides device memory and the current stream; every kernel is this library's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .simulator import plan as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(_ROOT, "include")
+LIB_PATH = os.path.join(_HERE, "libvmas_b200.so")
+SOURCES = [os.path.join(CSRC, "vmas_b200.cu")]
+HEADERS = [os.path.join(CSRC, "geometry.cuh"), os.path.join(INCLUDE, "vmas_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-lineinfo",
+    "-fmad=false",  # every mul/add rounds on its own, like the reference's eager op chain
+    "-std=c++17",
+    "-Xcompiler",
+    "-fPIC",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libvmas_b200.so")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(f) > built for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into ``libvmas_b200.so`` next to this file."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+# ---------------------------------------------------------------------------------------------
+# ctypes mirrors of the header structs
+# ---------------------------------------------------------------------------------------------
+class WorldConfig(C.Structure):
+    _fields_ = [
+        ("batch_dim", C.c_int32),
+        ("n_entities", C.c_int32),
+        ("n_agents", C.c_int32),
+        ("n_items", C.c_int32),
+        ("n_joints", C.c_int32),
+        ("n_masked", C.c_int32),
+        ("substeps", C.c_int32),
+        ("has_x_semidim", C.c_int32),
+        ("has_y_semidim", C.c_int32),
+        ("has_world_gravity", C.c_int32),
+        ("sub_dt", C.c_float),
+        ("x_semidim", C.c_float),
+        ("y_semidim", C.c_float),
+        ("collision_force", C.c_float),
+        ("joint_force", C.c_float),
+        ("torque_constraint_force", C.c_float),
+        ("contact_margin", C.c_float),
+        ("gravity_x", C.c_float),
+        ("gravity_y", C.c_float),
+    ]
+
+
+class PlanTablesC(C.Structure):
+    _fields_ = [
+        ("ent_f32", C.c_void_p),
+        ("ent_i32", C.c_void_p),
+        ("item_f32", C.c_void_p),
+        ("item_i32", C.c_void_p),
+        ("inc_off", C.c_void_p),
+        ("inc", C.c_void_p),
+        ("sched", C.c_void_p),
+        ("masked_items", C.c_void_p),
+        ("joint_rot", C.c_void_p),
+        ("n_rounds", C.c_int32),
+        ("group", C.c_int32),
+        ("ents_per_lane", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class StateC(C.Structure):
+    _fields_ = [
+        ("pos", C.c_void_p),
+        ("vel", C.c_void_p),
+        ("rot", C.c_void_p),
+        ("ang_vel", C.c_void_p),
+        ("force", C.c_void_p),
+        ("torque", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "vmas_b200_abi_version",
+    "vmas_b200_last_error",
+    "vmas_b200_world_step",
+    "vmas_b200_world_substeps",
+    "vmas_b200_cast_rays",
+    "vmas_b200_pair_query",
+    "vmas_b200_point_query",
+    "vmas_b200_broad_phase",
+]
+
+_lib = None
+
+
+def load():
+    """Load the built library (never builds implicitly on a GPU box: ship the ``.so``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(needs nvcc). vectorizedmultiagentsimulator_b200 has no CPU / torch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it")
+    lib.vmas_b200_abi_version.restype = C.c_int
+    lib.vmas_b200_last_error.restype = C.c_char_p
+    p_cfg, p_tb, p_st = C.POINTER(WorldConfig), C.POINTER(PlanTablesC), C.POINTER(StateC)
+    lib.vmas_b200_world_step.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_int, C.c_void_p]
+    lib.vmas_b200_world_substeps.argtypes = [
+        p_cfg, p_tb, p_st, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p
+    ]
+    lib.vmas_b200_cast_rays.argtypes = [
+        p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+        C.c_float, C.c_void_p, C.c_void_p,
+    ]
+    lib.vmas_b200_pair_query.argtypes = [
+        p_cfg, p_tb, p_st, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+    ]
+    lib.vmas_b200_point_query.argtypes = [p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_broad_phase.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p]
+    for name in EXPORTS[2:]:
+        getattr(lib, name).restype = C.c_int
+    if lib.vmas_b200_abi_version() != 1:
+        raise RuntimeError("libvmas_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc: int) -> int:
+    if rc < 0:
+        raise RuntimeError(f"vmas_b200: {lib.vmas_b200_last_error().decode()}")
+    return rc
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident plan
+# ---------------------------------------------------------------------------------------------
+def lane_layout(n_entities: int):
+    """(lanes per env, entities per lane) for the substep kernel."""
+    if n_entities <= 8:
+        return 8, 1
+    if n_entities <= 16:
+        return 16, 1
+    if n_entities <= 32:
+        return 32, 1
+    if n_entities <= 64:
+        return 32, 2
+    if n_entities <= 128:
+        return 32, 4
+    raise NotImplementedError(f"{n_entities} entities per env exceed the kernel's limit of 128")
+
+
+def make_config(tables: P.PlanTables, batch_dim: Optional[int] = None) -> WorldConfig:
+    d = tables.desc
+    cfg = WorldConfig()
+    cfg.batch_dim = d.batch_dim if batch_dim is None else batch_dim
+    cfg.n_entities = d.n_entities
+    cfg.n_agents = d.n_agents
+    cfg.n_items = len(d.items)
+    cfg.n_joints = tables.n_joints
+    cfg.n_masked = tables.n_masked
+    cfg.substeps = d.substeps
+    cfg.has_x_semidim = int(d.x_semidim is not None)
+    cfg.has_y_semidim = int(d.y_semidim is not None)
+    cfg.has_world_gravity = int(any(g != 0.0 for g in d.gravity))
+    cfg.sub_dt = d.dt / d.substeps
+    cfg.x_semidim = d.x_semidim or 0.0
+    cfg.y_semidim = d.y_semidim or 0.0
+    cfg.collision_force = d.collision_force
+    cfg.joint_force = d.joint_force
+    cfg.torque_constraint_force = d.torque_constraint_force
+    cfg.contact_margin = d.contact_margin
+    cfg.gravity_x, cfg.gravity_y = d.gravity
+    return cfg
+
+
+class DeviceTables:
+    """The plan tables uploaded to one GPU, plus the ctypes structs pointing at them."""
+
+    def __init__(self, tables: P.PlanTables, world, device):
+        self.tables = tables
+        self.device = torch.device(device)
+        desc = tables.desc
+        self.group, self.ents_per_lane = lane_layout(desc.n_entities)
+        sched, _ = tables.schedule(self.group)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
+        self.ent_f32 = up(tables.ent_f32)
+        self.ent_i32 = up(tables.ent_i32)
+        self.item_f32 = up(tables.item_f32)
+        self.item_i32 = up(tables.item_i32)
+        self.inc_off = up(tables.inc_off)
+        self.inc = up(tables.inc)
+        self.sched = up(sched if sched.size else np.full((1, self.group), -1, np.int32))
+        self.masked_items = up(tables.masked_items)
+        B = desc.batch_dim if world is None else world.batch_dim
+        needs_rot = any(it["kind"] == P.K_JOINT and not it["rotate"] for it in desc.items)
+        self.joint_rot = (
+            torch.zeros(B, max(tables.n_joints, 1), dtype=torch.float32, device=self.device)
+            if needs_rot
+            else None
+        )
+        if self.joint_rot is not None:
+            # every non-rotating joint reads its angle per env; scalar ones are broadcast here
+            self.item_i32[: tables.n_joints, 3] |= P.IFLAG_JOINT_ROT_PER_ENV
+            for k, it in enumerate(desc.items[: tables.n_joints]):
+                if not it["rotate"] and it["fixed_rotation"] is not None:
+                    self.joint_rot[:, k] = float(it["fixed_rotation"])
+        words = (tables.n_masked + 31) // 32
+        self.mask = torch.zeros(words + 1, dtype=torch.int32, device=self.device)
+        self.n_rounds = int(sched.shape[0])
+
+        self.cfg = make_config(tables, B)
+        tb = PlanTablesC()
+        tb.ent_f32 = self.ent_f32.data_ptr()
+        tb.ent_i32 = self.ent_i32.data_ptr()
+        tb.item_f32 = self.item_f32.data_ptr()
+        tb.item_i32 = self.item_i32.data_ptr()
+        tb.inc_off = self.inc_off.data_ptr()
+        tb.inc = self.inc.data_ptr()
+        tb.sched = self.sched.data_ptr()
+        tb.masked_items = self.masked_items.data_ptr()
+        tb.joint_rot = self.joint_rot.data_ptr() if self.joint_rot is not None else None
+        tb.n_rounds = self.n_rounds
+        tb.group = self.group
+        tb.ents_per_lane = self.ents_per_lane
+        self.tb = tb
+        self._state_key = None
+        self._state = None
+
+    def state_struct(self, slab) -> StateC:
+        key = tuple(t.data_ptr() for t in slab.tensors())
+        if key != self._state_key:
+            for t in slab.tensors():
+                assert t.is_contiguous() and t.dtype == torch.float32 and t.device == self.device
+            st = StateC()
+            st.pos, st.vel, st.rot, st.ang_vel, st.force, st.torque = key
+            self._state, self._state_key = st, key
+        return self._state
+
+
+# ---------------------------------------------------------------------------------------------
+# call wrappers
+# ---------------------------------------------------------------------------------------------
+def world_step(lib, dt: DeviceTables, slab, exact_broad_phase: bool = True) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_world_step(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase), _stream(dt.device)
+    )
+    return _check(lib, rc)
+
+
+def world_substeps(lib, dt: DeviceTables, slab, first: int, n: int, exact_broad_phase: bool = True) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_world_substeps(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase), first, n,
+        _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def cast_rays(lib, dt: DeviceTables, slab, src, targets, n_targets, angles, add_rot_of, max_range, out) -> int:
+    st = dt.state_struct(slab)
+    assert angles.is_contiguous() and out.is_contiguous() and angles.dtype == torch.float32
+    rc = lib.vmas_b200_cast_rays(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), int(src), targets.data_ptr(), int(n_targets),
+        angles.data_ptr(), int(angles.shape[-1]), -1 if add_rot_of is None else int(add_rot_of),
+        float(max_range), out.data_ptr(), _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def pair_query(lib, dt: DeviceTables, slab, a: int, b: int, mode: int, out) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_pair_query(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), a, b, mode, out.data_ptr(), _stream(dt.device)
+    )
+    return _check(lib, rc)
+
+
+def point_query(lib, dt: DeviceTables, slab, entity: int, point, out) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_point_query(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), entity, point.data_ptr(), out.data_ptr(), _stream(dt.device)
+    )
+    return _check(lib, rc)
+
+
+def broad_phase(lib, dt: DeviceTables, slab) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_broad_phase(C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), _stream(dt.device))
+    return _check(lib, rc)

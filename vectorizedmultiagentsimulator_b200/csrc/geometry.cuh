@@ -1,0 +1,212 @@
+// geometry.cuh — scalar (one pair, one env) narrow-phase geometry for the VMAS physics kernels.
+//
+// Each routine is the per-element arithmetic of one batched routine of the reference
+// (/root/reference/vmas/simulator/physics.py, cited per function), written for registers:
+// segments carry their precomputed unit direction so sin/cos are evaluated once per entity per
+// substep.  The file is compiled with -fmad=false: every multiply and add rounds separately,
+// like the reference's chain of eager elementwise ops; the only fused operation is inside
+// norm2(), which reproduces torch's vector_norm rounding (sqrt(fma(y, y, x*x))).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#define DEVI __device__ __forceinline__
+
+namespace vmas {
+
+struct V2 {
+  float x, y;
+};
+
+DEVI V2 mk(float x, float y) { V2 v; v.x = x; v.y = y; return v; }
+DEVI V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+DEVI V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+DEVI V2 operator*(V2 a, float k) { return mk(a.x * k, a.y * k); }
+DEVI V2 neg(V2 a) { return mk(-a.x, -a.y); }
+
+// torch.linalg.vector_norm over a length-2 last dim on CPU rounds as sqrt(fma(y, y, x*x)).
+DEVI float norm2(float x, float y) { return sqrtf(__fmaf_rn(y, y, __fmul_rn(x, x))); }
+DEVI float norm2(V2 v) { return norm2(v.x, v.y); }
+DEVI float dot2(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }           // (a*b).sum(-1)
+DEVI float cross2(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }         // ref utils.py:194-197
+DEVI float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }     // torch.sign
+// rotate `v` by the angle whose (cos, sin) is (c, s)  (ref utils.py:176-191)
+DEVI V2 rot2(V2 v, float c, float s) { return mk(v.x * c - v.y * s, v.x * s + v.y * c); }
+
+// A segment: centre, unit direction (cos, sin of its angle), half length.
+struct Seg {
+  V2 p;
+  float c, s;
+  float half;
+};
+DEVI Seg mkseg(V2 p, float c, float s, float half) { Seg g; g.p = p; g.c = c; g.s = s; g.half = half; return g; }
+
+// Closest point of a segment to q (ref physics.py:400-429, limit_to_line_length=True).
+DEVI V2 closest_point_seg(const Seg& l, V2 q) {
+  V2 d = l.p - q;
+  float along = d.x * l.c + d.y * l.s;
+  float reach = sgnf(along) * fminf(fabsf(along), l.half);
+  return mk(l.p.x - reach * l.c, l.p.y - reach * l.s);
+}
+
+// Same on the infinite carrier line (limit_to_line_length=False; used by the LIDAR).
+DEVI V2 closest_point_carrier(V2 p, float c, float s, V2 q) {
+  V2 d = p - q;
+  float along = d.x * c + d.y * s;
+  float reach = sgnf(along) * fabsf(along);
+  return mk(p.x - reach * c, p.y - reach * s);
+}
+
+struct Pair {
+  V2 a, b;
+};
+
+// Closest pair of points between two segments (ref physics.py:144-219, 222-260, 132-141).
+DEVI Pair closest_seg_seg(const Seg& l1, const Seg& l2) {
+  V2 o1 = mk(l1.half * l1.c, l1.half * l1.s);
+  V2 o2 = mk(l2.half * l2.c, l2.half * l2.s);
+  V2 a1 = l1.p + o1, a2 = l1.p - o1;
+  V2 b1 = l2.p + o2, b2 = l2.p - o2;
+
+  // four end-point projections, first strict minimum
+  Pair best;
+  best.a = mk(INFINITY, INFINITY);
+  best.b = mk(INFINITY, INFINITY);
+  float dbest = INFINITY;
+  {
+    V2 q = closest_point_seg(l2, a1);
+    float d = norm2(a1 - q);
+    if (d < dbest) { dbest = d; best.a = a1; best.b = q; }
+  }
+  {
+    V2 q = closest_point_seg(l2, a2);
+    float d = norm2(a2 - q);
+    if (d < dbest) { dbest = d; best.a = a2; best.b = q; }
+  }
+  {
+    V2 q = closest_point_seg(l1, b1);
+    float d = norm2(q - b1);
+    if (d < dbest) { dbest = d; best.a = q; best.b = b1; }
+  }
+  {
+    V2 q = closest_point_seg(l1, b2);
+    float d = norm2(q - b2);
+    if (d < dbest) { dbest = d; best.a = q; best.b = b2; }
+  }
+  // proper intersection overrides both points
+  V2 r = a2 - a1, s = b2 - b1, qp = b1 - a1;
+  float rxs = cross2(r, s);
+  float u = cross2(qp, r) / rxs;
+  float t = cross2(qp, s) / rxs;
+  if (rxs != 0.f && 0.f <= u && u <= 1.f && 0.f <= t && t <= 1.f) {
+    V2 x = mk(a1.x + t * r.x, a1.y + t * r.y);
+    best.a = x;
+    best.b = x;
+  }
+  return best;
+}
+
+// A box in world space: centre, (cos, sin) of its angle and of angle + pi/2, half extents.
+struct BoxG {
+  V2 p;
+  float c, s, c2, s2;
+  float half_l, half_w;
+};
+
+// Side i of a box as a segment (ref physics.py:298-325): the two `length`-end sides first.
+DEVI Seg box_side(const BoxG& b, int i) {
+  switch (i) {
+    case 0: return mkseg(mk(b.p.x + b.c * b.half_l, b.p.y + b.s * b.half_l), b.c2, b.s2, b.half_w);
+    case 1: return mkseg(mk(b.p.x - b.c * b.half_l, b.p.y - b.s * b.half_l), b.c2, b.s2, b.half_w);
+    case 2: return mkseg(mk(b.p.x + b.c2 * b.half_w, b.p.y + b.s2 * b.half_w), b.c, b.s, b.half_l);
+    default: return mkseg(mk(b.p.x - b.c2 * b.half_w, b.p.y - b.s2 * b.half_w), b.c, b.s, b.half_l);
+  }
+}
+
+// Closest point on the outline of a box to q (ref physics.py:263-295, 385-397).
+DEVI V2 closest_point_box(const BoxG& b, V2 q) {
+  V2 best = mk(INFINITY, INFINITY);
+  float dbest = INFINITY;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Seg sd = box_side(b, i);
+    V2 p = closest_point_seg(sd, q);
+    float d = norm2(q - p);
+    if (d < dbest) { dbest = d; best = p; }
+  }
+  return best;
+}
+
+// Closest (point on box, point on segment) (ref physics.py:328-382).
+DEVI Pair closest_box_seg(const BoxG& b, const Seg& l) {
+  Pair best;
+  best.a = mk(INFINITY, INFINITY);
+  best.b = mk(INFINITY, INFINITY);
+  float dbest = INFINITY;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    Seg sd = box_side(b, i);
+    Pair c = closest_seg_seg(sd, l);
+    float d = norm2(c.a - c.b);
+    if (d < dbest) { dbest = d; best = c; }
+  }
+  return best;
+}
+
+// Closest (point on box 1, point on box 2) (ref physics.py:26-129): the four sides of box 1
+// against box 2, then the four sides of box 2 against box 1; first strict minimum.
+DEVI Pair closest_box_box(const BoxG& b1, const BoxG& b2) {
+  Pair best;
+  best.a = mk(INFINITY, INFINITY);
+  best.b = mk(INFINITY, INFINITY);
+  float dbest = INFINITY;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    Seg sd = box_side(b1, i);
+    Pair c = closest_box_seg(b2, sd);  // c.a on box 2, c.b on the side of box 1
+    float d = norm2(c.b - c.a);
+    if (d < dbest) { dbest = d; best.a = c.b; best.b = c.a; }
+  }
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    Seg sd = box_side(b2, i);
+    Pair c = closest_box_seg(b1, sd);  // c.a on box 1, c.b on the side of box 2
+    float d = norm2(c.a - c.b);
+    if (d < dbest) { dbest = d; best.a = c.a; best.b = c.b; }
+  }
+  return best;
+}
+
+// Point inside a solid box the contact force is measured from, and its depth
+// (ref physics.py:13-23, incl. the 2*surface result when outside == surface).
+DEVI V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, float* depth) {
+  V2 v = surface - outside;
+  V2 u = box_pos - surface;
+  float vn = norm2(v);
+  float xm = (v.x * u.x + v.y * u.y) / vn;
+  V2 x = mk((v.x / vn) * xm, (v.y / vn) * xm);
+  if (vn == 0.f) {
+    x = surface;
+    xm = 0.f;
+  }
+  *depth = fabsf(xm);
+  return surface + x;
+}
+
+// Soft-plus penalty force on `a` (b receives the negative) (ref core.py:2805-2839).
+// k = contact margin, c = force multiplier.  Returns exactly 0 outside the active range, which is
+// also what the reference's masks produce; the transcendental path only runs for live contacts.
+DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {
+  V2 delta = pa - pb;
+  float d = norm2(delta);
+  if (d < 1e-6f) return mk(0.f, 0.f);
+  if (attractive ? (d < dmin) : (d > dmin)) return mk(0.f, 0.f);
+  float sign = attractive ? -1.f : 1.f;
+  float x = ((dmin - d) * sign) / k;
+  float pen = (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) * k;  // logaddexp(0, x) * k
+  float cc = sign * c;
+  float denom = d > 0.f ? d : 1e-8f;
+  return mk(((cc * delta.x) / denom) * pen, ((cc * delta.y) / denom) * pen);
+}
+
+}  // namespace vmas

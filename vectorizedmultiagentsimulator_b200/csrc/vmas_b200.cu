@@ -1,0 +1,918 @@
+// vmas_b200.cu — sm_100a kernels + C ABI for the VMAS physics hot path (see include/vmas_b200.h).
+//
+// Kernels
+//   step_kernel<G, EPL>   fused substep(s): per-entity forces -> joint/contact work items ->
+//                         ordered accumulation -> semi-implicit Euler -> write-back.
+//                         G lanes of a warp own one env (lane = entity); work items are spread
+//                         over the same lanes in kind-uniform rounds, results staged in shared
+//                         memory and summed per entity in the reference's order (deterministic,
+//                         no atomics).  Sphere-only worlds run all substeps in one launch with
+//                         the state held in registers.
+//   broad_phase_kernel    batch-wide activation mask of line/box pairs (ref core.py:2797-2801).
+//   cast_rays_kernel      LIDAR: thread per (env, ray), min over target entities.
+//   pair_query_kernel /   World.get_distance / is_overlapping / get_distance_from_point.
+//   point_query_kernel
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (no fast-math).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "geometry.cuh"
+#include "vmas_b200.h"
+
+namespace vmas {
+
+static thread_local char g_last_error[512] = "";
+
+static int fail(const char* fmt, const char* detail = "") {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, detail);
+  return -1;
+}
+
+#define CUDA_OK(expr)                                                    \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return fail("CUDA error: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr float HALF_PI_F = 1.57079632679489661923f;  // fp32(torch.pi / 2)
+constexpr float LINE_MIN_DIST_F = (float)(4.0 / 6e2);
+
+struct StepArgs {
+  VmasWorldConfig cfg;
+  VmasPlanTables tb;
+  VmasState st;
+  uint32_t* mask;      // [mask_words + 1]; last word counts blocks that have consumed the mask
+  int use_mask;
+  int mask_words;
+  int first_substep;
+  int n_substeps;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-entity geometry cached in shared memory for the work-item phase
+// ---------------------------------------------------------------------------------------------
+struct EnvShared {
+  float *px, *py, *rot, *c, *s, *c2, *s2;  // [ES] each (this env's slice)
+  float *rfx, *rfy, *rta, *rtb;      // [NI] each
+};
+
+DEVI V2 ent_pos(const EnvShared& sh, int e) { return mk(sh.px[e], sh.py[e]); }
+
+DEVI Seg ent_seg(const EnvShared& sh, int e, float length) {
+  return mkseg(ent_pos(sh, e), sh.c[e], sh.s[e], length / 2.f);
+}
+
+DEVI BoxG ent_box(const EnvShared& sh, int e, float length, float width) {
+  BoxG b;
+  b.p = ent_pos(sh, e);
+  b.c = sh.c[e];
+  b.s = sh.s[e];
+  b.c2 = sh.c2[e];
+  b.s2 = sh.s2[e];
+  b.half_l = length / 2.f;
+  b.half_w = width / 2.f;
+  return b;
+}
+
+// One work item -> (force on a, torque on a, torque on b); the force on b is the negative.
+DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, float* out_fx, float* out_fy,
+                    float* out_ta, float* out_tb) {
+  const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
+  const int kind = ii.x, ea = ii.y, eb = ii.z, flags = ii.w & 0xff;
+  const float* f32 = a.tb.item_f32 + (size_t)item * VMAS_IF_COLS;
+  const float dmin_base = __ldg(f32 + VMAS_IF_DMIN_BASE);
+  const float* pa_f = a.tb.ent_f32 + (size_t)ea * VMAS_EF_COLS;
+  const float* pb_f = a.tb.ent_f32 + (size_t)eb * VMAS_EF_COLS;
+  const float cf = a.cfg.collision_force, km = a.cfg.contact_margin;
+  V2 f = mk(0.f, 0.f);
+  float ta = 0.f, tb = 0.f;
+
+  switch (kind) {
+    case VMAS_K_JOINT: {  // ref core.py:2201-2292, joints.py:209-216
+      V2 pa = ent_pos(sh, ea), pb = ent_pos(sh, eb);
+      V2 da = mk(__ldg(f32 + VMAS_IF_AX), __ldg(f32 + VMAS_IF_AY));
+      V2 db = mk(__ldg(f32 + VMAS_IF_BX), __ldg(f32 + VMAS_IF_BY));
+      V2 qa = pa + rot2(da, sh.c[ea], sh.s[ea]);
+      V2 qb = pb + rot2(db, sh.c[eb], sh.s[eb]);
+      float dist = __ldg(f32 + VMAS_IF_DIST);
+      V2 f_attr = constraint_force(qa, qb, dist, a.cfg.joint_force, km, true);
+      V2 f_rep = constraint_force(qa, qb, dist, a.cfg.joint_force, km, false);
+      f = f_attr + f_rep;
+      V2 fb = neg(f_attr) + neg(f_rep);
+      ta = cross2(qa - pa, f);
+      tb = cross2(qb - pb, fb);
+      if (!(flags & VMAS_IFLAG_JOINT_ROTATE)) {  // ref core.py:2841-2858
+        float jr = (flags & VMAS_IFLAG_JOINT_ROT_PER_ENV)
+                       ? a.tb.joint_rot[(size_t)env * a.cfg.n_joints + item]
+                       : __ldg(f32 + VMAS_IF_FIXED_ROT);
+        float ra = sh.rot[ea], rb = sh.rot[eb];
+        float delta = ra - (rb + jr);
+        float mag = sqrtf(delta * delta);
+        float t = (a.cfg.torque_constraint_force * sgnf(delta)) * (expf(mag) - 1.f);
+        if (mag < 1e-9f) t = 0.f;
+        ta = ta + (-t);
+        tb = tb + t;
+      }
+      break;
+    }
+    case VMAS_K_SS: {  // ref core.py:2294-2339
+      f = constraint_force(ent_pos(sh, ea), ent_pos(sh, eb), dmin_base, cf, km, false);
+      break;
+    }
+    case VMAS_K_LS: {  // a = line, b = sphere; ref core.py:2341-2392
+      Seg l = ent_seg(sh, ea, __ldg(pa_f + VMAS_EF_D0));
+      V2 ps = ent_pos(sh, eb);
+      V2 cp = closest_point_seg(l, ps);
+      V2 f_sphere = constraint_force(ps, cp, dmin_base, cf, km, false);
+      f = neg(f_sphere);  // force on the line
+      ta = cross2(cp - l.p, f);
+      break;
+    }
+    case VMAS_K_LL: {  // ref core.py:2394-2457
+      Seg l1 = ent_seg(sh, ea, __ldg(pa_f + VMAS_EF_D0));
+      Seg l2 = ent_seg(sh, eb, __ldg(pb_f + VMAS_EF_D0));
+      Pair c = closest_seg_seg(l1, l2);
+      f = constraint_force(c.a, c.b, dmin_base, cf, km, false);
+      ta = cross2(c.a - l1.p, f);
+      tb = cross2(c.b - l2.p, neg(f));
+      break;
+    }
+    case VMAS_K_BS: {  // a = box, b = sphere; ref core.py:2459-2552
+      BoxG bx = ent_box(sh, ea, __ldg(pa_f + VMAS_EF_D0), __ldg(pa_f + VMAS_EF_D1));
+      const bool hollow = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
+      V2 ps = ent_pos(sh, eb);
+      V2 cp = closest_point_box(bx, ps);
+      V2 inner = cp;
+      float d = 0.f;
+      if (!hollow) inner = inner_point_box(ps, cp, bx.p, &d);
+      V2 f_sphere = constraint_force(ps, inner, dmin_base + d, cf, km, false);
+      f = neg(f_sphere);  // force on the box
+      ta = cross2(cp - bx.p, f);
+      break;
+    }
+    case VMAS_K_BL: {  // a = box, b = line; ref core.py:2554-2653
+      BoxG bx = ent_box(sh, ea, __ldg(pa_f + VMAS_EF_D0), __ldg(pa_f + VMAS_EF_D1));
+      const bool hollow = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
+      Seg l = ent_seg(sh, eb, __ldg(pb_f + VMAS_EF_D0));
+      Pair c = closest_box_seg(bx, l);
+      V2 inner = c.a;
+      float d = 0.f;
+      if (!hollow) inner = inner_point_box(c.b, c.a, bx.p, &d);
+      f = constraint_force(inner, c.b, dmin_base + d, cf, km, false);
+      ta = cross2(c.a - bx.p, f);
+      tb = cross2(c.b - l.p, neg(f));
+      break;
+    }
+    case VMAS_K_BB: {  // ref core.py:2655-2786
+      BoxG b1 = ent_box(sh, ea, __ldg(pa_f + VMAS_EF_D0), __ldg(pa_f + VMAS_EF_D1));
+      BoxG b2 = ent_box(sh, eb, __ldg(pb_f + VMAS_EF_D0), __ldg(pb_f + VMAS_EF_D1));
+      const bool hollow1 = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
+      const bool hollow2 = __ldg(a.tb.ent_i32 + eb * 4 + 1) & VMAS_F_HOLLOW;
+      Pair c = closest_box_box(b1, b2);
+      V2 in1 = c.a, in2 = c.b;
+      float d1 = 0.f, d2 = 0.f;
+      if (!hollow1) in1 = inner_point_box(c.b, c.a, b1.p, &d1);
+      if (!hollow2) in2 = inner_point_box(c.a, c.b, b2.p, &d2);
+      f = constraint_force(in1, in2, (d1 + d2) + dmin_base, cf, km, false);
+      ta = cross2(c.a - b1.p, f);
+      tb = cross2(c.b - b2.p, neg(f));
+      break;
+    }
+    default:
+      break;
+  }
+  *out_fx = f.x;
+  *out_fy = f.y;
+  *out_ta = ta;
+  *out_tb = tb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused substep kernel
+// ---------------------------------------------------------------------------------------------
+template <int G, int EPL>
+__global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
+  extern __shared__ float smem[];
+  constexpr int ES = G * EPL;
+  const int EPB = blockDim.x / G;
+  const int E = a.cfg.n_entities, NI = a.cfg.n_items, A = a.cfg.n_agents;
+  const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+  const long env = (long)blockIdx.x * EPB + grp;
+  const bool live = env < a.cfg.batch_dim;
+
+  // shared memory carve-up: 7 entity arrays, 4 result arrays, mask words
+  float* base = smem;
+  EnvShared sh;
+  sh.px = base + (size_t)(0 * EPB + grp) * ES;
+  sh.py = base + (size_t)(1 * EPB + grp) * ES;
+  sh.rot = base + (size_t)(2 * EPB + grp) * ES;
+  sh.c = base + (size_t)(3 * EPB + grp) * ES;
+  sh.s = base + (size_t)(4 * EPB + grp) * ES;
+  sh.c2 = base + (size_t)(5 * EPB + grp) * ES;
+  sh.s2 = base + (size_t)(6 * EPB + grp) * ES;
+  float* res = base + (size_t)7 * EPB * ES;
+  sh.rfx = res + (size_t)(0 * EPB + grp) * NI;
+  sh.rfy = res + (size_t)(1 * EPB + grp) * NI;
+  sh.rta = res + (size_t)(2 * EPB + grp) * NI;
+  sh.rtb = res + (size_t)(3 * EPB + grp) * NI;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(res + (size_t)4 * EPB * NI);
+
+  if (a.use_mask) {
+    for (int w = threadIdx.x; w < a.mask_words; w += blockDim.x) s_mask[w] = a.mask[w];
+    __syncthreads();
+    // the last block to have copied the mask clears it for the next broad-phase pass
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned done = atomicAdd(&a.mask[a.mask_words], 1u);
+      if (done == gridDim.x - 1) {
+        for (int w = 0; w < a.mask_words; ++w) a.mask[w] = 0u;
+        a.mask[a.mask_words] = 0u;
+      }
+    }
+  }
+
+  // ---- per-lane entity state -----------------------------------------------------------
+  float px[EPL], py[EPL], vx[EPL], vy[EPL], rt[EPL], w[EPL];
+  float afx[EPL], afy[EPL], atq[EPL];  // action force / torque (agents)
+  int flg[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const int e = lane + j * G;
+    flg[j] = 0;
+    px[j] = py[j] = vx[j] = vy[j] = rt[j] = w[j] = afx[j] = afy[j] = atq[j] = 0.f;
+    if (live && e < E) {
+      const size_t idx = (size_t)env * E + e;
+      flg[j] = __ldg(a.tb.ent_i32 + e * 4 + 1) | (1 << 30);  // bit 30: slot in use
+      const float2 p = reinterpret_cast<const float2*>(a.st.pos)[idx];
+      px[j] = p.x;
+      py[j] = p.y;
+      rt[j] = a.st.rot[idx];
+      if (flg[j] & VMAS_F_MOVABLE) {
+        const float2 v = reinterpret_cast<const float2*>(a.st.vel)[idx];
+        vx[j] = v.x;
+        vy[j] = v.y;
+      }
+      if (flg[j] & VMAS_F_ROTATABLE) w[j] = a.st.ang_vel[idx];
+      if (flg[j] & VMAS_F_AGENT) {
+        const int ai = __ldg(a.tb.ent_i32 + e * 4 + 2);
+        const size_t aidx = (size_t)env * A + ai;
+        if (flg[j] & VMAS_F_MOVABLE) {
+          const float2 f = reinterpret_cast<const float2*>(a.st.force)[aidx];
+          afx[j] = f.x;
+          afy[j] = f.y;
+        }
+        if (flg[j] & VMAS_F_ROTATABLE) atq[j] = a.st.torque[aidx];
+      }
+    }
+  }
+
+  const float sub_dt = a.cfg.sub_dt;
+  for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
+    float Fx[EPL], Fy[EPL], T[EPL];
+    // ---- phase A: publish geometry, per-entity forces (ref core.py:1995-2004) -------------
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + j * G;
+      Fx[j] = Fy[j] = T[j] = 0.f;
+      if (!(flg[j] >> 30)) continue;
+      const float* ef = a.tb.ent_f32 + (size_t)e * VMAS_EF_COLS;
+      sh.px[e] = px[j];
+      sh.py[e] = py[j];
+      sh.rot[e] = rt[j];
+      if (flg[j] & VMAS_F_TRIG) {
+        float sn, cs;
+        sincosf(rt[j], &sn, &cs);
+        sh.c[e] = cs;
+        sh.s[e] = sn;
+        if (__ldg(a.tb.ent_i32 + e * 4) == VMAS_SHAPE_BOX) {
+          sincosf(rt[j] + HALF_PI_F, &sn, &cs);
+          sh.c2[e] = cs;
+          sh.s2[e] = sn;
+        }
+      }
+      const float mass = __ldg(ef + VMAS_EF_MASS);
+      if (flg[j] & VMAS_F_AGENT) {  // ref core.py:2018-2041
+        if (flg[j] & VMAS_F_MOVABLE) {
+          if (flg[j] & VMAS_F_MAX_F) {
+            const float mx = __ldg(ef + VMAS_EF_MAX_F);
+            const float n = norm2(afx[j], afy[j]);
+            if (n > mx) {
+              afx[j] = (afx[j] / n) * mx;
+              afy[j] = (afy[j] / n) * mx;
+            }
+          }
+          if (flg[j] & VMAS_F_F_RANGE) {
+            const float r = __ldg(ef + VMAS_EF_F_RANGE);
+            afx[j] = fminf(fmaxf(afx[j], -r), r);
+            afy[j] = fminf(fmaxf(afy[j], -r), r);
+          }
+          Fx[j] = Fx[j] + afx[j];
+          Fy[j] = Fy[j] + afy[j];
+        }
+        if (flg[j] & VMAS_F_ROTATABLE) {
+          if (flg[j] & VMAS_F_MAX_T) {
+            const float mx = __ldg(ef + VMAS_EF_MAX_T);
+            const float n = sqrtf(atq[j] * atq[j]);
+            if (n > mx) atq[j] = (atq[j] / n) * mx;
+          }
+          if (flg[j] & VMAS_F_T_RANGE) {
+            const float r = __ldg(ef + VMAS_EF_T_RANGE);
+            atq[j] = fminf(fmaxf(atq[j], -r), r);
+          }
+          T[j] = T[j] + atq[j];
+        }
+      }
+      if (flg[j] & VMAS_F_LIN_FRIC) {  // ref core.py:2054-2088
+        const float speed = norm2(vx[j], vy[j]);
+        if (speed != 0.f) {
+          const float cap = __ldg(ef + VMAS_EF_LIN_FRIC) * mass;
+          Fx[j] = Fx[j] + (-(vx[j] / speed)) * fminf(cap, (fabsf(vx[j]) / sub_dt) * mass);
+          Fy[j] = Fy[j] + (-(vy[j] / speed)) * fminf(cap, (fabsf(vy[j]) / sub_dt) * mass);
+        }
+      }
+      if (flg[j] & VMAS_F_ANG_FRIC) {  // ref core.py:2089-2102
+        const float speed = sqrtf(w[j] * w[j]);
+        if (speed != 0.f) {
+          const float inertia = __ldg(ef + VMAS_EF_INERTIA);
+          const float cap = __ldg(ef + VMAS_EF_ANG_FRIC) * inertia;
+          T[j] = T[j] + (-(w[j] / speed)) * fminf(cap, (fabsf(w[j]) / sub_dt) * inertia);
+        }
+      }
+      if (flg[j] & VMAS_F_MOVABLE) {  // ref core.py:2043-2052
+        if (a.cfg.has_world_gravity) {
+          Fx[j] = Fx[j] + mass * a.cfg.gravity_x;
+          Fy[j] = Fy[j] + mass * a.cfg.gravity_y;
+        }
+        if (flg[j] & VMAS_F_GRAVITY) {
+          Fx[j] = Fx[j] + mass * __ldg(ef + VMAS_EF_GRAV_X);
+          Fy[j] = Fy[j] + mass * __ldg(ef + VMAS_EF_GRAV_Y);
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- phase B: joint / contact work items, one per lane per round ------------------------
+    for (int r = 0; r < a.tb.n_rounds; ++r) {
+      const int item = __ldg(a.tb.sched + r * G + lane);
+      if (item < 0 || !live) continue;
+      bool active = true;
+      if (a.use_mask) {
+        const int mbit = (__ldg(a.tb.item_i32 + item * 4 + 3) >> 8) - 1;
+        if (mbit >= 0) active = (s_mask[mbit >> 5] >> (mbit & 31)) & 1u;
+      }
+      float fx = 0.f, fy = 0.f, ta = 0.f, tb = 0.f;
+      if (active) eval_item(a, sh, item, env, &fx, &fy, &ta, &tb);
+      sh.rfx[item] = fx;
+      sh.rfy[item] = fy;
+      sh.rta[item] = ta;
+      sh.rtb[item] = tb;
+    }
+    __syncwarp();
+
+    // ---- phase C: ordered accumulation (ref core.py:2191-2199) + integration (:2862-2908) ----
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + j * G;
+      if (!(flg[j] >> 30)) continue;
+      const bool movable = flg[j] & VMAS_F_MOVABLE, rotatable = flg[j] & VMAS_F_ROTATABLE;
+      if (!movable && !rotatable) continue;
+      const int lo = __ldg(a.tb.inc_off + e), hi = __ldg(a.tb.inc_off + e + 1);
+      for (int i = lo; i < hi; ++i) {
+        const int v = __ldg(a.tb.inc + i);
+        const int item = v >> 1;
+        if (v & 1) {
+          if (movable) {
+            Fx[j] = Fx[j] + (-sh.rfx[item]);
+            Fy[j] = Fy[j] + (-sh.rfy[item]);
+          }
+          if (rotatable) T[j] = T[j] + sh.rtb[item];
+        } else {
+          if (movable) {
+            Fx[j] = Fx[j] + sh.rfx[item];
+            Fy[j] = Fy[j] + sh.rfy[item];
+          }
+          if (rotatable) T[j] = T[j] + sh.rta[item];
+        }
+      }
+      const float* ef = a.tb.ent_f32 + (size_t)e * VMAS_EF_COLS;
+      const float drag_mult = __ldg(ef + VMAS_EF_DRAG_MULT);
+      if (movable) {
+        const float mass = __ldg(ef + VMAS_EF_MASS);
+        if (sub == 0) {
+          vx[j] = vx[j] * drag_mult;
+          vy[j] = vy[j] * drag_mult;
+        }
+        vx[j] = vx[j] + (Fx[j] / mass) * sub_dt;
+        vy[j] = vy[j] + (Fy[j] / mass) * sub_dt;
+        if (flg[j] & VMAS_F_MAX_SPEED) {
+          const float mx = __ldg(ef + VMAS_EF_MAX_SPEED);
+          const float n = norm2(vx[j], vy[j]);
+          if (n > mx) {
+            vx[j] = (vx[j] / n) * mx;
+            vy[j] = (vy[j] / n) * mx;
+          }
+        }
+        if (flg[j] & VMAS_F_V_RANGE) {
+          const float r = __ldg(ef + VMAS_EF_V_RANGE);
+          vx[j] = fminf(fmaxf(vx[j], -r), r);
+          vy[j] = fminf(fmaxf(vy[j], -r), r);
+        }
+        px[j] = px[j] + vx[j] * sub_dt;
+        py[j] = py[j] + vy[j] * sub_dt;
+        if (a.cfg.has_x_semidim) px[j] = fminf(fmaxf(px[j], -a.cfg.x_semidim), a.cfg.x_semidim);
+        if (a.cfg.has_y_semidim) py[j] = fminf(fmaxf(py[j], -a.cfg.y_semidim), a.cfg.y_semidim);
+      }
+      if (rotatable) {
+        const float inertia = __ldg(ef + VMAS_EF_INERTIA);
+        if (sub == 0) w[j] = w[j] * drag_mult;
+        w[j] = w[j] + (T[j] / inertia) * sub_dt;
+        rt[j] = rt[j] + w[j] * sub_dt;
+      }
+    }
+  }
+
+  // ---- write-back: only what can have changed --------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const int e = lane + j * G;
+    if (!(flg[j] >> 30)) continue;
+    const size_t idx = (size_t)env * E + e;
+    if (flg[j] & VMAS_F_MOVABLE) {
+      reinterpret_cast<float2*>(a.st.pos)[idx] = make_float2(px[j], py[j]);
+      reinterpret_cast<float2*>(a.st.vel)[idx] = make_float2(vx[j], vy[j]);
+    }
+    if (flg[j] & VMAS_F_ROTATABLE) {
+      a.st.rot[idx] = rt[j];
+      a.st.ang_vel[idx] = w[j];
+    }
+    if (flg[j] & VMAS_F_AGENT) {
+      const int ai = __ldg(a.tb.ent_i32 + e * 4 + 2);
+      const size_t aidx = (size_t)env * A + ai;
+      if ((flg[j] & VMAS_F_MOVABLE) && (flg[j] & (VMAS_F_MAX_F | VMAS_F_F_RANGE)))
+        reinterpret_cast<float2*>(a.st.force)[aidx] = make_float2(afx[j], afy[j]);
+      if ((flg[j] & VMAS_F_ROTATABLE) && (flg[j] & (VMAS_F_MAX_T | VMAS_F_T_RANGE)))
+        a.st.torque[aidx] = atq[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch-wide broad phase (ref core.py:2797-2801): bit i <- any_env(|pa - pb| <= Ra + Rb)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) broad_phase_kernel(const StepArgs a) {
+  extern __shared__ uint32_t s_bits[];
+  const int W = a.mask_words;
+  for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = 0u;
+  __syncthreads();
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = env < a.cfg.batch_dim;
+  const int E = a.cfg.n_entities;
+  const float2* pos = reinterpret_cast<const float2*>(a.st.pos) + (size_t)(live ? env : 0) * E;
+  for (int w = 0; w < W; ++w) {
+    uint32_t bits = 0u;
+    const int n = min(32, a.cfg.n_masked - 32 * w);
+    for (int j = 0; j < n; ++j) {
+      const int item = __ldg(a.tb.masked_items + 32 * w + j);
+      const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
+      const float thr = __ldg(a.tb.item_f32 + (size_t)item * VMAS_IF_COLS + VMAS_IF_BROAD_THR);
+      if (live) {
+        const float2 pa = pos[ii.y], pb = pos[ii.z];
+        if (norm2(pa.x - pb.x, pa.y - pb.y) <= thr) bits |= 1u << j;
+      }
+    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits) atomicOr(&s_bits[w], bits);
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    const uint32_t b = s_bits[w];
+    if (b) atomicOr(&a.mask[w], b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LIDAR (ref core.py:1662-1786 and the three shape kernels 1281-1372, 1414-1490, 1544-1626)
+// ---------------------------------------------------------------------------------------------
+// torch.min / torch.max propagate NaN; fminf / fmaxf do not.
+DEVI float tmin(float x, float y) { return (x != x || y != y) ? NAN : fminf(x, y); }
+DEVI float tmax(float x, float y) { return (x != x || y != y) ? NAN : fmaxf(x, y); }
+
+struct RayArgs {
+  VmasWorldConfig cfg;
+  VmasPlanTables tb;
+  VmasState st;
+  const int32_t* targets;
+  const float* angles;
+  float* out;
+  int32_t src, n_targets, n_rays, add_rot_of;
+  float max_range;
+};
+
+DEVI float ray_vs_entity(const RayArgs& a, V2 o, float ang, float dc, float ds, int t, size_t env_base) {
+  const int shape = __ldg(a.tb.ent_i32 + t * 4);
+  const float* ef = a.tb.ent_f32 + (size_t)t * VMAS_EF_COLS;
+  const float2 tp = reinterpret_cast<const float2*>(a.st.pos)[env_base + t];
+  const V2 c = mk(tp.x, tp.y);
+  const float max_range = a.max_range;
+  if (shape == VMAS_SHAPE_SPHERE) {
+    const float radius = __ldg(ef + VMAS_EF_D0);
+    const float half = max_range / 2.f;
+    V2 line_pos = mk(o.x + dc * half, o.y + ds * half);
+    V2 closest = closest_point_carrier(line_pos, dc, ds, c);
+    float dn = norm2(c - closest);
+    bool hits = dn < radius;
+    float aa = radius * radius - dn * dn;
+    float m = sqrtf(aa > 0.f ? aa : 1e-8f);
+    V2 u = c - o;
+    bool front = (u.x * dc + u.y * ds) > 0.f;
+    float dist = norm2(closest - o) - m;
+    return (hits && front) ? dist : max_range;
+  }
+  const float trot = a.st.rot[env_base + t];
+  if (shape == VMAS_SHAPE_BOX) {
+    const float L = __ldg(ef + VMAS_EF_D0), Wd = __ldg(ef + VMAS_EF_D1);
+    float sn, cs;
+    sincosf(-trot, &sn, &cs);
+    V2 ol = rot2(o - c, cs, sn);
+    V2 dl = rot2(mk(dc, ds), cs, sn);
+    float tx1 = (-L / 2.f - ol.x) / dl.x, tx2 = (L / 2.f - ol.x) / dl.x;
+    float t0 = tmin(tx1, tx2), t1 = tmax(tx1, tx2);
+    float ty1 = (-Wd / 2.f - ol.y) / dl.y, ty2 = (Wd / 2.f - ol.y) / dl.y;
+    float ty0 = tmin(ty1, ty2), tyM = tmax(ty1, ty2);
+    t0 = tmax(t0, ty0);
+    t1 = tmin(t1, tyM);
+    V2 hl = mk(t0 * dl.x + ol.x, t0 * dl.y + ol.y);
+    float sn2, cs2;
+    sincosf(trot, &sn2, &cs2);
+    V2 hw = rot2(hl, cs2, sn2) + c;
+    bool hit = (t1 >= t0) && (t0 > 0.f);
+    return hit ? norm2(o - hw) : max_range;
+  }
+  // line
+  {
+    const float L = __ldg(ef + VMAS_EF_D0);
+    float sn, cs;
+    sincosf(trot, &sn, &cs);
+    V2 r = mk(cs * L, sn * L);
+    V2 s = mk(dc, ds);
+    float rxs = cross2(r, s);
+    V2 qp = o - c;
+    float tt = cross2(qp, mk(s.x / rxs, s.y / rxs));
+    float uu = cross2(qp, mk(r.x / rxs, r.y / rxs));
+    float d = norm2(uu * s.x, uu * s.y);
+    bool miss = (rxs == 0.f) || (tt > 0.5f) || (tt < -0.5f) || (uu < 0.f);
+    return miss ? max_range : d;
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_rays_kernel(const RayArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)a.cfg.batch_dim * a.n_rays;
+  if (idx >= total) return;
+  const long env = idx / a.n_rays;
+  const size_t env_base = (size_t)env * a.cfg.n_entities;
+  float ang = a.angles[idx];
+  if (a.add_rot_of >= 0) ang = ang + a.st.rot[env_base + a.add_rot_of];
+  float ds, dc;
+  sincosf(ang, &ds, &dc);
+  const float2 op = reinterpret_cast<const float2*>(a.st.pos)[env_base + a.src];
+  const V2 o = mk(op.x, op.y);
+  float best = a.max_range;
+  for (int i = 0; i < a.n_targets; ++i) {
+    const int t = __ldg(a.targets + i);
+    best = tmin(best, ray_vs_entity(a, o, ang, dc, ds, t, env_base));
+  }
+  a.out[idx] = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// distance / overlap queries (ref core.py:1788-1969)
+// ---------------------------------------------------------------------------------------------
+struct QueryArgs {
+  VmasWorldConfig cfg;
+  VmasPlanTables tb;
+  VmasState st;
+  int32_t a, b, mode;
+  const float* point;
+  void* out;
+};
+
+struct EntG {
+  int shape;
+  V2 p;
+  float rot, d0, d1;
+};
+
+DEVI EntG load_ent(const QueryArgs& q, int e, size_t env_base) {
+  EntG g;
+  g.shape = __ldg(q.tb.ent_i32 + e * 4);
+  const float2 p = reinterpret_cast<const float2*>(q.st.pos)[env_base + e];
+  g.p = mk(p.x, p.y);
+  g.rot = q.st.rot[env_base + e];
+  g.d0 = __ldg(q.tb.ent_f32 + (size_t)e * VMAS_EF_COLS + VMAS_EF_D0);
+  g.d1 = __ldg(q.tb.ent_f32 + (size_t)e * VMAS_EF_COLS + VMAS_EF_D1);
+  return g;
+}
+
+DEVI Seg seg_of(const EntG& g) {
+  float sn, cs;
+  sincosf(g.rot, &sn, &cs);
+  return mkseg(g.p, cs, sn, g.d0 / 2.f);
+}
+
+DEVI BoxG box_of(const EntG& g) {
+  BoxG b;
+  b.p = g.p;
+  sincosf(g.rot, &b.s, &b.c);
+  sincosf(g.rot + HALF_PI_F, &b.s2, &b.c2);
+  b.half_l = g.d0 / 2.f;
+  b.half_w = g.d1 / 2.f;
+  return b;
+}
+
+// ref core.py:1788-1820
+DEVI float dist_from_point(const EntG& g, V2 pt) {
+  if (g.shape == VMAS_SHAPE_SPHERE) return norm2(g.p - pt) - g.d0;
+  V2 cp = (g.shape == VMAS_SHAPE_BOX) ? closest_point_box(box_of(g), pt) : closest_point_seg(seg_of(g), pt);
+  return norm2(pt - cp) - LINE_MIN_DIST_F;
+}
+
+// ref core.py:1933-1964 (box / sphere overlap)
+DEVI bool box_sphere_overlap(const QueryArgs& q, const EntG& box, const EntG& sph, int sph_index) {
+  V2 cp = closest_point_box(box_of(box), sph.p);
+  float d_s_cp = norm2(sph.p - cp);
+  float d_s_b = norm2(sph.p - box.p);
+  float d_cp_b = norm2(box.p - cp);
+  // fp32(radius + LINE_MIN_DIST) with the sum taken in double, as the reference does
+  const float dist_min = __ldg(q.tb.ent_f32 + (size_t)sph_index * VMAS_EF_COLS + VMAS_EF_R_PLUS_LMD);
+  return (d_s_b < d_cp_b) || (d_s_cp < dist_min);
+}
+
+// ref core.py:1822-1905
+DEVI float pair_distance(const QueryArgs& q, const EntG& ga, const EntG& gb, int ia, int ib) {
+  const int sa = ga.shape, sb = gb.shape;
+  if (sa == VMAS_SHAPE_SPHERE && sb == VMAS_SHAPE_SPHERE) return dist_from_point(ga, gb.p) - gb.d0;
+  if ((sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_SPHERE) || (sb == VMAS_SHAPE_BOX && sa == VMAS_SHAPE_SPHERE)) {
+    const bool a_is_box = sa == VMAS_SHAPE_BOX;
+    const EntG& box = a_is_box ? ga : gb;
+    const EntG& sph = a_is_box ? gb : ga;
+    float d = dist_from_point(box, sph.p) - sph.d0;
+    return box_sphere_overlap(q, box, sph, a_is_box ? ib : ia) ? -1.f : d;
+  }
+  if ((sa == VMAS_SHAPE_LINE && sb == VMAS_SHAPE_SPHERE) || (sb == VMAS_SHAPE_LINE && sa == VMAS_SHAPE_SPHERE)) {
+    const EntG& line = sa == VMAS_SHAPE_LINE ? ga : gb;
+    const EntG& sph = sa == VMAS_SHAPE_LINE ? gb : ga;
+    return dist_from_point(line, sph.p) - sph.d0;
+  }
+  Pair c;
+  if (sa == VMAS_SHAPE_LINE && sb == VMAS_SHAPE_LINE) {
+    c = closest_seg_seg(seg_of(ga), seg_of(gb));
+  } else if (sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_BOX) {
+    c = closest_box_box(box_of(ga), box_of(gb));
+  } else {
+    const EntG& box = sa == VMAS_SHAPE_BOX ? ga : gb;
+    const EntG& line = sa == VMAS_SHAPE_BOX ? gb : ga;
+    c = closest_box_seg(box_of(box), seg_of(line));
+  }
+  return norm2(c.a - c.b) - LINE_MIN_DIST_F;
+}
+
+__global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= q.cfg.batch_dim) return;
+  const size_t env_base = (size_t)env * q.cfg.n_entities;
+  const EntG ga = load_ent(q, q.a, env_base), gb = load_ent(q, q.b, env_base);
+  if (q.mode == 0) {
+    static_cast<float*>(q.out)[env] = pair_distance(q, ga, gb, q.a, q.b);
+    return;
+  }
+  bool over;
+  const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
+                          (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
+  if (box_sphere) {
+    const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
+    over = box_sphere_overlap(q, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? q.b : q.a);
+  } else {
+    over = pair_distance(q, ga, gb, q.a, q.b) < 0.f;
+  }
+  static_cast<uint8_t*>(q.out)[env] = over ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) point_query_kernel(const QueryArgs q) {
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= q.cfg.batch_dim) return;
+  const EntG g = load_ent(q, q.a, (size_t)env * q.cfg.n_entities);
+  const float2 pt = reinterpret_cast<const float2*>(q.point)[env];
+  static_cast<float*>(q.out)[env] = dist_from_point(g, mk(pt.x, pt.y));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int check_common(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st) {
+  if (!cfg || !tb || !st) return fail("null argument%s");
+  if (cfg->batch_dim <= 0 || cfg->n_entities <= 0) return fail("empty world%s");
+  if (!st->pos || !st->vel || !st->rot || !st->ang_vel) return fail("null state pointer%s");
+  if (!tb->ent_f32 || !tb->ent_i32) return fail("null entity tables%s");
+  return 0;
+}
+
+template <int G, int EPL>
+static int launch_step(const StepArgs& args, cudaStream_t stream) {
+  const int E = args.cfg.n_entities, NI = args.cfg.n_items;
+  if (E > G * EPL) return fail("internal: entity count exceeds the lane layout%s");
+  // shrink the block (fewer envs per block) until the result staging fits in shared memory
+  int device = 0;
+  CUDA_OK(cudaGetDevice(&device));
+  static int max_optin[64] = {0};
+  if (device < 64 && max_optin[device] == 0)
+    CUDA_OK(cudaDeviceGetAttribute(&max_optin[device], cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const size_t limit = device < 64 ? (size_t)max_optin[device] : 48 * 1024;
+  int threads = 128;
+  size_t smem = 0;
+  for (;;) {
+    const int epb = threads / G;
+    smem = ((size_t)7 * epb * G * EPL + (size_t)4 * epb * NI) * sizeof(float) +
+           (size_t)(args.use_mask ? args.mask_words : 0) * sizeof(uint32_t);
+    if (smem <= limit || threads <= G) break;
+    threads /= 2;
+  }
+  if (smem > limit) return fail("world too large: work items do not fit in shared memory%s");
+  static size_t configured[64] = {0};
+  auto kern = step_kernel<G, EPL>;
+  if (smem > 48 * 1024 && (device >= 64 || configured[device] < smem)) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    if (device < 64) configured[device] = limit;
+  }
+  const int epb = threads / G;
+  const long blocks = ((long)args.cfg.batch_dim + epb - 1) / epb;
+  kern<<<(unsigned)blocks, threads, smem, stream>>>(args);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
+  const int G = args.tb.group, EPL = args.tb.ents_per_lane;
+  if (G == 8 && EPL == 1) return launch_step<8, 1>(args, stream);
+  if (G == 16 && EPL == 1) return launch_step<16, 1>(args, stream);
+  if (G == 32 && EPL == 1) return launch_step<32, 1>(args, stream);
+  if (G == 32 && EPL == 2) return launch_step<32, 2>(args, stream);
+  if (G == 32 && EPL == 4) return launch_step<32, 4>(args, stream);
+  return fail("unsupported lane layout (group, ents_per_lane)%s");
+}
+
+static int launch_broad_phase(const StepArgs& args, cudaStream_t stream) {
+  const int threads = 256;
+  const long blocks = ((long)args.cfg.batch_dim + threads - 1) / threads;
+  broad_phase_kernel<<<(unsigned)blocks, threads, args.mask_words * sizeof(uint32_t), stream>>>(args);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace vmas
+
+using namespace vmas;
+
+extern "C" {
+
+int vmas_b200_abi_version(void) { return VMAS_B200_ABI_VERSION; }
+
+const char* vmas_b200_last_error(void) { return g_last_error; }
+
+int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                             uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
+                             void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (cfg->n_agents > 0 && (!st->force || !st->torque)) return fail("null force/torque pointer%s");
+  if (cfg->n_items > 0 && (!tb->item_f32 || !tb->item_i32 || !tb->sched || !tb->inc || !tb->inc_off))
+    return fail("null item tables%s");
+  if (n_substeps <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  StepArgs args;
+  args.cfg = *cfg;
+  args.tb = *tb;
+  args.st = *st;
+  args.mask = mask;
+  args.mask_words = (cfg->n_masked + 31) / 32;
+  const bool masked = cfg->n_masked > 0 && exact_broad_phase;
+  if (masked && (!mask || !tb->masked_items)) return fail("broad-phase mask scratch missing%s");
+  int launches = 0;
+  if (!masked) {
+    args.use_mask = 0;
+    args.first_substep = first_substep;
+    args.n_substeps = n_substeps;
+    int r = dispatch_step(args, stream);
+    if (r < 0) return r;
+    return r;
+  }
+  args.use_mask = 1;
+  for (int s = first_substep; s < first_substep + n_substeps; ++s) {
+    args.first_substep = s;
+    args.n_substeps = 1;
+    int r = launch_broad_phase(args, stream);
+    if (r < 0) return r;
+    launches += r;
+    r = dispatch_step(args, stream);
+    if (r < 0) return r;
+    launches += r;
+  }
+  return launches;
+}
+
+int vmas_b200_world_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                         uint32_t* mask, int exact_broad_phase, void* cuda_stream) {
+  if (!cfg) return fail("null argument%s");
+  return vmas_b200_world_substeps(cfg, tb, st, mask, exact_broad_phase, 0, cfg->substeps, cuda_stream);
+}
+
+int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                          uint32_t* mask, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (cfg->n_masked <= 0) return 0;
+  if (!mask || !tb->masked_items) return fail("broad-phase mask scratch missing%s");
+  StepArgs args;
+  args.cfg = *cfg;
+  args.tb = *tb;
+  args.st = *st;
+  args.mask = mask;
+  args.mask_words = (cfg->n_masked + 31) / 32;
+  args.use_mask = 1;
+  args.first_substep = 0;
+  args.n_substeps = 1;
+  return launch_broad_phase(args, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vmas_b200_cast_rays(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                        int32_t src_entity, const int32_t* targets, int32_t n_targets,
+                        const float* angles, int32_t n_rays, int32_t add_rot_of, float max_range,
+                        float* out, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (!angles || !out || n_rays <= 0) return fail("bad ray buffers%s");
+  if (src_entity < 0 || src_entity >= cfg->n_entities) return fail("source entity out of range%s");
+  if (n_targets > 0 && !targets) return fail("null target list%s");
+  RayArgs a;
+  a.cfg = *cfg;
+  a.tb = *tb;
+  a.st = *st;
+  a.targets = targets;
+  a.angles = angles;
+  a.out = out;
+  a.src = src_entity;
+  a.n_targets = n_targets;
+  a.n_rays = n_rays;
+  a.add_rot_of = add_rot_of;
+  a.max_range = max_range;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * n_rays;
+  const long blocks = (total + threads - 1) / threads;
+  cast_rays_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_pair_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                         int32_t a, int32_t b, int32_t mode, void* out, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (!out) return fail("null output%s");
+  if (a < 0 || b < 0 || a >= cfg->n_entities || b >= cfg->n_entities) return fail("entity out of range%s");
+  QueryArgs q;
+  q.cfg = *cfg;
+  q.tb = *tb;
+  q.st = *st;
+  q.a = a;
+  q.b = b;
+  q.mode = mode;
+  q.point = nullptr;
+  q.out = out;
+  const int threads = 256;
+  const long blocks = ((long)cfg->batch_dim + threads - 1) / threads;
+  pair_query_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(q);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                          int32_t entity, const float* point, float* out, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (!out || !point) return fail("null buffer%s");
+  if (entity < 0 || entity >= cfg->n_entities) return fail("entity out of range%s");
+  QueryArgs q;
+  q.cfg = *cfg;
+  q.tb = *tb;
+  q.st = *st;
+  q.a = entity;
+  q.b = entity;
+  q.mode = 0;
+  q.point = point;
+  q.out = out;
+  const int threads = 256;
+  const long blocks = ((long)cfg->batch_dim + threads - 1) / threads;
+  point_query_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(q);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+}  // extern "C"

@@ -46,6 +46,7 @@ F_MAX_F = 1 << 9
 F_F_RANGE = 1 << 10
 F_MAX_T = 1 << 11
 F_T_RANGE = 1 << 12
+F_TRIG = 1 << 13  # kernel must evaluate sin/cos of this entity's rotation
 
 # columns of ent_f32
 (
@@ -65,8 +66,9 @@ F_T_RANGE = 1 << 12
     EF_MAX_T,
     EF_T_RANGE,
     EF_CIRC_R,
-) = range(16)
-EF_COLS = 16
+    EF_R_PLUS_LMD,
+) = range(17)
+EF_COLS = 20
 EI_COLS = 4  # shape kind, flags, agent index, reserved
 
 # columns of item_f32 / item_i32
@@ -302,7 +304,8 @@ class PlanTables:
     n_joints: int
     n_masked: int  # items subject to the batch-wide broad-phase mask (line/box pairs)
     mask_slot: np.ndarray  # [NI] bit index in the pair mask, -1 if the item is always active
-    spheres_only: bool  # every collision pair is sphere-sphere
+    spheres_only: bool = True  # every collision pair is sphere-sphere
+    masked_items: np.ndarray = None  # [n_masked] item index of each mask bit
 
     def schedule(self, group: int):
         """Round-robin assignment of work items to the ``group`` lanes that own one env.
@@ -330,8 +333,7 @@ def build_tables(desc: WorldDescription) -> PlanTables:
     E = desc.n_entities
     ent_f32 = np.zeros((max(E, 1), EF_COLS), np.float32)
     ent_i32 = np.zeros((max(E, 1), EI_COLS), np.int32)
-    sub_dt = desc.dt / desc.substeps
-    del sub_dt
+    ent_flags: List[int] = []
     for i, e in enumerate(desc.entities):
         flags = 0
         flags |= F_MOVABLE if e["movable"] else 0
@@ -371,7 +373,11 @@ def build_tables(desc: WorldDescription) -> PlanTables:
                 flags |= bit
                 row[col] = e[name]
         row[EF_CIRC_R] = e["circ_radius"]
-        ent_i32[i] = (e["shape"], flags, e["agent_index"], 0)
+        # is_overlapping(box, sphere) compares with fp32(radius + LINE_MIN_DIST), summed in double
+        row[EF_R_PLUS_LMD] = e["d0"] + LINE_MIN_DIST
+        if e["shape"] != SHAPE_SPHERE:
+            flags |= F_TRIG
+        ent_flags.append(flags)
 
     NI = len(desc.items)
     item_f32 = np.zeros((max(NI, 1), IF_COLS), np.float32)
@@ -412,9 +418,15 @@ def build_tables(desc: WorldDescription) -> PlanTables:
                     f[IF_DMIN_BASE] = np.float32(eb["d0"]) + lmd
                 else:  # L-L, B-L, B-B: LINE_MIN_DIST (+ inner-point depths at run time)
                     f[IF_DMIN_BASE] = lmd
-        item_i32[k] = (kind, a, b, flags)
+        if kind == K_JOINT:
+            ent_flags[a] |= F_TRIG
+            ent_flags[b] |= F_TRIG
+        item_i32[k] = (kind, a, b, flags | ((mask_slot[k] + 1) << 8))
         incident[a].append(2 * k)
         incident[b].append(2 * k + 1)
+
+    for i, e in enumerate(desc.entities):
+        ent_i32[i] = (e["shape"], ent_flags[i], e["agent_index"], 0)
 
     inc_off = np.zeros((E + 1,), np.int32)
     for i in range(E):
@@ -434,6 +446,9 @@ def build_tables(desc: WorldDescription) -> PlanTables:
         n_masked=n_masked,
         mask_slot=mask_slot,
         spheres_only=spheres_only,
+        masked_items=(
+            np.nonzero(mask_slot >= 0)[0].astype(np.int32) if n_masked else np.zeros((1,), np.int32)
+        ),
     )
 
 
