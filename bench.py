@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the VMAS physics hot path behind ``Environment.step`` on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: BASELINE.json configs[1] — scenario ``balance``, 32768 envs per GPU, 4 agents,
+continuous random actions pre-generated before the timed region (weak scaling: every rank
+steps its own independent shard of envs; no data-path collective).
+
+One JSON line is printed by rank 0:
+  value        whole-job env-steps/s, actions already resident in HBM
+  e2e          same metric through the public API with HOST buffers: per step the actions are
+               copied from pinned host memory and obs/rewards/dones are copied back to it
+  roofline     the fused substep kernel: algorithmic bytes per launch / CUDA-event duration
+  cpu_baseline the CPU oracle port of the same env on this box's host cores (bounded sample)
+Timing: per-iteration CUDA events on the launching stream, summed; L2 is flushed (512 MiB
+memset) between iterations outside the brackets; max over ranks.
+
+``--impl reference`` times the CPU oracle port of the path (the reference is pure Python and
+does not travel to the GPU box; the oracle is bit-identical to it, see tests/) on all host
+threads, through the same Environment API.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SCENARIO = "balance"
+SCENARIO_KWARGS = dict(n_agents=4)
+ENVS_PER_GPU = 32768
+METRIC = "env-steps/sec"
+
+
+# --------------------------------------------------------------------------------------------
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    p.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-flush", action="store_true", help="keep L2 warm between iterations (not a bench value)")
+    return p.parse_args()
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": mx,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def pregenerate_actions(env, steps, seed, device, pin=False):
+    """[steps][n_agents] tensors of shape [B, action_size], U(-u_range, u_range), from a CPU generator."""
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(steps):
+        per_agent = []
+        for a in env.agents:
+            u = (torch.rand(env.num_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor.cpu()
+            if pin:
+                u = u.pin_memory()
+            else:
+                u = u.to(device)
+            per_agent.append(u)
+        out.append(per_agent)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def run_cpu_oracle_env(n_envs, steps, warmup, threads):
+    """Times the CPU oracle port behind the same Environment API.  Returns (env_steps_per_s, seconds)."""
+    import vectorizedmultiagentsimulator_b200 as b200
+    from oracle.backend import use_oracle
+
+    torch.set_num_threads(threads)
+    with use_oracle():
+        env = b200.make_env(SCENARIO, num_envs=n_envs, device="cpu", seed=0, **SCENARIO_KWARGS)
+        actions = pregenerate_actions(env, warmup + steps, seed=1, device="cpu")
+        for t in range(warmup):
+            env.step(actions[t])
+        t0 = time.perf_counter()
+        for t in range(warmup, warmup + steps):
+            env.step(actions[t])
+        dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def main_reference(args):
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.envs_per_gpu
+    steps = max(1, args.steps)
+    # bounded sample: cap the work at ~60 s of CPU time (an env step of this size is ~0.1 s)
+    steps = min(steps, 100)
+    value, seconds = run_cpu_oracle_env(n_envs, steps, max(1, min(args.warmup, 3)), cores)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "env-steps/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)),
+        "ms_per_step": 1e3 * seconds / steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{SCENARIO} n_agents=4, {n_envs} envs, random continuous actions, CPU",
+            "note": "CPU oracle port of the reference path (bit-identical to the reference, tests/); the pure-Python reference does not travel to the GPU box",
+        },
+        "cpu_baseline": {
+            "value": value,
+            "unit": "env-steps/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{steps} env steps of {n_envs} envs",
+        },
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main_b200(args):
+    rank, world, local = dist_info()
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+
+    import vectorizedmultiagentsimulator_b200 as b200
+    from vectorizedmultiagentsimulator_b200.simulator import plan as P
+
+    B, K, W = args.envs_per_gpu, args.steps, max(args.warmup, 3)
+    env = b200.make_env(SCENARIO, num_envs=B, device=device, seed=rank, **SCENARIO_KWARGS)
+    backend = env.world._get_backend()
+    backend.refresh()
+    desc = backend.tables.desc
+    bytes_per_env_substep = P.algorithmic_bytes_per_env_substep(desc)
+
+    flush = None if args.no_flush else torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, n):
+        """Σ over iterations of the CUDA-event time of step_fn(i); L2 flushed outside the brackets."""
+        pairs = []
+        for i in range(n):
+            if flush is not None:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn(i)
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in pairs)  # ms
+
+    # ---- arm 1: actions resident in HBM --------------------------------------------------
+    dev_actions = pregenerate_actions(env, W + K, seed=1 + rank, device=device)
+    for t in range(W):
+        env.step(dev_actions[t])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches_before = backend.launches
+    backend.kernel_events = []
+    wall0 = time.perf_counter()
+    ms_total = timed_loop(lambda i: env.step(dev_actions[W + i]), K)
+    wall = time.perf_counter() - wall0
+    kernel_pairs = backend.kernel_events
+    backend.kernel_events = None
+    launches = backend.launches - launches_before
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / max(len(kernel_pairs), 1)
+
+    # ---- arm 2: end to end with host buffers --------------------------------------------------
+    host_actions = pregenerate_actions(env, W + K, seed=101 + rank, device=device, pin=True)
+    act_dev = [torch.empty_like(a, device=device) for a in host_actions[0]]
+    obs0, rew0, done0, _ = env.step(dev_actions[0])
+    host_obs = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in obs0]
+    host_rew = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in rew0]
+    host_done = torch.empty(done0.shape, dtype=done0.dtype).pin_memory()
+    h2d_bytes = sum(a.numel() * a.element_size() for a in host_actions[0])
+    d2h_bytes = sum(t.numel() * t.element_size() for t in host_obs + host_rew + [host_done])
+
+    def e2e_step(i):
+        for dst, src in zip(act_dev, host_actions[W + i]):
+            dst.copy_(src, non_blocking=True)
+        obs, rews, dones, _ = env.step(act_dev)
+        for dst, src in zip(host_obs, obs):
+            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(host_rew, rews):
+            dst.copy_(src, non_blocking=True)
+        host_done.copy_(dones, non_blocking=True)
+
+    for t in range(3):
+        e2e_step(t - W)
+    barrier()
+    ms_e2e = timed_loop(e2e_step, K)
+    barrier()
+    env.check_actions_now()
+
+    # ---- reduce over ranks ---------------------------------------------------------------------
+    stats = torch.tensor([ms_total, ms_e2e, kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, kernel_ms = (float(x) for x in stats.tolist())
+    value = world * B * K / (ms_total * 1e-3)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused substep kernel -----------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = bytes_per_env_substep * B  # one launch advances B envs by one substep (S=1 here)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": "step_kernel<8,1> (fused substep)",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "bytes_per_launch": alg_bytes,
+        "bytes_per_env_substep": bytes_per_env_substep,
+        "kernel_us": kernel_ms * 1e3,
+    }
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu_steps = args.cpu_steps or 40
+        v, seconds = run_cpu_oracle_env(B, cpu_steps, 2, cores)
+        cpu_baseline = {
+            "value": v,
+            "unit": "env-steps/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{cpu_steps} env steps of {B} envs ({seconds:.1f} s), CPU oracle port behind the same Environment API",
+        }
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "env-steps/s",
+        "n_gpus": world,
+        "steps": K,
+        "warmup": W,
+        "ms_per_step": ms_total / K,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{SCENARIO} n_agents=4, {B} envs per GPU, 1 substep, random continuous actions (BASELINE.json configs[1])",
+            "timing": "sum of per-iteration CUDA-event brackets around Environment.step; max over ranks",
+            "l2": "flushed between iterations (512 MiB memset outside the brackets)" if flush is not None else "NOT flushed",
+            "wall_ms_per_step_incl_flush": 1e3 * wall / K,
+        },
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_value,
+            "unit": "env-steps/s",
+            "h2d_bytes_per_step": h2d_bytes,
+            "d2h_bytes_per_step": d2h_bytes,
+            "ms_per_step": ms_e2e / K,
+        },
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_b200(args)

@@ -106,6 +106,16 @@ const char* vmas_b200_last_error(void);
 int vmas_b200_world_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                          uint32_t* mask, int exact_broad_phase, void* cuda_stream);
 
+/*
+ * Same as vmas_b200_world_step, additionally recording two caller-owned CUDA events
+ * (cudaEvent_t, may be NULL) on the stream: `ev_begin` right before the first substep kernel
+ * and `ev_end` right after the last one.  The broad-phase launches of worlds with line/box
+ * pairs fall inside the bracket only when S > 1.  Used by bench.py for the roofline figure.
+ */
+int vmas_b200_world_step_timed(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                               uint32_t* mask, int exact_broad_phase, void* cuda_stream,
+                               void* ev_begin, void* ev_end);
+
 /* Same, for a sub-range of substeps [first_substep, first_substep + n_substeps) (testing). */
 int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                              uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,

@@ -41,6 +41,7 @@ class OracleBackend(PlanRuntime):
         src = self.index_of(entity)
         targets = self.ray_targets(entity, entity_filter)
         slab = self.world.slab
+        angles = angles.to(torch.float32)
         return queries.cast_rays(self.tables, slab.pos, slab.rot, src, targets, angles, max_range)
 
     def lidar_measure(self, sensor):
@@ -49,21 +50,19 @@ class OracleBackend(PlanRuntime):
         )
 
     def pair_distance(self, a, b):
+        self.refresh()
         slab = self.world.slab
         return queries.pair_distance(self.tables, slab.pos, slab.rot, self.index_of(a), self.index_of(b))
 
     def pair_overlap(self, a, b):
+        self.refresh()
         slab = self.world.slab
         return queries.pair_overlap(self.tables, slab.pos, slab.rot, self.index_of(a), self.index_of(b))
 
     def distance_from_point(self, entity, point):
+        self.refresh()
         slab = self.world.slab
         return queries.distance_from_point(self.tables, slab.pos, slab.rot, self.index_of(entity), point)
-
-    def any_within_broad_phase(self, a, b):
-        thr = a.shape.circumscribed_radius() + b.shape.circumscribed_radius()
-        d = torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1)
-        return bool((d <= thr).any())
 
 
 @contextlib.contextmanager

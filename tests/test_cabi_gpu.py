@@ -5,11 +5,12 @@ forces) is loaded on the GPU, ``vmas_b200_world_step`` runs once, and the result
 with what the unmodified reference produced (tests/golden/, made by tests/make_golden.py) and
 with the CPU oracle run live on the same input.
 
-Tolerance (north star: 1e-4 relative, fp32): |got - want| <= ATOL + 1e-4 * |want|.
-ATOL is 1e-5 for contact-only worlds.  Worlds with zero-length joints get 2e-4: the reference's
-joint force is c * delta/|delta| * pen with |delta| ~ 1e-4, which amplifies a 1-ulp difference
-in a position by ~1e3 (the reference itself moves by 1e-5 when its own logaddexp switches
-between its vectorised and scalar code paths; see DESIGN.md "parity envelope").
+Tolerance (north star: 1e-4 relative, fp32): |got - want| <= 1e-5 + 1e-4 * |want|.
+Worlds with zero-length joints add the reference's own sensitivity: the joint force is
+c * delta/|delta| * pen with |delta| down to 1e-6 (anchors coincide right after a reset), which
+amplifies a 1-ulp difference in an anchor position (CUDA vs SLEEF sin/cos) by up to 1e5.  For
+those worlds the bound is widened by 4x what the CPU oracle itself moves when its inputs are
+perturbed by 1 ulp (measured live, per step and field; see DESIGN.md "parity envelope").
 """
 import pytest
 import torch
@@ -36,8 +37,24 @@ class _Slab:
         return tuple(self.t[k] for k in STATE_KEYS)
 
 
-def _atol(name):
-    return 2e-4 if name in JOINT_WORLDS else 1e-5
+ATOL = 1e-5
+
+
+def _ulp_sensitivity(tables, state_in, fixed_rot, trials=3):
+    """max |oracle(x) - oracle(x perturbed by +-1 ulp)| per field."""
+    base = {k: v.clone() for k, v in state_in.items()}
+    WS.world_step(tables, base, fixed_rot=fixed_rot)
+    gen = torch.Generator().manual_seed(0)
+    worst = {k: 0.0 for k in STATE_KEYS}
+    for _ in range(trials):
+        pert = {k: v.clone() for k, v in state_in.items()}
+        for k in ("pos", "rot"):
+            sign = torch.randint(0, 3, pert[k].shape, generator=gen).float() - 1.0
+            pert[k] = pert[k] * (1.0 + sign * 2.0**-23)
+        WS.world_step(tables, pert, fixed_rot=fixed_rot)
+        for k in STATE_KEYS:
+            worst[k] = max(worst[k], float((pert[k] - base[k]).abs().max()))
+    return worst
 
 
 def _device_tables(tables, fixed_rot, device):
@@ -47,7 +64,7 @@ def _device_tables(tables, fixed_rot, device):
     return dt
 
 
-def _close(got, want, atol):
+def _close(got, want, atol=ATOL):
     err = (got.cpu() - want).abs()
     bound = atol + RTOL * want.abs()
     return bool((err <= bound).all()), float(err.max())
@@ -64,10 +81,12 @@ def test_world_step_vs_reference_golden(name):
         slab = _Slab(state_in, device)
         n = _native.world_step(lib, dt, slab)
         assert n >= 1
+        sens = _ulp_sensitivity(tables, state_in, fixed_rot) if name in JOINT_WORLDS else None
         for k in STATE_KEYS:
-            ok, err = _close(slab.t[k], want[k], _atol(name))
+            atol = ATOL + (4.0 * sens[k] if sens else 0.0)
+            ok, err = _close(slab.t[k], want[k], atol)
             worst = max(worst, err)
-            assert ok, f"{name} step {t} field {k}: max |err| {err}"
+            assert ok, f"{name} step {t} field {k}: max |err| {err} (atol {atol:.2e})"
     print(f"{name}: max |err| vs reference {worst:.3e}")
 
 
@@ -85,9 +104,11 @@ def test_world_step_vs_live_oracle(name):
         dt = _device_tables(tables, fixed_rot, device)
         slab = _Slab(state_in, device)
         _native.world_step(lib, dt, slab)
+        sens = _ulp_sensitivity(tables, state_in, fixed_rot) if name in JOINT_WORLDS else None
         for k in STATE_KEYS:
-            ok, err = _close(slab.t[k], cpu[k], _atol(name))
-            assert ok, f"{name} step {t} field {k}: max |err| {err}"
+            atol = ATOL + (4.0 * sens[k] if sens else 0.0)
+            ok, err = _close(slab.t[k], cpu[k], atol)
+            assert ok, f"{name} step {t} field {k}: max |err| {err} (atol {atol:.2e})"
 
 
 @pytest.mark.parametrize("name", ["navigation", "flocking"])

@@ -1,0 +1,111 @@
+"""End-to-end parity on the GPU: ``make_env(...).step`` on CUDA vs the same env on the CPU oracle.
+
+The CPU-oracle env is itself pinned against the unmodified reference in
+tests/test_env_vs_reference.py (bit-equal obs / rewards / dones); here the CUDA env is compared
+with it teacher-forced (state re-synchronised before every step) and in a short free roll-out.
+"""
+import pytest
+import torch
+
+import vectorizedmultiagentsimulator_b200 as b200
+from envutil import flatten, sync_env
+from oracle.backend import use_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("balance", dict(n_agents=4)),
+    ("transport", dict(n_agents=4)),
+    ("transport", dict(n_agents=4, n_lines=2, substeps=3)),  # BASELINE.json configs[2] variant
+    ("navigation", dict(n_agents=8)),
+    ("flocking", dict(n_agents=5)),
+]
+
+
+def _make_pair(name, kwargs, n_envs):
+    with use_oracle():
+        cpu = b200.make_env(name, num_envs=n_envs, device="cpu", seed=0, **kwargs)
+    gpu = b200.make_env(name, num_envs=n_envs, device="cuda", seed=0, **kwargs)
+    return cpu, gpu
+
+
+def _compare(got, want, what, atol, rtol=1e-4):
+    g, w = flatten(got), flatten(want)
+    assert len(g) == len(w), what
+    for a, b in zip(g, w):
+        a = a.cpu()
+        assert a.shape == b.shape and a.dtype == b.dtype, what
+        if a.dtype == torch.bool:
+            assert torch.equal(a, b), what
+        else:
+            err = (a - b).abs()
+            assert bool((err <= atol + rtol * b.abs()).all()), f"{what}: max |err| {float(err.max())}"
+
+
+@pytest.mark.parametrize("name,kwargs", CASES)
+def test_env_step_teacher_forced(name, kwargs):
+    n_envs = 64
+    cpu, gpu = _make_pair(name, kwargs, n_envs)
+    gen = torch.Generator().manual_seed(7)
+    for t in range(12):
+        sync_env(cpu, gpu)
+        actions = [
+            (torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor for a in cpu.agents
+        ]
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step([a.to("cuda") for a in actions])
+        # rewards are differences of shaping terms ~1e2: compare with an absolute 1e-4
+        _compare(got[0], want[0], f"{name} step {t} obs", atol=1e-5)
+        _compare(got[1], want[1], f"{name} step {t} rews", atol=2e-4)
+        _compare(got[2], want[2], f"{name} step {t} dones", atol=0)
+        _compare(got[3], want[3], f"{name} step {t} infos", atol=2e-4)
+    gpu.check_actions_now()
+    assert gpu.world._get_backend().launches > 0
+
+
+@pytest.mark.parametrize("name,kwargs", CASES[:1] + CASES[3:])
+def test_env_free_rollout(name, kwargs):
+    n_envs = 32
+    cpu, gpu = _make_pair(name, kwargs, n_envs)
+    sync_env(cpu, gpu)
+    gen = torch.Generator().manual_seed(9)
+    for t in range(10):
+        actions = [
+            (torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor for a in cpu.agents
+        ]
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step([a.to("cuda") for a in actions])
+    _compare(got[0], want[0], f"{name} rollout obs", atol=1e-4)
+
+
+def test_reset_at_and_state_views_on_gpu():
+    env = b200.make_env("transport", num_envs=8, device="cuda", seed=0, n_agents=3)
+    agent = env.world.agents[0]
+    pos_view = agent.state.pos
+    env.step(env.get_random_actions())
+    assert pos_view.data_ptr() == agent.state.pos.data_ptr(), "state must stay a view into the slab"
+    before = env.world.slab.pos.clone()
+    env.reset_at(3)
+    after = env.world.slab.pos
+    changed = (before != after).flatten(1).any(1)
+    assert bool(changed[3]) and not bool(changed[[0, 1, 2, 4, 5, 6, 7]].any())
+    # in-place row write through the getter view lands in the slab
+    agent.state.pos[2] = torch.tensor([0.25, -0.5], device="cuda")
+    assert torch.equal(env.world.slab.pos[2, env.world.entities.index(agent)].cpu(), torch.tensor([0.25, -0.5]))
+
+
+def test_cpu_world_refuses_to_step():
+    env_world_error = None
+    try:
+        b200.make_env("balance", num_envs=2, device="cpu", seed=0)
+    except RuntimeError as err:  # the first observation needs is_overlapping -> CUDA only
+        env_world_error = str(err)
+    assert env_world_error and "no CPU fallback" in env_world_error
+
+
+def test_deferred_action_check_raises_next_step():
+    env = b200.make_env("navigation", num_envs=4, device="cuda", seed=0, n_agents=2)
+    bad = [torch.full((4, 2), 5.0, device="cuda") for _ in env.agents]
+    env.step(bad)  # flagged on the device, raised on the next call
+    with pytest.raises(AssertionError):
+        env.step(env.get_random_actions())

@@ -128,6 +128,7 @@ EXPORTS = [
     "vmas_b200_last_error",
     "vmas_b200_world_step",
     "vmas_b200_world_substeps",
+    "vmas_b200_world_step_timed",
     "vmas_b200_cast_rays",
     "vmas_b200_pair_query",
     "vmas_b200_point_query",
@@ -157,6 +158,9 @@ def load():
     lib.vmas_b200_world_step.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_int, C.c_void_p]
     lib.vmas_b200_world_substeps.argtypes = [
         p_cfg, p_tb, p_st, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p
+    ]
+    lib.vmas_b200_world_step_timed.argtypes = [
+        p_cfg, p_tb, p_st, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p
     ]
     lib.vmas_b200_cast_rays.argtypes = [
         p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
@@ -294,11 +298,24 @@ class DeviceTables:
 # ---------------------------------------------------------------------------------------------
 # call wrappers
 # ---------------------------------------------------------------------------------------------
-def world_step(lib, dt: DeviceTables, slab, exact_broad_phase: bool = True) -> int:
+def world_step(lib, dt: DeviceTables, slab, exact_broad_phase: bool = True, events=None) -> int:
+    """One World.step.  ``events``: optional (begin, end) torch.cuda.Event pair (timing enabled)
+    recorded around the substep kernel(s) only."""
     st = dt.state_struct(slab)
-    rc = lib.vmas_b200_world_step(
-        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase), _stream(dt.device)
-    )
+    if events is None:
+        rc = lib.vmas_b200_world_step(
+            C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase),
+            _stream(dt.device),
+        )
+    else:
+        # torch creates the underlying cudaEvent lazily on first record(): force creation
+        for ev in events:
+            if not ev.cuda_event:
+                ev.record()
+        rc = lib.vmas_b200_world_step_timed(
+            C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase),
+            _stream(dt.device), events[0].cuda_event, events[1].cuda_event,
+        )
     return _check(lib, rc)
 
 

@@ -118,6 +118,9 @@ class CudaBackend(PlanRuntime):
         self._mask = None
         self._ray_cache: Dict[Tuple[int, Callable], Tensor] = {}
         self.launches = 0
+        #: when set to a list, every step() appends a (begin, end) event pair bracketing the
+        #: substep kernel(s) (bench.py's roofline measurement)
+        self.kernel_events = None
 
     # -- tables ----------------------------------------------------------------------------
     def on_new_tables(self):
@@ -147,8 +150,12 @@ class CudaBackend(PlanRuntime):
         self.refresh()
         self._sync_fixed_rotations()
         slab = self.world.slab
+        events = None
+        if self.kernel_events is not None:
+            events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.kernel_events.append(events)
         self.launches += self._native.world_step(
-            self.lib, self._dev_tables, slab, exact_broad_phase=self.world.exact_broad_phase
+            self.lib, self._dev_tables, slab, exact_broad_phase=self.world.exact_broad_phase, events=events
         )
 
     def _targets_tensor(self, entity, entity_filter) -> Tuple[int, Tensor]:
@@ -220,10 +227,3 @@ class CudaBackend(PlanRuntime):
         self._native.point_query(self.lib, self._dev_tables, self.world.slab, ie, point, out)
         self.launches += 1
         return out
-
-    def any_within_broad_phase(self, a, b) -> bool:
-        ia, ib = self.index_of(a), self.index_of(b)
-        thr = a.shape.circumscribed_radius() + b.shape.circumscribed_radius()
-        pos = self.world.slab.pos
-        d = torch.linalg.vector_norm(pos[:, ia] - pos[:, ib], dim=-1)
-        return bool((d <= thr).any())

@@ -782,9 +782,9 @@ int vmas_b200_abi_version(void) { return VMAS_B200_ABI_VERSION; }
 
 const char* vmas_b200_last_error(void) { return g_last_error; }
 
-int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
-                             uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
-                             void* cuda_stream) {
+static int substeps_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                         uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
+                         void* cuda_stream, void* ev_begin, void* ev_end) {
   if (check_common(cfg, tb, st) < 0) return -1;
   if (cfg->n_agents > 0 && (!st->force || !st->torque)) return fail("null force/torque pointer%s");
   if (cfg->n_items > 0 && (!tb->item_f32 || !tb->item_i32 || !tb->sched || !tb->inc || !tb->inc_off))
@@ -804,8 +804,10 @@ int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* t
     args.use_mask = 0;
     args.first_substep = first_substep;
     args.n_substeps = n_substeps;
+    if (ev_begin) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), stream));
     int r = dispatch_step(args, stream);
     if (r < 0) return r;
+    if (ev_end) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), stream));
     return r;
   }
   args.use_mask = 1;
@@ -815,11 +817,27 @@ int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* t
     int r = launch_broad_phase(args, stream);
     if (r < 0) return r;
     launches += r;
+    if (ev_begin && s == first_substep) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), stream));
     r = dispatch_step(args, stream);
     if (r < 0) return r;
     launches += r;
   }
+  if (ev_end) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), stream));
   return launches;
+}
+
+int vmas_b200_world_substeps(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                             uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
+                             void* cuda_stream) {
+  return substeps_impl(cfg, tb, st, mask, exact_broad_phase, first_substep, n_substeps, cuda_stream, nullptr,
+                       nullptr);
+}
+
+int vmas_b200_world_step_timed(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                               uint32_t* mask, int exact_broad_phase, void* cuda_stream, void* ev_begin,
+                               void* ev_end) {
+  if (!cfg) return fail("null argument%s");
+  return substeps_impl(cfg, tb, st, mask, exact_broad_phase, 0, cfg->substeps, cuda_stream, ev_begin, ev_end);
 }
 
 int vmas_b200_world_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,

@@ -6,6 +6,7 @@ an unmodified reference checkout's scenario files can be dropped in.  Files from
 package import ``vmas.simulator...``; :func:`..compat.install_vmas_alias` is called so those
 imports resolve to this package.
 """
+import importlib
 import importlib.util
 import os
 from pathlib import Path
@@ -29,10 +30,14 @@ def _find(name: str):
 def load(name: str):
     pathname = _find(name)
     assert pathname is not None, f"{name} scenario not found."
-    if not os.path.abspath(pathname).startswith(os.path.dirname(os.path.abspath(__file__))):
-        from ..compat import install_vmas_alias
+    here = os.path.dirname(os.path.abspath(__file__))
+    if os.path.abspath(pathname).startswith(here + os.sep):
+        # one of this package's scenarios: a regular submodule (they use relative imports)
+        rel = os.path.relpath(os.path.abspath(pathname), here)[: -len(".py")]
+        return importlib.import_module(__name__ + "." + rel.replace(os.sep, "."))
+    from ..compat import install_vmas_alias
 
-        install_vmas_alias()
+    install_vmas_alias()
     spec = importlib.util.spec_from_file_location("", pathname)
     module = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(module)

@@ -1,0 +1,128 @@
+"""``transport``: agents push heavy box packages onto a goal.
+
+Task definition of the reference's ``vmas/scenarios/transport.py`` (world :16-67, reset :69-127,
+reward :129-166, observation :168-185, done :187-194) re-written on the public API.  Two extra
+kwargs build the BASELINE.json variant that the reference does not ship
+(``n_lines`` movable/rotatable Line landmarks, ``substeps``); with their defaults the world is
+the stock one.
+"""
+import torch
+
+from ..simulator.core import Agent, Box, Landmark, Line, Sphere, World
+from ..simulator.scenario import BaseScenario
+from ..simulator.utils import Color, ScenarioUtils
+
+
+class Scenario(BaseScenario):
+    def make_world(self, batch_dim: int, device: torch.device, **kwargs):
+        n_agents = kwargs.pop("n_agents", 4)
+        self.n_packages = kwargs.pop("n_packages", 1)
+        self.package_width = kwargs.pop("package_width", 0.15)
+        self.package_length = kwargs.pop("package_length", 0.15)
+        self.package_mass = kwargs.pop("package_mass", 50)
+        self.n_lines = kwargs.pop("n_lines", 0)  # B200-bench variant only
+        self.line_length = kwargs.pop("line_length", 0.3)
+        substeps = kwargs.pop("substeps", 1)
+        ScenarioUtils.check_kwargs_consumed(kwargs)
+
+        self.shaping_factor = 100
+        self.world_semidim = 1
+        self.agent_radius = 0.03
+
+        semidim = self.world_semidim + 2 * self.agent_radius + max(self.package_length, self.package_width)
+        world = World(batch_dim, device, x_semidim=semidim, y_semidim=semidim, substeps=substeps)
+        for i in range(n_agents):
+            world.add_agent(Agent(name=f"agent_{i}", shape=Sphere(self.agent_radius), u_multiplier=0.6))
+        goal = Landmark(name="goal", collide=False, shape=Sphere(radius=0.15), color=Color.LIGHT_GREEN)
+        world.add_landmark(goal)
+        self.packages = []
+        for i in range(self.n_packages):
+            package = Landmark(
+                name=f"package {i}",
+                collide=True,
+                movable=True,
+                mass=self.package_mass,
+                shape=Box(length=self.package_length, width=self.package_width),
+                color=Color.RED,
+            )
+            package.goal = goal
+            self.packages.append(package)
+            world.add_landmark(package)
+        self.lines = []
+        for i in range(self.n_lines):
+            line = Landmark(
+                name=f"line {i}",
+                collide=True,
+                movable=True,
+                rotatable=True,
+                shape=Line(length=self.line_length),
+                color=Color.BLACK,
+            )
+            self.lines.append(line)
+            world.add_landmark(line)
+        return world
+
+    def reset_world_at(self, env_index: int = None):
+        world = self.world
+        bounds = (-self.world_semidim, self.world_semidim)
+        ScenarioUtils.spawn_entities_randomly(
+            world.agents,
+            world,
+            env_index,
+            min_dist_between_entities=self.agent_radius * 2,
+            x_bounds=bounds,
+            y_bounds=bounds,
+        )
+        occupied = torch.stack([a.state.pos for a in world.agents], dim=1)
+        if env_index is not None:
+            occupied = occupied[env_index].unsqueeze(0)
+        goal = world.landmarks[0]
+        ScenarioUtils.spawn_entities_randomly(
+            [goal] + self.packages + self.lines,
+            world,
+            env_index,
+            min_dist_between_entities=max(
+                p.shape.circumscribed_radius() + goal.shape.radius + 0.01 for p in self.packages
+            ),
+            x_bounds=bounds,
+            y_bounds=bounds,
+            occupied_positions=occupied,
+        )
+        for package in self.packages:
+            package.on_goal = world.is_overlapping(package, package.goal)
+            dist = torch.linalg.vector_norm(package.state.pos - package.goal.state.pos, dim=1)
+            if env_index is None:
+                package.global_shaping = dist * self.shaping_factor
+            else:
+                package.global_shaping[env_index] = dist[env_index] * self.shaping_factor
+
+    def reward(self, agent: Agent):
+        if agent is self.world.agents[0]:
+            rew = torch.zeros(self.world.batch_dim, device=self.world.device, dtype=torch.float32)
+            red = torch.tensor(Color.RED.value, device=self.world.device, dtype=torch.float32)
+            green = torch.tensor(Color.GREEN.value, device=self.world.device, dtype=torch.float32)
+            for package in self.packages:
+                package.dist_to_goal = torch.linalg.vector_norm(
+                    package.state.pos - package.goal.state.pos, dim=1
+                )
+                package.on_goal = self.world.is_overlapping(package, package.goal)
+                package.color = torch.where(package.on_goal.unsqueeze(-1), green, red)
+                shaping = package.dist_to_goal * self.shaping_factor
+                rew = rew + torch.where(package.on_goal, 0.0, package.global_shaping - shaping)
+                package.global_shaping = shaping
+            self.rew = rew
+        return self.rew
+
+    def observation(self, agent: Agent):
+        parts = [agent.state.pos, agent.state.vel]
+        for package in self.packages:
+            parts += [
+                package.state.pos - package.goal.state.pos,
+                package.state.pos - agent.state.pos,
+                package.state.vel,
+                package.on_goal.unsqueeze(-1),
+            ]
+        return torch.cat(parts, dim=-1)
+
+    def done(self):
+        return torch.stack([p.on_goal for p in self.packages], dim=1).all(dim=-1)

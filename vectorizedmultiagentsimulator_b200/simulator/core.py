@@ -1134,7 +1134,19 @@ class World(TorchVectorizedObject):
         """Reference semantics incl. the batch-wide overlap test (one device→host sync)."""
         if not self.static_collides(a, b):
             return False
-        return self._get_backend().any_within_broad_phase(a, b)
+        return bool(self.collides_tensor(a, b))
+
+    def collides_tensor(self, a: Entity, b: Entity) -> Tensor:
+        """``collides`` as a 0-dim bool tensor on the world's device: no host sync.
+
+        True iff the static predicates hold and, in at least one env of the batch, the two
+        circumscribed circles overlap (ref core.py:2797-2801).
+        """
+        if not self.static_collides(a, b):
+            return torch.zeros((), dtype=torch.bool, device=self.device)
+        thr = a.shape.circumscribed_radius() + b.shape.circumscribed_radius()
+        d = torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1)
+        return (d <= thr).any()
 
     def to(self, device: torch.device):
         device = torch.device(device)

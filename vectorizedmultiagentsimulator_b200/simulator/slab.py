@@ -27,12 +27,25 @@ class StateSlab:
         self.n_agents = len(agents)
         B, E, A = batch_dim, max(self.n_entities, 1), max(self.n_agents, 1)
         kw = dict(device=device, dtype=torch.float32)
-        self.pos = torch.zeros(B, E, 2, **kw)
-        self.vel = torch.zeros(B, E, 2, **kw)
-        self.rot = torch.zeros(B, E, **kw)
-        self.ang_vel = torch.zeros(B, E, **kw)
-        self.force = torch.zeros(B, A, 2, **kw)
-        self.torque = torch.zeros(B, A, **kw)
+        # CUDA: env-major, contiguous [B, E, ...] — what the kernels stream.  A CPU world can only
+        # be driven by the test oracle; there the same logical [B, E, ...] tensors are backed by
+        # entity-major storage so each entity's [B, 2] view is contiguous, like the per-entity
+        # tensors of the reference (keeps the CPU baseline's memory behaviour honest).
+        self.env_major = torch.device(device).type != "cpu"
+        if self.env_major:
+            self.pos = torch.zeros(B, E, 2, **kw)
+            self.vel = torch.zeros(B, E, 2, **kw)
+            self.rot = torch.zeros(B, E, **kw)
+            self.ang_vel = torch.zeros(B, E, **kw)
+            self.force = torch.zeros(B, A, 2, **kw)
+            self.torque = torch.zeros(B, A, **kw)
+        else:
+            self.pos = torch.zeros(E, B, 2, **kw).permute(1, 0, 2)
+            self.vel = torch.zeros(E, B, 2, **kw).permute(1, 0, 2)
+            self.rot = torch.zeros(E, B, **kw).permute(1, 0)
+            self.ang_vel = torch.zeros(E, B, **kw).permute(1, 0)
+            self.force = torch.zeros(A, B, 2, **kw).permute(1, 0, 2)
+            self.torque = torch.zeros(A, B, **kw).permute(1, 0)
         self.entity_names = [e.name for e in entities]
 
     def tensors(self):
