@@ -136,34 +136,67 @@ def pregenerate_actions(env, steps, seed, device, pin=False):
 
 
 # --------------------------------------------------------------------------------------------
-def run_cpu_oracle_env(n_envs, steps, warmup, threads):
-    """Times the CPU oracle port behind the same Environment API.  Returns (env_steps_per_s, seconds)."""
+def usable_cpus() -> int:
+    """Host cores this process may actually use (affinity mask and cgroup quota, not os.cpu_count)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+def run_cpu_oracle_env(n_envs, max_steps, time_budget_s=20.0):
+    """Times the CPU oracle port behind the same Environment API on the host cores.
+
+    The intra-op thread count is calibrated first (one step each at a few candidates up to the
+    usable core count; eager torch on many tiny ops gets *slower* with too many threads), then
+    steps are timed until ``max_steps`` or ``time_budget_s``.
+    Returns (env_steps_per_s, seconds, steps, threads).
+    """
     import vectorizedmultiagentsimulator_b200 as b200
     from oracle.backend import use_oracle
 
-    torch.set_num_threads(threads)
+    cores = usable_cpus()
+    candidates = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True) or [1]
+    torch.set_num_threads(candidates[-1])
     with use_oracle():
         env = b200.make_env(SCENARIO, num_envs=n_envs, device="cpu", seed=0, **SCENARIO_KWARGS)
-        actions = pregenerate_actions(env, warmup + steps, seed=1, device="cpu")
-        for t in range(warmup):
-            env.step(actions[t])
-        t0 = time.perf_counter()
-        for t in range(warmup, warmup + steps):
-            env.step(actions[t])
+        actions = pregenerate_actions(env, 4, seed=1, device="cpu")
+        env.step(actions[0])  # warm-up (allocator, plan compile)
+        best, best_t = candidates[-1], float("inf")
+        for c in reversed(candidates):  # small thread counts first; stop when it gets worse
+            torch.set_num_threads(c)
+            t0 = time.perf_counter()
+            env.step(actions[1])
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = c, dt
+            elif dt > 1.5 * best_t:
+                break
+        torch.set_num_threads(best)
+        steps, t0 = 0, time.perf_counter()
+        while steps < max_steps:
+            env.step(actions[steps % 4])
+            steps += 1
+            if time.perf_counter() - t0 > time_budget_s and steps >= 2:
+                break
         dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt
+    return n_envs * steps / dt, dt, steps, best
 
 
 def main_reference(args):
     rank, world, _ = dist_info()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     n_envs = args.envs_per_gpu
-    steps = max(1, args.steps)
-    # bounded sample: cap the work at ~60 s of CPU time (an env step of this size is ~0.1 s)
-    steps = min(steps, 100)
-    value, seconds = run_cpu_oracle_env(n_envs, steps, max(1, min(args.warmup, 3)), cores)
+    # bounded sample: at most --steps env steps and ~60 s of CPU time
+    value, seconds, steps, cores = run_cpu_oracle_env(n_envs, max(1, args.steps), time_budget_s=60.0)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -171,7 +204,7 @@ def main_reference(args):
         "unit": "env-steps/s",
         "n_gpus": args.gpus,
         "steps": steps,
-        "warmup": max(1, min(args.warmup, 3)),
+        "warmup": 2,
         "ms_per_step": 1e3 * seconds / steps,
         "higher_is_better": True,
         "scaling": "weak",
@@ -187,7 +220,7 @@ def main_reference(args):
             "unit": "env-steps/s",
             "cores": cores,
             "kind": "port",
-            "sample": f"{steps} env steps of {n_envs} envs",
+            "sample": f"{steps} env steps of {n_envs} envs ({seconds:.1f} s), {cores} intra-op threads (calibrated) of {usable_cpus()} usable cores",
         },
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -254,7 +287,19 @@ def main_b200(args):
     launches = backend.launches - launches_before
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / max(len(kernel_pairs), 1)
+    kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / max(len(kernel_pairs), 1)
+
+    # ---- the substep kernel alone: world.step() back to back, L2 flushed before every launch.
+    # The flush (~100 us on the GPU) lets the host queue the next launch ahead, so the event
+    # bracket around the kernel holds no host latency (inside Environment.step it does).
+    backend.kernel_events = []
+    for _ in range(K):
+        if flush is not None:
+            flush.zero_()
+        env.world.step()
+    torch.cuda.synchronize()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in backend.kernel_events) / K
+    backend.kernel_events = None
 
     # ---- arm 2: end to end with host buffers --------------------------------------------------
     host_actions = pregenerate_actions(env, W + K, seed=101 + rank, device=device, pin=True)
@@ -284,10 +329,10 @@ def main_b200(args):
     env.check_actions_now()
 
     # ---- reduce over ranks ---------------------------------------------------------------------
-    stats = torch.tensor([ms_total, ms_e2e, kernel_ms], dtype=torch.float64, device=device)
+    stats = torch.tensor([ms_total, ms_e2e, kernel_ms, kernel_in_step_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, kernel_ms = (float(x) for x in stats.tolist())
+    ms_total, ms_e2e, kernel_ms, kernel_in_step_ms = (float(x) for x in stats.tolist())
     value = world * B * K / (ms_total * 1e-3)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
 
@@ -317,20 +362,21 @@ def main_b200(args):
         "bytes_per_launch": alg_bytes,
         "bytes_per_env_substep": bytes_per_env_substep,
         "kernel_us": kernel_ms * 1e3,
+        "kernel_us_inside_env_step": kernel_in_step_ms * 1e3,
+        "how": "CUDA events recorded by the library around the substep kernel; standalone world.step() loop, L2 flushed before each launch",
     }
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cpu_steps = args.cpu_steps or 40
-        v, seconds = run_cpu_oracle_env(B, cpu_steps, 2, cores)
+        v, seconds, cpu_steps, cores = run_cpu_oracle_env(B, args.cpu_steps or 200, time_budget_s=20.0)
         cpu_baseline = {
             "value": v,
             "unit": "env-steps/s",
             "cores": cores,
             "kind": "port",
-            "sample": f"{cpu_steps} env steps of {B} envs ({seconds:.1f} s), CPU oracle port behind the same Environment API",
+            "sample": f"{cpu_steps} env steps of {B} envs ({seconds:.1f} s), CPU oracle port behind the same "
+            f"Environment API, {cores} intra-op threads (calibrated) of {usable_cpus()} usable cores",
         }
 
     line = {

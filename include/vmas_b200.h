@@ -77,13 +77,14 @@ typedef struct VmasPlanTables {
   const int32_t* item_i32;    /* [NI, 4]: kind, a, b, flags | (mask bit + 1) << 8 */
   const int32_t* inc_off;     /* [E + 1] CSR offsets: items incident to each entity */
   const int32_t* inc;         /* item * 2 + side, ascending item order */
-  const int32_t* sched;       /* [n_rounds, group] item per lane, -1 = idle; rounds are kind-uniform */
+  const int32_t* sched;       /* [n_rounds, group] item per lane, -1 = idle; rounds are kind-uniform
+                                 (lane-per-entity mapping only; ignored when group == 1) */
   const int32_t* masked_items;/* [n_masked] item index of each mask bit */
   const float*   joint_rot;   /* [B, n_joints] per-env fixed rotations, or NULL */
   int32_t n_rounds;
-  int32_t group;              /* lanes per env: 8, 16 or 32 */
+  int32_t group;              /* lanes per env: 1 = one thread per env (default), or 8, 16, 32 */
   int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */
-  int32_t reserved;
+  int32_t specialization;     /* index from vmas_b200_find_specialization(), or -1: generic kernels */
 } VmasPlanTables;
 
 /* The state slab.  DEVICE pointers. */
@@ -93,6 +94,15 @@ typedef struct VmasState {
 
 int vmas_b200_abi_version(void);
 const char* vmas_b200_last_error(void);
+
+/*
+ * World-specialised kernels.  The library carries ahead-of-time specialisations of the substep
+ * kernel for a set of worlds (csrc/generated/, see codegen.py), keyed by a 64-bit hash of the
+ * world description.  find returns an index for VmasPlanTables.specialization, or -1.
+ */
+int vmas_b200_num_specializations(void);
+int vmas_b200_find_specialization(uint64_t world_hash);
+const char* vmas_b200_specialization_name(int index);
 
 /*
  * One World.step(): S substeps of force accumulation -> contact/joint resolution ->

@@ -57,8 +57,8 @@ def _ulp_sensitivity(tables, state_in, fixed_rot, trials=3):
     return worst
 
 
-def _device_tables(tables, fixed_rot, device):
-    dt = _native.DeviceTables(tables, None, device)
+def _device_tables(tables, fixed_rot, device, mapping=None):
+    dt = _native.DeviceTables(tables, None, device, mapping=mapping)
     for k, v in fixed_rot.items():
         dt.joint_rot[:, k] = v.reshape(-1).to(device)
     return dt
@@ -127,6 +127,58 @@ def test_fused_substeps_equal_single_substep_launches(name):
         _native.world_substeps(lib, dt, split, s, 1)
     for k in STATE_KEYS:
         assert torch.equal(fused.t[k], split.t[k])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_thread_per_env_and_lanes_per_env_agree_bitwise(name):
+    """Two independent thread mappings of the same arithmetic must produce identical bits."""
+    fix, desc, tables = load(name)
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    for t, state_in, fixed_rot, _ in teacher_forced_steps(fix):
+        if t % 4:
+            continue
+        outs = []
+        mappings = ["thread_per_env", "lanes_per_env"]
+        if _native.DeviceTables(tables, None, device).mapping == "specialized":
+            mappings.append("specialized")  # world-specialised, register-resident kernel
+        for mapping in mappings:
+            dt = _device_tables(tables, fixed_rot, device, mapping=mapping)
+            assert dt.mapping == mapping
+            slab = _Slab(state_in, device)
+            _native.world_step(lib, dt, slab)
+            outs.append(slab)
+        for other, mapping in zip(outs[1:], mappings[1:]):
+            for k in STATE_KEYS:
+                assert torch.equal(outs[0].t[k], other.t[k]), f"{name} step {t} field {k} ({mapping})"
+
+
+def test_config_worlds_have_specialised_kernels():
+    lib = _native.load()
+    assert lib.vmas_b200_num_specializations() >= 4
+    for name in ("balance", "transport", "navigation", "flocking"):
+        _, _, tables = load(name)
+        dt = _native.DeviceTables(tables, None, torch.device("cuda:0"))
+        assert dt.mapping == "specialized", name
+
+
+@pytest.mark.parametrize("mapping", ["thread_per_env", "lanes_per_env"])
+def test_world_step_vs_reference_golden_both_mappings(mapping):
+    for name in ("balance", "pollock", "waterfall"):
+        fix, desc, tables = load(name)
+        lib = _native.load()
+        device = torch.device("cuda:0")
+        for t, state_in, fixed_rot, want in teacher_forced_steps(fix):
+            if t > 6:
+                break
+            dt = _device_tables(tables, fixed_rot, device, mapping=mapping)
+            slab = _Slab(state_in, device)
+            _native.world_step(lib, dt, slab)
+            sens = _ulp_sensitivity(tables, state_in, fixed_rot) if name in JOINT_WORLDS else None
+            for k in STATE_KEYS:
+                atol = ATOL + (4.0 * sens[k] if sens else 0.0)
+                ok, err = _close(slab.t[k], want[k], atol)
+                assert ok, f"{mapping} {name} step {t} field {k}: max |err| {err}"
 
 
 def test_step_is_deterministic_and_mask_is_restored():

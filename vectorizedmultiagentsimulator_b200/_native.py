@@ -23,7 +23,13 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libvmas_b200.so")
 SOURCES = [os.path.join(CSRC, "vmas_b200.cu")]
-HEADERS = [os.path.join(CSRC, "geometry.cuh"), os.path.join(INCLUDE, "vmas_b200.h")]
+GENERATED = os.path.join(CSRC, "generated", "specializations.cuh")
+HEADERS = [
+    os.path.join(CSRC, "geometry.cuh"),
+    os.path.join(CSRC, "spec_kernel.cuh"),
+    os.path.join(INCLUDE, "vmas_b200.h"),
+    GENERATED,
+]
 
 NVCC_FLAGS = [
     "-gencode",
@@ -46,7 +52,7 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(GENERATED):
         return True
     built = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(f) > built for f in SOURCES + HEADERS)
@@ -54,6 +60,9 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into ``libvmas_b200.so`` next to this file."""
+    from . import codegen
+
+    codegen.generate(GENERATED)  # constexpr world tables for the specialised kernels (no-op if unchanged)
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + SOURCES
@@ -108,7 +117,7 @@ class PlanTablesC(C.Structure):
         ("n_rounds", C.c_int32),
         ("group", C.c_int32),
         ("ents_per_lane", C.c_int32),
-        ("reserved", C.c_int32),
+        ("specialization", C.c_int32),
     ]
 
 
@@ -126,6 +135,9 @@ class StateC(C.Structure):
 EXPORTS = [
     "vmas_b200_abi_version",
     "vmas_b200_last_error",
+    "vmas_b200_num_specializations",
+    "vmas_b200_find_specialization",
+    "vmas_b200_specialization_name",
     "vmas_b200_world_step",
     "vmas_b200_world_substeps",
     "vmas_b200_world_step_timed",
@@ -171,8 +183,11 @@ def load():
     ]
     lib.vmas_b200_point_query.argtypes = [p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_broad_phase.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
+    lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int
+    lib.vmas_b200_specialization_name.restype = C.c_char_p
     if lib.vmas_b200_abi_version() != 1:
         raise RuntimeError("libvmas_b200.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -186,6 +201,9 @@ def _check(lib, rc: int) -> int:
 
 
 def _stream(device) -> int:
+    # kernels launch on the calling thread's current device: make it the world's device
+    if torch.cuda.current_device() != device.index:
+        torch.cuda.set_device(device)
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -234,12 +252,30 @@ def make_config(tables: P.PlanTables, batch_dim: Optional[int] = None) -> WorldC
 class DeviceTables:
     """The plan tables uploaded to one GPU, plus the ctypes structs pointing at them."""
 
-    def __init__(self, tables: P.PlanTables, world, device):
+    def __init__(self, tables: P.PlanTables, world, device, mapping: Optional[str] = None):
         self.tables = tables
         self.device = torch.device(device)
         desc = tables.desc
-        self.group, self.ents_per_lane = lane_layout(desc.n_entities)
-        sched, _ = tables.schedule(self.group)
+        mapping = mapping or os.environ.get("VMAS_B200_MAPPING", "auto")
+        assert mapping in ("auto", "specialized", "thread_per_env", "lanes_per_env"), mapping
+        self.specialization = -1
+        if mapping in ("auto", "specialized"):
+            from . import codegen
+
+            self.specialization = load().vmas_b200_find_specialization(codegen.world_hash(desc))
+            if self.specialization < 0:
+                if mapping == "specialized":
+                    raise RuntimeError("no ahead-of-time specialisation of this world in libvmas_b200.so")
+                mapping = "thread_per_env"
+            else:
+                mapping = "specialized"
+        self.mapping = mapping
+        if mapping in ("thread_per_env", "specialized"):
+            self.group, self.ents_per_lane = 1, desc.n_entities
+            sched = np.zeros((0, 1), np.int32)
+        else:
+            self.group, self.ents_per_lane = lane_layout(desc.n_entities)
+            sched, _ = tables.schedule(self.group)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
         self.ent_f32 = up(tables.ent_f32)
         self.ent_i32 = up(tables.ent_i32)
@@ -280,6 +316,7 @@ class DeviceTables:
         tb.n_rounds = self.n_rounds
         tb.group = self.group
         tb.ents_per_lane = self.ents_per_lane
+        tb.specialization = self.specialization
         self.tb = tb
         self._state_key = None
         self._state = None

@@ -99,6 +99,8 @@ def _require_cuda(world):
             f"vectorizedmultiagentsimulator_b200 runs its physics only on CUDA (sm_100a); world device is "
             f"'{dev}'. There is no CPU fallback."
         )
+    if dev.index is None:  # "cuda" -> the concrete device its tensors live on
+        dev = torch.device("cuda", torch.cuda.current_device())
     return dev
 
 

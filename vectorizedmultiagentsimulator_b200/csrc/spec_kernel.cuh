@@ -1,0 +1,397 @@
+// spec_kernel.cuh — world-specialised substep kernel.
+//
+// The generic kernels in vmas_b200.cu interpret the plan tables at run time (table loads,
+// dynamically indexed shared memory, a switch per work item) and end up latency-bound.  Here the
+// world's static structure is a compile-time constant: a generated header (csrc/generated/) holds
+// one `struct World_<hash>` per pre-registered world with constexpr entity / item tables, and this
+// template unrolls every loop over entities and work items.  After unrolling all indices are
+// constants, so an env's whole state (positions, velocities, rotations, force accumulators, cached
+// sin/cos) lives in REGISTERS of the one thread that owns the env, shape parameters fold into
+// immediates, and the kind dispatch disappears.  The arithmetic is the same device functions
+// (geometry.cuh) in the same order as the generic kernels: results are bit-identical (tested).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+#include <utility>
+
+#include "geometry.cuh"
+#include "vmas_b200.h"
+
+namespace vmas {
+
+struct EntC {
+  int shape, flags, agent;
+  float d0, d1, mass, inertia, drag_mult, lin_fric, ang_fric, grav_x, grav_y, max_speed, v_range, max_f, f_range,
+      max_t, t_range, circ_r;
+};
+struct ItemC {
+  int kind, a, b, flags, mask_bit;
+  float dmin_base, ax, ay, bx, by, dist, fixed_rot;
+};
+struct CfgC {
+  int substeps, has_x_semidim, has_y_semidim, has_world_gravity;
+  float sub_dt, x_semidim, y_semidim, collision_force, joint_force, torque_constraint_force, contact_margin,
+      gravity_x, gravity_y;
+};
+
+struct SpecArgs {
+  VmasState st;
+  const float* joint_rot;  // [B, n_joints] or null
+  uint32_t* mask;          // [mask_words + 1]
+  int batch_dim;
+  int use_mask;
+  int first_substep;
+  int n_substeps;
+};
+
+template <class F, int... I>
+DEVI void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+DEVI void static_for(F&& f) {
+  static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+constexpr float SPEC_HALF_PI_F = 1.57079632679489661923f;
+constexpr float SPEC_FAR_MARGIN = 1e-3f;
+
+DEVI bool spec_far_apart(V2 a, V2 b, float reach) {
+  V2 d = a - b;
+  float lim = reach + SPEC_FAR_MARGIN;
+  return d.x * d.x + d.y * d.y > lim * lim;
+}
+
+// Register-resident state of one env.
+template <int E>
+struct EnvRegs {
+  float px[E], py[E], rot[E], vx[E], vy[E], w[E];
+  float c[E], s[E], c2[E], s2[E];
+  float Fx[E], Fy[E], T[E];
+};
+
+template <class W, int EI, int E>
+DEVI Seg spec_seg(const EnvRegs<E>& r) {
+  return mkseg(mk(r.px[EI], r.py[EI]), r.c[EI], r.s[EI], W::ent[EI].d0 / 2.f);
+}
+template <class W, int EI, int E>
+DEVI BoxG spec_box(const EnvRegs<E>& r) {
+  BoxG b;
+  b.p = mk(r.px[EI], r.py[EI]);
+  b.c = r.c[EI];
+  b.s = r.s[EI];
+  b.c2 = r.c2[EI];
+  b.s2 = r.s2[EI];
+  b.half_l = W::ent[EI].d0 / 2.f;
+  b.half_w = W::ent[EI].d1 / 2.f;
+  return b;
+}
+
+// One work item, fully resolved at compile time; accumulates into the env's force registers in
+// the reference's order (ref core.py:2191-2199).
+template <class W, int I, int E>
+DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* mask_words) {
+  constexpr ItemC it = W::item[I];
+  constexpr int A = it.a, B = it.b;
+  constexpr EntC ea = W::ent[A], eb = W::ent[B];
+  constexpr CfgC cfg = W::cfg;
+  if constexpr (it.mask_bit >= 0) {
+    if (a.use_mask && !((mask_words[it.mask_bit >> 5] >> (it.mask_bit & 31)) & 1u)) return;
+  }
+  V2 f = mk(0.f, 0.f);
+  float ta = 0.f, tb = 0.f;
+  const V2 pa = mk(r.px[A], r.py[A]), pb = mk(r.px[B], r.py[B]);
+
+  if constexpr (it.kind == VMAS_K_JOINT) {
+    V2 qa = pa + rot2(mk(it.ax, it.ay), r.c[A], r.s[A]);
+    V2 qb = pb + rot2(mk(it.bx, it.by), r.c[B], r.s[B]);
+    V2 f_attr = constraint_force(qa, qb, it.dist, cfg.joint_force, cfg.contact_margin, true);
+    V2 f_rep = constraint_force(qa, qb, it.dist, cfg.joint_force, cfg.contact_margin, false);
+    f = f_attr + f_rep;
+    V2 fb = neg(f_attr) + neg(f_rep);
+    ta = cross2(qa - pa, f);
+    tb = cross2(qb - pb, fb);
+    if constexpr (!(it.flags & VMAS_IFLAG_JOINT_ROTATE)) {
+      float jr = a.joint_rot ? a.joint_rot[(size_t)env * W::N_JOINTS + I] : it.fixed_rot;
+      float delta = r.rot[A] - (r.rot[B] + jr);
+      float mag = sqrtf(delta * delta);
+      float t = (cfg.torque_constraint_force * sgnf(delta)) * (expf(mag) - 1.f);
+      if (mag < 1e-9f) t = 0.f;
+      ta = ta + (-t);
+      tb = tb + t;
+    }
+  } else if constexpr (it.kind == VMAS_K_SS) {
+    f = constraint_force(pa, pb, it.dmin_base, cfg.collision_force, cfg.contact_margin, false);
+  } else if constexpr (it.kind == VMAS_K_LS) {  // a = line, b = sphere
+    Seg l = spec_seg<W, A>(r);
+    if (!spec_far_apart(l.p, pb, l.half + it.dmin_base)) {
+      V2 cp = closest_point_seg(l, pb);
+      V2 f_sphere = constraint_force(pb, cp, it.dmin_base, cfg.collision_force, cfg.contact_margin, false);
+      f = neg(f_sphere);
+      ta = cross2(cp - l.p, f);
+    }
+  } else if constexpr (it.kind == VMAS_K_LL) {
+    Seg l1 = spec_seg<W, A>(r), l2 = spec_seg<W, B>(r);
+    if (!spec_far_apart(l1.p, l2.p, l1.half + l2.half + it.dmin_base)) {
+      Pair c = closest_seg_seg(l1, l2);
+      f = constraint_force(c.a, c.b, it.dmin_base, cfg.collision_force, cfg.contact_margin, false);
+      ta = cross2(c.a - l1.p, f);
+      tb = cross2(c.b - l2.p, neg(f));
+    }
+  } else if constexpr (it.kind == VMAS_K_BS) {  // a = box, b = sphere
+    BoxG bx = spec_box<W, A>(r);
+    V2 d0 = pb - bx.p;
+    float lx = d0.x * bx.c + d0.y * bx.s, ly = d0.y * bx.c - d0.x * bx.s;
+    if (!(fabsf(lx) > bx.half_l + it.dmin_base + SPEC_FAR_MARGIN ||
+          fabsf(ly) > bx.half_w + it.dmin_base + SPEC_FAR_MARGIN)) {
+      V2 cp = closest_point_box(bx, pb);
+      V2 inner = cp;
+      float d = 0.f;
+      if constexpr (!(ea.flags & VMAS_F_HOLLOW)) inner = inner_point_box(pb, cp, bx.p, &d);
+      V2 f_sphere =
+          constraint_force(pb, inner, it.dmin_base + d, cfg.collision_force, cfg.contact_margin, false);
+      f = neg(f_sphere);
+      ta = cross2(cp - bx.p, f);
+    }
+  } else if constexpr (it.kind == VMAS_K_BL) {  // a = box, b = line
+    BoxG bx = spec_box<W, A>(r);
+    Seg l = spec_seg<W, B>(r);
+    V2 d0 = l.p - bx.p;
+    float lx = d0.x * bx.c + d0.y * bx.s, ly = d0.y * bx.c - d0.x * bx.s;
+    float ex = l.half * fabsf(l.c * bx.c + l.s * bx.s), ey = l.half * fabsf(l.s * bx.c - l.c * bx.s);
+    if (!(fabsf(lx) - ex > bx.half_l + it.dmin_base + SPEC_FAR_MARGIN ||
+          fabsf(ly) - ey > bx.half_w + it.dmin_base + SPEC_FAR_MARGIN)) {
+      Pair c = closest_box_seg(bx, l);
+      V2 inner = c.a;
+      float d = 0.f;
+      if constexpr (!(ea.flags & VMAS_F_HOLLOW)) inner = inner_point_box(c.b, c.a, bx.p, &d);
+      f = constraint_force(inner, c.b, it.dmin_base + d, cfg.collision_force, cfg.contact_margin, false);
+      ta = cross2(c.a - bx.p, f);
+      tb = cross2(c.b - l.p, neg(f));
+    }
+  } else if constexpr (it.kind == VMAS_K_BB) {
+    BoxG b1 = spec_box<W, A>(r), b2 = spec_box<W, B>(r);
+    if (!spec_far_apart(b1.p, b2.p, ea.circ_r + eb.circ_r + it.dmin_base)) {
+      Pair c = closest_box_box(b1, b2);
+      V2 in1 = c.a, in2 = c.b;
+      float d1 = 0.f, d2 = 0.f;
+      if constexpr (!(ea.flags & VMAS_F_HOLLOW)) in1 = inner_point_box(c.b, c.a, b1.p, &d1);
+      if constexpr (!(eb.flags & VMAS_F_HOLLOW)) in2 = inner_point_box(c.a, c.b, b2.p, &d2);
+      f = constraint_force(in1, in2, (d1 + d2) + it.dmin_base, cfg.collision_force, cfg.contact_margin, false);
+      ta = cross2(c.a - b1.p, f);
+      tb = cross2(c.b - b2.p, neg(f));
+    }
+  }
+
+  if constexpr (ea.flags & VMAS_F_MOVABLE) {
+    r.Fx[A] = r.Fx[A] + f.x;
+    r.Fy[A] = r.Fy[A] + f.y;
+  }
+  if constexpr (ea.flags & VMAS_F_ROTATABLE) r.T[A] = r.T[A] + ta;
+  if constexpr (eb.flags & VMAS_F_MOVABLE) {
+    r.Fx[B] = r.Fx[B] + (-f.x);
+    r.Fy[B] = r.Fy[B] + (-f.y);
+  }
+  if constexpr (eb.flags & VMAS_F_ROTATABLE) r.T[B] = r.T[B] + tb;
+}
+
+template <class W>
+__global__ void __launch_bounds__(W::BLOCK) step_spec_kernel(const SpecArgs a) {
+  constexpr int E = W::E, NA = W::A, NI = W::NI, MW = W::MASK_WORDS;
+    const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
+
+  uint32_t mask_words[MW > 0 ? MW : 1];
+  if constexpr (MW > 0) {
+    __shared__ uint32_t s_mask[MW];
+    if (a.use_mask) {
+      for (int w = threadIdx.x; w < MW; w += W::BLOCK) s_mask[w] = a.mask[w];
+      __syncthreads();
+      if (threadIdx.x == 0) {  // the last block to have copied the mask clears it
+        __threadfence();
+        unsigned done = atomicAdd(&a.mask[MW], 1u);
+        if (done == gridDim.x - 1) {
+          for (int w = 0; w < MW; ++w) a.mask[w] = 0u;
+          a.mask[MW] = 0u;
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
+    }
+  }
+  if (env >= a.batch_dim) return;
+
+  EnvRegs<E> r;
+  const size_t ebase = (size_t)env * E, abase = (size_t)env * NA;
+  const float2* gpos = reinterpret_cast<const float2*>(a.st.pos) + ebase;
+  const float2* gvel = reinterpret_cast<const float2*>(a.st.vel) + ebase;
+  float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
+
+  static_for<E>([&](auto ei) {
+    constexpr int e = decltype(ei)::value;
+    constexpr EntC en = W::ent[e];
+    const float2 p = gpos[e];
+    r.px[e] = p.x;
+    r.py[e] = p.y;
+    r.rot[e] = (en.flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE)) ? a.st.rot[ebase + e] : 0.f;
+    r.vx[e] = r.vy[e] = r.w[e] = 0.f;
+    r.c[e] = r.s[e] = r.c2[e] = r.s2[e] = 0.f;
+    if constexpr (en.flags & VMAS_F_MOVABLE) {
+      const float2 v = gvel[e];
+      r.vx[e] = v.x;
+      r.vy[e] = v.y;
+    }
+    if constexpr (en.flags & VMAS_F_ROTATABLE) r.w[e] = a.st.ang_vel[ebase + e];
+    if constexpr (en.flags & VMAS_F_AGENT) {
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        const float2 f = reinterpret_cast<const float2*>(a.st.force)[abase + en.agent];
+        afx[en.agent] = f.x;
+        afy[en.agent] = f.y;
+      }
+      if constexpr (en.flags & VMAS_F_ROTATABLE) atq[en.agent] = a.st.torque[abase + en.agent];
+    }
+  });
+
+  constexpr float sub_dt = W::cfg.sub_dt;
+  for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
+    // ---- per-entity forces (ref core.py:1995-2004) ------------------------------------------
+    static_for<E>([&](auto ei) {
+      constexpr int e = decltype(ei)::value;
+      constexpr EntC en = W::ent[e];
+      if constexpr (en.flags & VMAS_F_TRIG) {
+        sincosf(r.rot[e], &r.s[e], &r.c[e]);
+        if constexpr (en.shape == VMAS_SHAPE_BOX) sincosf(r.rot[e] + SPEC_HALF_PI_F, &r.s2[e], &r.c2[e]);
+      }
+      float Fx = 0.f, Fy = 0.f, T = 0.f;
+      if constexpr (en.flags & VMAS_F_AGENT) {
+        constexpr int ai = en.agent;
+        if constexpr (en.flags & VMAS_F_MOVABLE) {
+          if constexpr (en.flags & VMAS_F_MAX_F) {
+            const float n = norm2(afx[ai], afy[ai]);
+            if (n > en.max_f) {
+              afx[ai] = (afx[ai] / n) * en.max_f;
+              afy[ai] = (afy[ai] / n) * en.max_f;
+            }
+          }
+          if constexpr (en.flags & VMAS_F_F_RANGE) {
+            afx[ai] = fminf(fmaxf(afx[ai], -en.f_range), en.f_range);
+            afy[ai] = fminf(fmaxf(afy[ai], -en.f_range), en.f_range);
+          }
+          Fx = Fx + afx[ai];
+          Fy = Fy + afy[ai];
+        }
+        if constexpr (en.flags & VMAS_F_ROTATABLE) {
+          if constexpr (en.flags & VMAS_F_MAX_T) {
+            const float n = sqrtf(atq[ai] * atq[ai]);
+            if (n > en.max_t) atq[ai] = (atq[ai] / n) * en.max_t;
+          }
+          if constexpr (en.flags & VMAS_F_T_RANGE) atq[ai] = fminf(fmaxf(atq[ai], -en.t_range), en.t_range);
+          T = T + atq[ai];
+        }
+      }
+      if constexpr (en.flags & VMAS_F_LIN_FRIC) {
+        const float speed = norm2(r.vx[e], r.vy[e]);
+        if (speed != 0.f) {
+          const float cap = en.lin_fric * en.mass;
+          Fx = Fx + (-(r.vx[e] / speed)) * fminf(cap, (fabsf(r.vx[e]) / sub_dt) * en.mass);
+          Fy = Fy + (-(r.vy[e] / speed)) * fminf(cap, (fabsf(r.vy[e]) / sub_dt) * en.mass);
+        }
+      }
+      if constexpr (en.flags & VMAS_F_ANG_FRIC) {
+        const float speed = sqrtf(r.w[e] * r.w[e]);
+        if (speed != 0.f) {
+          const float cap = en.ang_fric * en.inertia;
+          T = T + (-(r.w[e] / speed)) * fminf(cap, (fabsf(r.w[e]) / sub_dt) * en.inertia);
+        }
+      }
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        if constexpr (W::cfg.has_world_gravity) {
+          Fx = Fx + en.mass * W::cfg.gravity_x;
+          Fy = Fy + en.mass * W::cfg.gravity_y;
+        }
+        if constexpr (en.flags & VMAS_F_GRAVITY) {
+          Fx = Fx + en.mass * en.grav_x;
+          Fy = Fy + en.mass * en.grav_y;
+        }
+      }
+      r.Fx[e] = Fx;
+      r.Fy[e] = Fy;
+      r.T[e] = T;
+    });
+
+    // ---- joints and contacts, in accumulation order ---------------------------------------------
+    static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value>(r, a, env, mask_words); });
+
+    // ---- semi-implicit Euler (ref core.py:2862-2908) ----------------------------------------------
+    static_for<E>([&](auto ei) {
+      constexpr int e = decltype(ei)::value;
+      constexpr EntC en = W::ent[e];
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        if (sub == 0) {
+          r.vx[e] = r.vx[e] * en.drag_mult;
+          r.vy[e] = r.vy[e] * en.drag_mult;
+        }
+        r.vx[e] = r.vx[e] + (r.Fx[e] / en.mass) * sub_dt;
+        r.vy[e] = r.vy[e] + (r.Fy[e] / en.mass) * sub_dt;
+        if constexpr (en.flags & VMAS_F_MAX_SPEED) {
+          const float n = norm2(r.vx[e], r.vy[e]);
+          if (n > en.max_speed) {
+            r.vx[e] = (r.vx[e] / n) * en.max_speed;
+            r.vy[e] = (r.vy[e] / n) * en.max_speed;
+          }
+        }
+        if constexpr (en.flags & VMAS_F_V_RANGE) {
+          r.vx[e] = fminf(fmaxf(r.vx[e], -en.v_range), en.v_range);
+          r.vy[e] = fminf(fmaxf(r.vy[e], -en.v_range), en.v_range);
+        }
+        r.px[e] = r.px[e] + r.vx[e] * sub_dt;
+        r.py[e] = r.py[e] + r.vy[e] * sub_dt;
+        if constexpr (W::cfg.has_x_semidim) r.px[e] = fminf(fmaxf(r.px[e], -W::cfg.x_semidim), W::cfg.x_semidim);
+        if constexpr (W::cfg.has_y_semidim) r.py[e] = fminf(fmaxf(r.py[e], -W::cfg.y_semidim), W::cfg.y_semidim);
+      }
+      if constexpr (en.flags & VMAS_F_ROTATABLE) {
+        if (sub == 0) r.w[e] = r.w[e] * en.drag_mult;
+        r.w[e] = r.w[e] + (r.T[e] / en.inertia) * sub_dt;
+        r.rot[e] = r.rot[e] + r.w[e] * sub_dt;
+      }
+    });
+  }
+
+  // ---- write-back ---------------------------------------------------------------------------------
+  static_for<E>([&](auto ei) {
+    constexpr int e = decltype(ei)::value;
+    constexpr EntC en = W::ent[e];
+    if constexpr (en.flags & VMAS_F_MOVABLE) {
+      reinterpret_cast<float2*>(a.st.pos)[ebase + e] = make_float2(r.px[e], r.py[e]);
+      reinterpret_cast<float2*>(a.st.vel)[ebase + e] = make_float2(r.vx[e], r.vy[e]);
+    }
+    if constexpr (en.flags & VMAS_F_ROTATABLE) {
+      a.st.rot[ebase + e] = r.rot[e];
+      a.st.ang_vel[ebase + e] = r.w[e];
+    }
+    if constexpr (en.flags & VMAS_F_AGENT) {
+      if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE)))
+        reinterpret_cast<float2*>(a.st.force)[abase + en.agent] = make_float2(afx[en.agent], afy[en.agent]);
+      if constexpr ((en.flags & VMAS_F_ROTATABLE) && (en.flags & (VMAS_F_MAX_T | VMAS_F_T_RANGE)))
+        a.st.torque[abase + en.agent] = atq[en.agent];
+    }
+  });
+}
+
+// host-side launcher used by the registry in generated/specializations.cuh
+template <class W>
+static cudaError_t launch_spec(const SpecArgs& a, cudaStream_t stream) {
+  const long blocks = ((long)a.batch_dim + W::BLOCK - 1) / W::BLOCK;
+  step_spec_kernel<W><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+struct SpecEntry {
+  uint64_t hash;
+  const char* name;
+  int n_entities, n_items;
+  cudaError_t (*launch)(const SpecArgs&, cudaStream_t);
+};
+
+}  // namespace vmas

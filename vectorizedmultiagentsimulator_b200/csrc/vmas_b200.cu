@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "geometry.cuh"
+#include "generated/specializations.cuh"
 #include "vmas_b200.h"
 
 namespace vmas {
@@ -54,32 +55,53 @@ struct StepArgs {
 // ---------------------------------------------------------------------------------------------
 // per-entity geometry cached in shared memory for the work-item phase
 // ---------------------------------------------------------------------------------------------
+// PITCH = distance (in floats) between consecutive entities of one env: 1 when a group of lanes
+// owns an env (entity-major slice per env), blockDim when one thread owns an env (the thread index
+// is the fastest-varying dimension, so a warp reads 32 consecutive words: no bank conflicts).
+template <int PITCH>
 struct EnvShared {
-  float *px, *py, *rot, *c, *s, *c2, *s2;  // [ES] each (this env's slice)
-  float *rfx, *rfy, *rta, *rtb;      // [NI] each
+  float *px, *py, *rot, *c, *s, *c2, *s2;  // per-entity geometry of this env
+  float *rfx, *rfy, *rta, *rtb;            // per-item results (lane-per-entity kernel only)
+  int pitch;                               // runtime pitch when PITCH == 0
+  DEVI int at(int e) const { return PITCH ? e * PITCH : e * pitch; }
 };
 
-DEVI V2 ent_pos(const EnvShared& sh, int e) { return mk(sh.px[e], sh.py[e]); }
+template <int PITCH>
+DEVI V2 ent_pos(const EnvShared<PITCH>& sh, int e) { return mk(sh.px[sh.at(e)], sh.py[sh.at(e)]); }
 
-DEVI Seg ent_seg(const EnvShared& sh, int e, float length) {
-  return mkseg(ent_pos(sh, e), sh.c[e], sh.s[e], length / 2.f);
+template <int PITCH>
+DEVI Seg ent_seg(const EnvShared<PITCH>& sh, int e, float length) {
+  return mkseg(ent_pos(sh, e), sh.c[sh.at(e)], sh.s[sh.at(e)], length / 2.f);
 }
 
-DEVI BoxG ent_box(const EnvShared& sh, int e, float length, float width) {
+template <int PITCH>
+DEVI BoxG ent_box(const EnvShared<PITCH>& sh, int e, float length, float width) {
   BoxG b;
   b.p = ent_pos(sh, e);
-  b.c = sh.c[e];
-  b.s = sh.s[e];
-  b.c2 = sh.c2[e];
-  b.s2 = sh.s2[e];
+  b.c = sh.c[sh.at(e)];
+  b.s = sh.s[sh.at(e)];
+  b.c2 = sh.c2[sh.at(e)];
+  b.s2 = sh.s2[sh.at(e)];
   b.half_l = length / 2.f;
   b.half_w = width / 2.f;
   return b;
 }
 
+// Conservative rejection used before the narrow phase.  A contact force is non-zero only while the
+// two shapes are within their contact threshold of each other; when even the bounding regions are
+// farther apart than that threshold plus FAR_MARGIN (>> any fp32 rounding of these coordinates)
+// the reference's result is an exact 0, which is what skipping produces.
+constexpr float FAR_MARGIN = 1e-3f;
+DEVI bool far_apart(V2 a, V2 b, float reach) {
+  V2 d = a - b;
+  float lim = reach + FAR_MARGIN;
+  return d.x * d.x + d.y * d.y > lim * lim;
+}
+
 // One work item -> (force on a, torque on a, torque on b); the force on b is the negative.
-DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, float* out_fx, float* out_fy,
-                    float* out_ta, float* out_tb) {
+template <int PITCH>
+DEVI void eval_item(const StepArgs& a, const EnvShared<PITCH>& sh, int item, long env, float* out_fx,
+                    float* out_fy, float* out_ta, float* out_tb) {
   const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
   const int kind = ii.x, ea = ii.y, eb = ii.z, flags = ii.w & 0xff;
   const float* f32 = a.tb.item_f32 + (size_t)item * VMAS_IF_COLS;
@@ -95,8 +117,8 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
       V2 pa = ent_pos(sh, ea), pb = ent_pos(sh, eb);
       V2 da = mk(__ldg(f32 + VMAS_IF_AX), __ldg(f32 + VMAS_IF_AY));
       V2 db = mk(__ldg(f32 + VMAS_IF_BX), __ldg(f32 + VMAS_IF_BY));
-      V2 qa = pa + rot2(da, sh.c[ea], sh.s[ea]);
-      V2 qb = pb + rot2(db, sh.c[eb], sh.s[eb]);
+      V2 qa = pa + rot2(da, sh.c[sh.at(ea)], sh.s[sh.at(ea)]);
+      V2 qb = pb + rot2(db, sh.c[sh.at(eb)], sh.s[sh.at(eb)]);
       float dist = __ldg(f32 + VMAS_IF_DIST);
       V2 f_attr = constraint_force(qa, qb, dist, a.cfg.joint_force, km, true);
       V2 f_rep = constraint_force(qa, qb, dist, a.cfg.joint_force, km, false);
@@ -108,7 +130,7 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
         float jr = (flags & VMAS_IFLAG_JOINT_ROT_PER_ENV)
                        ? a.tb.joint_rot[(size_t)env * a.cfg.n_joints + item]
                        : __ldg(f32 + VMAS_IF_FIXED_ROT);
-        float ra = sh.rot[ea], rb = sh.rot[eb];
+        float ra = sh.rot[sh.at(ea)], rb = sh.rot[sh.at(eb)];
         float delta = ra - (rb + jr);
         float mag = sqrtf(delta * delta);
         float t = (a.cfg.torque_constraint_force * sgnf(delta)) * (expf(mag) - 1.f);
@@ -125,6 +147,7 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
     case VMAS_K_LS: {  // a = line, b = sphere; ref core.py:2341-2392
       Seg l = ent_seg(sh, ea, __ldg(pa_f + VMAS_EF_D0));
       V2 ps = ent_pos(sh, eb);
+      if (far_apart(l.p, ps, l.half + dmin_base)) break;
       V2 cp = closest_point_seg(l, ps);
       V2 f_sphere = constraint_force(ps, cp, dmin_base, cf, km, false);
       f = neg(f_sphere);  // force on the line
@@ -134,6 +157,7 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
     case VMAS_K_LL: {  // ref core.py:2394-2457
       Seg l1 = ent_seg(sh, ea, __ldg(pa_f + VMAS_EF_D0));
       Seg l2 = ent_seg(sh, eb, __ldg(pb_f + VMAS_EF_D0));
+      if (far_apart(l1.p, l2.p, l1.half + l2.half + dmin_base)) break;
       Pair c = closest_seg_seg(l1, l2);
       f = constraint_force(c.a, c.b, dmin_base, cf, km, false);
       ta = cross2(c.a - l1.p, f);
@@ -144,6 +168,11 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
       BoxG bx = ent_box(sh, ea, __ldg(pa_f + VMAS_EF_D0), __ldg(pa_f + VMAS_EF_D1));
       const bool hollow = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
       V2 ps = ent_pos(sh, eb);
+      {  // sphere centre outside the box inflated by r + LINE_MIN_DIST (+ margin): force is exactly 0
+        V2 d = ps - bx.p;
+        float lx = d.x * bx.c + d.y * bx.s, ly = d.y * bx.c - d.x * bx.s;
+        if (fabsf(lx) > bx.half_l + dmin_base + FAR_MARGIN || fabsf(ly) > bx.half_w + dmin_base + FAR_MARGIN) break;
+      }
       V2 cp = closest_point_box(bx, ps);
       V2 inner = cp;
       float d = 0.f;
@@ -157,6 +186,13 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
       BoxG bx = ent_box(sh, ea, __ldg(pa_f + VMAS_EF_D0), __ldg(pa_f + VMAS_EF_D1));
       const bool hollow = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
       Seg l = ent_seg(sh, eb, __ldg(pb_f + VMAS_EF_D0));
+      {  // segment entirely outside the box inflated by LINE_MIN_DIST (+ margin): force is exactly 0
+        V2 d = l.p - bx.p;
+        float lx = d.x * bx.c + d.y * bx.s, ly = d.y * bx.c - d.x * bx.s;
+        float ex = l.half * fabsf(l.c * bx.c + l.s * bx.s), ey = l.half * fabsf(l.s * bx.c - l.c * bx.s);
+        if (fabsf(lx) - ex > bx.half_l + dmin_base + FAR_MARGIN || fabsf(ly) - ey > bx.half_w + dmin_base + FAR_MARGIN)
+          break;
+      }
       Pair c = closest_box_seg(bx, l);
       V2 inner = c.a;
       float d = 0.f;
@@ -171,6 +207,7 @@ DEVI void eval_item(const StepArgs& a, const EnvShared& sh, int item, long env, 
       BoxG b2 = ent_box(sh, eb, __ldg(pb_f + VMAS_EF_D0), __ldg(pb_f + VMAS_EF_D1));
       const bool hollow1 = __ldg(a.tb.ent_i32 + ea * 4 + 1) & VMAS_F_HOLLOW;
       const bool hollow2 = __ldg(a.tb.ent_i32 + eb * 4 + 1) & VMAS_F_HOLLOW;
+      if (far_apart(b1.p, b2.p, __ldg(pa_f + VMAS_EF_CIRC_R) + __ldg(pb_f + VMAS_EF_CIRC_R) + dmin_base)) break;
       Pair c = closest_box_box(b1, b2);
       V2 in1 = c.a, in2 = c.b;
       float d1 = 0.f, d2 = 0.f;
@@ -205,7 +242,8 @@ __global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
 
   // shared memory carve-up: 7 entity arrays, 4 result arrays, mask words
   float* base = smem;
-  EnvShared sh;
+  EnvShared<1> sh;
+  sh.pitch = 1;
   sh.px = base + (size_t)(0 * EPB + grp) * ES;
   sh.py = base + (size_t)(1 * EPB + grp) * ES;
   sh.rot = base + (size_t)(2 * EPB + grp) * ES;
@@ -457,6 +495,249 @@ __global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
         a.st.torque[aidx] = atq[j];
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-per-env substep kernel
+//
+// One thread owns one env and walks its entities and work items serially: every instruction does
+// useful work for 32 envs (no idle entity lanes, kind switches are warp-uniform because all envs
+// share the item table), forces accumulate straight into the per-entity accumulators in the
+// reference's order, and no intra-env synchronisation is needed.  The env's state lives in shared
+// memory as [field][entity][thread] so a warp always touches 32 consecutive words.
+// ---------------------------------------------------------------------------------------------
+enum { T_PX = 0, T_PY, T_ROT, T_C, T_S, T_C2, T_S2, T_VX, T_VY, T_W, T_FX, T_FY, T_TQ, T_NF };
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
+  extern __shared__ float smem[];
+  const int E = a.cfg.n_entities, NI = a.cfg.n_items, A = a.cfg.n_agents;
+  const int tid = threadIdx.x;
+  const long env = (long)blockIdx.x * BLOCK + tid;
+  const bool live = env < a.cfg.batch_dim;
+  float* col = smem + tid;  // this thread's column: field k of entity e at col[(k * E + e) * BLOCK]
+#define TF(k, e) col[((k)*E + (e)) * BLOCK]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + (size_t)T_NF * E * BLOCK);
+
+  if (a.use_mask) {
+    for (int w = tid; w < a.mask_words; w += BLOCK) s_mask[w] = a.mask[w];
+    __syncthreads();
+    if (tid == 0) {  // the last block to have copied the mask clears it for the next pass
+      __threadfence();
+      unsigned done = atomicAdd(&a.mask[a.mask_words], 1u);
+      if (done == gridDim.x - 1) {
+        for (int w = 0; w < a.mask_words; ++w) a.mask[w] = 0u;
+        a.mask[a.mask_words] = 0u;
+      }
+    }
+  }
+  if (!live) return;
+
+  EnvShared<BLOCK> sh;
+  sh.pitch = BLOCK;
+  sh.px = &TF(T_PX, 0);
+  sh.py = &TF(T_PY, 0);
+  sh.rot = &TF(T_ROT, 0);
+  sh.c = &TF(T_C, 0);
+  sh.s = &TF(T_S, 0);
+  sh.c2 = &TF(T_C2, 0);
+  sh.s2 = &TF(T_S2, 0);
+  sh.rfx = sh.rfy = sh.rta = sh.rtb = nullptr;
+
+  const size_t ebase = (size_t)env * E, abase = (size_t)env * A;
+  const float2* gpos = reinterpret_cast<const float2*>(a.st.pos) + ebase;
+  const float2* gvel = reinterpret_cast<const float2*>(a.st.vel) + ebase;
+
+  // ---- load the env's slab ------------------------------------------------------------------
+  for (int e = 0; e < E; ++e) {
+    const int flg = __ldg(a.tb.ent_i32 + e * 4 + 1);
+    const float2 p = gpos[e];
+    TF(T_PX, e) = p.x;
+    TF(T_PY, e) = p.y;
+    TF(T_ROT, e) = a.st.rot[ebase + e];
+    float2 v = make_float2(0.f, 0.f);
+    if (flg & VMAS_F_MOVABLE) v = gvel[e];
+    TF(T_VX, e) = v.x;
+    TF(T_VY, e) = v.y;
+    TF(T_W, e) = (flg & VMAS_F_ROTATABLE) ? a.st.ang_vel[ebase + e] : 0.f;
+  }
+
+  const float sub_dt = a.cfg.sub_dt;
+  for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
+    // ---- phase A: trig cache + per-entity forces (ref core.py:1995-2004) -------------------
+    for (int e = 0; e < E; ++e) {
+      const int flg = __ldg(a.tb.ent_i32 + e * 4 + 1);
+      const float* ef = a.tb.ent_f32 + (size_t)e * VMAS_EF_COLS;
+      if (flg & VMAS_F_TRIG) {
+        const float r = TF(T_ROT, e);
+        float sn, cs;
+        sincosf(r, &sn, &cs);
+        TF(T_C, e) = cs;
+        TF(T_S, e) = sn;
+        if (__ldg(a.tb.ent_i32 + e * 4) == VMAS_SHAPE_BOX) {
+          sincosf(r + HALF_PI_F, &sn, &cs);
+          TF(T_C2, e) = cs;
+          TF(T_S2, e) = sn;
+        }
+      }
+      float Fx = 0.f, Fy = 0.f, T = 0.f;
+      const float mass = __ldg(ef + VMAS_EF_MASS);
+      if (flg & VMAS_F_AGENT) {  // ref core.py:2018-2041
+        const int ai = __ldg(a.tb.ent_i32 + e * 4 + 2);
+        if (flg & VMAS_F_MOVABLE) {
+          float2 af = reinterpret_cast<const float2*>(a.st.force)[abase + ai];
+          if (flg & (VMAS_F_MAX_F | VMAS_F_F_RANGE)) {
+            if (flg & VMAS_F_MAX_F) {
+              const float mx = __ldg(ef + VMAS_EF_MAX_F);
+              const float n = norm2(af.x, af.y);
+              if (n > mx) {
+                af.x = (af.x / n) * mx;
+                af.y = (af.y / n) * mx;
+              }
+            }
+            if (flg & VMAS_F_F_RANGE) {
+              const float r = __ldg(ef + VMAS_EF_F_RANGE);
+              af.x = fminf(fmaxf(af.x, -r), r);
+              af.y = fminf(fmaxf(af.y, -r), r);
+            }
+            reinterpret_cast<float2*>(a.st.force)[abase + ai] = af;
+          }
+          Fx = Fx + af.x;
+          Fy = Fy + af.y;
+        }
+        if (flg & VMAS_F_ROTATABLE) {
+          float tq = a.st.torque[abase + ai];
+          if (flg & (VMAS_F_MAX_T | VMAS_F_T_RANGE)) {
+            if (flg & VMAS_F_MAX_T) {
+              const float mx = __ldg(ef + VMAS_EF_MAX_T);
+              const float n = sqrtf(tq * tq);
+              if (n > mx) tq = (tq / n) * mx;
+            }
+            if (flg & VMAS_F_T_RANGE) {
+              const float r = __ldg(ef + VMAS_EF_T_RANGE);
+              tq = fminf(fmaxf(tq, -r), r);
+            }
+            a.st.torque[abase + ai] = tq;
+          }
+          T = T + tq;
+        }
+      }
+      if (flg & VMAS_F_LIN_FRIC) {  // ref core.py:2054-2088
+        const float vx = TF(T_VX, e), vy = TF(T_VY, e);
+        const float speed = norm2(vx, vy);
+        if (speed != 0.f) {
+          const float cap = __ldg(ef + VMAS_EF_LIN_FRIC) * mass;
+          Fx = Fx + (-(vx / speed)) * fminf(cap, (fabsf(vx) / sub_dt) * mass);
+          Fy = Fy + (-(vy / speed)) * fminf(cap, (fabsf(vy) / sub_dt) * mass);
+        }
+      }
+      if (flg & VMAS_F_ANG_FRIC) {  // ref core.py:2089-2102
+        const float w = TF(T_W, e);
+        const float speed = sqrtf(w * w);
+        if (speed != 0.f) {
+          const float inertia = __ldg(ef + VMAS_EF_INERTIA);
+          const float cap = __ldg(ef + VMAS_EF_ANG_FRIC) * inertia;
+          T = T + (-(w / speed)) * fminf(cap, (fabsf(w) / sub_dt) * inertia);
+        }
+      }
+      if (flg & VMAS_F_MOVABLE) {  // ref core.py:2043-2052
+        if (a.cfg.has_world_gravity) {
+          Fx = Fx + mass * a.cfg.gravity_x;
+          Fy = Fy + mass * a.cfg.gravity_y;
+        }
+        if (flg & VMAS_F_GRAVITY) {
+          Fx = Fx + mass * __ldg(ef + VMAS_EF_GRAV_X);
+          Fy = Fy + mass * __ldg(ef + VMAS_EF_GRAV_Y);
+        }
+      }
+      TF(T_FX, e) = Fx;
+      TF(T_FY, e) = Fy;
+      TF(T_TQ, e) = T;
+    }
+
+    // ---- phase B: joints and contacts in the reference's accumulation order -----------------
+    for (int item = 0; item < NI; ++item) {
+      const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
+      if (a.use_mask) {
+        const int mbit = (ii.w >> 8) - 1;
+        if (mbit >= 0 && !((s_mask[mbit >> 5] >> (mbit & 31)) & 1u)) continue;
+      }
+      float fx, fy, ta, tb;
+      eval_item(a, sh, item, env, &fx, &fy, &ta, &tb);
+      const int fa = __ldg(a.tb.ent_i32 + ii.y * 4 + 1), fb = __ldg(a.tb.ent_i32 + ii.z * 4 + 1);
+      if (fa & VMAS_F_MOVABLE) {
+        TF(T_FX, ii.y) = TF(T_FX, ii.y) + fx;
+        TF(T_FY, ii.y) = TF(T_FY, ii.y) + fy;
+      }
+      if (fa & VMAS_F_ROTATABLE) TF(T_TQ, ii.y) = TF(T_TQ, ii.y) + ta;
+      if (fb & VMAS_F_MOVABLE) {
+        TF(T_FX, ii.z) = TF(T_FX, ii.z) + (-fx);
+        TF(T_FY, ii.z) = TF(T_FY, ii.z) + (-fy);
+      }
+      if (fb & VMAS_F_ROTATABLE) TF(T_TQ, ii.z) = TF(T_TQ, ii.z) + tb;
+    }
+
+    // ---- phase C: semi-implicit Euler (ref core.py:2862-2908) ------------------------------
+    for (int e = 0; e < E; ++e) {
+      const int flg = __ldg(a.tb.ent_i32 + e * 4 + 1);
+      if (!(flg & (VMAS_F_MOVABLE | VMAS_F_ROTATABLE))) continue;
+      const float* ef = a.tb.ent_f32 + (size_t)e * VMAS_EF_COLS;
+      const float drag_mult = __ldg(ef + VMAS_EF_DRAG_MULT);
+      if (flg & VMAS_F_MOVABLE) {
+        const float mass = __ldg(ef + VMAS_EF_MASS);
+        float vx = TF(T_VX, e), vy = TF(T_VY, e);
+        if (sub == 0) {
+          vx = vx * drag_mult;
+          vy = vy * drag_mult;
+        }
+        vx = vx + (TF(T_FX, e) / mass) * sub_dt;
+        vy = vy + (TF(T_FY, e) / mass) * sub_dt;
+        if (flg & VMAS_F_MAX_SPEED) {
+          const float mx = __ldg(ef + VMAS_EF_MAX_SPEED);
+          const float n = norm2(vx, vy);
+          if (n > mx) {
+            vx = (vx / n) * mx;
+            vy = (vy / n) * mx;
+          }
+        }
+        if (flg & VMAS_F_V_RANGE) {
+          const float r = __ldg(ef + VMAS_EF_V_RANGE);
+          vx = fminf(fmaxf(vx, -r), r);
+          vy = fminf(fmaxf(vy, -r), r);
+        }
+        float px = TF(T_PX, e) + vx * sub_dt;
+        float py = TF(T_PY, e) + vy * sub_dt;
+        if (a.cfg.has_x_semidim) px = fminf(fmaxf(px, -a.cfg.x_semidim), a.cfg.x_semidim);
+        if (a.cfg.has_y_semidim) py = fminf(fmaxf(py, -a.cfg.y_semidim), a.cfg.y_semidim);
+        TF(T_VX, e) = vx;
+        TF(T_VY, e) = vy;
+        TF(T_PX, e) = px;
+        TF(T_PY, e) = py;
+      }
+      if (flg & VMAS_F_ROTATABLE) {
+        const float inertia = __ldg(ef + VMAS_EF_INERTIA);
+        float w = TF(T_W, e);
+        if (sub == 0) w = w * drag_mult;
+        w = w + (TF(T_TQ, e) / inertia) * sub_dt;
+        TF(T_W, e) = w;
+        TF(T_ROT, e) = TF(T_ROT, e) + w * sub_dt;
+      }
+    }
+  }
+
+  // ---- write-back: only what can have changed --------------------------------------------------
+  for (int e = 0; e < E; ++e) {
+    const int flg = __ldg(a.tb.ent_i32 + e * 4 + 1);
+    if (flg & VMAS_F_MOVABLE) {
+      reinterpret_cast<float2*>(a.st.pos)[ebase + e] = make_float2(TF(T_PX, e), TF(T_PY, e));
+      reinterpret_cast<float2*>(a.st.vel)[ebase + e] = make_float2(TF(T_VX, e), TF(T_VY, e));
+    }
+    if (flg & VMAS_F_ROTATABLE) {
+      a.st.rot[ebase + e] = TF(T_ROT, e);
+      a.st.ang_vel[ebase + e] = TF(T_W, e);
+    }
+  }
+#undef TF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -754,7 +1035,58 @@ static int launch_step(const StepArgs& args, cudaStream_t stream) {
   return 1;
 }
 
+template <int BLOCK>
+static int launch_tpe(const StepArgs& args, cudaStream_t stream, size_t limit, int device) {
+  const size_t smem = (size_t)T_NF * args.cfg.n_entities * BLOCK * sizeof(float) +
+                      (size_t)(args.use_mask ? args.mask_words : 0) * sizeof(uint32_t);
+  if (smem > limit) return -2;  // caller tries a smaller block
+  auto kern = step_tpe_kernel<BLOCK>;
+  static size_t configured[64] = {0};
+  if (smem > 48 * 1024 && (device >= 64 || configured[device] < smem)) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    if (device < 64) configured[device] = limit;
+  }
+  const long blocks = ((long)args.cfg.batch_dim + BLOCK - 1) / BLOCK;
+  kern<<<(unsigned)blocks, BLOCK, smem, stream>>>(args);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+static int dispatch_tpe(const StepArgs& args, cudaStream_t stream) {
+  int device = 0;
+  CUDA_OK(cudaGetDevice(&device));
+  static int max_optin[64] = {0};
+  if (device < 64 && max_optin[device] == 0)
+    CUDA_OK(cudaDeviceGetAttribute(&max_optin[device], cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const size_t limit = device < 64 ? (size_t)max_optin[device] : 48 * 1024;
+  int r = launch_tpe<64>(args, stream, limit, device);
+  if (r == -2) r = launch_tpe<32>(args, stream, limit, device);
+  if (r == -2) return fail("world too large: an env's state does not fit in shared memory%s");
+  return r;
+}
+
+static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
+  const SpecEntry& sp = kSpecs[args.tb.specialization];
+  if (sp.n_entities != args.cfg.n_entities || sp.n_items != args.cfg.n_items)
+    return fail("specialization does not match the world (stale index?)%s");
+  SpecArgs sa;
+  sa.st = args.st;
+  sa.joint_rot = args.tb.joint_rot;
+  sa.mask = args.mask;
+  sa.batch_dim = args.cfg.batch_dim;
+  sa.use_mask = args.use_mask;
+  sa.first_substep = args.first_substep;
+  sa.n_substeps = args.n_substeps;
+  CUDA_OK(sp.launch(sa, stream));
+  return 1;
+}
+
 static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
+  if (args.tb.specialization >= 0) {
+    if (args.tb.specialization >= kNumSpecs) return fail("specialization index out of range%s");
+    return dispatch_spec(args, stream);
+  }
+  if (args.tb.group == 1) return dispatch_tpe(args, stream);
   const int G = args.tb.group, EPL = args.tb.ents_per_lane;
   if (G == 8 && EPL == 1) return launch_step<8, 1>(args, stream);
   if (G == 16 && EPL == 1) return launch_step<16, 1>(args, stream);
@@ -779,6 +1111,18 @@ using namespace vmas;
 extern "C" {
 
 int vmas_b200_abi_version(void) { return VMAS_B200_ABI_VERSION; }
+
+int vmas_b200_num_specializations(void) { return kNumSpecs; }
+
+int vmas_b200_find_specialization(uint64_t world_hash) {
+  for (int i = 0; i < kNumSpecs; ++i)
+    if (kSpecs[i].hash == world_hash) return i;
+  return -1;
+}
+
+const char* vmas_b200_specialization_name(int index) {
+  return (index >= 0 && index < kNumSpecs) ? kSpecs[index].name : "";
+}
 
 const char* vmas_b200_last_error(void) { return g_last_error; }
 
