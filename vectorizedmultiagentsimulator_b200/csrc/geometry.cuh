@@ -29,7 +29,7 @@ DEVI float norm2(float x, float y) { return sqrtf(__fmaf_rn(y, y, __fmul_rn(x, x
 DEVI float norm2(V2 v) { return norm2(v.x, v.y); }
 DEVI float dot2(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }           // (a*b).sum(-1)
 DEVI float cross2(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }         // ref utils.py:194-197
-DEVI float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }     // torch.sign
+DEVI float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }  // torch.sign
 // rotate `v` by the angle whose (cos, sin) is (c, s)  (ref utils.py:176-191)
 DEVI V2 rot2(V2 v, float c, float s) { return mk(v.x * c - v.y * s, v.x * s + v.y * c); }
 
@@ -45,16 +45,16 @@ DEVI Seg mkseg(V2 p, float c, float s, float half) { Seg g; g.p = p; g.c = c; g.
 DEVI V2 closest_point_seg(const Seg& l, V2 q) {
   V2 d = l.p - q;
   float along = d.x * l.c + d.y * l.s;
-  float reach = sgnf(along) * fminf(fabsf(along), l.half);
+  // sign(along) * min(|along|, half): multiplying by +-1 is exact, so this is a copysign
+  float reach = copysignf(fminf(fabsf(along), l.half), along);
   return mk(l.p.x - reach * l.c, l.p.y - reach * l.s);
 }
 
 // Same on the infinite carrier line (limit_to_line_length=False; used by the LIDAR).
 DEVI V2 closest_point_carrier(V2 p, float c, float s, V2 q) {
   V2 d = p - q;
-  float along = d.x * c + d.y * s;
-  float reach = sgnf(along) * fabsf(along);
-  return mk(p.x - reach * c, p.y - reach * s);
+  float along = d.x * c + d.y * s;  // sign(along) * |along| == along
+  return mk(p.x - along * c, p.y - along * s);
 }
 
 struct Pair {
@@ -123,12 +123,29 @@ DEVI Seg box_side(const BoxG& b, int i) {
   }
 }
 
-// Closest point on the outline of a box to q (ref physics.py:263-295, 385-397).
+// Closest point on the outline of a box to q (ref physics.py:263-295, 385-397): first strict
+// minimum over the four sides.  A side whose distance exceeds the smallest one by a clear margin
+// can never be that minimum, so it is skipped on the strength of a cheap box-frame estimate
+// (a^2 > 2 a_min^2 + 2 m^2  =>  a > a_min + m); the surviving sides are evaluated exactly and in
+// the reference's order, which leaves the result bit-identical.
 DEVI V2 closest_point_box(const BoxG& b, V2 q) {
   V2 best = mk(INFINITY, INFINITY);
   float dbest = INFINITY;
+  float est[4];
+  {
+    V2 d = q - b.p;
+    float lx = d.x * b.c + d.y * b.s, ly = d.y * b.c - d.x * b.s;
+    float ex = fmaxf(fabsf(lx) - b.half_l, 0.f), ey = fmaxf(fabsf(ly) - b.half_w, 0.f);
+    float dx0 = lx - b.half_l, dx1 = lx + b.half_l, dy2 = ly - b.half_w, dy3 = ly + b.half_w;
+    est[0] = dx0 * dx0 + ey * ey;
+    est[1] = dx1 * dx1 + ey * ey;
+    est[2] = dy2 * dy2 + ex * ex;
+    est[3] = dy3 * dy3 + ex * ex;
+  }
+  const float keep = 2.f * fminf(fminf(est[0], est[1]), fminf(est[2], est[3])) + 2e-6f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    if (est[i] > keep) continue;
     Seg sd = box_side(b, i);
     V2 p = closest_point_seg(sd, q);
     float d = norm2(q - p);

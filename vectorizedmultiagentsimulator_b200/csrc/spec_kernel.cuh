@@ -197,6 +197,86 @@ DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* 
   if constexpr (eb.flags & VMAS_F_ROTATABLE) r.T[B] = r.T[B] + tb;
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-thread row I/O.  One env's slice of a state tensor ("row", NF floats) is contiguous; the
+// owning thread moves it with the widest vector access the row size allows (16 bytes when
+// NF % 4 == 0), so a sector is touched by at most two requests instead of once per scalar.
+// MASK has one bit per column: vector chunks without any wanted column are skipped at compile
+// time; a chunk with at least one is moved whole.
+// ---------------------------------------------------------------------------------------------
+template <int NF>
+struct RowVec {
+  static constexpr int W = (NF % 4 == 0) ? 4 : (NF % 2 == 0) ? 2 : 1;
+};
+
+__host__ __device__ constexpr uint64_t chunk_closure(uint64_t mask, int nf, int w) {
+  uint64_t out = 0;
+  for (int c = 0; c < nf; c += w) {
+    const uint64_t bits = ((w >= 64 ? ~0ull : ((1ull << w) - 1)) << c);
+    if (mask & bits) out |= bits;
+  }
+  return out;
+}
+
+template <int NF, uint64_t MASK>
+DEVI void row_load(const float* __restrict__ g, float (&dst)[NF > 0 ? NF : 1]) {
+  if constexpr (NF > 0) {
+    constexpr int W = RowVec<NF>::W;
+    static_for<NF / W>([&](auto ci) {
+      constexpr int c = decltype(ci)::value * W;
+      if constexpr ((MASK >> c) & ((1ull << W) - 1)) {
+        if constexpr (W == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(g + c);
+          dst[c] = v.x; dst[c + 1] = v.y; dst[c + 2] = v.z; dst[c + 3] = v.w;
+        } else if constexpr (W == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(g + c);
+          dst[c] = v.x; dst[c + 1] = v.y;
+        } else {
+          dst[c] = g[c];
+        }
+      }
+    });
+  }
+}
+
+template <int NF, uint64_t MASK>
+DEVI void row_store(float* __restrict__ g, const float (&src)[NF > 0 ? NF : 1]) {
+  if constexpr (NF > 0) {
+    constexpr int W = RowVec<NF>::W;
+    static_for<NF / W>([&](auto ci) {
+      constexpr int c = decltype(ci)::value * W;
+      if constexpr ((MASK >> c) & ((1ull << W) - 1)) {
+        if constexpr (W == 4) {
+          *reinterpret_cast<float4*>(g + c) = make_float4(src[c], src[c + 1], src[c + 2], src[c + 3]);
+        } else if constexpr (W == 2) {
+          *reinterpret_cast<float2*>(g + c) = make_float2(src[c], src[c + 1]);
+        } else {
+          g[c] = src[c];
+        }
+      }
+    });
+  }
+}
+
+// column masks derived from the world's entity flags at compile time
+template <class W>
+__host__ __device__ constexpr uint64_t ent_cols(int flag_any, int width) {
+  uint64_t m = 0;
+  for (int e = 0; e < W::E; ++e)
+    if (W::ent[e].flags & flag_any) m |= ((width == 2 ? 3ull : 1ull) << (width * e));
+  return m;
+}
+template <class W>
+__host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, int width) {
+  uint64_t m = 0;
+  for (int e = 0; e < W::E; ++e) {
+    const int f = W::ent[e].flags;
+    if ((f & VMAS_F_AGENT) && (f & flag_all) == flag_all && (flag_any == 0 || (f & flag_any)))
+      m |= ((width == 2 ? 3ull : 1ull) << (width * W::ent[e].agent));
+  }
+  return m;
+}
+
 template <class W>
 __global__ void __launch_bounds__(W::BLOCK) step_spec_kernel(const SpecArgs a) {
   constexpr int E = W::E, NA = W::A, NI = W::NI, MW = W::MASK_WORDS;
@@ -220,36 +300,53 @@ __global__ void __launch_bounds__(W::BLOCK) step_spec_kernel(const SpecArgs a) {
       for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
     }
   }
+  // ---- load this env's rows with vector accesses -----------------------------------------------
+  constexpr uint64_t ALL_POS = (2 * E >= 64) ? ~0ull : ((1ull << (2 * E)) - 1);
+  constexpr uint64_t MOV2 = ent_cols<W>(VMAS_F_MOVABLE, 2);
+  constexpr uint64_t ROT1 = ent_cols<W>(VMAS_F_ROTATABLE, 1);
+  constexpr uint64_t F_DIRTY = agent_cols<W>(VMAS_F_MOVABLE, VMAS_F_MAX_F | VMAS_F_F_RANGE, 2);
+  constexpr uint64_t T_DIRTY = agent_cols<W>(VMAS_F_ROTATABLE, VMAS_F_MAX_T | VMAS_F_T_RANGE, 1);
+  // a vector chunk that will be stored must have been loaded whole (it carries unchanged columns)
+  constexpr uint64_t VEL_IO = chunk_closure(MOV2, 2 * E, RowVec<2 * E>::W);
+  constexpr uint64_t ROT_ST = chunk_closure(ROT1, E, RowVec<E>::W);
+  constexpr uint64_t ROT_LD = ROT_ST | ent_cols<W>(VMAS_F_TRIG | VMAS_F_ROTATABLE, 1);
+  constexpr uint64_t F_ST = chunk_closure(F_DIRTY, 2 * NA, RowVec<2 * NA>::W);
+  constexpr uint64_t T_ST = chunk_closure(T_DIRTY, NA, RowVec<NA>::W);
+  constexpr uint64_t F_LD = F_ST | agent_cols<W>(VMAS_F_MOVABLE, 0, 2);
+  constexpr uint64_t T_LD = T_ST | agent_cols<W>(VMAS_F_ROTATABLE, 0, 1);
   if (env >= a.batch_dim) return;
 
+  float row_pos[2 * E], row_vel[2 * E], row_rot[E], row_w[E];
+  float row_f[NA > 0 ? 2 * NA : 1], row_t[NA > 0 ? NA : 1];
+  row_load<2 * E, ALL_POS>(a.st.pos + (size_t)env * 2 * E, row_pos);
+  row_load<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, row_vel);
+  row_load<E, ROT_LD>(a.st.rot + (size_t)env * E, row_rot);
+  row_load<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, row_w);
+  row_load<2 * NA, F_LD>(a.st.force + (size_t)env * 2 * NA, row_f);
+  row_load<NA, T_LD>(a.st.torque + (size_t)env * NA, row_t);
+
   EnvRegs<E> r;
-  const size_t ebase = (size_t)env * E, abase = (size_t)env * NA;
-  const float2* gpos = reinterpret_cast<const float2*>(a.st.pos) + ebase;
-  const float2* gvel = reinterpret_cast<const float2*>(a.st.vel) + ebase;
   float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
 
   static_for<E>([&](auto ei) {
     constexpr int e = decltype(ei)::value;
     constexpr EntC en = W::ent[e];
-    const float2 p = gpos[e];
-    r.px[e] = p.x;
-    r.py[e] = p.y;
-    r.rot[e] = (en.flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE)) ? a.st.rot[ebase + e] : 0.f;
+    r.px[e] = row_pos[2 * e];
+    r.py[e] = row_pos[2 * e + 1];
+    r.rot[e] = (en.flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE)) ? row_rot[e] : 0.f;
     r.vx[e] = r.vy[e] = r.w[e] = 0.f;
     r.c[e] = r.s[e] = r.c2[e] = r.s2[e] = 0.f;
     if constexpr (en.flags & VMAS_F_MOVABLE) {
-      const float2 v = gvel[e];
-      r.vx[e] = v.x;
-      r.vy[e] = v.y;
+      r.vx[e] = row_vel[2 * e];
+      r.vy[e] = row_vel[2 * e + 1];
     }
-    if constexpr (en.flags & VMAS_F_ROTATABLE) r.w[e] = a.st.ang_vel[ebase + e];
+    if constexpr (en.flags & VMAS_F_ROTATABLE) r.w[e] = row_w[e];
     if constexpr (en.flags & VMAS_F_AGENT) {
       if constexpr (en.flags & VMAS_F_MOVABLE) {
-        const float2 f = reinterpret_cast<const float2*>(a.st.force)[abase + en.agent];
-        afx[en.agent] = f.x;
-        afy[en.agent] = f.y;
+        afx[en.agent] = row_f[2 * en.agent];
+        afy[en.agent] = row_f[2 * en.agent + 1];
       }
-      if constexpr (en.flags & VMAS_F_ROTATABLE) atq[en.agent] = a.st.torque[abase + en.agent];
+      if constexpr (en.flags & VMAS_F_ROTATABLE) atq[en.agent] = row_t[en.agent];
     }
   });
 
@@ -358,25 +455,35 @@ __global__ void __launch_bounds__(W::BLOCK) step_spec_kernel(const SpecArgs a) {
     });
   }
 
-  // ---- write-back ---------------------------------------------------------------------------------
+  // ---- write-back: vector stores of the chunks that hold a changed column ---------------------------
   static_for<E>([&](auto ei) {
     constexpr int e = decltype(ei)::value;
     constexpr EntC en = W::ent[e];
     if constexpr (en.flags & VMAS_F_MOVABLE) {
-      reinterpret_cast<float2*>(a.st.pos)[ebase + e] = make_float2(r.px[e], r.py[e]);
-      reinterpret_cast<float2*>(a.st.vel)[ebase + e] = make_float2(r.vx[e], r.vy[e]);
+      row_pos[2 * e] = r.px[e];
+      row_pos[2 * e + 1] = r.py[e];
+      row_vel[2 * e] = r.vx[e];
+      row_vel[2 * e + 1] = r.vy[e];
     }
     if constexpr (en.flags & VMAS_F_ROTATABLE) {
-      a.st.rot[ebase + e] = r.rot[e];
-      a.st.ang_vel[ebase + e] = r.w[e];
+      row_rot[e] = r.rot[e];
+      row_w[e] = r.w[e];
     }
     if constexpr (en.flags & VMAS_F_AGENT) {
-      if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE)))
-        reinterpret_cast<float2*>(a.st.force)[abase + en.agent] = make_float2(afx[en.agent], afy[en.agent]);
+      if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE))) {
+        row_f[2 * en.agent] = afx[en.agent];
+        row_f[2 * en.agent + 1] = afy[en.agent];
+      }
       if constexpr ((en.flags & VMAS_F_ROTATABLE) && (en.flags & (VMAS_F_MAX_T | VMAS_F_T_RANGE)))
-        a.st.torque[abase + en.agent] = atq[en.agent];
+        row_t[en.agent] = atq[en.agent];
     }
   });
+  row_store<2 * E, VEL_IO>(a.st.pos + (size_t)env * 2 * E, row_pos);
+  row_store<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, row_vel);
+  row_store<E, ROT_ST>(a.st.rot + (size_t)env * E, row_rot);
+  row_store<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, row_w);
+  row_store<2 * NA, F_ST>(a.st.force + (size_t)env * 2 * NA, row_f);
+  row_store<NA, T_ST>(a.st.torque + (size_t)env * NA, row_t);
 }
 
 // host-side launcher used by the registry in generated/specializations.cuh
