@@ -51,6 +51,7 @@ def parse_args():
     p.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="keep L2 warm between iterations (not a bench value)")
+    p.add_argument("--no-graph", action="store_true", help="step eagerly instead of replaying a CUDA graph")
     return p.parse_args()
 
 
@@ -241,7 +242,9 @@ def main_b200(args):
     from vectorizedmultiagentsimulator_b200.simulator import plan as P
 
     B, K, W = args.envs_per_gpu, args.steps, max(args.warmup, 3)
-    env = b200.make_env(SCENARIO, num_envs=B, device=device, seed=rank, **SCENARIO_KWARGS)
+    env = b200.make_env(
+        SCENARIO, num_envs=B, device=device, seed=rank, cuda_graph=not args.no_graph, **SCENARIO_KWARGS
+    )
     backend = env.world._get_backend()
     backend.refresh()
     desc = backend.tables.desc
@@ -287,7 +290,8 @@ def main_b200(args):
     launches = backend.launches - launches_before
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / max(len(kernel_pairs), 1)
+    # (empty in graph mode: the step is one graph replay, no per-kernel events inside it)
+    kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / len(kernel_pairs) if kernel_pairs else 0.0
 
     # ---- the substep kernel alone: world.step() back to back, L2 flushed before every launch.
     # The flush (~100 us on the GPU) lets the host queue the next launch ahead, so the event
@@ -362,7 +366,7 @@ def main_b200(args):
         "bytes_per_launch": alg_bytes,
         "bytes_per_env_substep": bytes_per_env_substep,
         "kernel_us": kernel_ms * 1e3,
-        "kernel_us_inside_env_step": kernel_in_step_ms * 1e3,
+        "kernel_us_inside_env_step": kernel_in_step_ms * 1e3 if kernel_in_step_ms else None,
         "how": "CUDA events recorded by the library around the substep kernel; standalone world.step() loop, L2 flushed before each launch",
     }
 
@@ -396,6 +400,7 @@ def main_b200(args):
             "workload": f"{SCENARIO} n_agents=4, {B} envs per GPU, 1 substep, random continuous actions (BASELINE.json configs[1])",
             "timing": "sum of per-iteration CUDA-event brackets around Environment.step; max over ranks",
             "l2": "flushed between iterations (512 MiB memset outside the brackets)" if flush is not None else "NOT flushed",
+            "api": "make_env(..., cuda_graph=%s); Environment.step" % (not args.no_graph),
             "wall_ms_per_step_incl_flush": 1e3 * wall / K,
         },
         "clocks": clocks,

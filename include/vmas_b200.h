@@ -154,6 +154,36 @@ int vmas_b200_pair_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, c
 int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                           int32_t entity, const float* point, float* out, void* cuda_stream);
 
+/*
+ * Action ingestion for continuous actions: validates, scales and routes the policy's actions of up
+ * to VMAS_MAX_INGEST_AGENTS agents in ONE launch.  Replaces, per agent, the chain of eager ops of
+ * ref environment.py:616-655, 707 (`Environment._set_action`: nan / range asserts, optional clamp,
+ * `u = action * u_multiplier`) and the Holonomic / HolonomicWithRotation dynamics
+ * (ref dynamics/holonomic.py:14-15, holonomic_with_rot.py: `state.force = u[:, :2]`,
+ * `state.torque = u[:, 2]`).
+ *   actions      device fp32 [B, action_size], contiguous
+ *   u            device fp32 [B, action_size]: receives action * u_multiplier (agent.action.u)
+ *   dynamics     0: holonomic (force <- u[0:2]), 1: holonomic with rotation (+ torque <- u[2]),
+ *                -1: only fill `u` (another dynamics model consumes it afterwards)
+ *   bad_flag     device uint8[1] or NULL: set to 1 if any action is NaN or outside +-u_range
+ *                (the reference asserts; here the host reads the flag back asynchronously)
+ */
+#define VMAS_MAX_INGEST_AGENTS 16
+#define VMAS_MAX_ACTION_SIZE 8
+typedef struct VmasAgentActions {
+  const float* actions;
+  float* u;
+  int32_t action_size;
+  int32_t agent_index;   /* row in force / torque */
+  int32_t dynamics;
+  int32_t reserved;
+  float u_range[VMAS_MAX_ACTION_SIZE];
+  float u_multiplier[VMAS_MAX_ACTION_SIZE];
+} VmasAgentActions;
+
+int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
+                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream);
+
 /* The broad-phase pass alone: ORs bit i of `mask` if masked item i is within range in any env. */
 int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                           uint32_t* mask, void* cuda_stream);

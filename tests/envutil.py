@@ -7,7 +7,10 @@ def _copy_tensor_attrs(src_obj, dst_obj, device):
         if isinstance(value, torch.Tensor) and name in dst_obj.__dict__:
             cur = dst_obj.__dict__[name]
             if isinstance(cur, torch.Tensor) and cur.shape == value.shape:
-                dst_obj.__dict__[name] = value.to(device).clone()
+                if cur.dtype == value.dtype and cur.device.type == torch.device(device).type:
+                    cur.copy_(value)  # in place: keeps addresses a captured CUDA graph reads
+                else:
+                    dst_obj.__dict__[name] = value.to(device).clone()
 
 
 def sync_env(src, dst):
@@ -18,7 +21,7 @@ def sync_env(src, dst):
     for e_src, e_dst in zip(src.world.entities, dst.world.entities):
         assert e_src.name == e_dst.name
         _copy_tensor_attrs(e_src, e_dst, device)
-    dst.steps = src.steps.to(device).clone()
+    dst.steps.copy_(src.steps)
     # per-env joint rotations (tensor-valued) follow the source too
     for c_src, c_dst in zip(src.world.joints, dst.world.joints):
         if not isinstance(c_src.fixed_rotation, (int, float)):

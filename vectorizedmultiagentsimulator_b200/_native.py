@@ -132,6 +132,23 @@ class StateC(C.Structure):
     ]
 
 
+MAX_INGEST_AGENTS = 16
+MAX_ACTION_SIZE = 8
+
+
+class AgentActionsC(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p),
+        ("u", C.c_void_p),
+        ("action_size", C.c_int32),
+        ("agent_index", C.c_int32),
+        ("dynamics", C.c_int32),
+        ("reserved", C.c_int32),
+        ("u_range", C.c_float * MAX_ACTION_SIZE),
+        ("u_multiplier", C.c_float * MAX_ACTION_SIZE),
+    ]
+
+
 EXPORTS = [
     "vmas_b200_abi_version",
     "vmas_b200_last_error",
@@ -145,6 +162,7 @@ EXPORTS = [
     "vmas_b200_pair_query",
     "vmas_b200_point_query",
     "vmas_b200_broad_phase",
+    "vmas_b200_ingest_actions",
 ]
 
 _lib = None
@@ -183,6 +201,9 @@ def load():
     ]
     lib.vmas_b200_point_query.argtypes = [p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_broad_phase.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_ingest_actions.argtypes = [
+        p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+    ]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     for name in EXPORTS[2:]:
@@ -395,4 +416,14 @@ def point_query(lib, dt: DeviceTables, slab, entity: int, point, out) -> int:
 def broad_phase(lib, dt: DeviceTables, slab) -> int:
     st = dt.state_struct(slab)
     rc = lib.vmas_b200_broad_phase(C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), _stream(dt.device))
+    return _check(lib, rc)
+
+
+def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, bad_flag) -> int:
+    """``agents_c``: a ctypes array of AgentActionsC whose pointers are already filled in."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_ingest_actions(
+        C.byref(dt.cfg), C.byref(st), agents_c, n, int(clamp),
+        None if bad_flag is None else bad_flag.data_ptr(), _stream(dt.device),
+    )
     return _check(lib, rc)

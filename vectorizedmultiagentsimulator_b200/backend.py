@@ -10,6 +10,7 @@ refuses to run anywhere else — there is deliberately no CPU or torch-eager fal
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -126,6 +127,7 @@ class CudaBackend(PlanRuntime):
 
     # -- tables ----------------------------------------------------------------------------
     def on_new_tables(self):
+        self._ingest_arr = None
         self._dev_tables = self._native.DeviceTables(self.tables, self.world, self.device)
         self._fixed_rot_versions = {}
         self._ray_cache.clear()
@@ -203,6 +205,37 @@ class CudaBackend(PlanRuntime):
         )
         self.launches += 1
         return out
+
+    # -- action ingestion ----------------------------------------------------------------------
+    def ingest_actions(self, actions, specs, clamp: bool, bad_flag) -> None:
+        """One launch: validate + scale the policy actions and write ``agent.action.u`` and the
+        force / torque rows of the slab.  ``specs``: [(agent, dynamics code, u buffer)]."""
+        self.refresh()
+        n = len(specs)
+        arr = getattr(self, "_ingest_arr", None)
+        if arr is None or len(arr) != n:
+            arr = (self._native.AgentActionsC * n)()
+            agent_row = {id(a): j for j, a in enumerate(self.world.agents)}
+            for c, (agent, dyn, u) in zip(arr, specs):
+                c.u = u.data_ptr()
+                c.action_size = agent.action_size
+                c.agent_index = agent_row[id(agent)]
+                c.dynamics = dyn
+                rng = agent.action.u_range_tensor.tolist()
+                mul = agent.action.u_multiplier_tensor.tolist()
+                for j in range(agent.action_size):
+                    c.u_range[j] = rng[j]
+                    c.u_multiplier[j] = mul[j]
+            self._ingest_arr = arr
+        for c, a in zip(arr, actions):
+            c.actions = a.data_ptr()
+        for lo in range(0, n, self._native.MAX_INGEST_AGENTS):
+            hi = min(n, lo + self._native.MAX_INGEST_AGENTS)
+            chunk = (self._native.AgentActionsC * (hi - lo)).from_address(
+                C.addressof(arr) + lo * C.sizeof(self._native.AgentActionsC)
+            )
+            self._native.ingest_actions(self.lib, self._dev_tables, self.world.slab, chunk, hi - lo, clamp, bad_flag)
+            self.launches += 1
 
     # -- queries -----------------------------------------------------------------------------
     def pair_distance(self, a, b) -> Tensor:

@@ -991,6 +991,49 @@ __global__ void __launch_bounds__(256) point_query_kernel(const QueryArgs q) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// action ingestion (ref environment.py:616-655, 707; dynamics/holonomic.py:14-15)
+// ---------------------------------------------------------------------------------------------
+struct IngestArgs {
+  VmasAgentActions ag[VMAS_MAX_INGEST_AGENTS];
+  float* force;
+  float* torque;
+  uint8_t* bad_flag;
+  int n_agents_total;  // A: row stride of force / torque
+  int n;               // agents in this launch
+  int batch_dim;
+  int clamp;
+};
+
+__global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)a.batch_dim * a.n) return;
+  const long env = idx / a.n;
+  const int k = (int)(idx % a.n);
+  const VmasAgentActions& ag = a.ag[k];
+  const int sz = ag.action_size;
+  float u[VMAS_MAX_ACTION_SIZE];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < VMAS_MAX_ACTION_SIZE; ++j) {
+    u[j] = 0.f;
+    if (j < sz) {
+      float v = ag.actions[env * sz + j];
+      const float r = ag.u_range[j];
+      if (a.clamp) v = fminf(fmaxf(v, -r), r);       // torch.clamp keeps NaN
+      bad |= (v != v) || (fabsf(v) > r);
+      u[j] = v * ag.u_multiplier[j];
+      ag.u[env * sz + j] = u[j];
+    }
+  }
+  if (bad && a.bad_flag) *a.bad_flag = 1;
+  if (ag.dynamics >= 0) {
+    const size_t row = (size_t)env * a.n_agents_total + ag.agent_index;
+    reinterpret_cast<float2*>(a.force)[row] = make_float2(u[0], u[1]);
+    if (ag.dynamics == 1) a.torque[row] = u[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int check_common(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st) {
@@ -1273,6 +1316,36 @@ int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, 
   const int threads = 256;
   const long blocks = ((long)cfg->batch_dim + threads - 1) / threads;
   point_query_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(q);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
+                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream) {
+  if (!cfg || !st || !agents) return fail("null argument%s");
+  if (n_agents <= 0 || n_agents > VMAS_MAX_INGEST_AGENTS) return fail("1..16 agents per ingest call%s");
+  IngestArgs a;
+  for (int i = 0; i < n_agents; ++i) {
+    a.ag[i] = agents[i];
+    if (!agents[i].actions || !agents[i].u) return fail("null action buffer%s");
+    if (agents[i].action_size < 0 || agents[i].action_size > VMAS_MAX_ACTION_SIZE) return fail("action size > 8%s");
+    if (agents[i].dynamics >= 0) {
+      if (!st->force || !st->torque) return fail("null force/torque pointer%s");
+      if (agents[i].agent_index < 0 || agents[i].agent_index >= cfg->n_agents) return fail("agent index%s");
+      if (agents[i].action_size < (agents[i].dynamics == 1 ? 3 : 2)) return fail("action too small for dynamics%s");
+    }
+  }
+  a.force = st->force;
+  a.torque = st->torque;
+  a.bad_flag = bad_flag;
+  a.n_agents_total = cfg->n_agents;
+  a.n = n_agents;
+  a.batch_dim = cfg->batch_dim;
+  a.clamp = clamp;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * n_agents;
+  ingest_actions_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                          static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

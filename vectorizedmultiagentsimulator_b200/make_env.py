@@ -23,6 +23,8 @@ def make_env(
     grad_enabled: bool = False,
     terminated_truncated: bool = False,
     wrapper_kwargs: Optional[dict] = None,
+    cuda_graph: bool = False,
+    action_checks: Optional[str] = None,
     **kwargs,
 ):
     """Create a vectorised environment.
@@ -31,7 +33,9 @@ def make_env(
     among this package's scenarios, then in ``$VMAS_SCENARIO_PATH`` directories — e.g. an
     unmodified reference checkout's ``vmas/scenarios``), a path to a scenario file, or a
     ``BaseScenario`` instance.  ``device`` defaults to ``"cuda"``: the physics only runs there.
-    Remaining ``kwargs`` go to ``Scenario.make_world``.
+    ``cuda_graph=True`` replays one captured CUDA graph per ``step`` (graph-safe scenarios only),
+    ``action_checks`` selects ``"sync"`` / ``"deferred"`` / ``"off"`` validation of the input
+    actions (see ``Environment``).  Remaining ``kwargs`` go to ``Scenario.make_world``.
     """
     if isinstance(scenario, str):
         if not scenario.endswith(".py"):
@@ -50,6 +54,8 @@ def make_env(
         clamp_actions=clamp_actions,
         grad_enabled=grad_enabled,
         terminated_truncated=terminated_truncated,
+        cuda_graph=cuda_graph,
+        action_checks=action_checks,
         **kwargs,
     )
     if wrapper is not None and isinstance(wrapper, str):

@@ -107,10 +107,7 @@ class Scenario(BaseScenario):
         )
         self.compute_on_the_ground()
         dist = torch.linalg.vector_norm(self.package.state.pos - self.package.goal.state.pos, dim=1)
-        if env_index is None:
-            self.global_shaping = dist * self.shaping_factor
-        else:
-            self.global_shaping[env_index] = dist[env_index] * self.shaping_factor
+        self.keep(self, "global_shaping", dist * self.shaping_factor, env_index)
 
     def compute_on_the_ground(self):
         self.on_the_ground = self.world.is_overlapping(self.line, self.floor) + self.world.is_overlapping(
@@ -129,7 +126,7 @@ class Scenario(BaseScenario):
             ).to(torch.float32)
             shaping = self.package_dist * self.shaping_factor
             self.pos_rew = self.global_shaping - shaping
-            self.global_shaping = shaping
+            self.keep(self, "global_shaping", shaping)  # carried to the next step: in place
         return self.ground_rew + self.pos_rew
 
     def observation(self, agent: Agent):

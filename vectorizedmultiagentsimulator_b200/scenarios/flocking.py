@@ -95,15 +95,8 @@ class Scenario(BaseScenario):
             occupied_positions=target_pos.unsqueeze(1),
         )
         for agent in world.policy_agents:
-            cost = self._separation_cost(agent)
-            if env_index is None:
-                agent.distance_shaping = cost
-            else:
-                agent.distance_shaping[env_index] = cost[env_index]
-        if env_index is None:
-            self.t = torch.zeros(world.batch_dim, device=world.device)
-        else:
-            self.t[env_index] = 0
+            self.keep(agent, "distance_shaping", self._separation_cost(agent), env_index)
+        self.keep(self, "t", torch.zeros(world.batch_dim, device=world.device), env_index)
 
     def reward(self, agent: Agent):
         world = self.world
@@ -123,7 +116,7 @@ class Scenario(BaseScenario):
                             b.collision_rew = b.collision_rew + penalty
         cost = self._separation_cost(agent)
         agent.dist_rew = agent.distance_shaping - cost
-        agent.distance_shaping = cost
+        self.keep(agent, "distance_shaping", cost)
         return agent.collision_rew + agent.dist_rew
 
     def observation(self, agent: Agent):

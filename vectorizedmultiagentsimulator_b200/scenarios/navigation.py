@@ -122,17 +122,14 @@ class Scenario(BaseScenario):
                 which = 0 if i < self.agents_with_same_goal else i
             agent.goal.set_pos(goal_positions[which], batch_index=env_index)
             dist = torch.linalg.vector_norm(agent.state.pos - agent.goal.state.pos, dim=1)
-            if env_index is None:
-                agent.pos_shaping = dist * self.pos_shaping_factor
-            else:
-                agent.pos_shaping[env_index] = dist[env_index] * self.pos_shaping_factor
+            self.keep(agent, "pos_shaping", dist * self.pos_shaping_factor, env_index)
 
     def _agent_progress(self, agent: Agent):
         agent.distance_to_goal = torch.linalg.vector_norm(agent.state.pos - agent.goal.state.pos, dim=-1)
         agent.on_goal = agent.distance_to_goal < agent.goal.shape.radius
         shaping = agent.distance_to_goal * self.pos_shaping_factor
         agent.pos_rew = agent.pos_shaping - shaping
-        agent.pos_shaping = shaping
+        self.keep(agent, "pos_shaping", shaping)
         return agent.pos_rew
 
     def reward(self, agent: Agent):

@@ -91,10 +91,7 @@ class Scenario(BaseScenario):
         for package in self.packages:
             package.on_goal = world.is_overlapping(package, package.goal)
             dist = torch.linalg.vector_norm(package.state.pos - package.goal.state.pos, dim=1)
-            if env_index is None:
-                package.global_shaping = dist * self.shaping_factor
-            else:
-                package.global_shaping[env_index] = dist[env_index] * self.shaping_factor
+            self.keep(package, "global_shaping", dist * self.shaping_factor, env_index)
 
     def reward(self, agent: Agent):
         if agent is self.world.agents[0]:
@@ -109,7 +106,7 @@ class Scenario(BaseScenario):
                 package.color = torch.where(package.on_goal.unsqueeze(-1), green, red)
                 shaping = package.dist_to_goal * self.shaping_factor
                 rew = rew + torch.where(package.on_goal, 0.0, package.global_shaping - shaping)
-                package.global_shaping = shaping
+                self.keep(package, "global_shaping", shaping)
             self.rew = rew
         return self.rew
 

@@ -347,7 +347,8 @@ class Action(TorchVectorizedObject):
 
     def _as_tensor(self, key, value):
         t = self._cache.get(key)
-        if t is None or t.device != torch.device(self.device):
+        dev = torch.device(self.device)
+        if t is None or t.device.type != dev.type or (dev.index is not None and t.device.index != dev.index):
             t = torch.tensor(
                 list(value) if isinstance(value, Sequence) else [value] * self.action_size,
                 device=self.device,

@@ -8,7 +8,14 @@ with one ``[num_envs, ...]`` tensor per policy agent).  What differs is undernea
   are evaluated on the device into a flag that is read back asynchronously and raised on the
   next call, instead of forcing two host syncs per agent per step (ref environment.py:621,
   651-653).  ``"sync"`` reproduces the reference timing of the asserts, ``"off"`` skips them;
-* ``grad_enabled=True`` is rejected: the kernels are forward-only.
+* ``grad_enabled=True`` is rejected: the kernels are forward-only;
+* ``cuda_graph=True`` captures one whole ``step`` (action decoding → dynamics → physics kernels →
+  scenario reward / observation / done / info) into a CUDA graph after two eager warm-up steps
+  and replays it afterwards: no Python, no per-kernel launch latency.  It requires a
+  *graph-safe* scenario: no host synchronisation inside the step callbacks and every tensor that
+  carries information from one step to the next updated in place (``BaseScenario.keep``).  The
+  scenarios shipped with this package are; arbitrary third-party scenario files may not be,
+  which is why the mode is opt-in.
 """
 from __future__ import annotations
 
@@ -55,6 +62,16 @@ def _seeded(method):
     return wrapper
 
 
+def _clone_tree(x):
+    if isinstance(x, Tensor):
+        return x.clone()
+    if isinstance(x, dict):
+        return {k: _clone_tree(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_clone_tree(v) for v in x)
+    return x
+
+
 class Environment(TorchVectorizedObject):
     metadata = {"render.modes": ["human", "rgb_array"], "runtime.vectorized": True}
     vmas_random_state = [torch.random.get_rng_state(), np.random.get_state(), random.getstate()]
@@ -73,6 +90,7 @@ class Environment(TorchVectorizedObject):
         grad_enabled: bool = False,
         terminated_truncated: bool = False,
         action_checks: Optional[str] = None,
+        cuda_graph: bool = False,
         **kwargs,
     ):
         if multidiscrete_actions:
@@ -104,6 +122,16 @@ class Environment(TorchVectorizedObject):
             self._bad_action_flag = None  # device uint8 [1], set by deferred checks
             self._bad_action_host = None
             self._bad_action_event = None
+            self._bad_action_messages = []
+            if cuda_graph and self.device.type != "cuda":
+                raise ValueError("cuda_graph=True needs a CUDA device")
+            self.cuda_graph = cuda_graph
+            self._graph = None
+            self._graph_inputs = None
+            self._graph_outputs = None
+            self._graph_plan_version = None
+            self._graph_warmup_left = 2
+            self.graph_replays = 0
 
             observations = self._reset(seed=seed)
 
@@ -180,7 +208,10 @@ class Environment(TorchVectorizedObject):
         if seed is not None:
             self._seed(seed)
         self.scenario.env_reset_world_at(env_index=None)
-        self.steps = torch.zeros(self.num_envs, device=self.device)
+        if getattr(self, "steps", None) is not None:
+            self.steps.zero_()  # in place: a captured step graph keeps reading this tensor
+        else:
+            self.steps = torch.zeros(self.num_envs, device=self.device)
         result = self._get_from_scenario(
             get_observations=return_observations,
             get_infos=return_info,
@@ -246,8 +277,7 @@ class Environment(TorchVectorizedObject):
         random.seed(seed)
         return [seed]
 
-    def _step(self, actions):
-        self._raise_deferred_action_errors()
+    def _normalize_actions(self, actions) -> List[Tensor]:
         if isinstance(actions, Dict):
             by_name = actions
             actions = []
@@ -277,22 +307,139 @@ class Environment(TorchVectorizedObject):
                 f" but should have shape {expected}"
             )
             actions[i] = a
+        return actions
 
-        for action, agent in zip(actions, self.agents):
-            self._set_action(action, agent)
-        # scripted agents + scenario-specific processing + dynamics (action -> force/torque)
-        for agent in self.world.agents:
-            self.scenario.env_process_action(agent)
+    def _step(self, actions):
+        self._raise_deferred_action_errors()
+        actions = self._normalize_actions(actions)
+        if self.cuda_graph:
+            result = self._step_graphed(actions)
+        else:
+            result = self._step_device(actions)
+        self._launch_deferred_action_readback()
+        return result
+
+    def _fused_ingest_specs(self):
+        """[(agent, dynamics code, u buffer)] if the fused action-ingest kernel reproduces what
+        ``_set_action`` + ``env_process_action`` would do for every policy agent, else None.
+
+        That holds for continuous, noise-free, non-communicating agents with (rotating) holonomic
+        dynamics in scenarios that do not override ``process_action``.
+        """
+        version = self.world._plan_version
+        cached = getattr(self, "_ingest_cache", None)
+        if cached is not None and cached[0] == version:
+            return cached[1]
+        from ..dynamics.holonomic import Holonomic
+        from ..dynamics.holonomic_with_rot import HolonomicWithRotation
+
+        specs = None
+        ok = (
+            self.device.type == "cuda"
+            and self.continuous_actions
+            and self.action_checks != "sync"
+            and type(self.scenario).process_action is BaseScenario.process_action
+            and self.n_agents > 0
+        )
+        if ok:
+            specs = []
+            for agent in self.agents:
+                noise = agent.action.u_noise
+                noisy = (max(noise) if isinstance(noise, Sequence) else noise) > 0
+                dyn = {Holonomic: 0, HolonomicWithRotation: 1}.get(type(agent.dynamics))
+                if noisy or dyn is None or self._comm_dims(agent) > 0 or not (0 < agent.action_size <= 8):
+                    specs = None
+                    break
+                u = torch.zeros(self.num_envs, agent.action_size, device=self.device, dtype=torch.float32)
+                specs.append((agent, dyn, u))
+        self._ingest_cache = (version, specs)
+        return specs
+
+    def _step_device(self, actions: List[Tensor]):
+        """The device-side work of one step; this is exactly what graph mode captures."""
+        specs = self._fused_ingest_specs()
+        if specs is not None and all(
+            a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions
+        ):
+            # one kernel instead of ~10 eager ops per agent (checks, scaling, force routing)
+            flag = None
+            if self.action_checks == "deferred":
+                if self._bad_action_flag is None:
+                    self._bad_action_flag = torch.zeros(1, dtype=torch.bool, device=self.device)
+                    self._bad_action_messages = []
+                flag = self._bad_action_flag
+                msg = "an action is NaN or outside its agent's u_range"
+                if msg not in self._bad_action_messages:
+                    self._bad_action_messages.append(msg)
+            self.world._get_backend().ingest_actions(actions, specs, self.clamp_action, flag)
+            for agent, _, u in specs:
+                agent.action.u = u
+            for agent in self.world.scripted_agents:
+                self.scenario.env_process_action(agent)
+        else:
+            for action, agent in zip(actions, self.agents):
+                self._set_action(action, agent)
+            # scripted agents + scenario-specific processing + dynamics (action -> force/torque)
+            for agent in self.world.agents:
+                self.scenario.env_process_action(agent)
 
         self.scenario.pre_step()
         self.world.step()
         self.scenario.post_step()
         self.steps += 1
-
-        self._launch_deferred_action_readback()
         return self._get_from_scenario(
             get_observations=True, get_infos=True, get_rewards=True, get_dones=True
         )
+
+    # ---- CUDA-graph mode -------------------------------------------------------------------
+    def _step_graphed(self, actions: List[Tensor]):
+        world = self.world
+        if self._graph is not None and (
+            self._graph_plan_version != world._plan_version
+            or any(a.shape != s.shape or a.dtype != s.dtype for a, s in zip(actions, self._graph_inputs))
+        ):
+            self._graph = None  # the world or the action layout changed: capture again
+            self._graph_warmup_left = 1
+        if self._graph is None:
+            if self._graph_warmup_left > 0:
+                self._graph_warmup_left -= 1
+                return self._step_device([a.to(self.device) for a in actions])
+            self._capture(actions)
+        for static, a in zip(self._graph_inputs, actions):
+            static.copy_(a, non_blocking=True)
+        self._graph.replay()
+        self.graph_replays += 1
+        backend = world._get_backend()
+        backend.launches += self._graph_launches
+        return _clone_tree(self._graph_outputs)
+
+    def _capture(self, actions: List[Tensor]):
+        if self.action_checks == "sync":
+            raise RuntimeError("cuda_graph=True cannot be combined with action_checks='sync' (host sync per step)")
+        if self.action_checks == "deferred" and self._bad_action_flag is None:
+            self._bad_action_flag = torch.zeros(1, dtype=torch.bool, device=self.device)
+        self._graph_inputs = [torch.empty_like(a, device=self.device) for a in actions]
+        for static, a in zip(self._graph_inputs, actions):
+            static.copy_(a)
+        backend = self.world._get_backend()
+        backend.refresh()
+        torch.cuda.synchronize(self.device)
+        before = backend.launches
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph):
+                outputs = self._step_device(self._graph_inputs)
+        except Exception as err:  # noqa: BLE001
+            raise RuntimeError(
+                "cuda_graph=True: capturing Environment.step failed. The scenario (or a dynamics / "
+                "action script) is not graph-safe: it must not synchronise with the host inside "
+                f"process_action / pre_step / post_step / reward / observation / done / info. Cause: {err}"
+            ) from err
+        self._graph_launches = backend.launches - before
+        backend.launches = before
+        self._graph = graph
+        self._graph_outputs = outputs
+        self._graph_plan_version = self.world._plan_version
 
     def _done(self):
         terminated = self.scenario.done().clone()
@@ -400,7 +547,6 @@ class Environment(TorchVectorizedObject):
             return
         if self._bad_action_flag is None:
             self._bad_action_flag = torch.zeros(1, dtype=torch.bool, device=self.device)
-            self._bad_action_messages = []
         self._bad_action_flag |= condition.any()
         if message not in self._bad_action_messages:
             self._bad_action_messages.append(message)

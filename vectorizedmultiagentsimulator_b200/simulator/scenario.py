@@ -44,6 +44,24 @@ class BaseScenario(ABC):
                 self.__dict__[attr] = value.to(device)
         self.world.to(device)
 
+    @staticmethod
+    def keep(owner, name: str, value: Tensor, env_index=None) -> Tensor:
+        """Store a tensor that carries state from one step to the next (shaping terms, timers).
+
+        The first call binds ``owner.<name>``; later calls write into the existing tensor so its
+        address never changes — the rule that makes a scenario replayable as a CUDA graph.
+        With ``env_index`` only that env's row is written.
+        """
+        cur = getattr(owner, name, None)
+        if not isinstance(cur, Tensor) or cur.shape != value.shape or cur.dtype != value.dtype:
+            setattr(owner, name, value.clone())
+            return getattr(owner, name)
+        if env_index is None:
+            cur.copy_(value)
+        else:
+            cur[env_index] = value[env_index]
+        return cur
+
     # ---- glue (do not override) -----------------------------------------------------------
     def env_make_world(self, batch_dim: int, device: torch.device, **kwargs) -> World:
         self._world = self.make_world(batch_dim, device, **kwargs)
