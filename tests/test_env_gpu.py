@@ -127,8 +127,10 @@ def test_cuda_graph_mode_is_bit_identical_to_eager(name, kwargs):
         ]
         want = eager.step([a.clone() for a in actions])
         got = graph.step([a.clone() for a in actions])
-        for g, w in zip(flatten(got), flatten(want)):
-            assert torch.equal(g, w), f"{name} step {t}"
+        for i, (g, w) in enumerate(zip(flatten(got), flatten(want))):
+            assert g.is_contiguous(), f"{name}: output {i} is not contiguous"
+            diff = float((g.float() - w.float()).abs().max())
+            assert torch.equal(g, w), f"{name} step {t} output {i} shape {tuple(g.shape)} max diff {diff}"
         if t == 4:
             eager.reset_at(5)
             graph.reset_at(5)

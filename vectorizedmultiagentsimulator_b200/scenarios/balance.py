@@ -129,22 +129,41 @@ class Scenario(BaseScenario):
             self.keep(self, "global_shaping", shaping)  # carried to the next step: in place
         return self.ground_rew + self.pos_rew
 
-    def observation(self, agent: Agent):
-        pkg, line = self.package, self.line
-        return torch.cat(
+    def _observe_all(self):
+        """Observations of every agent in one pass over the state slab -> ``[A, B, 16]``.
+
+        Same elementwise arithmetic as a per-agent ``torch.cat`` of the nine terms, but the
+        agent-independent terms are computed once and the agent-relative ones for all agents at
+        once (the agents are consecutive rows of the slab).  Agent-major output: each agent's
+        ``[B, 16]`` observation is a contiguous slice.
+        """
+        world = self.world
+        slab = world.slab
+        ents = world.entities
+        a0, n = ents.index(world.agents[0]), len(world.agents)
+        ip, il, ig = ents.index(self.package), ents.index(self.line), ents.index(self.package.goal)
+        apos = slab.pos[:, a0 : a0 + n].transpose(0, 1)  # [A, B, 2] views of the slab
+        avel = slab.vel[:, a0 : a0 + n].transpose(0, 1)
+        pkg_pos, line_pos = slab.pos[:, ip].unsqueeze(0), slab.pos[:, il].unsqueeze(0)  # [1, B, 2]
+        shared = torch.cat(
             [
-                agent.state.pos,
-                agent.state.vel,
-                agent.state.pos - pkg.state.pos,
-                agent.state.pos - line.state.pos,
-                pkg.state.pos - pkg.goal.state.pos,
-                pkg.state.vel,
-                line.state.vel,
-                line.state.ang_vel,
-                line.state.rot % torch.pi,
+                pkg_pos - slab.pos[:, ig].unsqueeze(0),
+                slab.vel[:, ip].unsqueeze(0),
+                slab.vel[:, il].unsqueeze(0),
+                slab.ang_vel[:, il : il + 1].unsqueeze(0),
+                (slab.rot[:, il : il + 1] % torch.pi).unsqueeze(0),
             ],
             dim=-1,
         )
+        return torch.cat(
+            [apos, avel, apos - pkg_pos, apos - line_pos, shared.expand(n, -1, -1)], dim=-1
+        )
+
+    def observation(self, agent: Agent):
+        agents = self.world.agents
+        if agent is agents[0] or getattr(self, "_obs_all", None) is None:
+            self._obs_all = self._observe_all()
+        return self._obs_all[agents.index(agent)]
 
     def done(self):
         return self.on_the_ground + self.world.is_overlapping(self.package, self.package.goal)

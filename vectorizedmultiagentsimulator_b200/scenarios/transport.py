@@ -96,8 +96,12 @@ class Scenario(BaseScenario):
     def reward(self, agent: Agent):
         if agent is self.world.agents[0]:
             rew = torch.zeros(self.world.batch_dim, device=self.world.device, dtype=torch.float32)
-            red = torch.tensor(Color.RED.value, device=self.world.device, dtype=torch.float32)
-            green = torch.tensor(Color.GREEN.value, device=self.world.device, dtype=torch.float32)
+            if getattr(self, "_colors", None) is None:  # constants: uploaded once, not every step
+                self._colors = (
+                    torch.tensor(Color.RED.value, device=self.world.device, dtype=torch.float32),
+                    torch.tensor(Color.GREEN.value, device=self.world.device, dtype=torch.float32),
+                )
+            red, green = self._colors
             for package in self.packages:
                 package.dist_to_goal = torch.linalg.vector_norm(
                     package.state.pos - package.goal.state.pos, dim=1

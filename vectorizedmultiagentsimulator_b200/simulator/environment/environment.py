@@ -62,13 +62,24 @@ def _seeded(method):
     return wrapper
 
 
-def _clone_tree(x):
+def _clone_tree(x, _bases=None):
+    """Deep copy of a nest of tensors.  Disjoint views of one base tensor (e.g. the per-agent
+    slices of a batched ``[B, A, k]`` observation) are copied with a single clone of the base."""
+    top = _bases is None
+    if top:
+        _bases = {}
     if isinstance(x, Tensor):
+        base = x._base
+        if base is not None and base.is_contiguous() and x.dim() >= 1:
+            key = id(base)
+            if key not in _bases:
+                _bases[key] = base.clone()
+            return _bases[key].as_strided(x.size(), x.stride(), x.storage_offset() - base.storage_offset())
         return x.clone()
     if isinstance(x, dict):
-        return {k: _clone_tree(v) for k, v in x.items()}
+        return {k: _clone_tree(v, _bases) for k, v in x.items()}
     if isinstance(x, (list, tuple)):
-        return type(x)(_clone_tree(v) for v in x)
+        return type(x)(_clone_tree(v, _bases) for v in x)
     return x
 
 
@@ -233,11 +244,15 @@ class Environment(TorchVectorizedObject):
         return result[0] if result and len(result) == 1 else result
 
     def _get_from_scenario(
-        self, get_observations, get_rewards, get_infos, get_dones, dict_agent_names=None
+        self, get_observations, get_rewards, get_infos, get_dones, dict_agent_names=None, clone=True
     ):
         if not (get_infos or get_dones or get_rewards or get_observations):
             return
         by_name = self.dict_spaces if dict_agent_names is None else dict_agent_names
+        # the reference clones everything it hands out (environment.py:278, 285, 294, 415);
+        # graph mode clones once, outside the captured region, instead
+        _c = (lambda t: t.clone()) if clone else (lambda t: t)
+        _rc = TorchUtils.recursive_clone if clone else (lambda t: t)
 
         def collect(fn):
             out = {} if by_name else []
@@ -250,22 +265,16 @@ class Environment(TorchVectorizedObject):
             return out
 
         # order matters: scenarios cache shared terms while computing agent 0's reward
-        rewards = collect(lambda a: self.scenario.reward(a).clone()) if get_rewards else None
-        obs = (
-            collect(lambda a: TorchUtils.recursive_clone(self.scenario.observation(a)))
-            if get_observations
-            else None
-        )
-        infos = (
-            collect(lambda a: TorchUtils.recursive_clone(self.scenario.info(a))) if get_infos else None
-        )
+        rewards = collect(lambda a: _c(self.scenario.reward(a))) if get_rewards else None
+        obs = collect(lambda a: _rc(self.scenario.observation(a))) if get_observations else None
+        infos = collect(lambda a: _rc(self.scenario.info(a))) if get_infos else None
         if self.terminated_truncated:
             terminated = truncated = None
             if get_dones:
-                terminated, truncated = self._done()
+                terminated, truncated = self._done(clone)
             result = [obs, rewards, terminated, truncated, infos]
         else:
-            dones = self._done() if get_dones else None
+            dones = self._done(clone) if get_dones else None
             result = [obs, rewards, dones, infos]
         return [data for data in result if data is not None]
 
@@ -355,7 +364,7 @@ class Environment(TorchVectorizedObject):
         self._ingest_cache = (version, specs)
         return specs
 
-    def _step_device(self, actions: List[Tensor]):
+    def _step_device(self, actions: List[Tensor], clone_outputs: bool = True):
         """The device-side work of one step; this is exactly what graph mode captures."""
         specs = self._fused_ingest_specs()
         if specs is not None and all(
@@ -388,7 +397,7 @@ class Environment(TorchVectorizedObject):
         self.scenario.post_step()
         self.steps += 1
         return self._get_from_scenario(
-            get_observations=True, get_infos=True, get_rewards=True, get_dones=True
+            get_observations=True, get_infos=True, get_rewards=True, get_dones=True, clone=clone_outputs
         )
 
     # ---- CUDA-graph mode -------------------------------------------------------------------
@@ -428,7 +437,8 @@ class Environment(TorchVectorizedObject):
         graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(graph):
-                outputs = self._step_device(self._graph_inputs)
+                # outputs stay un-cloned inside the graph: _clone_tree copies them after each replay
+                outputs = self._step_device(self._graph_inputs, clone_outputs=False)
         except Exception as err:  # noqa: BLE001
             raise RuntimeError(
                 "cuda_graph=True: capturing Environment.step failed. The scenario (or a dynamics / "
@@ -441,8 +451,10 @@ class Environment(TorchVectorizedObject):
         self._graph_outputs = outputs
         self._graph_plan_version = self.world._plan_version
 
-    def _done(self):
-        terminated = self.scenario.done().clone()
+    def _done(self, clone=True):
+        terminated = self.scenario.done()
+        if clone:
+            terminated = terminated.clone()
         truncated = self.steps >= self.max_steps if self.max_steps is not None else None
         if self.terminated_truncated:
             if truncated is None:
