@@ -1,14 +1,15 @@
 """ORACLE (test infrastructure, not product code) — closest-point geometry on CPU.
 
 A plain torch-fp32 restatement of the reference's batched closest-point routines
-(``/root/reference/vmas/simulator/physics.py``), one *pair* at a time instead of the
-reference's stacked ``[B, P, ...]`` buckets.  Every function cites the reference lines it
-follows.  Arithmetic order and fp32 scalar rounding follow the reference expression by
+(``/root/reference/vmas/simulator/physics.py``).  Every function is shape-generic: it works
+on one pair (``[B, 2]``) or on a whole stacked bucket (``[B, P, 2]`` with per-pair lengths
+``[P, 1]``), which is how ``oracle/world_step.py`` calls it.  Every function cites the
+reference lines it follows.  Arithmetic order and fp32 scalar rounding follow the reference expression by
 expression so that results are bit-comparable with it (checked in
 ``tests/test_oracle_vs_reference.py`` and pinned by ``tests/golden/``).
 
-Conventions: points are ``[B, 2]``, angles ``[B, 1]``, lengths python floats that were
-already rounded to fp32 by the plan compiler.
+Conventions: points are ``[..., 2]``, angles ``[..., 1]``, lengths python floats (rounded to
+fp32 here, as the reference does with ``torch.tensor``) or fp32 tensors ``[P, 1]``.
 """
 from __future__ import annotations
 
@@ -20,7 +21,10 @@ INF = float("inf")
 
 
 def _len_t(length, like):
-    """A python-float length as the fp32 tensor the reference builds with ``torch.tensor``."""
+    """A python-float length as the fp32 tensor the reference builds with ``torch.tensor``.
+    Tensors (one length per stacked pair, shape ``[P, 1]``) pass through."""
+    if isinstance(length, torch.Tensor):
+        return length
     return torch.tensor(length, dtype=torch.float32, device=like.device)
 
 

@@ -100,7 +100,12 @@ class BaseScenario(ABC):
 
     # ---- optional --------------------------------------------------------------------------
     def done(self) -> Tensor:
-        return torch.tensor([False], device=self.world.device).expand(self.world.batch_dim)
+        never = getattr(self, "_never_done", None)
+        if never is None or never.shape[0] != self.world.batch_dim or never.device != self.world.slab.pos.device:
+            # allocated on the device once (a per-call torch.tensor([...]) would be an H2D copy per step)
+            never = torch.zeros(self.world.batch_dim, dtype=torch.bool, device=self.world.device)
+            self._never_done = never
+        return never
 
     def info(self, agent: Agent) -> AGENT_INFO_TYPE:
         return {}
