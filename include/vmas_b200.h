@@ -36,7 +36,7 @@ enum {
   VMAS_F_MOVABLE = 1 << 0, VMAS_F_ROTATABLE = 1 << 1, VMAS_F_HOLLOW = 1 << 2, VMAS_F_AGENT = 1 << 3,
   VMAS_F_LIN_FRIC = 1 << 4, VMAS_F_ANG_FRIC = 1 << 5, VMAS_F_GRAVITY = 1 << 6, VMAS_F_MAX_SPEED = 1 << 7,
   VMAS_F_V_RANGE = 1 << 8, VMAS_F_MAX_F = 1 << 9, VMAS_F_F_RANGE = 1 << 10, VMAS_F_MAX_T = 1 << 11,
-  VMAS_F_T_RANGE = 1 << 12, VMAS_F_TRIG = 1 << 13
+  VMAS_F_T_RANGE = 1 << 12, VMAS_F_TRIG = 1 << 13, VMAS_F_GRAVITY_ENV = 1 << 14
 };
 /* columns of ent_f32 [E, 20] */
 enum {
@@ -81,6 +81,8 @@ typedef struct VmasPlanTables {
                                  (lane-per-entity mapping only; ignored when group == 1) */
   const int32_t* masked_items;/* [n_masked] item index of each mask bit */
   const float*   joint_rot;   /* [B, n_joints] per-env fixed rotations, or NULL */
+  const float*   ent_gravity; /* [B, E, 2] per-env gravity of entities flagged VMAS_F_GRAVITY_ENV, or NULL
+                                 (ref core.py:594-601, 2049-2052: Entity.gravity given as a tensor) */
   int32_t n_rounds;
   int32_t group;              /* lanes per env: 1 = one thread per env (default), or 8, 16, 32 */
   int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */

@@ -35,6 +35,11 @@ class OracleBackend(PlanRuntime):
             self._state(),
             fixed_rot=self.per_env_fixed_rotations(),
             exact_broad_phase=self.world.exact_broad_phase,
+            ent_gravity={
+                i: e.gravity
+                for i, e in enumerate(self.world.entities)
+                if self.tables.desc.entities[i].get("gravity_per_env")
+            },
         )
 
     def cast_rays(self, entity, angles, max_range, entity_filter):

@@ -28,6 +28,8 @@ def teacher_forced_steps(fix):
         state_in = {k: base[k].clone() for k in ("pos", "vel", "rot", "ang_vel")}
         state_in["force"] = entry["force"].clone()
         state_in["torque"] = entry["torque"].clone()
+        if "ent_gravity" in entry:  # per-env Entity.gravity tensors (wind_flocking)
+            state_in["ent_gravity"] = {k: v.clone() for k, v in entry["ent_gravity"].items()}
         yield t, state_in, entry.get("fixed_rot", {}), entry["out"]
         prev = entry["out"]
 

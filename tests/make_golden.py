@@ -38,6 +38,9 @@ CASES = [
     ("give_way", dict(), 16, 20),
     ("wheel", dict(), 16, 20),
     ("dropout", dict(), 16, 15),
+    ("wind_flocking", dict(), 16, 15),  # per-env gravity tensors (Entity.gravity as [B, 2])
+    ("football", dict(), 8, 10),
+    ("passage", dict(), 16, 15),
 ]
 
 
@@ -57,6 +60,9 @@ def record(vmas, name, kwargs, num_envs, steps):
         pre_step(env, actions)
         state_in = world_state(world)
         fixed = per_env_fixed_rotations(world, desc)
+        gravity = {
+            i: e.gravity.clone() for i, e in enumerate(world.entities) if desc.entities[i].get("gravity_per_env")
+        }
         world.step()
         state_out = world_state(world)
         entry = dict(force=state_in["force"], torque=state_in["torque"], out=state_out)
@@ -67,6 +73,8 @@ def record(vmas, name, kwargs, num_envs, steps):
             entry["state_in"] = {k: state_in[k] for k in ("pos", "vel", "rot", "ang_vel")}
         if fixed:
             entry["fixed_rot"] = fixed
+        if gravity:
+            entry["ent_gravity"] = gravity
         fix["steps"].append(entry)
         prev_out = state_out
         obs, rews, dones, infos = post_step(env)
@@ -116,8 +124,10 @@ def main():
     out_dir = os.path.join(HERE, "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, kwargs, num_envs, steps in CASES:
-        fix = record(vmas, name, kwargs, num_envs, steps)
         path = os.path.join(out_dir, f"{name}.pt")
+        if os.path.exists(path) and "--all" not in sys.argv:
+            continue  # fixtures are append-only; pass --all to regenerate everything
+        fix = record(vmas, name, kwargs, num_envs, steps)
         torch.save(fix, path)
         print(f"{name:20s} B={num_envs:3d} T={steps:3d} lidar={len(fix['lidar']):3d} -> {os.path.getsize(path)/1e6:.2f} MB")
 

@@ -57,10 +57,12 @@ def _ulp_sensitivity(tables, state_in, fixed_rot, trials=3):
     return worst
 
 
-def _device_tables(tables, fixed_rot, device, mapping=None):
+def _device_tables(tables, fixed_rot, device, mapping=None, ent_gravity=None):
     dt = _native.DeviceTables(tables, None, device, mapping=mapping)
     for k, v in fixed_rot.items():
         dt.joint_rot[:, k] = v.reshape(-1).to(device)
+    for e, g in (ent_gravity or {}).items():
+        dt.ent_gravity[:, e] = g.to(device)
     return dt
 
 
@@ -77,7 +79,11 @@ def test_world_step_vs_reference_golden(name):
     device = torch.device("cuda:0")
     worst = 0.0
     for t, state_in, fixed_rot, want in teacher_forced_steps(fix):
-        dt = _device_tables(tables, fixed_rot, device) if (t == 0 or fixed_rot) else dt
+        dt = (
+            _device_tables(tables, fixed_rot, device, ent_gravity=state_in.get("ent_gravity"))
+            if (t == 0 or fixed_rot or "ent_gravity" in state_in)
+            else dt
+        )
         slab = _Slab(state_in, device)
         n = _native.world_step(lib, dt, slab)
         assert n >= 1
@@ -101,7 +107,7 @@ def test_world_step_vs_live_oracle(name):
             continue
         cpu = {k: v.clone() for k, v in state_in.items()}
         WS.world_step(tables, cpu, fixed_rot=fixed_rot)
-        dt = _device_tables(tables, fixed_rot, device)
+        dt = _device_tables(tables, fixed_rot, device, ent_gravity=state_in.get("ent_gravity"))
         slab = _Slab(state_in, device)
         _native.world_step(lib, dt, slab)
         sens = _ulp_sensitivity(tables, state_in, fixed_rot) if name in JOINT_WORLDS else None
@@ -143,7 +149,7 @@ def test_thread_per_env_and_lanes_per_env_agree_bitwise(name):
         if _native.DeviceTables(tables, None, device).mapping == "specialized":
             mappings.append("specialized")  # world-specialised, register-resident kernel
         for mapping in mappings:
-            dt = _device_tables(tables, fixed_rot, device, mapping=mapping)
+            dt = _device_tables(tables, fixed_rot, device, mapping=mapping, ent_gravity=state_in.get("ent_gravity"))
             assert dt.mapping == mapping
             slab = _Slab(state_in, device)
             _native.world_step(lib, dt, slab)
@@ -171,7 +177,7 @@ def test_world_step_vs_reference_golden_both_mappings(mapping):
         for t, state_in, fixed_rot, want in teacher_forced_steps(fix):
             if t > 6:
                 break
-            dt = _device_tables(tables, fixed_rot, device, mapping=mapping)
+            dt = _device_tables(tables, fixed_rot, device, mapping=mapping, ent_gravity=state_in.get("ent_gravity"))
             slab = _Slab(state_in, device)
             _native.world_step(lib, dt, slab)
             sens = _ulp_sensitivity(tables, state_in, fixed_rot) if name in JOINT_WORLDS else None

@@ -106,9 +106,13 @@ def test_cpu_world_refuses_to_step():
 def test_deferred_action_check_raises_next_step():
     env = b200.make_env("navigation", num_envs=4, device="cuda", seed=0, n_agents=2)
     bad = [torch.full((4, 2), 5.0, device="cuda") for _ in env.agents]
-    env.step(bad)  # flagged on the device, raised on the next call
+    env.step(bad)  # flagged on the device, raised by a later call once the read-back has landed
+    torch.cuda.synchronize()
     with pytest.raises(AssertionError):
         env.step(env.get_random_actions())
+    env.step(bad)
+    with pytest.raises(AssertionError):
+        env.check_actions_now()  # deterministic variant: waits for the flag
 
 
 @pytest.mark.parametrize("name,kwargs", CASES)

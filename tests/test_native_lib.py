@@ -28,7 +28,7 @@ def test_abi_version_and_struct_sizes():
     assert lib.vmas_b200_abi_version() == 1
     # 10 int32 + 9 float
     assert ctypes.sizeof(_native.WorldConfig) == 19 * 4
-    assert ctypes.sizeof(_native.PlanTablesC) == 9 * 8 + 4 * 4
+    assert ctypes.sizeof(_native.PlanTablesC) == 10 * 8 + 4 * 4
     assert ctypes.sizeof(_native.StateC) == 6 * 8
 
 

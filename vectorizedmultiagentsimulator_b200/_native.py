@@ -114,6 +114,7 @@ class PlanTablesC(C.Structure):
         ("sched", C.c_void_p),
         ("masked_items", C.c_void_p),
         ("joint_rot", C.c_void_p),
+        ("ent_gravity", C.c_void_p),
         ("n_rounds", C.c_int32),
         ("group", C.c_int32),
         ("ents_per_lane", C.c_int32),
@@ -319,6 +320,12 @@ class DeviceTables:
             for k, it in enumerate(desc.items[: tables.n_joints]):
                 if not it["rotate"] and it["fixed_rotation"] is not None:
                     self.joint_rot[:, k] = float(it["fixed_rotation"])
+        self.gravity_entities = [i for i, e in enumerate(desc.entities) if e.get("gravity_per_env")]
+        self.ent_gravity = (
+            torch.zeros(B, desc.n_entities, 2, dtype=torch.float32, device=self.device)
+            if self.gravity_entities
+            else None
+        )
         words = (tables.n_masked + 31) // 32
         self.mask = torch.zeros(words + 1, dtype=torch.int32, device=self.device)
         self.n_rounds = int(sched.shape[0])
@@ -334,6 +341,7 @@ class DeviceTables:
         tb.sched = self.sched.data_ptr()
         tb.masked_items = self.masked_items.data_ptr()
         tb.joint_rot = self.joint_rot.data_ptr() if self.joint_rot is not None else None
+        tb.ent_gravity = self.ent_gravity.data_ptr() if self.ent_gravity is not None else None
         tb.n_rounds = self.n_rounds
         tb.group = self.group
         tb.ents_per_lane = self.ents_per_lane

@@ -150,9 +150,18 @@ class CudaBackend(PlanRuntime):
             self._fixed_rot_versions[k] = ver
 
     # -- hot path ---------------------------------------------------------------------------
+    def _sync_entity_gravity(self):
+        dt = self._dev_tables
+        if dt.ent_gravity is None:
+            return
+        ents = self.world.entities
+        for i in dt.gravity_entities:
+            dt.ent_gravity[:, i].copy_(ents[i].gravity)
+
     def step(self):
         self.refresh()
         self._sync_fixed_rotations()
+        self._sync_entity_gravity()
         slab = self.world.slab
         events = None
         if self.kernel_events is not None:

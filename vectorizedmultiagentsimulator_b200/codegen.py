@@ -45,6 +45,8 @@ def world_hash(desc: P.WorldDescription) -> int:
     d.pop("batch_dim")
     for e in d["entities"]:
         e.pop("name")
+        if not e.get("gravity_per_env"):
+            e.pop("gravity_per_env", None)  # absent in descriptions written before the field existed
     blob = json.dumps(d, sort_keys=True).encode()
     h = 0xCBF29CE484222325
     for byte in blob:
@@ -59,6 +61,8 @@ def _item_cost(kind: int) -> int:
 
 def specializable(desc: P.WorldDescription) -> bool:
     if desc.n_entities > MAX_ENTITIES or desc.n_entities == 0:
+        return False
+    if any(e.get("gravity_per_env") for e in desc.entities):
         return False
     return sum(_item_cost(it["kind"]) for it in desc.items) <= MAX_ITEM_COST
 

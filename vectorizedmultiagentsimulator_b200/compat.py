@@ -27,6 +27,11 @@ _MODULES = [
     "simulator.dynamics.forward",
     "simulator.dynamics.roatation",
     "simulator.dynamics.static",
+    "simulator.dynamics.diff_drive",
+    "simulator.dynamics.kinematic_bicycle",
+    "simulator.dynamics.drone",
+    "simulator.controllers",
+    "simulator.controllers.velocity_controller",
     "simulator.environment",
     "simulator.environment.environment",
     "simulator.heuristic_policy",

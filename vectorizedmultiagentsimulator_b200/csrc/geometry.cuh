@@ -154,14 +154,49 @@ DEVI V2 closest_point_box(const BoxG& b, V2 q) {
   return best;
 }
 
-// Closest (point on box, point on segment) (ref physics.py:328-382).
+// Closest (point on box, point on segment) (ref physics.py:328-382): first strict minimum over the
+// four sides of the segment/segment result.  Sides are pruned exactly like in closest_point_box:
+// in the box frame, lo[i] is a lower bound of the distance between the segment and side i (axis
+// separation), up an upper bound of the final minimum (an end point of the segment projected on
+// a side is one of the candidates the segment/segment routine considers); a side with
+// lo^2 > 2 up^2 + 2 m^2 cannot be the minimum and is skipped.
 DEVI Pair closest_box_seg(const BoxG& b, const Seg& l) {
   Pair best;
   best.a = mk(INFINITY, INFINITY);
   best.b = mk(INFINITY, INFINITY);
   float dbest = INFINITY;
+  unsigned skip = 0u;  // bit i: side i cannot be the minimum
+  {
+    V2 d = l.p - b.p;
+    const float cx = d.x * b.c + d.y * b.s, cy = d.y * b.c - d.x * b.s;          // segment centre, box frame
+    const float ux = l.half * (l.c * b.c + l.s * b.s), uy = l.half * (l.s * b.c - l.c * b.s);
+    const float x1 = cx + ux, x2 = cx - ux, y1 = cy + uy, y2 = cy - uy;          // end points, box frame
+    const float xmin = fminf(x1, x2), xmax = fmaxf(x1, x2), ymin = fminf(y1, y2), ymax = fmaxf(y1, y2);
+    // separation of the segment's bounding box from the box's extent along each axis
+    const float sepx = fmaxf(fmaxf(xmin - b.half_l, -b.half_l - xmax), 0.f);
+    const float sepy = fmaxf(fmaxf(ymin - b.half_w, -b.half_w - ymax), 0.f);
+    // distance of the segment's bounding box from each side's carrier line (0 if it straddles it)
+    const float g0 = fmaxf(fmaxf(xmin - b.half_l, b.half_l - xmax), 0.f);
+    const float g1 = fmaxf(fmaxf(xmin + b.half_l, -b.half_l - xmax), 0.f);
+    const float g2 = fmaxf(fmaxf(ymin - b.half_w, b.half_w - ymax), 0.f);
+    const float g3 = fmaxf(fmaxf(ymin + b.half_w, -b.half_w - ymax), 0.f);
+    const float lo0 = fmaxf(g0, sepy), lo1 = fmaxf(g1, sepy), lo2 = fmaxf(g2, sepx), lo3 = fmaxf(g3, sepx);
+    // upper bound: squared distance of either end point to the nearest side
+    float u2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float px = k ? x2 : x1, py = k ? y2 : y1;
+      const float ex = fmaxf(fabsf(px) - b.half_l, 0.f), ey = fmaxf(fabsf(py) - b.half_w, 0.f);
+      const float a0 = px - b.half_l, a1 = px + b.half_l, a2 = py - b.half_w, a3 = py + b.half_w;
+      u2 = fminf(u2, fminf(fminf(a0 * a0 + ey * ey, a1 * a1 + ey * ey), fminf(a2 * a2 + ex * ex, a3 * a3 + ex * ex)));
+    }
+    const float up = 2.f * u2 + 2e-6f;
+    skip = (lo0 * lo0 > up ? 1u : 0u) | (lo1 * lo1 > up ? 2u : 0u) | (lo2 * lo2 > up ? 4u : 0u) |
+           (lo3 * lo3 > up ? 8u : 0u);
+  }
 #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
+    if ((skip >> i) & 1u) continue;
     Seg sd = box_side(b, i);
     Pair c = closest_seg_seg(sd, l);
     float d = norm2(c.a - c.b);

@@ -388,6 +388,11 @@ __global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
           Fx[j] = Fx[j] + mass * __ldg(ef + VMAS_EF_GRAV_X);
           Fy[j] = Fy[j] + mass * __ldg(ef + VMAS_EF_GRAV_Y);
         }
+        if (flg[j] & VMAS_F_GRAVITY_ENV) {
+          const float2 g = reinterpret_cast<const float2*>(a.tb.ent_gravity)[(size_t)env * E + e];
+          Fx[j] = Fx[j] + mass * g.x;
+          Fy[j] = Fy[j] + mass * g.y;
+        }
       }
     }
     __syncwarp();
@@ -648,6 +653,11 @@ __global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
         if (flg & VMAS_F_GRAVITY) {
           Fx = Fx + mass * __ldg(ef + VMAS_EF_GRAV_X);
           Fy = Fy + mass * __ldg(ef + VMAS_EF_GRAV_Y);
+        }
+        if (flg & VMAS_F_GRAVITY_ENV) {
+          const float2 g = reinterpret_cast<const float2*>(a.tb.ent_gravity)[ebase + e];
+          Fx = Fx + mass * g.x;
+          Fy = Fy + mass * g.y;
         }
       }
       TF(T_FX, e) = Fx;

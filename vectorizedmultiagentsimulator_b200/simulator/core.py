@@ -557,8 +557,11 @@ class Entity(TorchVectorizedObject, Observable, ABC):
 
     @gravity.setter
     def gravity(self, value):
+        old = self._gravity
         self._gravity = value
-        self._touch()
+        per_env = lambda g: isinstance(g, Tensor) and g.dim() == 2  # noqa: E731
+        if not (per_env(old) and per_env(value) and old.shape == value.shape):
+            self._touch()  # a new [B, 2] wind field is data, not structure: the plan stays valid
 
     @property
     def collision_filter(self):

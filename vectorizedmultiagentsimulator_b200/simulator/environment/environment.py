@@ -201,7 +201,6 @@ class Environment(TorchVectorizedObject):
     def done(self):
         return self._done()
 
-    @_seeded
     def step(self, actions: Union[List, Dict]):
         """One vectorised step.
 
@@ -212,7 +211,12 @@ class Environment(TorchVectorizedObject):
             ``obs, rewards, dones, infos`` (or ``obs, rewards, terminated, truncated, infos``),
             lists (or dicts) with one entry per policy agent.
         """
-        return self._step(actions)
+        if self._graph is not None:
+            # a graph replay runs no Python scenario code and draws no host random numbers:
+            # the swap of the env's private RNG streams (3 get/set state pairs) is skipped
+            return self._step(actions)
+        with local_seed(Environment.vmas_random_state):
+            return self._step(actions)
 
     # ------------------------------------------------------------------------------------
     def _reset(self, seed=None, return_observations=True, return_info=False, return_dones=False):
@@ -414,13 +418,65 @@ class Environment(TorchVectorizedObject):
                 self._graph_warmup_left -= 1
                 return self._step_device([a.to(self.device) for a in actions])
             self._capture(actions)
-        for static, a in zip(self._graph_inputs, actions):
-            static.copy_(a, non_blocking=True)
+        # one multi-tensor copy for all agents' actions, one replay, one clone per output dtype
+        if all(a.device == s.device and a.dtype == s.dtype for a, s in zip(actions, self._graph_inputs)):
+            torch._foreach_copy_(self._graph_inputs, list(actions))
+        else:
+            for static, a in zip(self._graph_inputs, actions):
+                static.copy_(a, non_blocking=True)
         self._graph.replay()
         self.graph_replays += 1
         backend = world._get_backend()
         backend.launches += self._graph_launches
-        return _clone_tree(self._graph_outputs)
+        return self._unpack_graph_outputs()
+
+    def _pack_graph_outputs(self, outputs):
+        """(inside the capture) concatenates every output leaf into one flat buffer per dtype."""
+        leaves = []
+
+        def index(x):
+            if isinstance(x, Tensor):
+                leaves.append(x)
+                return ("leaf", len(leaves) - 1)
+            if isinstance(x, dict):
+                return ("dict", {k: index(v) for k, v in x.items()})
+            if isinstance(x, (list, tuple)):
+                return ("list" if isinstance(x, list) else "tuple", [index(v) for v in x])
+            return ("const", x)
+
+        spec = index(outputs)
+        groups = {}
+        for i, t in enumerate(leaves):
+            groups.setdefault(t.dtype, []).append(i)
+        packs = {}
+        for dtype, ids in groups.items():
+            packs[dtype] = (torch.cat([leaves[i].reshape(-1) for i in ids]), ids)
+        self._graph_out_spec = spec
+        self._graph_out_shapes = [tuple(t.shape) for t in leaves]
+        self._graph_out_packs = packs
+
+    def _unpack_graph_outputs(self):
+        """Fresh output tensors: one clone per dtype, then views (no further kernel launches)."""
+        fresh = [None] * len(self._graph_out_shapes)
+        for pack, ids in self._graph_out_packs.values():
+            flat = pack.clone()
+            sizes = [math.prod(self._graph_out_shapes[i]) for i in ids]
+            for i, piece in zip(ids, flat.split(sizes)):
+                fresh[i] = piece.view(self._graph_out_shapes[i])
+
+        def build(node):
+            kind, payload = node
+            if kind == "leaf":
+                return fresh[payload]
+            if kind == "dict":
+                return {k: build(v) for k, v in payload.items()}
+            if kind == "list":
+                return [build(v) for v in payload]
+            if kind == "tuple":
+                return tuple(build(v) for v in payload)
+            return payload
+
+        return build(self._graph_out_spec)
 
     def _capture(self, actions: List[Tensor]):
         if self.action_checks == "sync":
@@ -437,8 +493,10 @@ class Environment(TorchVectorizedObject):
         graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(graph):
-                # outputs stay un-cloned inside the graph: _clone_tree copies them after each replay
+                # outputs stay un-cloned inside the graph; they are packed into one flat buffer per
+                # dtype there, and each replay hands out clones of those buffers
                 outputs = self._step_device(self._graph_inputs, clone_outputs=False)
+                self._pack_graph_outputs(outputs)
         except Exception as err:  # noqa: BLE001
             raise RuntimeError(
                 "cuda_graph=True: capturing Environment.step failed. The scenario (or a dynamics / "
@@ -569,16 +627,23 @@ class Environment(TorchVectorizedObject):
         if self._bad_action_host is None:
             pin = self.device.type == "cuda"
             self._bad_action_host = torch.zeros(1, dtype=torch.bool, pin_memory=pin)
+            self._bad_action_event = torch.cuda.Event() if pin else None
+        elif self._bad_action_event is not None and not self._bad_action_event.query():
+            return  # the previous read-back is still in flight; the flag is sticky, nothing is lost
         self._bad_action_host.copy_(self._bad_action_flag, non_blocking=True)
-        if self.device.type == "cuda":
-            self._bad_action_event = torch.cuda.Event()
+        if self._bad_action_event is not None:
             self._bad_action_event.record()
 
-    def _raise_deferred_action_errors(self):
+    def _raise_deferred_action_errors(self, wait: bool = False):
+        """Raises if a previous step flagged an invalid action.  Never stalls the pipeline: the
+        flag is looked at only once its asynchronous read-back has landed (``wait=True`` forces it)."""
         if self._bad_action_host is None:
             return
         if self._bad_action_event is not None:
-            self._bad_action_event.synchronize()
+            if wait:
+                self._bad_action_event.synchronize()
+            elif not self._bad_action_event.query():
+                return
         if bool(self._bad_action_host.item()):
             self._bad_action_flag.zero_()
             self._bad_action_host.zero_()
@@ -589,7 +654,7 @@ class Environment(TorchVectorizedObject):
     def check_actions_now(self):
         """Force the deferred action checks to be read back and raised (one host sync)."""
         self._launch_deferred_action_readback()
-        self._raise_deferred_action_errors()
+        self._raise_deferred_action_errors(wait=True)
 
     def _check_discrete_action(self, action: Tensor, low: int, high: int, type: str):
         self._flag_if(

@@ -47,6 +47,7 @@ F_F_RANGE = 1 << 10
 F_MAX_T = 1 << 11
 F_T_RANGE = 1 << 12
 F_TRIG = 1 << 13  # kernel must evaluate sin/cos of this entity's rotation
+F_GRAVITY_ENV = 1 << 14  # per-env gravity rows in ent_gravity[B, E, 2]
 
 # columns of ent_f32
 (
@@ -161,9 +162,10 @@ def describe_entity(entity, agent_index: int) -> Dict:
     is_agent = _is_agent(entity)
     gravity = getattr(entity, "gravity", None)
     gravity_pair = _as_pair(gravity)
-    if gravity is not None and gravity_pair is None:
+    gravity_per_env = gravity is not None and gravity_pair is None
+    if gravity_per_env and not (hasattr(gravity, "shape") and tuple(gravity.shape[-1:]) == (2,) and gravity.dim() == 2):
         raise NotImplementedError(
-            f"Entity '{entity.name}' has a per-env gravity tensor; the B200 kernels take a scalar or (x, y) pair"
+            f"Entity '{entity.name}': gravity must be a scalar, an (x, y) pair or a [batch_dim, 2] tensor"
         )
     for attr in ("linear_friction", "angular_friction"):
         v = getattr(entity, attr, None)
@@ -192,6 +194,7 @@ def describe_entity(entity, agent_index: int) -> Dict:
         linear_friction=None if entity.linear_friction is None else float(entity.linear_friction),
         angular_friction=None if entity.angular_friction is None else float(entity.angular_friction),
         gravity=None if gravity_pair is None else list(gravity_pair),
+        gravity_per_env=bool(gravity_per_env),
         max_speed=opt("max_speed"),
         v_range=opt("v_range"),
         max_f=opt("max_f"),
@@ -361,6 +364,8 @@ def build_tables(desc: WorldDescription) -> PlanTables:
         if e["gravity"] is not None:
             flags |= F_GRAVITY
             row[EF_GRAV_X], row[EF_GRAV_Y] = e["gravity"]
+        if e.get("gravity_per_env"):
+            flags |= F_GRAVITY_ENV
         for name, col, bit in (
             ("max_speed", EF_MAX_SPEED, F_MAX_SPEED),
             ("v_range", EF_V_RANGE, F_V_RANGE),
