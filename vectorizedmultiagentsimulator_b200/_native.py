@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
-LIB_PATH = os.path.join(_HERE, "libvmas_b200.so")
+LIB_PATH = os.environ.get("VMAS_B200_LIB") or os.path.join(_HERE, "libvmas_b200.so")
 SOURCES = [os.path.join(CSRC, "vmas_b200.cu")]
 GENERATED = os.path.join(CSRC, "generated", "specializations.cuh")
 HEADERS = [
@@ -37,6 +37,7 @@ NVCC_FLAGS = [
     "-O3",
     "-lineinfo",
     "-fmad=false",  # every mul/add rounds on its own, like the reference's eager op chain
+    "-DSPEC_MIN_BLOCKS=8",  # <= 128 registers for the specialised kernels: 16 warps/SM (measured best)
     "-std=c++17",
     "-Xcompiler",
     "-fPIC",
@@ -65,7 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     codegen.generate(GENERATED)  # constexpr world tables for the specialised kernels (no-op if unchanged)
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("VMAS_B200_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -62,7 +62,7 @@ struct Pair {
 };
 
 // Closest pair of points between two segments (ref physics.py:144-219, 222-260, 132-141).
-DEVI Pair closest_seg_seg(const Seg& l1, const Seg& l2) {
+__device__ __noinline__ Pair closest_seg_seg(const Seg& l1, const Seg& l2) {
   V2 o1 = mk(l1.half * l1.c, l1.half * l1.s);
   V2 o2 = mk(l2.half * l2.c, l2.half * l2.s);
   V2 a1 = l1.p + o1, a2 = l1.p - o1;
@@ -231,7 +231,7 @@ DEVI Pair closest_box_box(const BoxG& b1, const BoxG& b2) {
 
 // Point inside a solid box the contact force is measured from, and its depth
 // (ref physics.py:13-23, incl. the 2*surface result when outside == surface).
-DEVI V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, float* depth) {
+__device__ __noinline__ V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, float* depth) {
   V2 v = surface - outside;
   V2 u = box_pos - surface;
   float vn = norm2(v);
@@ -247,18 +247,28 @@ DEVI V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, float* depth) {
 
 // Soft-plus penalty force on `a` (b receives the negative) (ref core.py:2805-2839).
 // k = contact margin, c = force multiplier.  Returns exactly 0 outside the active range, which is
-// also what the reference's masks produce; the transcendental path only runs for live contacts.
-DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {
-  V2 delta = pa - pb;
-  float d = norm2(delta);
-  if (d < 1e-6f) return mk(0.f, 0.f);
-  if (attractive ? (d < dmin) : (d > dmin)) return mk(0.f, 0.f);
-  float sign = attractive ? -1.f : 1.f;
+// also what the reference's masks produce.  The live-contact arithmetic (IEEE divisions, expf,
+// log1pf) is kept out of line: it is rare, and one shared copy instead of one per unrolled work
+// item keeps the specialised kernels' code small enough for the instruction cache.
+__device__ __noinline__ V2 constraint_force_live(float dx, float dy, float d, float dmin, float c, float k,
+                                                 float sign) {
   float x = ((dmin - d) * sign) / k;
   float pen = (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) * k;  // logaddexp(0, x) * k
   float cc = sign * c;
   float denom = d > 0.f ? d : 1e-8f;
-  return mk(((cc * delta.x) / denom) * pen, ((cc * delta.y) / denom) * pen);
+  return mk(((cc * dx) / denom) * pen, ((cc * dy) / denom) * pen);
+}
+
+DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {
+  V2 delta = pa - pb;
+  // |delta|^2 exactly as norm2() forms it.  sqrt is monotone, so s > dmin^2 (1 + 2e-6) implies
+  // sqrtf(s) > dmin: the common "far apart" case is decided without the square root.
+  const float s = __fmaf_rn(delta.y, delta.y, __fmul_rn(delta.x, delta.x));
+  if (!attractive && s > dmin * dmin * 1.000002f) return mk(0.f, 0.f);
+  float d = sqrtf(s);
+  if (d < 1e-6f) return mk(0.f, 0.f);
+  if (attractive ? (d < dmin) : (d > dmin)) return mk(0.f, 0.f);
+  return constraint_force_live(delta.x, delta.y, d, dmin, c, k, attractive ? -1.f : 1.f);
 }
 
 }  // namespace vmas

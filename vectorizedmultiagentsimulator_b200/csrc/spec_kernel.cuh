@@ -277,8 +277,13 @@ __host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, in
   return m;
 }
 
+// SPEC_MIN_BLOCKS: resident blocks per SM the register allocator must leave room for (tuning knob)
+#ifndef SPEC_MIN_BLOCKS
+#define SPEC_MIN_BLOCKS 1
+#endif
+
 template <class W>
-__global__ void __launch_bounds__(W::BLOCK) step_spec_kernel(const SpecArgs a) {
+__global__ void __launch_bounds__(W::BLOCK, SPEC_MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
   constexpr int E = W::E, NA = W::A, NI = W::NI, MW = W::MASK_WORDS;
     const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
 
