@@ -353,6 +353,14 @@ def main_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = bytes_per_env_substep * B  # one launch advances B envs by one substep (S=1 here)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = traffic_src = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj["%s_%s" % (SCENARIO, "_".join(f"{k}={v}" for k, v in SCENARIO_KWARGS.items()))][str(B)]
+        traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+        traffic_src = ent["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {
         "bound": "hbm",
         "kernel": "substep kernel, mapping=%s" % backend._dev_tables.mapping,
@@ -360,7 +368,8 @@ def main_b200(args):
         "peak": peak,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peak_src,
         "bytes_per_launch": alg_bytes,
         "bytes_per_env_substep": bytes_per_env_substep,

@@ -30,6 +30,10 @@ DEVI float norm2(V2 v) { return norm2(v.x, v.y); }
 DEVI float dot2(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }           // (a*b).sum(-1)
 DEVI float cross2(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }         // ref utils.py:194-197
 DEVI float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }  // torch.sign
+// a / b for a positive divisor.  IEEE division takes a ~40-instruction slow path when the numerator
+// is zero (FCHK), which is the common case here (contact normals along an axis, resting bodies,
+// zero torque); (+-0) / b == +-0 for b > 0, so the numerator itself is the exact quotient.
+DEVI float div_pos(float a, float b) { return (a == 0.f && b > 0.f) ? a : a / b; }
 // rotate `v` by the angle whose (cos, sin) is (c, s)  (ref utils.py:176-191)
 DEVI V2 rot2(V2 v, float c, float s) { return mk(v.x * c - v.y * s, v.x * s + v.y * c); }
 
@@ -235,8 +239,8 @@ __device__ __noinline__ V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, f
   V2 v = surface - outside;
   V2 u = box_pos - surface;
   float vn = norm2(v);
-  float xm = (v.x * u.x + v.y * u.y) / vn;
-  V2 x = mk((v.x / vn) * xm, (v.y / vn) * xm);
+  float xm = div_pos(v.x * u.x + v.y * u.y, vn);
+  V2 x = mk(div_pos(v.x, vn) * xm, div_pos(v.y, vn) * xm);
   if (vn == 0.f) {
     x = surface;
     xm = 0.f;
@@ -252,11 +256,11 @@ __device__ __noinline__ V2 inner_point_box(V2 outside, V2 surface, V2 box_pos, f
 // item keeps the specialised kernels' code small enough for the instruction cache.
 __device__ __noinline__ V2 constraint_force_live(float dx, float dy, float d, float dmin, float c, float k,
                                                  float sign) {
-  float x = ((dmin - d) * sign) / k;
+  float x = div_pos((dmin - d) * sign, k);
   float pen = (fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)))) * k;  // logaddexp(0, x) * k
   float cc = sign * c;
   float denom = d > 0.f ? d : 1e-8f;
-  return mk(((cc * dx) / denom) * pen, ((cc * dy) / denom) * pen);
+  return mk(div_pos(cc * dx, denom) * pen, div_pos(cc * dy, denom) * pen);
 }
 
 DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {

@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(W::BLOCK, SPEC_MIN_BLOCKS) step_spec_kernel(co
           r.vx[e] = r.vx[e] * en.drag_mult;
           r.vy[e] = r.vy[e] * en.drag_mult;
         }
-        r.vx[e] = r.vx[e] + (r.Fx[e] / en.mass) * sub_dt;
-        r.vy[e] = r.vy[e] + (r.Fy[e] / en.mass) * sub_dt;
+        r.vx[e] = r.vx[e] + div_pos(r.Fx[e], en.mass) * sub_dt;
+        r.vy[e] = r.vy[e] + div_pos(r.Fy[e], en.mass) * sub_dt;
         if constexpr (en.flags & VMAS_F_MAX_SPEED) {
           const float n = norm2(r.vx[e], r.vy[e]);
           if (n > en.max_speed) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(W::BLOCK, SPEC_MIN_BLOCKS) step_spec_kernel(co
       }
       if constexpr (en.flags & VMAS_F_ROTATABLE) {
         if (sub == 0) r.w[e] = r.w[e] * en.drag_mult;
-        r.w[e] = r.w[e] + (r.T[e] / en.inertia) * sub_dt;
+        r.w[e] = r.w[e] + div_pos(r.T[e], en.inertia) * sub_dt;
         r.rot[e] = r.rot[e] + r.w[e] * sub_dt;
       }
     });

@@ -448,8 +448,8 @@ __global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
           vx[j] = vx[j] * drag_mult;
           vy[j] = vy[j] * drag_mult;
         }
-        vx[j] = vx[j] + (Fx[j] / mass) * sub_dt;
-        vy[j] = vy[j] + (Fy[j] / mass) * sub_dt;
+        vx[j] = vx[j] + div_pos(Fx[j], mass) * sub_dt;
+        vy[j] = vy[j] + div_pos(Fy[j], mass) * sub_dt;
         if (flg[j] & VMAS_F_MAX_SPEED) {
           const float mx = __ldg(ef + VMAS_EF_MAX_SPEED);
           const float n = norm2(vx[j], vy[j]);
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(128) step_kernel(const StepArgs a) {
       if (rotatable) {
         const float inertia = __ldg(ef + VMAS_EF_INERTIA);
         if (sub == 0) w[j] = w[j] * drag_mult;
-        w[j] = w[j] + (T[j] / inertia) * sub_dt;
+        w[j] = w[j] + div_pos(T[j], inertia) * sub_dt;
         rt[j] = rt[j] + w[j] * sub_dt;
       }
     }
@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
           vx = vx * drag_mult;
           vy = vy * drag_mult;
         }
-        vx = vx + (TF(T_FX, e) / mass) * sub_dt;
-        vy = vy + (TF(T_FY, e) / mass) * sub_dt;
+        vx = vx + div_pos(TF(T_FX, e), mass) * sub_dt;
+        vy = vy + div_pos(TF(T_FY, e), mass) * sub_dt;
         if (flg & VMAS_F_MAX_SPEED) {
           const float mx = __ldg(ef + VMAS_EF_MAX_SPEED);
           const float n = norm2(vx, vy);
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
         const float inertia = __ldg(ef + VMAS_EF_INERTIA);
         float w = TF(T_W, e);
         if (sub == 0) w = w * drag_mult;
-        w = w + (TF(T_TQ, e) / inertia) * sub_dt;
+        w = w + div_pos(TF(T_TQ, e), inertia) * sub_dt;
         TF(T_W, e) = w;
         TF(T_ROT, e) = TF(T_ROT, e) + w * sub_dt;
       }
