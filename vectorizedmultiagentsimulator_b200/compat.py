@@ -22,6 +22,7 @@ _MODULES = [
     "simulator.joints",
     "simulator.dynamics",
     "simulator.dynamics.common",
+    "simulator.dynamics.basic",
     "simulator.dynamics.holonomic",
     "simulator.dynamics.holonomic_with_rot",
     "simulator.dynamics.forward",

@@ -1,11 +1,2 @@
-"""An agent that ignores its action (ref dynamics/static.py)."""
-from .common import Dynamics
-
-
-class Static(Dynamics):
-    @property
-    def needed_action_size(self) -> int:
-        return 0
-
-    def process_action(self):
-        pass
+"""Import location scenarios use for ``Static`` (defined in :mod:`.basic`)."""
+from .basic import Static  # noqa: F401
