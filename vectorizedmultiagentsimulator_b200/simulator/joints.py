@@ -16,7 +16,25 @@ from . import core as _core
 from .utils import Color, Observer, TorchUtils, X, Y
 
 
+def _check_anchor(anchor):
+    assert (
+        max(anchor) <= 1 and min(anchor) >= -1
+    ), f"Joint anchor points should be between -1 and 1, got {anchor}"
+
+
+def _check_pair(entity_a, entity_b, anchor_a, anchor_b, dist):
+    assert entity_a != entity_b, "Cannot join same entity"
+    _check_anchor(anchor_a)
+    _check_anchor(anchor_b)
+    assert dist >= 0, f"Joint dist must be >= 0, got {dist}"
+
+
 class Joint(Observer):
+    """User-facing joint.  ``dist == 0`` pins the two anchors together with one constraint;
+    ``dist > 0`` spawns a movable link landmark (a Line, or a Box when ``width > 0``) whose two ends
+    are pinned to the entities' anchors, and keeps it placed between them whenever an end point is
+    repositioned through the state API (observer protocol)."""
+
     def __init__(
         self,
         entity_a,
@@ -32,36 +50,27 @@ class Joint(Observer):
         fixed_rotation_a: Optional[float] = None,
         fixed_rotation_b: Optional[float] = None,
     ):
-        assert entity_a != entity_b, "Cannot join same entity"
-        for anchor in (anchor_a, anchor_b):
-            assert (
-                max(anchor) <= 1 and min(anchor) >= -1
-            ), f"Joint anchor points should be between -1 and 1, got {anchor}"
-        assert dist >= 0, f"Joint dist must be >= 0, got {dist}"
-        if dist == 0:
+        _check_pair(entity_a, entity_b, anchor_a, anchor_b, dist)
+        pinned = dist == 0
+        if pinned:
             assert not collidable, "Cannot have collidable joint with dist 0"
             assert width == 0, "Cannot have width for joint with dist 0"
             assert (
                 fixed_rotation_a == fixed_rotation_b
             ), "If dist is 0, fixed_rotation_a and fixed_rotation_b should be the same"
-        if fixed_rotation_a is not None:
-            assert not rotate_a, "If you provide a fixed rotation for a, rotate_a should be False"
-        if fixed_rotation_b is not None:
-            assert not rotate_b, "If you provide a fixed rotation for b, rotate_b should be False"
+        for fixed, free, side in ((fixed_rotation_a, rotate_a, "a"), (fixed_rotation_b, rotate_b, "b")):
+            if fixed is not None:
+                assert not free, f"If you provide a fixed rotation for {side}, rotate_{side} should be False"
         if width > 0:
             assert collidable
 
-        self.entity_a = entity_a
-        self.entity_b = entity_b
-        self.rotate_a = rotate_a
-        self.rotate_b = rotate_b
-        self.fixed_rotation_a = fixed_rotation_a
-        self.fixed_rotation_b = fixed_rotation_b
+        self.entity_a, self.entity_b = entity_a, entity_b
+        self.rotate_a, self.rotate_b = rotate_a, rotate_b
+        self.fixed_rotation_a, self.fixed_rotation_b = fixed_rotation_a, fixed_rotation_b
         self.landmark = None
-        self.joint_constraints = []
 
-        if dist == 0:
-            self.joint_constraints.append(
+        if pinned:
+            self.joint_constraints = [
                 JointConstraint(
                     entity_a,
                     entity_b,
@@ -71,43 +80,30 @@ class Joint(Observer):
                     rotate=rotate_a and rotate_b,
                     fixed_rotation=fixed_rotation_a,
                 )
-            )
+            ]
             return
 
-        entity_a.subscribe(self)
-        entity_b.subscribe(self)
-        link_shape = (
-            _core.Box(length=dist, width=width) if width != 0 else _core.Line(length=dist)
-        )
+        for end in (entity_a, entity_b):
+            end.subscribe(self)
         self.landmark = _core.Landmark(
             name=f"joint {entity_a.name} {entity_b.name}",
             collide=collidable,
             movable=True,
             rotatable=True,
             mass=mass,
-            shape=link_shape,
+            shape=_core.Box(length=dist, width=width) if width != 0 else _core.Line(length=dist),
             color=Color.BLACK,
             is_joint=True,
         )
-        self.joint_constraints += [
+        ends = (
+            ((-1, 0), entity_a, anchor_a, rotate_a, fixed_rotation_a),
+            ((1, 0), entity_b, anchor_b, rotate_b, fixed_rotation_b),
+        )
+        self.joint_constraints = [
             JointConstraint(
-                self.landmark,
-                entity_a,
-                anchor_a=(-1, 0),
-                anchor_b=anchor_a,
-                dist=0.0,
-                rotate=rotate_a,
-                fixed_rotation=fixed_rotation_a,
-            ),
-            JointConstraint(
-                self.landmark,
-                entity_b,
-                anchor_a=(1, 0),
-                anchor_b=anchor_b,
-                dist=0.0,
-                rotate=rotate_b,
-                fixed_rotation=fixed_rotation_b,
-            ),
+                self.landmark, entity, anchor_a=link_end, anchor_b=anchor, dist=0.0, rotate=free, fixed_rotation=fixed
+            )
+            for link_end, entity, anchor, free, fixed in ends
         ]
 
     def notify(self, observable, *args, **kwargs):
@@ -137,12 +133,7 @@ class JointConstraint:
         rotate: bool = True,
         fixed_rotation: Optional[float] = None,
     ):
-        assert entity_a != entity_b, "Cannot join same entity"
-        for anchor in (anchor_a, anchor_b):
-            assert (
-                max(anchor) <= 1 and min(anchor) >= -1
-            ), f"Joint anchor points should be between -1 and 1, got {anchor}"
-        assert dist >= 0, f"Joint dist must be >= 0, got {dist}"
+        _check_pair(entity_a, entity_b, anchor_a, anchor_b, dist)
         if fixed_rotation is not None:
             assert not rotate, "If fixed rotation is provided, rotate should be False"
         if rotate:
