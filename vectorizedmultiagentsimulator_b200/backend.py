@@ -13,7 +13,6 @@ from __future__ import annotations
 import ctypes as C
 from typing import Callable, Dict, List, Optional, Tuple
 
-import numpy as np
 import torch
 from torch import Tensor
 
@@ -116,9 +115,7 @@ class CudaBackend(PlanRuntime):
         self.lib = _native.load()  # raises if the extension is not built
         self._native = _native
         self._dev_tables = None
-        self._fixed_rot = None
         self._fixed_rot_versions = {}
-        self._mask = None
         self._ray_cache: Dict[Tuple[int, Callable], Tensor] = {}
         self.launches = 0
         #: when set to a list, every step() appends a (begin, end) event pair bracketing the

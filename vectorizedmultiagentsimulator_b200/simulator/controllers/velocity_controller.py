@@ -7,7 +7,6 @@ torch ops right before ``World.step``; it is not part of the CUDA hot path.
 """
 from __future__ import annotations
 
-import math
 import warnings
 from typing import Optional
 

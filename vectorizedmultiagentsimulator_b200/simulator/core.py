@@ -32,7 +32,6 @@ from .utils import (
     Color,
     DRAG,
     JOINT_FORCE,
-    LINE_MIN_DIST,
     LINEAR_FRICTION,
     Observable,
     TORQUE_CONSTRAINT_FORCE,

@@ -7,8 +7,6 @@ Host-side torch ops that run just before ``World.step``; not o
 """
 from __future__ import annotations
 
-import torch
-
 from .common import Dynamics
 
 

@@ -62,27 +62,6 @@ def _seeded(method):
     return wrapper
 
 
-def _clone_tree(x, _bases=None):
-    """Deep copy of a nest of tensors.  Disjoint views of one base tensor (e.g. the per-agent
-    slices of a batched ``[B, A, k]`` observation) are copied with a single clone of the base."""
-    top = _bases is None
-    if top:
-        _bases = {}
-    if isinstance(x, Tensor):
-        base = x._base
-        if base is not None and base.is_contiguous() and x.dim() >= 1:
-            key = id(base)
-            if key not in _bases:
-                _bases[key] = base.clone()
-            return _bases[key].as_strided(x.size(), x.stride(), x.storage_offset() - base.storage_offset())
-        return x.clone()
-    if isinstance(x, dict):
-        return {k: _clone_tree(v, _bases) for k, v in x.items()}
-    if isinstance(x, (list, tuple)):
-        return type(x)(_clone_tree(v, _bases) for v in x)
-    return x
-
-
 class Environment(TorchVectorizedObject):
     metadata = {"render.modes": ["human", "rgb_array"], "runtime.vectorized": True}
     vmas_random_state = [torch.random.get_rng_state(), np.random.get_state(), random.getstate()]

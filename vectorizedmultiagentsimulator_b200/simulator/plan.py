@@ -18,7 +18,6 @@ What is evaluated here, once, instead of every substep as the reference does:
 from __future__ import annotations
 
 import json
-import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -79,10 +78,6 @@ II_COLS = 4  # kind, a, b, flags
 IFLAG_JOINT_ROTATE = 1
 IFLAG_JOINT_ROT_PER_ENV = 2
 IFLAG_ALWAYS_ACTIVE = 4  # broad phase not applied (joints)
-
-
-def _f32(x) -> float:
-    return float(np.float32(x))
 
 
 def _shape_kind(shape) -> int:
