@@ -146,6 +146,30 @@ int vmas_b200_cast_rays(const VmasWorldConfig* cfg, const VmasPlanTables* tb, co
                         float* out, void* cuda_stream);
 
 /*
+ * Batched LIDAR: every ray of `n_sensors` sensors in ONE launch (the reference runs one
+ * World.cast_rays per agent per step, sensors.py:116-121).  All sensors share `n_rays`.
+ *   src          device int32[Q]      source entity of each sensor (its rotation is added to the angles)
+ *   target_off   device int32[Q + 1]  CSR offsets into `targets`
+ *   targets      device int32[...]    entity indices each sensor's rays may hit
+ *   angles       device fp32 [Q, n_rays]  sensor-frame ray angles
+ *   max_range    device fp32 [Q]
+ *   out          device fp32 [Q, B, n_rays]  (sensor-major: each sensor's [B, R] block is contiguous)
+ */
+int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                int32_t n_sensors, const int32_t* src, const int32_t* target_off,
+                                const int32_t* targets, const float* angles, const float* max_range,
+                                int32_t n_rays, float* out, void* cuda_stream);
+
+/*
+ * K entity pairs in one launch: mode 0 = World.get_distance (fp32), 1 = World.is_overlapping
+ * (uint8), 2 = distance between the two centres (fp32; the quantity World.collides thresholds,
+ * ref core.py:2797-2799).   pairs: device int32[K, 2];  out: [K, B].
+ */
+int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                 const int32_t* pairs, int32_t n_pairs, int32_t mode, void* out,
+                                 void* cuda_stream);
+
+/*
  * World.get_distance (mode 0 -> fp32 out[B]) / World.is_overlapping (mode 1 -> uint8 out[B]) for
  * the entity pair (a, b).  Replaces ref core.py:1822-1969.
  */

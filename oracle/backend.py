@@ -54,6 +54,16 @@ class OracleBackend(PlanRuntime):
             sensor.agent, sensor._angles + sensor.agent.state.rot, sensor._max_range, sensor.entity_filter
         )
 
+    def lidar_measure_many(self, sensors):
+        return torch.stack([self.lidar_measure(s) for s in sensors])
+
+    def pair_query_many(self, pairs, mode):
+        if mode == 0:
+            return torch.stack([self.pair_distance(a, b) for a, b in pairs])
+        if mode == 1:
+            return torch.stack([self.pair_overlap(a, b) for a, b in pairs])
+        return torch.stack([torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1) for a, b in pairs])
+
     def pair_distance(self, a, b):
         self.refresh()
         slab = self.world.slab

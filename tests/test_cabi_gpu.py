@@ -290,3 +290,75 @@ def test_large_batch_properties():
         tiles = slab.t[k].reshape(reps, 64, *slab.t[k].shape[1:])
         assert torch.equal(tiles[0], small.t[k])
         assert torch.equal(tiles, tiles[0:1].expand_as(tiles)), f"{k}: envs are not independent"
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if load(n)[0]["lidar"]])
+def test_batched_lidar_equals_per_sensor_launches(name):
+    """vmas_b200_cast_rays_batched == one vmas_b200_cast_rays per sensor, bit for bit."""
+    fix, desc, tables = load(name)
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    by_step = {}
+    for rec in fix["lidar"]:
+        by_step.setdefault(rec["step"], []).append(rec)
+    checked = 0
+    for step, recs in by_step.items():
+        n_rays = recs[0]["angles"].shape[-1]
+        recs = [r for r in recs if r["angles"].shape[-1] == n_rays and r["targets"]]
+        # the batched entry takes sensor-frame angles shared by the whole batch
+        recs = [r for r in recs if bool((r["angles"] == r["angles"][:1]).all())]
+        if not recs:
+            continue
+        slab = _Slab(dict(fix["steps"][step]["out"]), device)
+        src = torch.tensor([r["src"] for r in recs], dtype=torch.int32, device=device)
+        offs, flat = [0], []
+        for r in recs:
+            flat += r["targets"]
+            offs.append(len(flat))
+        target_off = torch.tensor(offs, dtype=torch.int32, device=device)
+        targets = torch.tensor(flat, dtype=torch.int32, device=device)
+        angles = torch.stack([r["angles"][0] for r in recs]).to(device).contiguous()
+        max_range = torch.tensor([r["max_range"] for r in recs], dtype=torch.float32, device=device)
+        B = desc.batch_dim
+        out = torch.empty(len(recs), B, n_rays, device=device)
+        _native.cast_rays_batched(lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, out)
+        for q, r in enumerate(recs):
+            one = torch.empty(B, n_rays, device=device)
+            t = torch.tensor(r["targets"], dtype=torch.int32, device=device)
+            _native.cast_rays(lib, dt, slab, r["src"], t, len(r["targets"]), r["angles"].to(device).contiguous(),
+                              r["src"], r["max_range"], one)
+            assert torch.equal(out[q], one), f"{name} step {step} sensor {q}"
+            ok, err = _close(out[q], r["out"], 1e-5)
+            assert ok, f"{name} step {step} sensor {q}: max |err| {err}"
+            checked += 1
+    assert checked > 0
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_batched_pair_query_equals_per_pair_launches(name):
+    fix, desc, tables = load(name)
+    if not fix["queries"]:
+        pytest.skip("fixture has no pair queries")
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    slab = _Slab(fix["final_state"], device)
+    B = desc.batch_dim
+    pairs = torch.tensor([[q["a"], q["b"]] for q in fix["queries"]], dtype=torch.int32, device=device)
+    K = pairs.shape[0]
+    dist = torch.empty(K, B, device=device)
+    over = torch.empty(K, B, dtype=torch.bool, device=device)
+    centre = torch.empty(K, B, device=device)
+    _native.pair_query_batched(lib, dt, slab, pairs, 0, dist)
+    _native.pair_query_batched(lib, dt, slab, pairs, 1, over)
+    _native.pair_query_batched(lib, dt, slab, pairs, 2, centre)
+    pos = slab.t["pos"]
+    for k, q in enumerate(fix["queries"]):
+        d = torch.empty(B, device=device)
+        o = torch.empty(B, dtype=torch.bool, device=device)
+        _native.pair_query(lib, dt, slab, q["a"], q["b"], 0, d)
+        _native.pair_query(lib, dt, slab, q["a"], q["b"], 1, o)
+        assert torch.equal(dist[k], d) and torch.equal(over[k], o), f"{name} pair {k}"
+        want = torch.linalg.vector_norm(pos[:, q["a"]] - pos[:, q["b"]], dim=-1)
+        assert torch.allclose(centre[k], want, rtol=1e-6, atol=1e-7)

@@ -166,6 +166,8 @@ EXPORTS = [
     "vmas_b200_point_query",
     "vmas_b200_broad_phase",
     "vmas_b200_ingest_actions",
+    "vmas_b200_cast_rays_batched",
+    "vmas_b200_pair_query_batched",
 ]
 
 _lib = None
@@ -204,6 +206,13 @@ def load():
     ]
     lib.vmas_b200_point_query.argtypes = [p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_broad_phase.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_cast_rays_batched.argtypes = [
+        p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+        C.c_void_p, C.c_void_p,
+    ]
+    lib.vmas_b200_pair_query_batched.argtypes = [
+        p_cfg, p_tb, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+    ]
     lib.vmas_b200_ingest_actions.argtypes = [
         p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
@@ -435,5 +444,23 @@ def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, b
     rc = lib.vmas_b200_ingest_actions(
         C.byref(dt.cfg), C.byref(st), agents_c, n, int(clamp),
         None if bad_flag is None else bad_flag.data_ptr(), _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def cast_rays_batched(lib, dt: DeviceTables, slab, src, target_off, targets, angles, max_range, n_rays, out) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_cast_rays_batched(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), int(src.shape[0]), src.data_ptr(), target_off.data_ptr(),
+        targets.data_ptr(), angles.data_ptr(), max_range.data_ptr(), int(n_rays), out.data_ptr(), _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def pair_query_batched(lib, dt: DeviceTables, slab, pairs, mode: int, out) -> int:
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_pair_query_batched(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), pairs.data_ptr(), int(pairs.shape[0]), mode, out.data_ptr(),
+        _stream(dt.device),
     )
     return _check(lib, rc)

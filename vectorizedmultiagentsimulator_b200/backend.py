@@ -212,6 +212,54 @@ class CudaBackend(PlanRuntime):
         self.launches += 1
         return out
 
+    # -- batched sensors / queries (one launch for many sensors or pairs) ---------------------------
+    def lidar_measure_many(self, sensors) -> Tensor:
+        """``[Q, B, R]`` ranges of ``Q`` LIDARs with the same number of rays, in one launch."""
+        self.refresh()
+        key = ("lidars",) + tuple(id(s) for s in sensors)
+        pack = self._ray_cache.get(key)
+        if pack is None:
+            n_rays = {s._angles.shape[1] for s in sensors}
+            assert len(n_rays) == 1, "sensors measured together must have the same number of rays"
+            src, off, flat = [], [0], []
+            for s in sensors:
+                src.append(self.index_of(s.agent))
+                flat += self.ray_targets(s.agent, s.entity_filter)
+                off.append(len(flat))
+            i32 = lambda v: torch.tensor(v if v else [0], dtype=torch.int32, device=self.device)  # noqa: E731
+            pack = (
+                i32(src),
+                i32(off),
+                i32(flat),
+                torch.stack([s._angles[0] for s in sensors]).to(self.device, torch.float32).contiguous(),
+                torch.tensor([float(s._max_range) for s in sensors], dtype=torch.float32, device=self.device),
+                n_rays.pop(),
+            )
+            self._ray_cache[key] = pack
+        src, off, flat, angles, ranges, n_rays = pack
+        out = torch.empty(len(sensors), self.world.batch_dim, n_rays, dtype=torch.float32, device=self.device)
+        self._native.cast_rays_batched(
+            self.lib, self._dev_tables, self.world.slab, src, off, flat, angles, ranges, n_rays, out
+        )
+        self.launches += 1
+        return out
+
+    def pair_query_many(self, pairs, mode: int) -> Tensor:
+        """``[K, B]``: mode 0 distances, 1 overlaps (bool), 2 centre distances, one launch."""
+        self.refresh()
+        key = ("pairs",) + tuple((id(a), id(b)) for a, b in pairs)
+        idx = self._ray_cache.get(key)
+        if idx is None:
+            idx = torch.tensor(
+                [[self.index_of(a), self.index_of(b)] for a, b in pairs], dtype=torch.int32, device=self.device
+            )
+            self._ray_cache[key] = idx
+        dtype = torch.bool if mode == 1 else torch.float32
+        out = torch.empty(len(pairs), self.world.batch_dim, dtype=dtype, device=self.device)
+        self._native.pair_query_batched(self.lib, self._dev_tables, self.world.slab, idx, mode, out)
+        self.launches += 1
+        return out
+
     # -- action ingestion ----------------------------------------------------------------------
     def ingest_actions(self, actions, specs, clamp: bool, bad_flag) -> None:
         """One launch: validate + scale the policy actions and write ``agent.action.u`` and the

@@ -879,6 +879,39 @@ __global__ void __launch_bounds__(256) cast_rays_kernel(const RayArgs a) {
   a.out[idx] = best;
 }
 
+struct RayBatchArgs {
+  RayArgs base;              // cfg / tables / state; per-sensor fields are filled per thread
+  const int32_t* src;        // [Q]
+  const int32_t* target_off; // [Q + 1]
+  const int32_t* all_targets;
+  const float* range;        // [Q]
+  int32_t n_sensors;
+};
+
+__global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = a.base.n_rays;
+  const long per_sensor = (long)a.base.cfg.batch_dim * R;
+  if (idx >= per_sensor * a.n_sensors) return;
+  const int q = (int)(idx / per_sensor);
+  const long rem = idx - (long)q * per_sensor;
+  const long env = rem / R;
+  const int ray = (int)(rem - env * R);
+  RayArgs s = a.base;  // per-thread copy with this sensor's parameters
+  s.src = __ldg(a.src + q);
+  s.max_range = __ldg(a.range + q);
+  const int lo = __ldg(a.target_off + q), hi = __ldg(a.target_off + q + 1);
+  const size_t env_base = (size_t)env * s.cfg.n_entities;
+  const float ang = __ldg(s.angles + q * R + ray) + s.st.rot[env_base + s.src];
+  float ds, dc;
+  sincosf(ang, &ds, &dc);
+  const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
+  const V2 o = mk(op.x, op.y);
+  float best = s.max_range;
+  for (int i = lo; i < hi; ++i) best = tmin(best, ray_vs_entity(s, o, ang, dc, ds, __ldg(a.all_targets + i), env_base));
+  s.out[idx] = best;
+}
+
 // ---------------------------------------------------------------------------------------------
 // distance / overlap queries (ref core.py:1788-1969)
 // ---------------------------------------------------------------------------------------------
@@ -990,6 +1023,39 @@ __global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
     over = pair_distance(q, ga, gb, q.a, q.b) < 0.f;
   }
   static_cast<uint8_t*>(q.out)[env] = over ? 1 : 0;
+}
+
+struct PairBatchArgs {
+  QueryArgs base;
+  const int32_t* pairs;  // [K, 2]
+  int32_t n_pairs;
+};
+
+__global__ void __launch_bounds__(256) pair_query_batched_kernel(const PairBatchArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long B = a.base.cfg.batch_dim;
+  if (idx >= B * a.n_pairs) return;
+  const int k = (int)(idx / B);
+  const long env = idx - (long)k * B;
+  const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
+  const size_t env_base = (size_t)env * a.base.cfg.n_entities;
+  const EntG ga = load_ent(a.base, ia, env_base), gb = load_ent(a.base, ib, env_base);
+  if (a.base.mode == 0) {
+    static_cast<float*>(a.base.out)[idx] = pair_distance(a.base, ga, gb, ia, ib);
+  } else if (a.base.mode == 2) {
+    static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
+  } else {
+    bool over;
+    const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
+                            (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
+    if (box_sphere) {
+      const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
+      over = box_sphere_overlap(a.base, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
+    } else {
+      over = pair_distance(a.base, ga, gb, ia, ib) < 0.f;
+    }
+    static_cast<uint8_t*>(a.base.out)[idx] = over ? 1 : 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) point_query_kernel(const QueryArgs q) {
@@ -1356,6 +1422,62 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
   const long total = (long)cfg->batch_dim * n_agents;
   ingest_actions_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
                           static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                int32_t n_sensors, const int32_t* src, const int32_t* target_off,
+                                const int32_t* targets, const float* angles, const float* max_range,
+                                int32_t n_rays, float* out, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (n_sensors <= 0 || n_rays <= 0) return fail("empty sensor batch%s");
+  if (!src || !target_off || !angles || !max_range || !out) return fail("null sensor buffer%s");
+  RayBatchArgs a;
+  a.base.cfg = *cfg;
+  a.base.tb = *tb;
+  a.base.st = *st;
+  a.base.targets = nullptr;
+  a.base.angles = angles;
+  a.base.out = out;
+  a.base.src = 0;
+  a.base.n_targets = 0;
+  a.base.n_rays = n_rays;
+  a.base.add_rot_of = 0;
+  a.base.max_range = 0.f;
+  a.src = src;
+  a.target_off = target_off;
+  a.all_targets = targets;
+  a.range = max_range;
+  a.n_sensors = n_sensors;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * n_rays * n_sensors;
+  cast_rays_batched_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                             static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                 const int32_t* pairs, int32_t n_pairs, int32_t mode, void* out,
+                                 void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  if (!pairs || !out || n_pairs <= 0) return fail("bad pair batch%s");
+  if (mode < 0 || mode > 2) return fail("unknown pair query mode%s");
+  PairBatchArgs a;
+  a.base.cfg = *cfg;
+  a.base.tb = *tb;
+  a.base.st = *st;
+  a.base.a = a.base.b = 0;
+  a.base.mode = mode;
+  a.base.point = nullptr;
+  a.base.out = out;
+  a.pairs = pairs;
+  a.n_pairs = n_pairs;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * n_pairs;
+  pair_query_batched_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                              static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

@@ -98,7 +98,79 @@ class Scenario(BaseScenario):
             self.keep(agent, "distance_shaping", self._separation_cost(agent), env_index)
         self.keep(self, "t", torch.zeros(world.batch_dim, device=world.device), env_index)
 
+    # ---- batched fast path: all policy agents at once ([A, B, ...] blocks of the state slab) -------
+    def _batch_setup(self):
+        world = self.world
+        cache = getattr(self, "_batch", None)
+        if cache is not None and cache["version"] == world._plan_version:
+            return cache
+        agents, policy, ents = world.agents, world.policy_agents, world.entities
+        dev = world.device
+        a0 = ents.index(agents[0])
+        assert [ents.index(a) for a in agents] == list(range(a0, a0 + len(agents)))
+        assert agents[0] is self._target and policy == agents[1:]
+        pairs = [(agents[i], agents[j]) for i in range(len(agents)) for j in range(i + 1, len(agents))]
+        incidence = torch.zeros(len(policy), len(pairs), device=dev)
+        for k, (a, b) in enumerate(pairs):
+            for e in (a, b):
+                if e.action_script is None:
+                    incidence[policy.index(e), k] = 1.0
+        n = len(agents)
+        others = torch.tensor([[j for j in range(n) if j != i] for i in range(1, n)], device=dev)  # [P, n-1]
+        cache = dict(
+            version=world._plan_version,
+            a0=a0,
+            n=n,
+            pairs=pairs,
+            incidence=incidence,
+            others=others.unsqueeze(-1).expand(-1, -1, world.batch_dim),
+            sensors=[a.sensors[0] for a in policy],
+            shaping=torch.stack([a.distance_shaping for a in policy]),
+        )
+        for i, a in enumerate(policy):
+            a.distance_shaping = cache["shaping"][i]
+        self._batch = cache
+        return cache
+
+    def _reward_batched(self, agent: Agent):
+        world = self.world
+        policy = world.policy_agents
+        c = self._batch_setup()
+        if agent is policy[0]:
+            self.t += 1
+            n_env = world.batch_dim
+            if self.collision_reward != 0:
+                touching = world.get_distances(c["pairs"]) <= self.min_collision_distance  # [K, B]
+                collision_rew = (c["incidence"] @ touching.to(torch.float32)) * float(self.collision_reward)
+            else:
+                collision_rew = torch.zeros(len(policy), n_env, device=world.device)
+            pos = world.slab.pos[:, c["a0"] : c["a0"] + c["n"]].transpose(0, 1)  # [n, B, 2]
+            dist = torch.linalg.vector_norm(pos[1:].unsqueeze(1) - pos.unsqueeze(0), dim=-1)  # [P, n, B]
+            to_others = dist.gather(1, c["others"])  # [P, n-1, B], world.agents order, self skipped
+            cost = (to_others - self.desired_distance).pow(2).mean(1) * self.dist_shaping_factor
+            dist_rew = c["shaping"] - cost
+            c["shaping"].copy_(cost)
+            for i, a in enumerate(policy):
+                a.collision_rew, a.dist_rew = collision_rew[i], dist_rew[i]
+        return agent.collision_rew + agent.dist_rew
+
+    def _observation_batched(self, agent: Agent):
+        world = self.world
+        policy = world.policy_agents
+        c = self._batch_setup()
+        if agent is policy[0] or getattr(self, "_obs_all", None) is None:
+            slab = world.slab
+            lo, hi = c["a0"] + 1, c["a0"] + c["n"]
+            pos = slab.pos[:, lo:hi].transpose(0, 1)
+            vel = slab.vel[:, lo:hi].transpose(0, 1)
+            target = slab.pos[:, c["a0"]].unsqueeze(0)
+            self._obs_all = torch.cat([pos, vel, pos - target, world.measure_lidars(c["sensors"])], dim=-1)
+        return self._obs_all[policy.index(agent)]
+
     def reward(self, agent: Agent):
+        return self._reward_batched(agent)
+
+    def _reward_simple(self, agent: Agent):
         world = self.world
         if world.policy_agents.index(agent) == 0:
             self.t += 1
@@ -120,6 +192,9 @@ class Scenario(BaseScenario):
         return agent.collision_rew + agent.dist_rew
 
     def observation(self, agent: Agent):
+        return self._observation_batched(agent)
+
+    def _observation_simple(self, agent: Agent):
         return torch.cat(
             [
                 agent.state.pos,

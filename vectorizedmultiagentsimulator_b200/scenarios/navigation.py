@@ -124,6 +124,98 @@ class Scenario(BaseScenario):
             dist = torch.linalg.vector_norm(agent.state.pos - agent.goal.state.pos, dim=1)
             self.keep(agent, "pos_shaping", dist * self.pos_shaping_factor, env_index)
 
+    # ---- batched fast path ---------------------------------------------------------------------
+    # All agents are consecutive rows of the state slab, so the per-agent terms of reward and
+    # observation are evaluated for every agent at once ([A, B, ...] tensors), the pairwise
+    # collision tests and the LIDARs in one kernel launch each.  Arithmetic per element is the same
+    # as in the per-agent formulation below (which remains the path for non-default options).
+    def _batched_ok(self) -> bool:
+        return self.collisions and not self.observe_all_goals
+
+    def _batch_setup(self):
+        world = self.world
+        cache = getattr(self, "_batch", None)
+        if cache is not None and cache["version"] == world._plan_version:
+            return cache
+        agents, ents = world.agents, world.entities
+        dev = world.device
+        a0 = ents.index(agents[0])
+        assert [ents.index(a) for a in agents] == list(range(a0, a0 + len(agents)))
+        pairs = [(agents[i], agents[j]) for i in range(len(agents)) for j in range(i) if world.static_collides(agents[i], agents[j])]
+        incidence = torch.zeros(len(agents), max(len(pairs), 1), device=dev)
+        for k, (a, b) in enumerate(pairs):
+            incidence[agents.index(a), k] = 1.0
+            incidence[agents.index(b), k] = 1.0
+        cache = dict(
+            version=world._plan_version,
+            a0=a0,
+            n=len(agents),
+            goal_idx=torch.tensor([ents.index(a.goal) for a in agents], device=dev),
+            goal_radius=torch.tensor([a.goal.shape.radius for a in agents], device=dev).unsqueeze(-1),
+            agent_radius=torch.tensor([a.shape.radius for a in agents], device=dev).unsqueeze(-1),
+            pairs=pairs,
+            incidence=incidence,
+            sensors=[a.sensors[0] for a in agents],
+            max_range=torch.tensor([a.sensors[0]._max_range for a in agents], device=dev).view(-1, 1, 1),
+            # every agent's shaping term lives in one [A, B] block; agent.pos_shaping is row i of it
+            pos_shaping=torch.stack([a.pos_shaping for a in agents]),
+        )
+        for i, a in enumerate(agents):
+            a.pos_shaping = cache["pos_shaping"][i]
+        self._batch = cache
+        return cache
+
+    def _agent_goal_offsets(self, c):
+        slab = self.world.slab
+        apos = slab.pos[:, c["a0"] : c["a0"] + c["n"]].transpose(0, 1)  # [A, B, 2] view
+        gpos = slab.pos.index_select(1, c["goal_idx"]).transpose(0, 1)
+        return apos, apos - gpos
+
+    def _reward_batched(self, agent: Agent):
+        agents = self.world.agents
+        c = self._batch_setup()
+        if agent is agents[0]:
+            _, offset = self._agent_goal_offsets(c)
+            dist = torch.linalg.vector_norm(offset, dim=-1)  # [A, B]
+            on_goal = dist < c["goal_radius"]
+            shaping_now = dist * self.pos_shaping_factor
+            pos_rew_all = c["pos_shaping"] - shaping_now
+            c["pos_shaping"].copy_(shaping_now)  # carried to the next step, in place ([A, B] block)
+            shared = torch.zeros_like(self.pos_rew)
+            for i, a in enumerate(agents):
+                a.distance_to_goal, a.on_goal, a.pos_rew = dist[i], on_goal[i], pos_rew_all[i]
+                shared = shared + pos_rew_all[i]  # sequential, like the reference's running sum
+            self.pos_rew = shared
+            self.all_goal_reached = on_goal.all(dim=0)
+            self.final_rew = torch.where(self.all_goal_reached, float(self.final_reward), 0.0).to(torch.float32)
+            if c["pairs"]:
+                touching = (self.world.get_distances(c["pairs"]) <= self.min_collision_distance) & self.world.collide_gates(
+                    c["pairs"]
+                ).unsqueeze(-1)
+                collision_rew = (c["incidence"] @ touching.to(torch.float32)) * float(self.agent_collision_penalty)
+            else:
+                collision_rew = torch.zeros(len(agents), self.world.batch_dim, device=self.world.device)
+            for i, a in enumerate(agents):
+                a.agent_collision_rew = collision_rew[i]
+        pos_reward = self.pos_rew if self.shared_rew else agent.pos_rew
+        return pos_reward + self.final_rew + agent.agent_collision_rew
+
+    def _observation_batched(self, agent: Agent):
+        agents = self.world.agents
+        c = self._batch_setup()
+        if agent is agents[0] or getattr(self, "_obs_all", None) is None:
+            slab = self.world.slab
+            apos, offset = self._agent_goal_offsets(c)
+            avel = slab.vel[:, c["a0"] : c["a0"] + c["n"]].transpose(0, 1)
+            lidar = self.world.measure_lidars(c["sensors"])  # [A, B, R], one launch
+            self._obs_all = torch.cat([apos, avel, offset, c["max_range"] - lidar], dim=-1)
+        return self._obs_all[agents.index(agent)]
+
+    def _done_batched(self):
+        c = self._batch_setup()
+        _, offset = self._agent_goal_offsets(c)
+        return (torch.linalg.vector_norm(offset, dim=-1) < c["agent_radius"]).all(dim=0)
+
     def _agent_progress(self, agent: Agent):
         agent.distance_to_goal = torch.linalg.vector_norm(agent.state.pos - agent.goal.state.pos, dim=-1)
         agent.on_goal = agent.distance_to_goal < agent.goal.shape.radius
@@ -133,6 +225,8 @@ class Scenario(BaseScenario):
         return agent.pos_rew
 
     def reward(self, agent: Agent):
+        if self._batched_ok():
+            return self._reward_batched(agent)
         agents = self.world.agents
         if agent is agents[0]:
             pos_rew = torch.zeros_like(self.pos_rew)
@@ -161,6 +255,8 @@ class Scenario(BaseScenario):
         return pos_reward + self.final_rew + agent.agent_collision_rew
 
     def observation(self, agent: Agent):
+        if self._batched_ok():
+            return self._observation_batched(agent)
         if self.observe_all_goals:
             goal_rel = [agent.state.pos - a.goal.state.pos for a in self.world.agents]
         else:
@@ -172,6 +268,8 @@ class Scenario(BaseScenario):
         return torch.cat(parts, dim=-1)
 
     def done(self):
+        if self._batched_ok():
+            return self._done_batched()
         reached = [
             torch.linalg.vector_norm(a.state.pos - a.goal.state.pos, dim=-1) < a.shape.radius
             for a in self.world.agents

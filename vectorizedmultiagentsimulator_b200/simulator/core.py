@@ -1123,6 +1123,44 @@ class World(TorchVectorizedObject):
             out = out[env_index]
         return out
 
+    # -- batched variants (extensions of the reference API: one kernel launch for many queries) -----
+    def measure_lidars(self, sensors) -> Tensor:
+        """``[Q, B, R]`` ranges of several LIDARs (same ray count) in one launch; equals
+        ``torch.stack([s.measure() for s in sensors])`` and updates their last measurement."""
+        out = self._get_backend().lidar_measure_many(list(sensors))
+        for q, s in enumerate(sensors):
+            s._last_measurement = out[q]
+        return out
+
+    def get_distances(self, pairs) -> Tensor:
+        """``[K, B]``: ``get_distance(a, b)`` for every ``(a, b)`` in ``pairs``, one launch."""
+        return self._get_backend().pair_query_many(list(pairs), 0)
+
+    def are_overlapping(self, pairs) -> Tensor:
+        """``[K, B]`` bool: ``is_overlapping(a, b)`` for every pair, one launch."""
+        return self._get_backend().pair_query_many(list(pairs), 1)
+
+    def get_center_distances(self, pairs) -> Tensor:
+        """``[K, B]``: distance between the two entities' centres (what ``collides`` thresholds)."""
+        return self._get_backend().pair_query_many(list(pairs), 2)
+
+    def collide_gates(self, pairs) -> Tensor:
+        """``[K]`` bool: ``collides(a, b)`` for every pair as device flags (no host sync)."""
+        pairs = list(pairs)
+        key = (self._plan_version,) + tuple((id(a), id(b)) for a, b in pairs)
+        cached = self.__dict__.setdefault("_gate_consts", {}).get(key)
+        if cached is None:  # constants live on the device: no per-step upload (CUDA-graph safe)
+            static = torch.tensor([self.static_collides(a, b) for a, b in pairs], device=self.device)
+            thr = torch.tensor(
+                [a.shape.circumscribed_radius() + b.shape.circumscribed_radius() for a, b in pairs],
+                dtype=torch.float32,
+                device=self.device,
+            ).unsqueeze(-1)
+            self._gate_consts.clear()
+            cached = self._gate_consts[key] = (static, thr)
+        static, thr = cached
+        return static & (self.get_center_distances(pairs) <= thr).any(dim=-1)
+
     def static_collides(self, a: Entity, b: Entity) -> bool:
         """The batch-independent predicates of ref ``World.collides`` (core.py:2788-2796)."""
         if (not a.collides(b)) or (not b.collides(a)) or a is b:
