@@ -153,12 +153,42 @@ int vmas_b200_cast_rays(const VmasWorldConfig* cfg, const VmasPlanTables* tb, co
  *   targets      device int32[...]    entity indices each sensor's rays may hit
  *   angles       device fp32 [Q, n_rays]  sensor-frame ray angles
  *   max_range    device fp32 [Q]
- *   out          device fp32 [Q, B, n_rays]  (sensor-major: each sensor's [B, R] block is contiguous)
+ *   out          device fp32; sensor q's reading of (env, ray) goes to
+ *                out[out_offsets[q] + env * out_env_stride + ray]
+ *   out_offsets  device int64[Q] or NULL (= q * B * n_rays: a dense [Q, B, n_rays] block)
+ *   out_env_stride  elements between consecutive envs (0 = n_rays).  A stride > n_rays lets the
+ *                readings land directly in columns of an observation block [A, B, F].
+ *   flags        VMAS_RAYS_RANGE_MINUS_DISTANCE: store max_range - distance (the form
+ *                scenarios/navigation.py:260 feeds to the policy) instead of the distance
  */
+#define VMAS_RAYS_RANGE_MINUS_DISTANCE 1
 int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                                 int32_t n_sensors, const int32_t* src, const int32_t* target_off,
                                 const int32_t* targets, const float* angles, const float* max_range,
-                                int32_t n_rays, float* out, void* cuda_stream);
+                                int32_t n_rays, float* out, const int64_t* out_offsets, int64_t out_env_stride,
+                                int32_t flags, void* cuda_stream);
+
+/*
+ * Observation assembly: fills the slab-derived columns of an observation block out[R, B, F] in one
+ * launch (the reference builds each agent's observation with per-term slices and torch.cat,
+ * e.g. scenarios/balance.py:236-262, navigation.py:252-265).
+ *   columns  device int32[R * F * 4]: per (row, column) {op, source a, source b, param}
+ *            op: VMAS_OBS_SKIP (left untouched: LIDAR readings, scenario-specific terms),
+ *                VMAS_OBS_COPY a, VMAS_OBS_DIFF a - b, VMAS_OBS_REMAINDER torch.remainder(a, param)
+ *            source: (field << 24) | element offset within the env's row of that field
+ *                    (pos / vel: 2 * entity + axis; rot / ang_vel: entity)
+ *            param: fp32 bit pattern
+ */
+#define VMAS_OBS_SKIP 0
+#define VMAS_OBS_COPY 1
+#define VMAS_OBS_DIFF 2
+#define VMAS_OBS_REMAINDER 3
+#define VMAS_OBS_POS 0
+#define VMAS_OBS_VEL 1
+#define VMAS_OBS_ROT 2
+#define VMAS_OBS_ANG_VEL 3
+int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
+                                  int32_t n_rows, int32_t width, float* out, void* cuda_stream);
 
 /*
  * K entity pairs in one launch: mode 0 = World.get_distance (fp32), 1 = World.is_overlapping

@@ -57,6 +57,31 @@ class OracleBackend(PlanRuntime):
     def lidar_measure_many(self, sensors):
         return torch.stack([self.lidar_measure(s) for s in sensors])
 
+    def observe(self, plan):
+        """CPU statement of ``World.observe``: the per-term torch expressions the reference's
+        scenarios write (e.g. balance.py:236-262), concatenated per row."""
+        from vectorizedmultiagentsimulator_b200.simulator import observe as O
+
+        plan.compile(self.world)  # validates the plan
+        rows = []
+        for row in plan.rows:
+            parts = []
+            for t in row:
+                if isinstance(t, O._State):
+                    value = getattr(t.entity.state, t.field)
+                    if t.minus is not None:
+                        value = value - getattr(t.minus.state, t.field)
+                    elif t.modulus is not None:
+                        value = value % t.modulus
+                    parts.append(value)
+                elif isinstance(t, O._Lidar):
+                    reading = t.sensor.measure()
+                    parts.append(t.sensor._max_range - reading if t.range_minus_distance else reading)
+                else:
+                    parts.append(torch.zeros(self.world.batch_dim, t.width, device=self.world.device))
+            rows.append(torch.cat(parts, dim=-1))
+        return torch.stack(rows)
+
     def pair_query_many(self, pairs, mode):
         if mode == 0:
             return torch.stack([self.pair_distance(a, b) for a, b in pairs])

@@ -362,3 +362,80 @@ def test_batched_pair_query_equals_per_pair_launches(name):
         assert torch.equal(dist[k], d) and torch.equal(over[k], o), f"{name} pair {k}"
         want = torch.linalg.vector_norm(pos[:, q["a"]] - pos[:, q["b"]], dim=-1)
         assert torch.allclose(centre[k], want, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["balance", "pollock"])
+def test_gather_observations_equals_torch_expressions(name):
+    """vmas_b200_gather_observations: COPY / DIFF / REMAINDER columns == the torch expressions
+    a scenario would concatenate, bit for bit; SKIP columns are left untouched."""
+    fix, desc, tables = load(name)
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    slab = _Slab(fix["final_state"], device)
+    pos, vel, rot, ang_vel = (slab.t[k] for k in ("pos", "vel", "rot", "ang_vel"))
+    B, E = pos.shape[0], pos.shape[1]
+    rows = min(3, E)
+    N = _native
+    table, want = [], []
+    for r in range(rows):
+        e, other = r, (r + 1) % E
+        cols, parts = [], []
+        for k in range(2):
+            cols.append((N.OBS_COPY, (N.OBS_POS << 24) | (2 * e + k), 0, 0))
+        parts.append(pos[:, e])
+        for k in range(2):
+            cols.append((N.OBS_DIFF, (N.OBS_VEL << 24) | (2 * e + k), (N.OBS_VEL << 24) | (2 * other + k), 0))
+        parts.append(vel[:, e] - vel[:, other])
+        for k in range(2):
+            cols.append((N.OBS_DIFF, (N.OBS_POS << 24) | (2 * other + k), (N.OBS_POS << 24) | (2 * e + k), 0))
+        parts.append(pos[:, other] - pos[:, e])
+        cols.append((N.OBS_SKIP, 0, 0, 0))
+        parts.append(torch.full((B, 1), -7.0, device=device))
+        cols.append((N.OBS_COPY, (N.OBS_ANG_VEL << 24) | e, 0, 0))
+        parts.append(ang_vel[:, e : e + 1])
+        for modulus in (torch.pi, -2.0):
+            bits = torch.tensor(modulus, dtype=torch.float32).view(torch.int32).item()
+            cols.append((N.OBS_REMAINDER, (N.OBS_ROT << 24) | e, 0, bits))
+            parts.append(rot[:, e : e + 1] % modulus)
+        table.append(cols)
+        want.append(torch.cat(parts, dim=-1))
+    want = torch.stack(want)
+    width = want.shape[-1]
+    columns = torch.tensor(table, dtype=torch.int32, device=device).contiguous()
+    out = torch.full((rows, B, width), -7.0, device=device)
+    _native.gather_observations(lib, dt, slab, columns, rows, width, out)
+    assert torch.equal(out, want)
+
+
+def test_batched_lidar_strided_output_and_range_flip():
+    """Readings scattered into columns of a wider block (and max_range - d) == the dense result."""
+    fix, desc, tables = load("navigation")
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    recs = [r for r in fix["lidar"] if r["step"] == fix["lidar"][0]["step"]]
+    slab = _Slab(dict(fix["steps"][recs[0]["step"]]["out"]), device)
+    n_rays = recs[0]["angles"].shape[-1]
+    src = torch.tensor([r["src"] for r in recs], dtype=torch.int32, device=device)
+    offs, flat = [0], []
+    for r in recs:
+        flat += r["targets"]
+        offs.append(len(flat))
+    target_off = torch.tensor(offs, dtype=torch.int32, device=device)
+    targets = torch.tensor(flat, dtype=torch.int32, device=device)
+    angles = torch.stack([r["angles"][0] for r in recs]).to(device).contiguous()
+    max_range = torch.tensor([r["max_range"] for r in recs], dtype=torch.float32, device=device)
+    B, Q = desc.batch_dim, len(recs)
+    dense = torch.empty(Q, B, n_rays, device=device)
+    _native.cast_rays_batched(lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, dense)
+    width, col = n_rays + 5, 3
+    for flags in (0, _native.RAYS_RANGE_MINUS_DISTANCE):
+        block = torch.full((Q, B, width), -1.0, device=device)
+        out_off = torch.tensor([q * B * width + col for q in range(Q)], dtype=torch.int64, device=device)
+        _native.cast_rays_batched(
+            lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, block, out_off, width, flags
+        )
+        want = max_range.view(-1, 1, 1) - dense if flags else dense
+        assert torch.equal(block[:, :, col : col + n_rays], want)
+        assert bool((block[:, :, :col] == -1.0).all()) and bool((block[:, :, col + n_rays :] == -1.0).all())

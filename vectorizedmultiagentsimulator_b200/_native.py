@@ -168,6 +168,7 @@ EXPORTS = [
     "vmas_b200_ingest_actions",
     "vmas_b200_cast_rays_batched",
     "vmas_b200_pair_query_batched",
+    "vmas_b200_gather_observations",
 ]
 
 _lib = None
@@ -208,7 +209,10 @@ def load():
     lib.vmas_b200_broad_phase.argtypes = [p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p]
     lib.vmas_b200_cast_rays_batched.argtypes = [
         p_cfg, p_tb, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-        C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+    ]
+    lib.vmas_b200_gather_observations.argtypes = [
+        p_cfg, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
     lib.vmas_b200_pair_query_batched.argtypes = [
         p_cfg, p_tb, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
@@ -448,11 +452,32 @@ def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, b
     return _check(lib, rc)
 
 
-def cast_rays_batched(lib, dt: DeviceTables, slab, src, target_off, targets, angles, max_range, n_rays, out) -> int:
+def cast_rays_batched(
+    lib, dt: DeviceTables, slab, src, target_off, targets, angles, max_range, n_rays, out, out_offsets=None,
+    out_env_stride: int = 0, flags: int = 0,
+) -> int:
+    """``out``: dense [Q, B, R] block, or (with ``out_offsets`` int64[Q] and ``out_env_stride``)
+    any fp32 tensor the readings are scattered into (columns of an observation block)."""
     st = dt.state_struct(slab)
     rc = lib.vmas_b200_cast_rays_batched(
         C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), int(src.shape[0]), src.data_ptr(), target_off.data_ptr(),
-        targets.data_ptr(), angles.data_ptr(), max_range.data_ptr(), int(n_rays), out.data_ptr(), _stream(dt.device),
+        targets.data_ptr(), angles.data_ptr(), max_range.data_ptr(), int(n_rays), out.data_ptr(),
+        out_offsets.data_ptr() if out_offsets is not None else None, int(out_env_stride), int(flags),
+        _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+RAYS_RANGE_MINUS_DISTANCE = 1
+OBS_SKIP, OBS_COPY, OBS_DIFF, OBS_REMAINDER = 0, 1, 2, 3
+OBS_POS, OBS_VEL, OBS_ROT, OBS_ANG_VEL = 0, 1, 2, 3
+
+
+def gather_observations(lib, dt: DeviceTables, slab, columns, n_rows: int, width: int, out) -> int:
+    """``columns`` int32[R, F, 4] on the device, ``out`` fp32 [R, B, F] (see include/vmas_b200.h)."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_gather_observations(
+        C.byref(dt.cfg), C.byref(st), columns.data_ptr(), int(n_rows), int(width), out.data_ptr(), _stream(dt.device)
     )
     return _check(lib, rc)
 

@@ -244,6 +244,54 @@ class CudaBackend(PlanRuntime):
         self.launches += 1
         return out
 
+    def observe(self, plan) -> Tensor:
+        """``[rows, B, width]`` observation block of an ``observe.ObservationPlan``: one launch
+        for the state-slab columns, one for all LIDAR columns."""
+        self.refresh()
+        cols, lidars = plan.compile(self.world)
+        dev = plan.device_cache.get(id(self))
+        B, F = self.world.batch_dim, plan.width
+        if dev is None:
+            dev = {"cols": torch.from_numpy(cols).to(self.device).contiguous(), "rays": None}
+            dev["any_state"] = bool((cols[..., 0] != 0).any())
+            if lidars:
+                sensors = [s for _, _, s, _ in lidars]
+                n_rays = {s._angles.shape[1] for s in sensors}
+                assert len(n_rays) == 1, "LIDARs of one observation plan must have the same number of rays"
+                src, off, flat = [], [0], []
+                for s in sensors:
+                    src.append(self.index_of(s.agent))
+                    flat += self.ray_targets(s.agent, s.entity_filter)
+                    off.append(len(flat))
+                i32 = lambda v: torch.tensor(v if v else [0], dtype=torch.int32, device=self.device)  # noqa: E731
+                dev["rays"] = (
+                    i32(src),
+                    i32(off),
+                    i32(flat),
+                    torch.stack([s._angles[0] for s in sensors]).to(self.device, torch.float32).contiguous(),
+                    torch.tensor([float(s._max_range) for s in sensors], dtype=torch.float32, device=self.device),
+                    n_rays.pop(),
+                    torch.tensor([r * B * F + c for r, c, _, _ in lidars], dtype=torch.int64, device=self.device),
+                    self._native.RAYS_RANGE_MINUS_DISTANCE if lidars[0][3] else 0,
+                )
+            plan.device_cache[id(self)] = dev
+        out = torch.empty(plan.n_rows, B, F, dtype=torch.float32, device=self.device)
+        if dev["any_state"]:
+            self._native.gather_observations(
+                self.lib, self._dev_tables, self.world.slab, dev["cols"], plan.n_rows, F, out
+            )
+            self.launches += 1
+        if dev["rays"] is not None:
+            src, off, flat, angles, ranges, n_rays, out_off, flags = dev["rays"]
+            self._native.cast_rays_batched(
+                self.lib, self._dev_tables, self.world.slab, src, off, flat, angles, ranges, n_rays, out, out_off, F,
+                flags,
+            )
+            self.launches += 1
+            for r, c, sensor, flipped in lidars:
+                sensor._last_measurement = None if flipped else out[r, :, c : c + n_rays]
+        return out
+
     def pair_query_many(self, pairs, mode: int) -> Tensor:
         """``[K, B]``: mode 0 distances, 1 overlaps (bool), 2 centre distances, one launch."""
         self.refresh()

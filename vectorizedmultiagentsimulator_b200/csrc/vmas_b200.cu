@@ -859,6 +859,36 @@ DEVI float ray_vs_entity(const RayArgs& a, V2 o, float ang, float dc, float ds, 
   }
 }
 
+// Exact early-out shared by both ray kernels: a target whose circumscribed circle lies beyond the
+// sensor's range cannot shorten a ray (any hit distance is >= |c - o| - circ_r > max_range, and the
+// result is min(max_range, ...)), so its shape test — and, when no target is in reach, the ray's
+// sin/cos — is skipped.  The margin dwarfs fp32 rounding of the skipped arithmetic.
+DEVI bool ray_target_in_reach(const RayArgs& a, V2 o, int t, size_t env_base) {
+  const float2 tp = reinterpret_cast<const float2*>(a.st.pos)[env_base + t];
+  const float reach = (a.max_range + __ldg(a.tb.ent_f32 + (size_t)t * VMAS_EF_COLS + VMAS_EF_CIRC_R)) * 1.001f + 1e-3f;
+  const float dx = tp.x - o.x, dy = tp.y - o.y;
+  return !(dx * dx + dy * dy > reach * reach);  // NaN positions stay "in reach"
+}
+
+template <class TargetAt>
+DEVI float cast_one_ray(const RayArgs& a, float ang, int n_targets, TargetAt target_at, size_t env_base) {
+  const float2 op = reinterpret_cast<const float2*>(a.st.pos)[env_base + a.src];
+  const V2 o = mk(op.x, op.y);
+  float best = a.max_range;
+  float ds = 0.f, dc = 0.f;
+  bool have_dir = false;
+  for (int i = 0; i < n_targets; ++i) {
+    const int t = target_at(i);
+    if (!ray_target_in_reach(a, o, t, env_base)) continue;
+    if (!have_dir) {
+      sincosf(ang, &ds, &dc);
+      have_dir = true;
+    }
+    best = tmin(best, ray_vs_entity(a, o, ang, dc, ds, t, env_base));
+  }
+  return best;
+}
+
 __global__ void __launch_bounds__(256) cast_rays_kernel(const RayArgs a) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)a.cfg.batch_dim * a.n_rays;
@@ -867,16 +897,7 @@ __global__ void __launch_bounds__(256) cast_rays_kernel(const RayArgs a) {
   const size_t env_base = (size_t)env * a.cfg.n_entities;
   float ang = a.angles[idx];
   if (a.add_rot_of >= 0) ang = ang + a.st.rot[env_base + a.add_rot_of];
-  float ds, dc;
-  sincosf(ang, &ds, &dc);
-  const float2 op = reinterpret_cast<const float2*>(a.st.pos)[env_base + a.src];
-  const V2 o = mk(op.x, op.y);
-  float best = a.max_range;
-  for (int i = 0; i < a.n_targets; ++i) {
-    const int t = __ldg(a.targets + i);
-    best = tmin(best, ray_vs_entity(a, o, ang, dc, ds, t, env_base));
-  }
-  a.out[idx] = best;
+  a.out[idx] = cast_one_ray(a, ang, a.n_targets, [&](int i) { return __ldg(a.targets + i); }, env_base);
 }
 
 struct RayBatchArgs {
@@ -885,7 +906,10 @@ struct RayBatchArgs {
   const int32_t* target_off; // [Q + 1]
   const int32_t* all_targets;
   const float* range;        // [Q]
+  const int64_t* out_off;    // [Q] element offset of (env 0, ray 0) of each sensor, or null
+  int64_t out_env_stride;    // elements between consecutive envs of one sensor
   int32_t n_sensors;
+  int32_t flags;
 };
 
 __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchArgs a) {
@@ -903,13 +927,9 @@ __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchAr
   const int lo = __ldg(a.target_off + q), hi = __ldg(a.target_off + q + 1);
   const size_t env_base = (size_t)env * s.cfg.n_entities;
   const float ang = __ldg(s.angles + q * R + ray) + s.st.rot[env_base + s.src];
-  float ds, dc;
-  sincosf(ang, &ds, &dc);
-  const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
-  const V2 o = mk(op.x, op.y);
-  float best = s.max_range;
-  for (int i = lo; i < hi; ++i) best = tmin(best, ray_vs_entity(s, o, ang, dc, ds, __ldg(a.all_targets + i), env_base));
-  s.out[idx] = best;
+  const float d = cast_one_ray(s, ang, hi - lo, [&](int i) { return __ldg(a.all_targets + lo + i); }, env_base);
+  const int64_t base = a.out_off ? __ldg(a.out_off + q) : (int64_t)q * per_sensor;
+  s.out[base + env * a.out_env_stride + ray] = (a.flags & VMAS_RAYS_RANGE_MINUS_DISTANCE) ? s.max_range - d : d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1064,6 +1084,50 @@ __global__ void __launch_bounds__(256) point_query_kernel(const QueryArgs q) {
   const EntG g = load_ent(q, q.a, (size_t)env * q.cfg.n_entities);
   const float2 pt = reinterpret_cast<const float2*>(q.point)[env];
   static_cast<float*>(q.out)[env] = dist_from_point(g, mk(pt.x, pt.y));
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation assembly: every slab-derived column of every agent's observation in one launch
+// (the reference concatenates per-agent slices with torch.cat, e.g. scenarios/balance.py:236-262)
+// ---------------------------------------------------------------------------------------------
+struct ObsArgs {
+  VmasState st;
+  const int32_t* cols;  // [rows * width * 4]
+  float* out;           // [rows, B, width]
+  int32_t rows, width, batch_dim, n_entities;
+};
+
+DEVI float obs_source(const ObsArgs& a, int code, long env) {
+  const int field = code >> 24, off = code & 0xFFFFFF;
+  const size_t E = (size_t)a.n_entities;
+  switch (field) {
+    case VMAS_OBS_POS: return a.st.pos[(size_t)env * 2 * E + off];
+    case VMAS_OBS_VEL: return a.st.vel[(size_t)env * 2 * E + off];
+    case VMAS_OBS_ROT: return a.st.rot[(size_t)env * E + off];
+    default: return a.st.ang_vel[(size_t)env * E + off];
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long per_row = (long)a.batch_dim * a.width;
+  if (idx >= per_row * a.rows) return;
+  const int row = (int)(idx / per_row);
+  const long rem = idx - (long)row * per_row;
+  const long env = rem / a.width;
+  const int col = (int)(rem - env * a.width);
+  const int4 c = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + col);
+  if (c.x == VMAS_OBS_SKIP) return;  // column owned by another producer (LIDAR, the scenario)
+  float v = obs_source(a, c.y, env);
+  if (c.x == VMAS_OBS_DIFF) {
+    v = v - obs_source(a, c.z, env);
+  } else if (c.x == VMAS_OBS_REMAINDER) {  // torch.remainder: sign follows the modulus
+    const float m = __int_as_float(c.w);
+    float r = fmodf(v, m);
+    if (r != 0.f && (signbit(m) != signbit(r))) r = r + m;
+    v = r;
+  }
+  a.out[idx] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1429,8 +1493,10 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
 int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                                 int32_t n_sensors, const int32_t* src, const int32_t* target_off,
                                 const int32_t* targets, const float* angles, const float* max_range,
-                                int32_t n_rays, float* out, void* cuda_stream) {
+                                int32_t n_rays, float* out, const int64_t* out_offsets, int64_t out_env_stride,
+                                int32_t flags, void* cuda_stream) {
   if (check_common(cfg, tb, st) < 0) return -1;
+  if (out_env_stride != 0 && out_env_stride < n_rays) return fail("out_env_stride < n_rays%s");
   if (n_sensors <= 0 || n_rays <= 0) return fail("empty sensor batch%s");
   if (!src || !target_off || !angles || !max_range || !out) return fail("null sensor buffer%s");
   RayBatchArgs a;
@@ -1449,11 +1515,35 @@ int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables
   a.target_off = target_off;
   a.all_targets = targets;
   a.range = max_range;
+  a.out_off = out_offsets;
+  a.out_env_stride = out_env_stride ? out_env_stride : n_rays;
   a.n_sensors = n_sensors;
+  a.flags = flags;
   const int threads = 256;
   const long total = (long)cfg->batch_dim * n_rays * n_sensors;
   cast_rays_batched_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
                              static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
+                                  int32_t n_rows, int32_t width, float* out, void* cuda_stream) {
+  if (!cfg || !st || !columns || !out) return fail("null argument%s");
+  if (!st->pos || !st->vel || !st->rot || !st->ang_vel) return fail("null state pointer%s");
+  if (n_rows <= 0 || width <= 0 || cfg->batch_dim <= 0) return fail("empty observation block%s");
+  ObsArgs a;
+  a.st = *st;
+  a.cols = columns;
+  a.out = out;
+  a.rows = n_rows;
+  a.width = width;
+  a.batch_dim = cfg->batch_dim;
+  a.n_entities = cfg->n_entities;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * n_rows * width;
+  gather_observations_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                               static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

@@ -8,6 +8,7 @@ overlap tests are single kernel launches.
 """
 import torch
 
+from ..simulator import observe as O
 from ..simulator.core import Agent, Box, Landmark, Line, Sphere, World
 from ..simulator.scenario import BaseScenario
 from ..simulator.utils import Color, ScenarioUtils
@@ -15,6 +16,7 @@ from ..simulator.utils import Color, ScenarioUtils
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
+        self._obs_plan = self._rew_consts = self._package_on_goal = None
         self.n_agents = kwargs.pop("n_agents", 3)
         self.package_mass = kwargs.pop("package_mass", 5)
         self.random_package_pos_on_line = kwargs.pop("random_package_pos_on_line", True)
@@ -110,9 +112,12 @@ class Scenario(BaseScenario):
         self.keep(self, "global_shaping", dist * self.shaping_factor, env_index)
 
     def compute_on_the_ground(self):
-        self.on_the_ground = self.world.is_overlapping(self.line, self.floor) + self.world.is_overlapping(
-            self.package, self.floor
+        # the three overlap tests of a step (two here, one in done()) in one launch
+        overlaps = self.world.are_overlapping(
+            [(self.line, self.floor), (self.package, self.floor), (self.package, self.package.goal)]
         )
+        self.on_the_ground = overlaps[0] + overlaps[1]
+        self._package_on_goal = overlaps[2]  # consumed by the next done()
 
     # -- per-step callbacks --------------------------------------------------------------------
     def reward(self, agent: Agent):
@@ -121,43 +126,49 @@ class Scenario(BaseScenario):
             self.package_dist = torch.linalg.vector_norm(
                 self.package.state.pos - self.package.goal.state.pos, dim=1
             )
-            self.ground_rew = torch.where(
-                self.on_the_ground, float(self.fall_reward), 0.0
-            ).to(torch.float32)
+            fall, zero = self._reward_constants()
+            self.ground_rew = torch.where(self.on_the_ground, fall, zero)
             shaping = self.package_dist * self.shaping_factor
             self.pos_rew = self.global_shaping - shaping
             self.keep(self, "global_shaping", shaping)  # carried to the next step: in place
-        return self.ground_rew + self.pos_rew
+            self._shared_rew = self.ground_rew + self.pos_rew  # the same for every agent
+        return self._shared_rew
+
+    def _reward_constants(self):
+        """Device-resident scalars (created once: no fill kernels inside the step)."""
+        consts = getattr(self, "_rew_consts", None)
+        if consts is None or consts[0].device != self.world.slab.pos.device:
+            dev = self.world.slab.pos.device
+            consts = self._rew_consts = (
+                torch.tensor(float(self.fall_reward), dtype=torch.float32, device=dev),
+                torch.tensor(0.0, dtype=torch.float32, device=dev),
+            )
+        return consts
 
     def _observe_all(self):
-        """Observations of every agent in one pass over the state slab -> ``[A, B, 16]``.
-
-        Same elementwise arithmetic as a per-agent ``torch.cat`` of the nine terms, but the
-        agent-independent terms are computed once and the agent-relative ones for all agents at
-        once (the agents are consecutive rows of the slab).  Agent-major output: each agent's
-        ``[B, 16]`` observation is a contiguous slice.
-        """
-        world = self.world
-        slab = world.slab
-        ents = world.entities
-        a0, n = ents.index(world.agents[0]), len(world.agents)
-        ip, il, ig = ents.index(self.package), ents.index(self.line), ents.index(self.package.goal)
-        apos = slab.pos[:, a0 : a0 + n].transpose(0, 1)  # [A, B, 2] views of the slab
-        avel = slab.vel[:, a0 : a0 + n].transpose(0, 1)
-        pkg_pos, line_pos = slab.pos[:, ip].unsqueeze(0), slab.pos[:, il].unsqueeze(0)  # [1, B, 2]
-        shared = torch.cat(
-            [
-                pkg_pos - slab.pos[:, ig].unsqueeze(0),
-                slab.vel[:, ip].unsqueeze(0),
-                slab.vel[:, il].unsqueeze(0),
-                slab.ang_vel[:, il : il + 1].unsqueeze(0),
-                (slab.rot[:, il : il + 1] % torch.pi).unsqueeze(0),
-            ],
-            dim=-1,
-        )
-        return torch.cat(
-            [apos, avel, apos - pkg_pos, apos - line_pos, shared.expand(n, -1, -1)], dim=-1
-        )
+        """Observations of every agent, ``[A, B, 16]``, assembled by one kernel over the state
+        slab (same fp32 arithmetic as a per-agent ``torch.cat`` of the nine terms).  Agent-major:
+        each agent's ``[B, 16]`` observation is a contiguous slice."""
+        plan = getattr(self, "_obs_plan", None)
+        if plan is None:
+            package, line = self.package, self.line
+            plan = self._obs_plan = O.ObservationPlan(
+                [
+                    [
+                        O.pos(a),
+                        O.vel(a),
+                        O.rel_pos(a, package),
+                        O.rel_pos(a, line),
+                        O.rel_pos(package, package.goal),
+                        O.vel(package),
+                        O.vel(line),
+                        O.ang_vel(line),
+                        O.rot_remainder(line, torch.pi),
+                    ]
+                    for a in self.world.agents
+                ]
+            )
+        return self.world.observe(plan)
 
     def observation(self, agent: Agent):
         agents = self.world.agents
@@ -166,7 +177,10 @@ class Scenario(BaseScenario):
         return self._obs_all[agents.index(agent)]
 
     def done(self):
-        return self.on_the_ground + self.world.is_overlapping(self.package, self.package.goal)
+        on_goal, self._package_on_goal = getattr(self, "_package_on_goal", None), None
+        if on_goal is None:  # no reward() / reset since the last done(): test the current state
+            on_goal = self.world.is_overlapping(self.package, self.package.goal)
+        return self.on_the_ground + on_goal
 
     def info(self, agent: Agent):
         return {"pos_rew": self.pos_rew, "ground_rew": self.ground_rew}

@@ -9,6 +9,7 @@ from typing import Dict
 import torch
 from torch import Tensor
 
+from ..simulator import observe as O
 from ..simulator.core import Agent, Landmark, Sphere, World
 from ..simulator.scenario import BaseScenario
 from ..simulator.sensors import Lidar
@@ -109,21 +110,28 @@ class Scenario(BaseScenario):
         a0 = ents.index(agents[0])
         assert [ents.index(a) for a in agents] == list(range(a0, a0 + len(agents)))
         assert agents[0] is self._target and policy == agents[1:]
-        pairs = [(agents[i], agents[j]) for i in range(len(agents)) for j in range(i + 1, len(agents))]
+        n = len(agents)
+        pairs = [(agents[i], agents[j]) for i in range(n) for j in range(i + 1, n)]
         incidence = torch.zeros(len(policy), len(pairs), device=dev)
         for k, (a, b) in enumerate(pairs):
             for e in (a, b):
                 if e.action_script is None:
                     incidence[policy.index(e), k] = 1.0
-        n = len(agents)
-        others = torch.tensor([[j for j in range(n) if j != i] for i in range(1, n)], device=dev)  # [P, n-1]
+        pair_row = {}
+        for k, (a, b) in enumerate(pairs):
+            pair_row[(id(a), id(b))] = pair_row[(id(b), id(a))] = k
+        # row of `pairs` holding the distance from policy agent i to every other agent, in
+        # world.agents order with itself skipped  -> [P, n-1]
+        others = torch.tensor(
+            [[pair_row[(id(agents[i]), id(agents[j]))] for j in range(n) if j != i] for i in range(1, n)], device=dev
+        )
         cache = dict(
             version=world._plan_version,
             a0=a0,
             n=n,
             pairs=pairs,
             incidence=incidence,
-            others=others.unsqueeze(-1).expand(-1, -1, world.batch_dim),
+            others=others,
             sensors=[a.sensors[0] for a in policy],
             shaping=torch.stack([a.distance_shaping for a in policy]),
         )
@@ -132,7 +140,7 @@ class Scenario(BaseScenario):
         self._batch = cache
         return cache
 
-    def _reward_batched(self, agent: Agent):
+    def reward(self, agent: Agent):
         world = self.world
         policy = world.policy_agents
         c = self._batch_setup()
@@ -144,9 +152,7 @@ class Scenario(BaseScenario):
                 collision_rew = (c["incidence"] @ touching.to(torch.float32)) * float(self.collision_reward)
             else:
                 collision_rew = torch.zeros(len(policy), n_env, device=world.device)
-            pos = world.slab.pos[:, c["a0"] : c["a0"] + c["n"]].transpose(0, 1)  # [n, B, 2]
-            dist = torch.linalg.vector_norm(pos[1:].unsqueeze(1) - pos.unsqueeze(0), dim=-1)  # [P, n, B]
-            to_others = dist.gather(1, c["others"])  # [P, n-1, B], world.agents order, self skipped
+            to_others = world.get_center_distances(c["pairs"])[c["others"]]  # [P, n-1, B]
             cost = (to_others - self.desired_distance).pow(2).mean(1) * self.dist_shaping_factor
             dist_rew = c["shaping"] - cost
             c["shaping"].copy_(cost)
@@ -154,56 +160,18 @@ class Scenario(BaseScenario):
                 a.collision_rew, a.dist_rew = collision_rew[i], dist_rew[i]
         return agent.collision_rew + agent.dist_rew
 
-    def _observation_batched(self, agent: Agent):
+    def observation(self, agent: Agent):
         world = self.world
         policy = world.policy_agents
         c = self._batch_setup()
         if agent is policy[0] or getattr(self, "_obs_all", None) is None:
-            slab = world.slab
-            lo, hi = c["a0"] + 1, c["a0"] + c["n"]
-            pos = slab.pos[:, lo:hi].transpose(0, 1)
-            vel = slab.vel[:, lo:hi].transpose(0, 1)
-            target = slab.pos[:, c["a0"]].unsqueeze(0)
-            self._obs_all = torch.cat([pos, vel, pos - target, world.measure_lidars(c["sensors"])], dim=-1)
+            plan = c.get("obs_plan")
+            if plan is None:
+                plan = c["obs_plan"] = O.ObservationPlan(
+                    [[O.pos(a), O.vel(a), O.rel_pos(a, self._target), O.lidar(a.sensors[0])] for a in policy]
+                )
+            self._obs_all = world.observe(plan)
         return self._obs_all[policy.index(agent)]
-
-    def reward(self, agent: Agent):
-        return self._reward_batched(agent)
-
-    def _reward_simple(self, agent: Agent):
-        world = self.world
-        if world.policy_agents.index(agent) == 0:
-            self.t += 1
-            if self.collision_reward != 0:
-                for a in world.policy_agents:
-                    a.collision_rew = torch.zeros_like(a.collision_rew)
-                agents = world.agents
-                for i, a in enumerate(agents):
-                    for b in agents[i + 1 :]:
-                        touching = world.get_distance(a, b) <= self.min_collision_distance
-                        penalty = torch.where(touching, float(self.collision_reward), 0.0)
-                        if a.action_script is None:
-                            a.collision_rew = a.collision_rew + penalty
-                        if b.action_script is None:
-                            b.collision_rew = b.collision_rew + penalty
-        cost = self._separation_cost(agent)
-        agent.dist_rew = agent.distance_shaping - cost
-        self.keep(agent, "distance_shaping", cost)
-        return agent.collision_rew + agent.dist_rew
-
-    def observation(self, agent: Agent):
-        return self._observation_batched(agent)
-
-    def _observation_simple(self, agent: Agent):
-        return torch.cat(
-            [
-                agent.state.pos,
-                agent.state.vel,
-                agent.state.pos - self._target.state.pos,
-                agent.sensors[0].measure(),
-            ],
-            dim=-1,
-        )
 
     def info(self, agent: Agent) -> Dict[str, Tensor]:
         return {"agent_collision_rew": agent.collision_rew, "agent_distance_rew": agent.dist_rew}

@@ -10,6 +10,7 @@ from typing import Dict
 import torch
 from torch import Tensor
 
+from ..simulator import observe as O
 from ..simulator.core import Agent, Landmark, Sphere, World
 from ..simulator.scenario import BaseScenario
 from ..simulator.sensors import Lidar
@@ -159,6 +160,8 @@ class Scenario(BaseScenario):
             max_range=torch.tensor([a.sensors[0]._max_range for a in agents], device=dev).view(-1, 1, 1),
             # every agent's shaping term lives in one [A, B] block; agent.pos_shaping is row i of it
             pos_shaping=torch.stack([a.pos_shaping for a in agents]),
+            final_reward=torch.tensor(float(self.final_reward), dtype=torch.float32, device=dev),
+            zero=torch.tensor(0.0, dtype=torch.float32, device=dev),
         )
         for i, a in enumerate(agents):
             a.pos_shaping = cache["pos_shaping"][i]
@@ -187,7 +190,8 @@ class Scenario(BaseScenario):
                 shared = shared + pos_rew_all[i]  # sequential, like the reference's running sum
             self.pos_rew = shared
             self.all_goal_reached = on_goal.all(dim=0)
-            self.final_rew = torch.where(self.all_goal_reached, float(self.final_reward), 0.0).to(torch.float32)
+            self.final_rew = torch.where(self.all_goal_reached, c["final_reward"], c["zero"])
+            c["dist_for_done"] = dist  # consumed by the next done()
             if c["pairs"]:
                 touching = (self.world.get_distances(c["pairs"]) <= self.min_collision_distance) & self.world.collide_gates(
                     c["pairs"]
@@ -195,26 +199,37 @@ class Scenario(BaseScenario):
                 collision_rew = (c["incidence"] @ touching.to(torch.float32)) * float(self.agent_collision_penalty)
             else:
                 collision_rew = torch.zeros(len(agents), self.world.batch_dim, device=self.world.device)
+            # (pos + final) + collision for every agent at once, same order as the per-agent sum
+            if self.shared_rew:
+                total = (self.pos_rew + self.final_rew).unsqueeze(0) + collision_rew
+            else:
+                total = (pos_rew_all + self.final_rew.unsqueeze(0)) + collision_rew
             for i, a in enumerate(agents):
-                a.agent_collision_rew = collision_rew[i]
-        pos_reward = self.pos_rew if self.shared_rew else agent.pos_rew
-        return pos_reward + self.final_rew + agent.agent_collision_rew
+                a.agent_collision_rew, a._total_rew = collision_rew[i], total[i]
+        return agent._total_rew
 
     def _observation_batched(self, agent: Agent):
         agents = self.world.agents
         c = self._batch_setup()
         if agent is agents[0] or getattr(self, "_obs_all", None) is None:
-            slab = self.world.slab
-            apos, offset = self._agent_goal_offsets(c)
-            avel = slab.vel[:, c["a0"] : c["a0"] + c["n"]].transpose(0, 1)
-            lidar = self.world.measure_lidars(c["sensors"])  # [A, B, R], one launch
-            self._obs_all = torch.cat([apos, avel, offset, c["max_range"] - lidar], dim=-1)
+            plan = c.get("obs_plan")
+            if plan is None:
+                plan = c["obs_plan"] = O.ObservationPlan(
+                    [
+                        [O.pos(a), O.vel(a), O.rel_pos(a, a.goal), O.lidar(a.sensors[0], range_minus_distance=True)]
+                        for a in agents
+                    ]
+                )
+            self._obs_all = self.world.observe(plan)  # [A, B, 18]: one gather + one LIDAR launch
         return self._obs_all[agents.index(agent)]
 
     def _done_batched(self):
         c = self._batch_setup()
-        _, offset = self._agent_goal_offsets(c)
-        return (torch.linalg.vector_norm(offset, dim=-1) < c["agent_radius"]).all(dim=0)
+        dist = c.pop("dist_for_done", None)
+        if dist is None:  # no reward() since the last done(): measure the current state
+            _, offset = self._agent_goal_offsets(c)
+            dist = torch.linalg.vector_norm(offset, dim=-1)
+        return (dist < c["agent_radius"]).all(dim=0)
 
     def _agent_progress(self, agent: Agent):
         agent.distance_to_goal = torch.linalg.vector_norm(agent.state.pos - agent.goal.state.pos, dim=-1)

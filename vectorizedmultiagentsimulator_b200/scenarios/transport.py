@@ -8,6 +8,7 @@ the stock one.
 """
 import torch
 
+from ..simulator import observe as O
 from ..simulator.core import Agent, Box, Landmark, Line, Sphere, World
 from ..simulator.scenario import BaseScenario
 from ..simulator.utils import Color, ScenarioUtils
@@ -15,6 +16,7 @@ from ..simulator.utils import Color, ScenarioUtils
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
+        self._obs_plan = self._obs_all = None
         n_agents = kwargs.pop("n_agents", 4)
         self.n_packages = kwargs.pop("n_packages", 1)
         self.package_width = kwargs.pop("package_width", 0.15)
@@ -115,15 +117,27 @@ class Scenario(BaseScenario):
         return self.rew
 
     def observation(self, agent: Agent):
-        parts = [agent.state.pos, agent.state.vel]
-        for package in self.packages:
-            parts += [
-                package.state.pos - package.goal.state.pos,
-                package.state.pos - agent.state.pos,
-                package.state.vel,
-                package.on_goal.unsqueeze(-1),
-            ]
-        return torch.cat(parts, dim=-1)
+        agents = self.world.agents
+        if agent is agents[0] or getattr(self, "_obs_all", None) is None:
+            plan = getattr(self, "_obs_plan", None)
+            if plan is None:
+                self._on_goal_terms = [O.blank(1) for _ in self.packages]
+                plan = self._obs_plan = O.ObservationPlan(
+                    [
+                        [O.pos(a), O.vel(a)]
+                        + [
+                            t
+                            for package, flag in zip(self.packages, self._on_goal_terms)
+                            for t in (O.rel_pos(package, package.goal), O.rel_pos(package, a), O.vel(package), flag)
+                        ]
+                        for a in agents
+                    ]
+                )
+            block = self.world.observe(plan)  # [A, B, 4 + 7 * n_packages], one launch
+            for package, flag in zip(self.packages, self._on_goal_terms):
+                block[:, :, plan.column_of(0, flag)] = package.on_goal  # bool -> 0. / 1., every agent
+            self._obs_all = block
+        return self._obs_all[agents.index(agent)]
 
     def done(self):
         return torch.stack([p.on_goal for p in self.packages], dim=1).all(dim=-1)

@@ -1132,6 +1132,11 @@ class World(TorchVectorizedObject):
             s._last_measurement = out[q]
         return out
 
+    def observe(self, plan) -> Tensor:
+        """The ``[rows, B, width]`` block of an :class:`observe.ObservationPlan` (one row per
+        agent): state-slab terms in one launch, all LIDAR terms in one more."""
+        return self._get_backend().observe(plan)
+
     def get_distances(self, pairs) -> Tensor:
         """``[K, B]``: ``get_distance(a, b)`` for every ``(a, b)`` in ``pairs``, one launch."""
         return self._get_backend().pair_query_many(list(pairs), 0)

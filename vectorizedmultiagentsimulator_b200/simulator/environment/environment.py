@@ -347,12 +347,16 @@ class Environment(TorchVectorizedObject):
         self._ingest_cache = (version, specs)
         return specs
 
-    def _step_device(self, actions: List[Tensor], clone_outputs: bool = True):
-        """The device-side work of one step; this is exactly what graph mode captures."""
-        specs = self._fused_ingest_specs()
-        if specs is not None and all(
+    def _fused_ingest_applies(self, actions: List[Tensor]) -> bool:
+        return self._fused_ingest_specs() is not None and all(
             a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions
-        ):
+        )
+
+    def _apply_actions(self, actions: List[Tensor]) -> bool:
+        """Decodes the policy agents' actions into ``agent.action.u`` and slab forces.  Returns
+        True if the fused kernel did it (scripted agents are then still to be processed)."""
+        if self._fused_ingest_applies(actions):
+            specs = self._fused_ingest_specs()
             # one kernel instead of ~10 eager ops per agent (checks, scaling, force routing)
             flag = None
             if self.action_checks == "deferred":
@@ -366,15 +370,19 @@ class Environment(TorchVectorizedObject):
             self.world._get_backend().ingest_actions(actions, specs, self.clamp_action, flag)
             for agent, _, u in specs:
                 agent.action.u = u
+            return True
+        for action, agent in zip(actions, self.agents):
+            self._set_action(action, agent)
+        # scripted agents + scenario-specific processing + dynamics (action -> force/torque)
+        for agent in self.world.agents:
+            self.scenario.env_process_action(agent)
+        return False
+
+    def _finish_step(self, fused_ingest: bool, clone_outputs: bool = True):
+        """Everything after the policy actions are decoded: scripted agents, physics, callbacks."""
+        if fused_ingest:
             for agent in self.world.scripted_agents:
                 self.scenario.env_process_action(agent)
-        else:
-            for action, agent in zip(actions, self.agents):
-                self._set_action(action, agent)
-            # scripted agents + scenario-specific processing + dynamics (action -> force/torque)
-            for agent in self.world.agents:
-                self.scenario.env_process_action(agent)
-
         self.scenario.pre_step()
         self.world.step()
         self.scenario.post_step()
@@ -383,12 +391,16 @@ class Environment(TorchVectorizedObject):
             get_observations=True, get_infos=True, get_rewards=True, get_dones=True, clone=clone_outputs
         )
 
+    def _step_device(self, actions: List[Tensor], clone_outputs: bool = True):
+        """The device-side work of one step."""
+        return self._finish_step(self._apply_actions(actions), clone_outputs)
+
     # ---- CUDA-graph mode -------------------------------------------------------------------
     def _step_graphed(self, actions: List[Tensor]):
         world = self.world
         if self._graph is not None and (
             self._graph_plan_version != world._plan_version
-            or any(a.shape != s.shape or a.dtype != s.dtype for a, s in zip(actions, self._graph_inputs))
+            or any(a.shape != s or a.dtype != d for a, (s, d) in zip(actions, self._graph_action_layout))
         ):
             self._graph = None  # the world or the action layout changed: capture again
             self._graph_warmup_left = 1
@@ -397,8 +409,14 @@ class Environment(TorchVectorizedObject):
                 self._graph_warmup_left -= 1
                 return self._step_device([a.to(self.device) for a in actions])
             self._capture(actions)
-        # one multi-tensor copy for all agents' actions, one replay, one clone per output dtype
-        if all(a.device == s.device and a.dtype == s.dtype for a, s in zip(actions, self._graph_inputs)):
+        if self._graph_inputs is None:
+            # the fused ingest kernel reads the caller's tensors directly (one eager launch in
+            # front of the replay; no staging copy into graph-owned input buffers)
+            if not self._fused_ingest_applies(actions):
+                actions = [a.to(self.device, torch.float32).contiguous() for a in actions]
+            self._apply_actions(actions)
+        elif all(a.device == s.device and a.dtype == s.dtype for a, s in zip(actions, self._graph_inputs)):
+            # one multi-tensor copy for all agents' actions
             torch._foreach_copy_(self._graph_inputs, list(actions))
         else:
             for static, a in zip(self._graph_inputs, actions):
@@ -408,6 +426,10 @@ class Environment(TorchVectorizedObject):
         backend = world._get_backend()
         backend.launches += self._graph_launches
         return self._unpack_graph_outputs()
+
+    #: a run of adjacent output leaves at least this large is cloned straight from where the
+    #: scenario wrote it instead of being gathered into the per-dtype buffer first
+    PACK_ALONE_BYTES = 1 << 20
 
     def _pack_graph_outputs(self, outputs):
         """(inside the capture) concatenates every output leaf into one flat buffer per dtype."""
@@ -424,20 +446,43 @@ class Environment(TorchVectorizedObject):
             return ("const", x)
 
         spec = index(outputs)
-        groups = {}
+        # Runs of leaves that already sit back to back in one allocation (e.g. the rows of a
+        # batched [A, B, F] observation block) are handed out as ONE view.  A big run is its own
+        # pack (cloned as is: no gather copy in the graph); the small rest is concatenated into
+        # one flat buffer per dtype.
+        runs = []  # [first leaf, n leaves, numel]
         for i, t in enumerate(leaves):
-            groups.setdefault(t.dtype, []).append(i)
-        packs = {}
-        for dtype, ids in groups.items():
-            packs[dtype] = (torch.cat([leaves[i].reshape(-1) for i in ids]), ids)
+            if runs and t.is_contiguous() and t.numel() > 0:
+                first, n, numel = runs[-1]
+                head = leaves[first]
+                if (
+                    head.is_contiguous()
+                    and head.dtype == t.dtype
+                    and t.untyped_storage().data_ptr() == head.untyped_storage().data_ptr()
+                    and t.data_ptr() == head.data_ptr() + numel * head.element_size()
+                ):
+                    runs[-1] = [first, n + 1, numel + t.numel()]
+                    continue
+            runs.append([i, 1, t.numel()])
+        packs = []  # (buffer the graph fills, leaf ids in order)
+        small = {}
+        for first, n, numel in runs:
+            head = leaves[first]
+            ids = list(range(first, first + n))
+            if head.is_contiguous() and numel * head.element_size() >= self.PACK_ALONE_BYTES:
+                packs.append((head.as_strided((numel,), (1,)), ids))
+            else:
+                small.setdefault(head.dtype, []).extend(ids)
+        for dtype, ids in small.items():
+            packs.append((torch.cat([leaves[i].reshape(-1) for i in ids]), ids))
         self._graph_out_spec = spec
         self._graph_out_shapes = [tuple(t.shape) for t in leaves]
         self._graph_out_packs = packs
 
     def _unpack_graph_outputs(self):
-        """Fresh output tensors: one clone per dtype, then views (no further kernel launches)."""
+        """Fresh output tensors: one clone per pack, then views (no further kernel launches)."""
         fresh = [None] * len(self._graph_out_shapes)
-        for pack, ids in self._graph_out_packs.values():
+        for pack, ids in self._graph_out_packs:
             flat = pack.clone()
             sizes = [math.prod(self._graph_out_shapes[i]) for i in ids]
             for i, piece in zip(ids, flat.split(sizes)):
@@ -462,19 +507,30 @@ class Environment(TorchVectorizedObject):
             raise RuntimeError("cuda_graph=True cannot be combined with action_checks='sync' (host sync per step)")
         if self.action_checks == "deferred" and self._bad_action_flag is None:
             self._bad_action_flag = torch.zeros(1, dtype=torch.bool, device=self.device)
-        self._graph_inputs = [torch.empty_like(a, device=self.device) for a in actions]
-        for static, a in zip(self._graph_inputs, actions):
-            static.copy_(a)
+        self._graph_action_layout = [(a.shape, a.dtype) for a in actions]
+        dev_actions = [a.to(self.device) for a in actions]
+        ingest_outside = self._fused_ingest_applies(
+            [a.to(torch.float32).contiguous() for a in dev_actions]
+        )
+        if ingest_outside:
+            self._graph_inputs = None
+        else:
+            self._graph_inputs = [a.clone() for a in dev_actions]
         backend = self.world._get_backend()
         backend.refresh()
         torch.cuda.synchronize(self.device)
-        before = backend.launches
         graph = torch.cuda.CUDAGraph()
         try:
+            if ingest_outside:
+                self._apply_actions([a.to(torch.float32).contiguous() for a in dev_actions])
+            before = backend.launches
             with torch.cuda.graph(graph):
-                # outputs stay un-cloned inside the graph; they are packed into one flat buffer per
-                # dtype there, and each replay hands out clones of those buffers
-                outputs = self._step_device(self._graph_inputs, clone_outputs=False)
+                # outputs stay un-cloned inside the graph; they are packed into flat buffers
+                # there, and each replay hands out clones of those buffers
+                if ingest_outside:
+                    outputs = self._finish_step(True, clone_outputs=False)
+                else:
+                    outputs = self._step_device(self._graph_inputs, clone_outputs=False)
                 self._pack_graph_outputs(outputs)
         except Exception as err:  # noqa: BLE001
             raise RuntimeError(
