@@ -44,7 +44,7 @@ METRIC = "env-steps/sec"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--steps", type=int, default=1000)
     p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -91,6 +91,13 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def wait_first_sample(self, timeout_s: float = 8.0):
+        """nvidia-smi takes a while to attach (and slows launches while it does): the timed
+        region must not start before its first line has arrived."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
 
     def stop(self):
         if self.proc is None:
@@ -274,12 +281,14 @@ def main_b200(args):
 
     # ---- arm 1: actions resident in HBM --------------------------------------------------
     dev_actions = pregenerate_actions(env, W + K, seed=1 + rank, device=device)
-    for t in range(W):
-        env.step(dev_actions[t])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # samples every timed region below (Environment.step, kernel-only, e2e)
+    for t in range(W):
+        env.step(dev_actions[t])
+    if rank == 0:
+        sampler.wait_first_sample()
+    barrier()
     launches_before = backend.launches
     backend.kernel_events = []
     wall0 = time.perf_counter()
@@ -289,7 +298,6 @@ def main_b200(args):
     backend.kernel_events = None
     launches = backend.launches - launches_before
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     # (empty in graph mode: the step is one graph replay, no per-kernel events inside it)
     kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / len(kernel_pairs) if kernel_pairs else 0.0
 
@@ -329,6 +337,7 @@ def main_b200(args):
     barrier()
     ms_e2e = timed_loop(e2e_step, K)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     env.check_actions_now()
 
     # ---- reduce over ranks ---------------------------------------------------------------------

@@ -58,6 +58,22 @@ def main():
                 "env_steps_per_s": round(B / (mean * 1e-3), 1),
             }), flush=True)
             del env
+    # host cost of one Environment.step: a tiny batch, so the GPU is never the limiter
+    import time
+
+    for label, name, _, kwargs in CONFIGS[:1] + CONFIGS[3:5]:
+        env = b200.make_env(name, num_envs=32, device="cuda", seed=0, cuda_graph=True, **kwargs)
+        env.reset()
+        acts = [env.get_random_actions() for _ in range(16)]
+        for i in range(20):
+            env.step(acts[i % 16])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(500):
+            env.step(acts[i % 16])
+        host = (time.perf_counter() - t0) / 500
+        torch.cuda.synchronize()
+        print(json.dumps({"config": label, "num_envs": 32, "mode": "cuda_graph", "host_us_per_step": round(host * 1e6, 1)}), flush=True)
 
 
 main()

@@ -1108,16 +1108,7 @@ DEVI float obs_source(const ObsArgs& a, int code, long env) {
   }
 }
 
-__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long per_row = (long)a.batch_dim * a.width;
-  if (idx >= per_row * a.rows) return;
-  const int row = (int)(idx / per_row);
-  const long rem = idx - (long)row * per_row;
-  const long env = rem / a.width;
-  const int col = (int)(rem - env * a.width);
-  const int4 c = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + col);
-  if (c.x == VMAS_OBS_SKIP) return;  // column owned by another producer (LIDAR, the scenario)
+DEVI float obs_column(const ObsArgs& a, int4 c, long env) {
   float v = obs_source(a, c.y, env);
   if (c.x == VMAS_OBS_DIFF) {
     v = v - obs_source(a, c.z, env);
@@ -1127,7 +1118,49 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
     if (r != 0.f && (signbit(m) != signbit(r))) r = r + m;
     v = r;
   }
-  a.out[idx] = v;
+  return v;
+}
+
+// One block row (blockIdx.y) per observation row; the row's column table sits in shared memory;
+// each thread produces VEC adjacent columns of one env (independent loads, one vector store), so
+// consecutive threads write consecutive 4*VEC-byte pieces of the output.
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
+  extern __shared__ int4 s_cols[];
+  const int row = blockIdx.y;
+  for (int c = threadIdx.x; c < a.width; c += blockDim.x)
+    s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + c);
+  __syncthreads();
+  const unsigned groups = (unsigned)a.width / VEC;  // column groups per env
+  const unsigned long long gi = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= (unsigned long long)a.batch_dim * groups) return;
+  const unsigned env = (unsigned)(gi / groups);
+  const unsigned col = (unsigned)(gi - (unsigned long long)env * groups) * VEC;
+  float v[VEC];
+  bool any = false, all = true;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const int4 c = s_cols[col + k];
+    const bool live = c.x != VMAS_OBS_SKIP;  // SKIP: column owned by another producer
+    any |= live;
+    all &= live;
+    v[k] = live ? obs_column(a, c, env) : 0.f;
+  }
+  if (!any) return;
+  float* dst = a.out + ((size_t)row * a.batch_dim + env) * a.width + col;
+  if (all) {
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (VEC == 2) {
+      *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    } else {
+      dst[0] = v[0];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (s_cols[col + k].x != VMAS_OBS_SKIP) dst[k] = v[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1540,10 +1573,22 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   a.width = width;
   a.batch_dim = cfg->batch_dim;
   a.n_entities = cfg->n_entities;
+  if (n_rows > 65535) return fail("more than 65535 observation rows%s");
   const int threads = 256;
-  const long total = (long)cfg->batch_dim * n_rows * width;
-  gather_observations_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
-                               static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  const size_t smem = (size_t)width * sizeof(int4);
+  if (smem > 48 * 1024) return fail("observation rows wider than 3072 columns%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  // vector width: the widest that divides the row (and keeps every store aligned)
+  const int vec = (width % 4 == 0 && ((uintptr_t)out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)out % 8 == 0)) ? 2 : 1;
+  const long groups = (long)cfg->batch_dim * (width / vec);
+  const dim3 grid((unsigned)((groups + threads - 1) / threads), (unsigned)n_rows);
+  if (vec == 4) {
+    gather_observations_kernel<4><<<grid, threads, smem, stream>>>(a);
+  } else if (vec == 2) {
+    gather_observations_kernel<2><<<grid, threads, smem, stream>>>(a);
+  } else {
+    gather_observations_kernel<1><<<grid, threads, smem, stream>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
 }

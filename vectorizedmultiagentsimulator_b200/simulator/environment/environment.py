@@ -413,7 +413,12 @@ class Environment(TorchVectorizedObject):
             # the fused ingest kernel reads the caller's tensors directly (one eager launch in
             # front of the replay; no staging copy into graph-owned input buffers)
             if not self._fused_ingest_applies(actions):
-                actions = [a.to(self.device, torch.float32).contiguous() for a in actions]
+                # pinned host tensors are uploaded asynchronously (stream-ordered before the kernel)
+                actions = [
+                    a.to(self.device, torch.float32, non_blocking=a.is_pinned() if a.device.type == "cpu" else False)
+                    .contiguous()
+                    for a in actions
+                ]
             self._apply_actions(actions)
         elif all(a.device == s.device and a.dtype == s.dtype for a, s in zip(actions, self._graph_inputs)):
             # one multi-tensor copy for all agents' actions
@@ -482,8 +487,16 @@ class Environment(TorchVectorizedObject):
     def _unpack_graph_outputs(self):
         """Fresh output tensors: one clone per pack, then views (no further kernel launches)."""
         fresh = [None] * len(self._graph_out_shapes)
-        for pack, ids in self._graph_out_packs:
-            flat = pack.clone()
+        packs = self._graph_out_packs
+        copies = [torch.empty_like(pack) for pack, _ in packs]
+        if len(packs) > 1:
+            torch._foreach_copy_(copies, [pack for pack, _ in packs])  # one launch for every pack
+        else:
+            copies[0].copy_(packs[0][0])
+        for flat, (_, ids) in zip(copies, packs):
+            if len(ids) == 1:
+                fresh[ids[0]] = flat.view(self._graph_out_shapes[ids[0]])
+                continue
             sizes = [math.prod(self._graph_out_shapes[i]) for i in ids]
             for i, piece in zip(ids, flat.split(sizes)):
                 fresh[i] = piece.view(self._graph_out_shapes[i])
@@ -656,8 +669,15 @@ class Environment(TorchVectorizedObject):
         if message not in self._bad_action_messages:
             self._bad_action_messages.append(message)
 
-    def _launch_deferred_action_readback(self):
+    #: deferred action checks copy their (sticky) device flag to the host every this many steps
+    ACTION_READBACK_EVERY = 8
+
+    def _launch_deferred_action_readback(self, force: bool = False):
         if self.action_checks != "deferred" or self._bad_action_flag is None:
+            return
+        # the device flag is sticky: looking at it every few steps loses nothing
+        self._readback_tick = getattr(self, "_readback_tick", 0) + 1
+        if self._bad_action_host is not None and self._readback_tick % self.ACTION_READBACK_EVERY and not force:
             return
         if self._bad_action_host is None:
             pin = self.device.type == "cuda"
@@ -688,7 +708,7 @@ class Environment(TorchVectorizedObject):
 
     def check_actions_now(self):
         """Force the deferred action checks to be read back and raised (one host sync)."""
-        self._launch_deferred_action_readback()
+        self._launch_deferred_action_readback(force=True)
         self._raise_deferred_action_errors(wait=True)
 
     def _check_discrete_action(self, action: Tensor, low: int, high: int, type: str):
