@@ -812,15 +812,14 @@ DEVI float ray_vs_entity(const RayArgs& a, V2 o, float ang, float dc, float ds, 
     const float radius = __ldg(ef + VMAS_EF_D0);
     const float half = max_range / 2.f;
     V2 line_pos = mk(o.x + dc * half, o.y + ds * half);
+    V2 u = c - o;
+    if (!((u.x * dc + u.y * ds) > 0.f)) return max_range;  // behind the sensor
     V2 closest = closest_point_carrier(line_pos, dc, ds, c);
     float dn = norm2(c - closest);
-    bool hits = dn < radius;
+    if (!(dn < radius)) return max_range;  // the carrier passes the sphere by
     float aa = radius * radius - dn * dn;
     float m = sqrtf(aa > 0.f ? aa : 1e-8f);
-    V2 u = c - o;
-    bool front = (u.x * dc + u.y * ds) > 0.f;
-    float dist = norm2(closest - o) - m;
-    return (hits && front) ? dist : max_range;
+    return norm2(closest - o) - m;
   }
   const float trot = a.st.rot[env_base + t];
   if (shape == VMAS_SHAPE_BOX) {
@@ -912,24 +911,72 @@ struct RayBatchArgs {
   int32_t flags;
 };
 
+// Block = (rays, envs): blockDim.x rays of blockDim.y consecutive envs of sensor blockIdx.y.
+// Phase A: one thread per env of the block finds the targets within the sensor's reach (a bit per
+// target, up to RAY_MASK_BITS; more targets fall back to testing reach per ray).  Phase B: one
+// thread per ray; rays of an env without any target in reach store max_range straight away, the
+// others take sin/cos once and test only the flagged targets.  Results equal the per-ray
+// formulation bit for bit (the reach test is an exact early-out, see ray_target_in_reach).
+constexpr int RAY_MASK_WORDS = 2, RAY_MASK_BITS = 32 * RAY_MASK_WORDS;
+
 __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchArgs a) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ uint32_t s_reach[];  // [blockDim.y][RAY_MASK_WORDS]
   const int R = a.base.n_rays;
-  const long per_sensor = (long)a.base.cfg.batch_dim * R;
-  if (idx >= per_sensor * a.n_sensors) return;
-  const int q = (int)(idx / per_sensor);
-  const long rem = idx - (long)q * per_sensor;
-  const long env = rem / R;
-  const int ray = (int)(rem - env * R);
+  const int q = blockIdx.y;
+  const long env0 = (long)blockIdx.x * blockDim.y;
   RayArgs s = a.base;  // per-thread copy with this sensor's parameters
   s.src = __ldg(a.src + q);
   s.max_range = __ldg(a.range + q);
-  const int lo = __ldg(a.target_off + q), hi = __ldg(a.target_off + q + 1);
+  const int lo = __ldg(a.target_off + q), n_targets = __ldg(a.target_off + q + 1) - lo;
+  const bool masked = n_targets <= RAY_MASK_BITS;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (masked && tid < blockDim.y && env0 + tid < s.cfg.batch_dim) {
+    const size_t env_base = (size_t)(env0 + tid) * s.cfg.n_entities;
+    const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
+    const V2 o = mk(op.x, op.y);
+    uint32_t bits[RAY_MASK_WORDS] = {};
+    for (int i = 0; i < n_targets; ++i)
+      if (ray_target_in_reach(s, o, __ldg(a.all_targets + lo + i), env_base)) bits[i >> 5] |= 1u << (i & 31);
+#pragma unroll
+    for (int w = 0; w < RAY_MASK_WORDS; ++w) s_reach[tid * RAY_MASK_WORDS + w] = bits[w];
+  }
+  __syncthreads();
+  const long env = env0 + threadIdx.y;
+  if (env >= s.cfg.batch_dim) return;
   const size_t env_base = (size_t)env * s.cfg.n_entities;
-  const float ang = __ldg(s.angles + q * R + ray) + s.st.rot[env_base + s.src];
-  const float d = cast_one_ray(s, ang, hi - lo, [&](int i) { return __ldg(a.all_targets + lo + i); }, env_base);
-  const int64_t base = a.out_off ? __ldg(a.out_off + q) : (int64_t)q * per_sensor;
-  s.out[base + env * a.out_env_stride + ray] = (a.flags & VMAS_RAYS_RANGE_MINUS_DISTANCE) ? s.max_range - d : d;
+  const int64_t base = (a.out_off ? __ldg(a.out_off + q) : (int64_t)q * s.cfg.batch_dim * R) + env * a.out_env_stride;
+  const bool flip = a.flags & VMAS_RAYS_RANGE_MINUS_DISTANCE;
+  uint32_t bits[RAY_MASK_WORDS] = {};
+  bool any = !masked;
+  if (masked) {
+#pragma unroll
+    for (int w = 0; w < RAY_MASK_WORDS; ++w) {
+      bits[w] = s_reach[threadIdx.y * RAY_MASK_WORDS + w];
+      any |= bits[w] != 0u;
+    }
+  }
+  for (int ray = threadIdx.x; ray < R; ray += blockDim.x) {
+    float d = s.max_range;
+    if (any) {
+      const float ang = __ldg(s.angles + q * R + ray) + s.st.rot[env_base + s.src];
+      if (masked) {
+        const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
+        const V2 o = mk(op.x, op.y);
+        float ds, dc;
+        sincosf(ang, &ds, &dc);
+#pragma unroll
+        for (int w = 0; w < RAY_MASK_WORDS; ++w) {
+          for (uint32_t rest = bits[w]; rest; rest &= rest - 1) {
+            const int t = __ldg(a.all_targets + lo + 32 * w + __ffs(rest) - 1);
+            d = tmin(d, ray_vs_entity(s, o, ang, dc, ds, t, env_base));
+          }
+        }
+      } else {
+        d = cast_one_ray(s, ang, n_targets, [&](int i) { return __ldg(a.all_targets + lo + i); }, env_base);
+      }
+    }
+    s.out[base + ray] = flip ? s.max_range - d : d;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1051,30 +1098,37 @@ struct PairBatchArgs {
   int32_t n_pairs;
 };
 
-__global__ void __launch_bounds__(256) pair_query_batched_kernel(const PairBatchArgs a) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+// Thread = env; a block evaluates PAIR_CHUNK pairs for its tile of envs, so the tile's slab rows
+// are fetched from L2 once and re-read from L1 for the other pairs (one thread per (pair, env)
+// made every pair re-fetch 32 strided sectors per warp).  Stores are coalesced over envs.
+constexpr int PAIR_CHUNK = 8;
+
+__global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatchArgs a) {
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long B = a.base.cfg.batch_dim;
-  if (idx >= B * a.n_pairs) return;
-  const int k = (int)(idx / B);
-  const long env = idx - (long)k * B;
-  const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
+  if (env >= B) return;
   const size_t env_base = (size_t)env * a.base.cfg.n_entities;
-  const EntG ga = load_ent(a.base, ia, env_base), gb = load_ent(a.base, ib, env_base);
-  if (a.base.mode == 0) {
-    static_cast<float*>(a.base.out)[idx] = pair_distance(a.base, ga, gb, ia, ib);
-  } else if (a.base.mode == 2) {
-    static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
-  } else {
-    bool over;
-    const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
-                            (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
-    if (box_sphere) {
-      const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
-      over = box_sphere_overlap(a.base, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
+  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * PAIR_CHUNK);
+  for (int k = blockIdx.y * PAIR_CHUNK; k < k_end; ++k) {
+    const long idx = (long)k * B + env;
+    const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
+    const EntG ga = load_ent(a.base, ia, env_base), gb = load_ent(a.base, ib, env_base);
+    if (a.base.mode == 0) {
+      static_cast<float*>(a.base.out)[idx] = pair_distance(a.base, ga, gb, ia, ib);
+    } else if (a.base.mode == 2) {
+      static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
     } else {
-      over = pair_distance(a.base, ga, gb, ia, ib) < 0.f;
+      bool over;
+      const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
+                              (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
+      if (box_sphere) {
+        const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
+        over = box_sphere_overlap(a.base, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
+      } else {
+        over = pair_distance(a.base, ga, gb, ia, ib) < 0.f;
+      }
+      static_cast<uint8_t*>(a.base.out)[idx] = over ? 1 : 0;
     }
-    static_cast<uint8_t*>(a.base.out)[idx] = over ? 1 : 0;
   }
 }
 
@@ -1128,38 +1182,41 @@ template <int VEC>
 __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
   extern __shared__ int4 s_cols[];
   const int row = blockIdx.y;
-  for (int c = threadIdx.x; c < a.width; c += blockDim.x)
+  for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < a.width; c += blockDim.x * blockDim.y)
     s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + c);
   __syncthreads();
-  const unsigned groups = (unsigned)a.width / VEC;  // column groups per env
-  const unsigned long long gi = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= (unsigned long long)a.batch_dim * groups) return;
-  const unsigned env = (unsigned)(gi / groups);
-  const unsigned col = (unsigned)(gi - (unsigned long long)env * groups) * VEC;
-  float v[VEC];
-  bool any = false, all = true;
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    const int4 c = s_cols[col + k];
-    const bool live = c.x != VMAS_OBS_SKIP;  // SKIP: column owned by another producer
-    any |= live;
-    all &= live;
-    v[k] = live ? obs_column(a, c, env) : 0.f;
-  }
-  if (!any) return;
-  float* dst = a.out + ((size_t)row * a.batch_dim + env) * a.width + col;
-  if (all) {
-    if constexpr (VEC == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (VEC == 2) {
-      *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-    } else {
-      dst[0] = v[0];
+  // threadIdx.x = column group, threadIdx.y = env within the block: no index arithmetic, and
+  // consecutive lanes write consecutive pieces of the same env's row
+  const long env = (long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (env >= a.batch_dim) return;
+  const int groups = a.width / VEC;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const int col = g * VEC;
+    float v[VEC];
+    bool any = false, all = true;
+  #pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int4 c = s_cols[col + k];
+      const bool live = c.x != VMAS_OBS_SKIP;  // SKIP: column owned by another producer
+      any |= live;
+      all &= live;
+      v[k] = live ? obs_column(a, c, env) : 0.f;
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      if (s_cols[col + k].x != VMAS_OBS_SKIP) dst[k] = v[k];
+    if (!any) continue;
+    float* dst = a.out + ((size_t)row * a.batch_dim + env) * a.width + col;
+    if (all) {
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+      } else {
+        dst[0] = v[0];
+      }
+    } else {
+  #pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (s_cols[col + k].x != VMAS_OBS_SKIP) dst[k] = v[k];
+    }
   }
 }
 
@@ -1552,9 +1609,11 @@ int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables
   a.out_env_stride = out_env_stride ? out_env_stride : n_rays;
   a.n_sensors = n_sensors;
   a.flags = flags;
-  const int threads = 256;
-  const long total = (long)cfg->batch_dim * n_rays * n_sensors;
-  cast_rays_batched_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+  if (n_sensors > 65535) return fail("more than 65535 sensors in one batch%s");
+  const unsigned bx = (unsigned)(n_rays < 256 ? n_rays : 256), by = 256 / bx;
+  const dim3 block(bx, by);
+  const dim3 grid((unsigned)((cfg->batch_dim + by - 1) / by), (unsigned)n_sensors);
+  cast_rays_batched_kernel<<<grid, block, by * RAY_MASK_WORDS * sizeof(uint32_t),
                              static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
@@ -1574,20 +1633,21 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   a.batch_dim = cfg->batch_dim;
   a.n_entities = cfg->n_entities;
   if (n_rows > 65535) return fail("more than 65535 observation rows%s");
-  const int threads = 256;
   const size_t smem = (size_t)width * sizeof(int4);
   if (smem > 48 * 1024) return fail("observation rows wider than 3072 columns%s");
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   // vector width: the widest that divides the row (and keeps every store aligned)
   const int vec = (width % 4 == 0 && ((uintptr_t)out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)out % 8 == 0)) ? 2 : 1;
-  const long groups = (long)cfg->batch_dim * (width / vec);
-  const dim3 grid((unsigned)((groups + threads - 1) / threads), (unsigned)n_rows);
+  const int groups = width / vec;
+  const unsigned bx = (unsigned)(groups < 256 ? groups : 256), by = 256 / bx;
+  const dim3 block(bx, by);
+  const dim3 grid((unsigned)((cfg->batch_dim + by - 1) / by), (unsigned)n_rows);
   if (vec == 4) {
-    gather_observations_kernel<4><<<grid, threads, smem, stream>>>(a);
+    gather_observations_kernel<4><<<grid, block, smem, stream>>>(a);
   } else if (vec == 2) {
-    gather_observations_kernel<2><<<grid, threads, smem, stream>>>(a);
+    gather_observations_kernel<2><<<grid, block, smem, stream>>>(a);
   } else {
-    gather_observations_kernel<1><<<grid, threads, smem, stream>>>(a);
+    gather_observations_kernel<1><<<grid, block, smem, stream>>>(a);
   }
   CUDA_OK(cudaGetLastError());
   return 1;
@@ -1609,10 +1669,11 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   a.base.out = out;
   a.pairs = pairs;
   a.n_pairs = n_pairs;
-  const int threads = 256;
-  const long total = (long)cfg->batch_dim * n_pairs;
-  pair_query_batched_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
-                              static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  const int threads = 128;
+  const int chunks = (n_pairs + PAIR_CHUNK - 1) / PAIR_CHUNK;
+  if (chunks > 65535) return fail("too many pairs in one batch%s");
+  const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
+  pair_query_batched_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

@@ -35,6 +35,22 @@ from . import spaces
 
 
 @contextlib.contextmanager
+def _rebuild_outputs(node, fresh):
+    """Output structure of a captured step with fresh leaves.  A module-level function: a
+    recursive closure would form a reference cycle that keeps every step's output tensors alive
+    until the cyclic garbage collector runs."""
+    kind, payload = node
+    if kind == "leaf":
+        return fresh[payload]
+    if kind == "dict":
+        return {k: _rebuild_outputs(v, fresh) for k, v in payload.items()}
+    if kind == "list":
+        return [_rebuild_outputs(v, fresh) for v in payload]
+    if kind == "tuple":
+        return tuple(_rebuild_outputs(v, fresh) for v in payload)
+    return payload
+
+
 def local_seed(vmas_random_state):
     """Runs the body on the environment's private (torch-CPU, numpy, python) RNG streams."""
     outer = (torch.random.get_rng_state(), np.random.get_state(), random.getstate())
@@ -451,6 +467,7 @@ class Environment(TorchVectorizedObject):
             return ("const", x)
 
         spec = index(outputs)
+        index = None  # the recursive closure references itself: break the cycle
         # Runs of leaves that already sit back to back in one allocation (e.g. the rows of a
         # batched [A, B, F] observation block) are handed out as ONE view.  A big run is its own
         # pack (cloned as is: no gather copy in the graph); the small rest is concatenated into
@@ -501,19 +518,7 @@ class Environment(TorchVectorizedObject):
             for i, piece in zip(ids, flat.split(sizes)):
                 fresh[i] = piece.view(self._graph_out_shapes[i])
 
-        def build(node):
-            kind, payload = node
-            if kind == "leaf":
-                return fresh[payload]
-            if kind == "dict":
-                return {k: build(v) for k, v in payload.items()}
-            if kind == "list":
-                return [build(v) for v in payload]
-            if kind == "tuple":
-                return tuple(build(v) for v in payload)
-            return payload
-
-        return build(self._graph_out_spec)
+        return _rebuild_outputs(self._graph_out_spec, fresh)
 
     def _capture(self, actions: List[Tensor]):
         if self.action_checks == "sync":
