@@ -34,7 +34,6 @@ from ..utils import AGENT_OBS_TYPE, DEVICE_TYPING, TorchUtils
 from . import spaces
 
 
-@contextlib.contextmanager
 def _rebuild_outputs(node, fresh):
     """Output structure of a captured step with fresh leaves.  A module-level function: a
     recursive closure would form a reference cycle that keeps every step's output tensors alive
@@ -51,6 +50,7 @@ def _rebuild_outputs(node, fresh):
     return payload
 
 
+@contextlib.contextmanager
 def local_seed(vmas_random_state):
     """Runs the body on the environment's private (torch-CPU, numpy, python) RNG streams."""
     outer = (torch.random.get_rng_state(), np.random.get_state(), random.getstate())
