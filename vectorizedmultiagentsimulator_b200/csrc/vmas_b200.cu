@@ -753,6 +753,8 @@ __global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
 // ---------------------------------------------------------------------------------------------
 // batch-wide broad phase (ref core.py:2797-2801): bit i <- any_env(|pa - pb| <= Ra + Rb)
 // ---------------------------------------------------------------------------------------------
+DEVI void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __global__ void __launch_bounds__(256) broad_phase_kernel(const StepArgs a) {
   extern __shared__ uint32_t s_bits[];
   const int W = a.mask_words;
@@ -762,6 +764,7 @@ __global__ void __launch_bounds__(256) broad_phase_kernel(const StepArgs a) {
   const bool live = env < a.cfg.batch_dim;
   const int E = a.cfg.n_entities;
   const float2* pos = reinterpret_cast<const float2*>(a.st.pos) + (size_t)(live ? env : 0) * E;
+  for (int j = 0; j < E; j += 4) prefetch_l1(pos + j);  // the whole row is on its way before item 0 asks
   for (int w = 0; w < W; ++w) {
     uint32_t bits = 0u;
     const int n = min(32, a.cfg.n_masked - 32 * w);
@@ -929,21 +932,30 @@ __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchAr
   s.max_range = __ldg(a.range + q);
   const int lo = __ldg(a.target_off + q), n_targets = __ldg(a.target_off + q + 1) - lo;
   const bool masked = n_targets <= RAY_MASK_BITS;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (masked && tid < blockDim.y && env0 + tid < s.cfg.batch_dim) {
-    const size_t env_base = (size_t)(env0 + tid) * s.cfg.n_entities;
-    const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
-    const V2 o = mk(op.x, op.y);
-    uint32_t bits[RAY_MASK_WORDS] = {};
-    for (int i = 0; i < n_targets; ++i)
-      if (ray_target_in_reach(s, o, __ldg(a.all_targets + lo + i), env_base)) bits[i >> 5] |= 1u << (i & 31);
-#pragma unroll
-    for (int w = 0; w < RAY_MASK_WORDS; ++w) s_reach[tid * RAY_MASK_WORDS + w] = bits[w];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_threads = blockDim.x * blockDim.y;
+  // this thread's own inputs are requested before phase A so their latency overlaps it
+  const long env = env0 + threadIdx.y;
+  const bool live = env < s.cfg.batch_dim;
+  const size_t env_base = (size_t)(live ? env : 0) * s.cfg.n_entities;
+  const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
+  const float src_rot = s.st.rot[env_base + s.src];
+  const float ang0 = threadIdx.x < R ? __ldg(s.angles + q * R + threadIdx.x) : 0.f;
+  if (masked) {
+    for (int i = tid; i < blockDim.y * RAY_MASK_WORDS; i += n_threads) s_reach[i] = 0u;
+    __syncthreads();
+    // phase A: one (env, target) reach test per thread, all loads independent
+    for (int i = tid; i < (int)blockDim.y * n_targets; i += n_threads) {
+      const int e = i / n_targets, ti = i - e * n_targets;
+      if (env0 + e < s.cfg.batch_dim) {
+        const size_t eb = (size_t)(env0 + e) * s.cfg.n_entities;
+        const float2 sp = reinterpret_cast<const float2*>(s.st.pos)[eb + s.src];
+        if (ray_target_in_reach(s, mk(sp.x, sp.y), __ldg(a.all_targets + lo + ti), eb))
+          atomicOr(&s_reach[e * RAY_MASK_WORDS + (ti >> 5)], 1u << (ti & 31));
+      }
+    }
   }
   __syncthreads();
-  const long env = env0 + threadIdx.y;
-  if (env >= s.cfg.batch_dim) return;
-  const size_t env_base = (size_t)env * s.cfg.n_entities;
+  if (!live) return;
   const int64_t base = (a.out_off ? __ldg(a.out_off + q) : (int64_t)q * s.cfg.batch_dim * R) + env * a.out_env_stride;
   const bool flip = a.flags & VMAS_RAYS_RANGE_MINUS_DISTANCE;
   uint32_t bits[RAY_MASK_WORDS] = {};
@@ -958,9 +970,8 @@ __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchAr
   for (int ray = threadIdx.x; ray < R; ray += blockDim.x) {
     float d = s.max_range;
     if (any) {
-      const float ang = __ldg(s.angles + q * R + ray) + s.st.rot[env_base + s.src];
+      const float ang = (ray == threadIdx.x ? ang0 : __ldg(s.angles + q * R + ray)) + src_rot;
       if (masked) {
-        const float2 op = reinterpret_cast<const float2*>(s.st.pos)[env_base + s.src];
         const V2 o = mk(op.x, op.y);
         float ds, dc;
         sincosf(ang, &ds, &dc);
@@ -1108,6 +1119,10 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
   const long B = a.base.cfg.batch_dim;
   if (env >= B) return;
   const size_t env_base = (size_t)env * a.base.cfg.n_entities;
+  // request the env's pos / rot rows up front: the per-pair loads below then hit L1 instead of
+  // paying one cold-miss latency per pair, one after the other
+  for (int j = 0; j < 2 * a.base.cfg.n_entities; j += 8) prefetch_l1(a.base.st.pos + 2 * env_base + j);
+  for (int j = 0; j < a.base.cfg.n_entities; j += 8) prefetch_l1(a.base.st.rot + env_base + j);
   const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * PAIR_CHUNK);
   for (int k = blockIdx.y * PAIR_CHUNK; k < k_end; ++k) {
     const long idx = (long)k * B + env;
@@ -1175,47 +1190,47 @@ DEVI float obs_column(const ObsArgs& a, int4 c, long env) {
   return v;
 }
 
-// One block row (blockIdx.y) per observation row; the row's column table sits in shared memory;
-// each thread produces VEC adjacent columns of one env (independent loads, one vector store), so
-// consecutive threads write consecutive 4*VEC-byte pieces of the output.
-template <int VEC>
+// Block = OBS_TILE consecutive envs of one observation row (blockIdx.y).  Phase 1: lanes are
+// envs and each warp walks a slice of the columns, so the column's op / source are uniform across
+// the warp (no divergence; the env tile's slab rows are fetched once and re-read from L1) and the
+// value goes to a shared-memory tile.  Phase 2: the tile is contiguous in the output
+// ([row][env][col]), so it is streamed out with fully coalesced stores, skipping SKIP columns.
+constexpr int OBS_TILE = 64;
+
 __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
-  extern __shared__ int4 s_cols[];
+  extern __shared__ int4 s_cols[];                                  // [width]
+  const int F = a.width, pitch = F | 1;                             // odd pitch: conflict-free
+  float* tile = reinterpret_cast<float*>(s_cols + F);               // [OBS_TILE][pitch]
   const int row = blockIdx.y;
-  for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < a.width; c += blockDim.x * blockDim.y)
-    s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + c);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int c = tid; c < F; c += 256) s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * F + c);
   __syncthreads();
-  // threadIdx.x = column group, threadIdx.y = env within the block: no index arithmetic, and
-  // consecutive lanes write consecutive pieces of the same env's row
-  const long env = (long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (env >= a.batch_dim) return;
-  const int groups = a.width / VEC;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const int col = g * VEC;
-    float v[VEC];
-    bool any = false, all = true;
-  #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const int4 c = s_cols[col + k];
-      const bool live = c.x != VMAS_OBS_SKIP;  // SKIP: column owned by another producer
-      any |= live;
-      all &= live;
-      v[k] = live ? obs_column(a, c, env) : 0.f;
-    }
-    if (!any) continue;
-    float* dst = a.out + ((size_t)row * a.batch_dim + env) * a.width + col;
-    if (all) {
-      if constexpr (VEC == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      } else if constexpr (VEC == 2) {
-        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-      } else {
-        dst[0] = v[0];
+  const long env0 = (long)blockIdx.x * OBS_TILE;
+  const size_t E = (size_t)a.n_entities;
+#pragma unroll
+  for (int half = 0; half < OBS_TILE / 32; ++half) {
+    const int e = half * 32 + threadIdx.x;
+    const long env = env0 + e;
+    if (env < a.batch_dim) {
+      for (int c = threadIdx.y; c < F; c += 8) {
+        const int4 col = s_cols[c];
+        if (col.x == VMAS_OBS_SKIP) continue;  // warp-uniform
+        tile[e * pitch + c] = obs_column(a, col, env);
       }
-    } else {
-  #pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        if (s_cols[col + k].x != VMAS_OBS_SKIP) dst[k] = v[k];
+    }
+  }
+  __syncthreads();
+  const long n_env = min((long)OBS_TILE, (long)a.batch_dim - env0);
+  float* dst = a.out + ((size_t)row * a.batch_dim + env0) * F;
+  int e = tid / F, c = tid - e * F;
+  const int de = 256 / F, dc = 256 - de * F;
+  for (long i = tid; i < n_env * F; i += 256) {
+    if (s_cols[c].x != VMAS_OBS_SKIP) dst[i] = tile[e * pitch + c];
+    e += de;
+    c += dc;
+    if (c >= F) {
+      c -= F;
+      ++e;
     }
   }
 }
@@ -1633,22 +1648,11 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   a.batch_dim = cfg->batch_dim;
   a.n_entities = cfg->n_entities;
   if (n_rows > 65535) return fail("more than 65535 observation rows%s");
-  const size_t smem = (size_t)width * sizeof(int4);
-  if (smem > 48 * 1024) return fail("observation rows wider than 3072 columns%s");
-  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  // vector width: the widest that divides the row (and keeps every store aligned)
-  const int vec = (width % 4 == 0 && ((uintptr_t)out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)out % 8 == 0)) ? 2 : 1;
-  const int groups = width / vec;
-  const unsigned bx = (unsigned)(groups < 256 ? groups : 256), by = 256 / bx;
-  const dim3 block(bx, by);
-  const dim3 grid((unsigned)((cfg->batch_dim + by - 1) / by), (unsigned)n_rows);
-  if (vec == 4) {
-    gather_observations_kernel<4><<<grid, block, smem, stream>>>(a);
-  } else if (vec == 2) {
-    gather_observations_kernel<2><<<grid, block, smem, stream>>>(a);
-  } else {
-    gather_observations_kernel<1><<<grid, block, smem, stream>>>(a);
-  }
+  const size_t smem = (size_t)width * sizeof(int4) + (size_t)OBS_TILE * (width | 1) * sizeof(float);
+  if (smem > 48 * 1024) return fail("observation rows wider than 140 columns are not supported%s");
+  const dim3 block(32, 8);
+  const dim3 grid((unsigned)((cfg->batch_dim + OBS_TILE - 1) / OBS_TILE), (unsigned)n_rows);
+  gather_observations_kernel<<<grid, block, smem, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

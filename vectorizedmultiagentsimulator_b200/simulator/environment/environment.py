@@ -500,6 +500,18 @@ class Environment(TorchVectorizedObject):
         self._graph_out_spec = spec
         self._graph_out_shapes = [tuple(t.shape) for t in leaves]
         self._graph_out_packs = packs
+        # per pack: runs of consecutive equal-shape leaves [(count, shape, numel per leaf)]
+        layouts = []
+        for _, ids in packs:
+            layout = []
+            for i in ids:
+                shape = self._graph_out_shapes[i]
+                if layout and layout[-1][1] == shape:
+                    layout[-1][0] += 1
+                else:
+                    layout.append([1, shape, math.prod(shape)])
+            layouts.append([tuple(run) for run in layout])
+        self._graph_out_layouts = layouts
 
     def _unpack_graph_outputs(self):
         """Fresh output tensors: one clone per pack, then views (no further kernel launches)."""
@@ -510,13 +522,17 @@ class Environment(TorchVectorizedObject):
             torch._foreach_copy_(copies, [pack for pack, _ in packs])  # one launch for every pack
         else:
             copies[0].copy_(packs[0][0])
-        for flat, (_, ids) in zip(copies, packs):
-            if len(ids) == 1:
-                fresh[ids[0]] = flat.view(self._graph_out_shapes[ids[0]])
-                continue
-            sizes = [math.prod(self._graph_out_shapes[i]) for i in ids]
-            for i, piece in zip(ids, flat.split(sizes)):
-                fresh[i] = piece.view(self._graph_out_shapes[i])
+        # leaves of equal shape that sit next to each other come out of ONE view + unbind
+        for flat, (_, ids), layout in zip(copies, packs, self._graph_out_layouts):
+            pieces = [flat] if len(layout) == 1 else flat.split_with_sizes([n * numel for n, _, numel in layout])
+            k = 0
+            for piece, (n, shape, _) in zip(pieces, layout):
+                if n == 1:
+                    fresh[ids[k]] = piece.view(shape)
+                else:
+                    for j, leaf in enumerate(piece.view((n,) + shape).unbind(0)):
+                        fresh[ids[k + j]] = leaf
+                k += n
 
         return _rebuild_outputs(self._graph_out_spec, fresh)
 
