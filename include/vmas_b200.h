@@ -191,6 +191,17 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
                                   int32_t n_rows, int32_t width, float* out, void* cuda_stream);
 
 /*
+ * Distance shaping for K entity pairs in one launch — the reward pattern of
+ * scenarios/balance.py:197-214, navigation.py:203-216, transport.py:139-152:
+ *     dist = |pos_a - pos_b|;  rew = prev - dist * factor;  prev <- dist * factor   (fp32, in this order)
+ *   pairs  device int32[K, 2];  prev device fp32[K, B] (in / out);  dist fp32[K, B] or NULL;  rew fp32[K, B]
+ */
+int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* pairs,
+                               int32_t n_pairs, float factor, float* prev, float* dist, float* rew,
+                               void* cuda_stream);
+
+
+/*
  * K entity pairs in one launch: mode 0 = World.get_distance (fp32), 1 = World.is_overlapping
  * (uint8), 2 = distance between the two centres (fp32; the quantity World.collides thresholds,
  * ref core.py:2797-2799).   pairs: device int32[K, 2];  out: [K, B].

@@ -82,6 +82,14 @@ class OracleBackend(PlanRuntime):
             rows.append(torch.cat(parts, dim=-1))
         return torch.stack(rows)
 
+    def distance_shaping(self, pairs, factor, prev):
+        """CPU statement of ``World.distance_shaping`` (ref scenarios/balance.py:197-214)."""
+        dist = torch.stack([torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1) for a, b in pairs])
+        shaping = dist * factor
+        rew = prev - shaping
+        prev.copy_(shaping)
+        return dist, rew
+
     def pair_query_many(self, pairs, mode):
         if mode == 0:
             return torch.stack([self.pair_distance(a, b) for a, b in pairs])

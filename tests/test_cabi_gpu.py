@@ -439,3 +439,35 @@ def test_batched_lidar_strided_output_and_range_flip():
         want = max_range.view(-1, 1, 1) - dense if flags else dense
         assert torch.equal(block[:, :, col : col + n_rays], want)
         assert bool((block[:, :, :col] == -1.0).all()) and bool((block[:, :, col + n_rays :] == -1.0).all())
+
+
+def test_distance_shaping_equals_torch_expressions():
+    """vmas_b200_distance_shaping: dist / rew / carried shaping == the torch formulation."""
+    fix, desc, tables = load("navigation")
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    slab = _Slab(fix["final_state"], device)
+    pos = slab.t["pos"]
+    B, E = pos.shape[0], pos.shape[1]
+    pairs_list = [(i, (i + 3) % E) for i in range(E)] + [(0, 0)]
+    pairs = torch.tensor(pairs_list, dtype=torch.int32, device=device)
+    K = len(pairs_list)
+    gen = torch.Generator().manual_seed(5)
+    prev0 = torch.rand(K, B, generator=gen).to(device)
+    prev = prev0.clone()
+    dist = torch.empty(K, B, device=device)
+    rew = torch.empty(K, B, device=device)
+    factor = 0.7
+    _native.distance_shaping(lib, dt, slab, pairs, factor, prev, dist, rew)
+    want_dist = torch.stack([torch.linalg.vector_norm(pos[:, a] - pos[:, b], dim=-1) for a, b in pairs_list])
+    assert torch.allclose(dist, want_dist, rtol=2e-7, atol=0)
+    # given the distance, the rest is exact fp32 arithmetic in the reference's order
+    assert torch.equal(prev, dist * factor)
+    assert torch.equal(rew, prev0 - dist * factor)
+    assert bool((dist[-1] == 0).all())
+    # dist is optional
+    prev2 = prev0.clone()
+    rew2 = torch.empty(K, B, device=device)
+    _native.distance_shaping(lib, dt, slab, pairs, factor, prev2, None, rew2)
+    assert torch.equal(rew2, rew) and torch.equal(prev2, prev)

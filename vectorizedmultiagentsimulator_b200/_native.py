@@ -10,6 +10,7 @@ import ctypes as C
 import os
 import shutil
 import subprocess
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -169,6 +170,7 @@ EXPORTS = [
     "vmas_b200_cast_rays_batched",
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
+    "vmas_b200_distance_shaping",
 ]
 
 _lib = None
@@ -214,6 +216,9 @@ def load():
     lib.vmas_b200_gather_observations.argtypes = [
         p_cfg, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
+    lib.vmas_b200_distance_shaping.argtypes = [
+        p_cfg, p_st, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    ]
     lib.vmas_b200_pair_query_batched.argtypes = [
         p_cfg, p_tb, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
@@ -239,9 +244,18 @@ def _check(lib, rc: int) -> int:
 
 def _stream(device) -> int:
     # kernels launch on the calling thread's current device: make it the world's device
-    if torch.cuda.current_device() != device.index:
+    index = device.index
+    if torch.cuda.current_device() != index:
         torch.cuda.set_device(device)
-    return torch.cuda.current_stream(device).cuda_stream
+    return _raw_stream(index)
+
+
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+
+    def _raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 # ---------------------------------------------------------------------------------------------
@@ -363,9 +377,15 @@ class DeviceTables:
         tb.specialization = self.specialization
         self.tb = tb
         self._state_key = None
+        self._state_ref = None
         self._state = None
 
     def state_struct(self, slab) -> StateC:
+        # a slab's tensors are allocated once: the struct is cached per (live) slab object
+        ref = self._state_ref
+        if ref is not None and ref() is slab:
+            return self._state
+        self._state_ref = weakref.ref(slab)
         key = tuple(t.data_ptr() for t in slab.tensors())
         if key != self._state_key:
             for t in slab.tensors():
@@ -464,6 +484,16 @@ def cast_rays_batched(
         targets.data_ptr(), angles.data_ptr(), max_range.data_ptr(), int(n_rays), out.data_ptr(),
         out_offsets.data_ptr() if out_offsets is not None else None, int(out_env_stride), int(flags),
         _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def distance_shaping(lib, dt: DeviceTables, slab, pairs, factor: float, prev, dist, rew) -> int:
+    """``pairs`` int32[K, 2]; ``prev`` fp32[K, B] updated in place; ``dist`` (or None) and ``rew`` fp32[K, B]."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_distance_shaping(
+        C.byref(dt.cfg), C.byref(st), pairs.data_ptr(), int(pairs.shape[0]), float(factor), prev.data_ptr(),
+        None if dist is None else dist.data_ptr(), rew.data_ptr(), _stream(dt.device),
     )
     return _check(lib, rc)
 

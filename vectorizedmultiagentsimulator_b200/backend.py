@@ -292,6 +292,24 @@ class CudaBackend(PlanRuntime):
                 sensor._last_measurement = None if flipped else out[r, :, c : c + n_rays]
         return out
 
+    def distance_shaping(self, pairs, factor: float, prev: Tensor):
+        """``(dist, rew)`` of shape ``[K, B]`` with ``rew = prev - dist * factor``; ``prev`` (fp32
+        ``[K, B]``, contiguous) is overwritten with ``dist * factor``.  One launch."""
+        self.refresh()
+        key = ("pairs",) + tuple((id(a), id(b)) for a, b in pairs)
+        idx = self._ray_cache.get(key)
+        if idx is None:
+            idx = torch.tensor(
+                [[self.index_of(a), self.index_of(b)] for a, b in pairs], dtype=torch.int32, device=self.device
+            )
+            self._ray_cache[key] = idx
+        K, B = len(pairs), self.world.batch_dim
+        assert prev.shape == (K, B) and prev.dtype == torch.float32 and prev.is_contiguous()
+        out = torch.empty(2, K, B, dtype=torch.float32, device=self.device)
+        self._native.distance_shaping(self.lib, self._dev_tables, self.world.slab, idx, factor, prev, out[0], out[1])
+        self.launches += 1
+        return out[0], out[1]
+
     def pair_query_many(self, pairs, mode: int) -> Tensor:
         """``[K, B]``: mode 0 distances, 1 overlaps (bool), 2 centre distances, one launch."""
         self.refresh()

@@ -1147,6 +1147,37 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// distance shaping: the reward pattern  dist = |pa - pb|;  rew = prev - dist * factor;  prev <- dist * factor
+// (ref scenarios/balance.py:197-214, navigation.py:203-216, transport.py:139-152) for K pairs at once
+// ---------------------------------------------------------------------------------------------
+struct ShapingArgs {
+  const float* pos;
+  const int32_t* pairs;  // [K, 2]
+  float* prev;           // [K, B] in / out
+  float* dist;           // [K, B] or null
+  float* rew;            // [K, B]
+  float factor;
+  int32_t n_pairs, n_entities, batch_dim;
+};
+
+__global__ void __launch_bounds__(128) distance_shaping_kernel(const ShapingArgs a) {
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.batch_dim) return;
+  const float2* row = reinterpret_cast<const float2*>(a.pos) + (size_t)env * a.n_entities;
+  for (int j = 0; j < a.n_entities; j += 4) prefetch_l1(row + j);
+  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * PAIR_CHUNK);
+  for (int k = blockIdx.y * PAIR_CHUNK; k < k_end; ++k) {
+    const size_t idx = (size_t)k * a.batch_dim + env;
+    const float2 pa = row[__ldg(a.pairs + 2 * k)], pb = row[__ldg(a.pairs + 2 * k + 1)];
+    const float d = norm2(pa.x - pb.x, pa.y - pb.y);
+    const float shaping = d * a.factor;
+    if (a.dist) a.dist[idx] = d;
+    a.rew[idx] = a.prev[idx] - shaping;
+    a.prev[idx] = shaping;
+  }
+}
+
 __global__ void __launch_bounds__(256) point_query_kernel(const QueryArgs q) {
   const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= q.cfg.batch_dim) return;
@@ -1678,6 +1709,30 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
   pair_query_batched_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* pairs,
+                               int32_t n_pairs, float factor, float* prev, float* dist, float* rew,
+                               void* cuda_stream) {
+  if (!cfg || !st || !st->pos || !pairs || !prev || !rew) return fail("null argument%s");
+  if (n_pairs <= 0 || cfg->batch_dim <= 0) return fail("empty pair batch%s");
+  ShapingArgs a;
+  a.pos = st->pos;
+  a.pairs = pairs;
+  a.prev = prev;
+  a.dist = dist;
+  a.rew = rew;
+  a.factor = factor;
+  a.n_pairs = n_pairs;
+  a.n_entities = cfg->n_entities;
+  a.batch_dim = cfg->batch_dim;
+  const int threads = 128;
+  const int chunks = (n_pairs + PAIR_CHUNK - 1) / PAIR_CHUNK;
+  if (chunks > 65535) return fail("too many pairs in one batch%s");
+  const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
+  distance_shaping_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

@@ -123,14 +123,13 @@ class Scenario(BaseScenario):
     def reward(self, agent: Agent):
         if agent is self.world.agents[0]:
             self.compute_on_the_ground()
-            self.package_dist = torch.linalg.vector_norm(
-                self.package.state.pos - self.package.goal.state.pos, dim=1
+            # |package - goal|, the shaping difference and the carried shaping term: one launch
+            dist, rew = self.world.distance_shaping(
+                [(self.package, self.package.goal)], self.shaping_factor, self.global_shaping.unsqueeze(0)
             )
+            self.package_dist, self.pos_rew = dist[0], rew[0]
             fall, zero = self._reward_constants()
             self.ground_rew = torch.where(self.on_the_ground, fall, zero)
-            shaping = self.package_dist * self.shaping_factor
-            self.pos_rew = self.global_shaping - shaping
-            self.keep(self, "global_shaping", shaping)  # carried to the next step: in place
             self._shared_rew = self.ground_rew + self.pos_rew  # the same for every agent
         return self._shared_rew
 

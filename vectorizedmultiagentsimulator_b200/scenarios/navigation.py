@@ -155,6 +155,7 @@ class Scenario(BaseScenario):
             goal_radius=torch.tensor([a.goal.shape.radius for a in agents], device=dev).unsqueeze(-1),
             agent_radius=torch.tensor([a.shape.radius for a in agents], device=dev).unsqueeze(-1),
             pairs=pairs,
+            goal_pairs=[(a, a.goal) for a in agents],
             incidence=incidence,
             sensors=[a.sensors[0] for a in agents],
             max_range=torch.tensor([a.sensors[0]._max_range for a in agents], device=dev).view(-1, 1, 1),
@@ -178,12 +179,9 @@ class Scenario(BaseScenario):
         agents = self.world.agents
         c = self._batch_setup()
         if agent is agents[0]:
-            _, offset = self._agent_goal_offsets(c)
-            dist = torch.linalg.vector_norm(offset, dim=-1)  # [A, B]
+            # distances to the goals, shaping differences and the carried shaping block: one launch
+            dist, pos_rew_all = self.world.distance_shaping(c["goal_pairs"], self.pos_shaping_factor, c["pos_shaping"])
             on_goal = dist < c["goal_radius"]
-            shaping_now = dist * self.pos_shaping_factor
-            pos_rew_all = c["pos_shaping"] - shaping_now
-            c["pos_shaping"].copy_(shaping_now)  # carried to the next step, in place ([A, B] block)
             shared = torch.zeros_like(self.pos_rew)
             for i, a in enumerate(agents):
                 a.distance_to_goal, a.on_goal, a.pos_rew = dist[i], on_goal[i], pos_rew_all[i]

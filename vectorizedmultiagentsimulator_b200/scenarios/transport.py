@@ -16,7 +16,7 @@ from ..simulator.utils import Color, ScenarioUtils
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
-        self._obs_plan = self._obs_all = None
+        self._obs_plan = self._obs_all = self._shaping_block = self._zero = None
         n_agents = kwargs.pop("n_agents", 4)
         self.n_packages = kwargs.pop("n_packages", 1)
         self.package_width = kwargs.pop("package_width", 0.15)
@@ -104,17 +104,28 @@ class Scenario(BaseScenario):
                     torch.tensor(Color.GREEN.value, device=self.world.device, dtype=torch.float32),
                 )
             red, green = self._colors
-            for package in self.packages:
-                package.dist_to_goal = torch.linalg.vector_norm(
-                    package.state.pos - package.goal.state.pos, dim=1
-                )
+            block = getattr(self, "_shaping_block", None)
+            if block is None:  # every package's carried shaping term as one [K, B] block
+                block = self._shaping_block = torch.stack([p.global_shaping for p in self.packages])
+                for k, package in enumerate(self.packages):
+                    package.global_shaping = block[k]
+            dist, shaped = self.world.distance_shaping(
+                [(p, p.goal) for p in self.packages], self.shaping_factor, block
+            )
+            zero = self._zero_reward()
+            for k, package in enumerate(self.packages):
+                package.dist_to_goal = dist[k]
                 package.on_goal = self.world.is_overlapping(package, package.goal)
                 package.color = torch.where(package.on_goal.unsqueeze(-1), green, red)
-                shaping = package.dist_to_goal * self.shaping_factor
-                rew = rew + torch.where(package.on_goal, 0.0, package.global_shaping - shaping)
-                self.keep(package, "global_shaping", shaping)
+                rew = rew + torch.where(package.on_goal, zero, shaped[k])
             self.rew = rew
         return self.rew
+
+    def _zero_reward(self):
+        zero = getattr(self, "_zero", None)
+        if zero is None or zero.device != self.world.slab.pos.device:
+            zero = self._zero = torch.tensor(0.0, dtype=torch.float32, device=self.world.slab.pos.device)
+        return zero
 
     def observation(self, agent: Agent):
         agents = self.world.agents

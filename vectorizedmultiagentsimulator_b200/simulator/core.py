@@ -1137,6 +1137,12 @@ class World(TorchVectorizedObject):
         agent): state-slab terms in one launch, all LIDAR terms in one more."""
         return self._get_backend().observe(plan)
 
+    def distance_shaping(self, pairs, factor: float, prev: Tensor):
+        """The shaping-reward pattern for ``K`` entity pairs in one launch: returns ``(dist, rew)``
+        (``[K, B]`` each) with ``dist = |pos_a - pos_b|`` and ``rew = prev - dist * factor``, and
+        overwrites ``prev`` (fp32 ``[K, B]``) with ``dist * factor`` for the next step."""
+        return self._get_backend().distance_shaping(list(pairs), float(factor), prev)
+
     def get_distances(self, pairs) -> Tensor:
         """``[K, B]``: ``get_distance(a, b)`` for every ``(a, b)`` in ``pairs``, one launch."""
         return self._get_backend().pair_query_many(list(pairs), 0)

@@ -300,6 +300,10 @@ class Environment(TorchVectorizedObject):
             len(actions) == self.n_agents
         ), f"Expecting actions for {self.n_agents}, got {len(actions)} actions"
         actions = list(actions)
+        sizes = self._action_sizes()
+        n_env = self.num_envs
+        if all(type(a) is Tensor and a.dim() == 2 and a.shape[0] == n_env and a.shape[1] == k for a, k in zip(actions, sizes)):
+            return actions  # the common case: nothing to convert, nothing to report
         for i, agent in enumerate(self.agents):
             a = actions[i]
             if not isinstance(a, Tensor):
@@ -316,6 +320,15 @@ class Environment(TorchVectorizedObject):
             )
             actions[i] = a
         return actions
+
+    def _action_sizes(self) -> List[int]:
+        sizes = getattr(self, "_action_size_cache", None)
+        if sizes is None or sizes[0] != self.world._plan_version or len(sizes[1]) != self.n_agents:
+            sizes = self._action_size_cache = (
+                self.world._plan_version,
+                [self.get_agent_action_size(a) for a in self.agents],
+            )
+        return sizes[1]
 
     def _step(self, actions):
         self._raise_deferred_action_errors()
@@ -368,10 +381,11 @@ class Environment(TorchVectorizedObject):
             a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions
         )
 
-    def _apply_actions(self, actions: List[Tensor]) -> bool:
+    def _apply_actions(self, actions: List[Tensor], fused: Optional[bool] = None) -> bool:
         """Decodes the policy agents' actions into ``agent.action.u`` and slab forces.  Returns
-        True if the fused kernel did it (scripted agents are then still to be processed)."""
-        if self._fused_ingest_applies(actions):
+        True if the fused kernel did it (scripted agents are then still to be processed).
+        ``fused``: the caller's answer to ``_fused_ingest_applies(actions)``, if it already asked."""
+        if self._fused_ingest_applies(actions) if fused is None else fused:
             specs = self._fused_ingest_specs()
             # one kernel instead of ~10 eager ops per agent (checks, scaling, force routing)
             flag = None
@@ -435,7 +449,7 @@ class Environment(TorchVectorizedObject):
                     .contiguous()
                     for a in actions
                 ]
-            self._apply_actions(actions)
+            self._apply_actions(actions, fused=True)
         elif all(a.device == s.device and a.dtype == s.dtype for a, s in zip(actions, self._graph_inputs)):
             # one multi-tensor copy for all agents' actions
             torch._foreach_copy_(self._graph_inputs, list(actions))
