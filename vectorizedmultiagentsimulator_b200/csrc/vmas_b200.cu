@@ -1234,10 +1234,23 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
   float* tile = reinterpret_cast<float*>(s_cols + F);               // [OBS_TILE][pitch]
   const int row = blockIdx.y;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int c = tid; c < F; c += 256) s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * F + c);
-  __syncthreads();
   const long env0 = (long)blockIdx.x * OBS_TILE;
   const size_t E = (size_t)a.n_entities;
+  // the tile's slab rows are contiguous: ask for them now, while the column table is on its way
+  {
+    const long n_env = min((long)OBS_TILE, (long)a.batch_dim - env0);
+    const size_t lines2 = (size_t)n_env * 2 * E / 32 + 1, lines1 = (size_t)n_env * E / 32 + 1;
+    for (size_t l = tid; l < lines2; l += 256) {
+      prefetch_l1(a.st.pos + (size_t)env0 * 2 * E + 32 * l);
+      prefetch_l1(a.st.vel + (size_t)env0 * 2 * E + 32 * l);
+    }
+    for (size_t l = tid; l < lines1; l += 256) {
+      prefetch_l1(a.st.rot + (size_t)env0 * E + 32 * l);
+      prefetch_l1(a.st.ang_vel + (size_t)env0 * E + 32 * l);
+    }
+  }
+  for (int c = tid; c < F; c += 256) s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * F + c);
+  __syncthreads();
 #pragma unroll
   for (int half = 0; half < OBS_TILE / 32; ++half) {
     const int e = half * 32 + threadIdx.x;

@@ -399,7 +399,8 @@ class Environment(TorchVectorizedObject):
                     self._bad_action_messages.append(msg)
             self.world._get_backend().ingest_actions(actions, specs, self.clamp_action, flag)
             for agent, _, u in specs:
-                agent.action.u = u
+                if agent.action._u is not u:  # the u buffers are static: bind them once
+                    agent.action.u = u
             return True
         for action, agent in zip(actions, self.agents):
             self._set_action(action, agent)
@@ -721,19 +722,21 @@ class Environment(TorchVectorizedObject):
         elif self._bad_action_event is not None and not self._bad_action_event.query():
             return  # the previous read-back is still in flight; the flag is sticky, nothing is lost
         self._bad_action_host.copy_(self._bad_action_flag, non_blocking=True)
+        self._readback_pending = True
         if self._bad_action_event is not None:
             self._bad_action_event.record()
 
     def _raise_deferred_action_errors(self, wait: bool = False):
         """Raises if a previous step flagged an invalid action.  Never stalls the pipeline: the
         flag is looked at only once its asynchronous read-back has landed (``wait=True`` forces it)."""
-        if self._bad_action_host is None:
+        if self._bad_action_host is None or not getattr(self, "_readback_pending", False):
             return
         if self._bad_action_event is not None:
             if wait:
                 self._bad_action_event.synchronize()
             elif not self._bad_action_event.query():
                 return
+        self._readback_pending = False  # the copy has landed: look at it once
         if bool(self._bad_action_host.item()):
             self._bad_action_flag.zero_()
             self._bad_action_host.zero_()
