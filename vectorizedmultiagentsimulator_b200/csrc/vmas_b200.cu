@@ -755,33 +755,34 @@ __global__ void __launch_bounds__(BLOCK) step_tpe_kernel(const StepArgs a) {
 // ---------------------------------------------------------------------------------------------
 DEVI void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(256) broad_phase_kernel(const StepArgs a) {
+// Block = (32 envs, BROAD_SLICES item slices): lane = env, each warp tests every
+// BROAD_SLICES-th masked item for its 32 envs (item parameters are warp-uniform), so the chain
+// of dependent loads per thread is short and there are B * BROAD_SLICES / 32 warps to hide it.
+constexpr int BROAD_SLICES = 8;
+
+__global__ void __launch_bounds__(32 * BROAD_SLICES) broad_phase_kernel(const StepArgs a) {
   extern __shared__ uint32_t s_bits[];
   const int W = a.mask_words;
-  for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = 0u;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int w = tid; w < W; w += 32 * BROAD_SLICES) s_bits[w] = 0u;
   __syncthreads();
-  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long env = (long)blockIdx.x * 32 + threadIdx.x;
   const bool live = env < a.cfg.batch_dim;
   const int E = a.cfg.n_entities;
   const float2* pos = reinterpret_cast<const float2*>(a.st.pos) + (size_t)(live ? env : 0) * E;
-  for (int j = 0; j < E; j += 4) prefetch_l1(pos + j);  // the whole row is on its way before item 0 asks
-  for (int w = 0; w < W; ++w) {
-    uint32_t bits = 0u;
-    const int n = min(32, a.cfg.n_masked - 32 * w);
-    for (int j = 0; j < n; ++j) {
-      const int item = __ldg(a.tb.masked_items + 32 * w + j);
-      const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
-      const float thr = __ldg(a.tb.item_f32 + (size_t)item * VMAS_IF_COLS + VMAS_IF_BROAD_THR);
-      if (live) {
-        const float2 pa = pos[ii.y], pb = pos[ii.z];
-        if (norm2(pa.x - pb.x, pa.y - pb.y) <= thr) bits |= 1u << j;
-      }
+  for (int j = threadIdx.y; j < a.cfg.n_masked; j += BROAD_SLICES) {
+    const int item = __ldg(a.tb.masked_items + j);
+    const int4 ii = __ldg(reinterpret_cast<const int4*>(a.tb.item_i32) + item);
+    const float thr = __ldg(a.tb.item_f32 + (size_t)item * VMAS_IF_COLS + VMAS_IF_BROAD_THR);
+    bool near = false;
+    if (live) {
+      const float2 pa = pos[ii.y], pb = pos[ii.z];
+      near = norm2(pa.x - pb.x, pa.y - pb.y) <= thr;
     }
-    bits = __reduce_or_sync(0xffffffffu, bits);
-    if ((threadIdx.x & 31) == 0 && bits) atomicOr(&s_bits[w], bits);
+    if (__any_sync(0xffffffffu, near) && threadIdx.x == 0) atomicOr(&s_bits[j >> 5], 1u << (j & 31));
   }
   __syncthreads();
-  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+  for (int w = tid; w < W; w += 32 * BROAD_SLICES) {
     const uint32_t b = s_bits[w];
     if (b) atomicOr(&a.mask[w], b);
   }
@@ -1107,6 +1108,7 @@ struct PairBatchArgs {
   QueryArgs base;
   const int32_t* pairs;  // [K, 2]
   int32_t n_pairs;
+  int32_t chunk;  // pairs per thread
 };
 
 // Thread = env; a block evaluates PAIR_CHUNK pairs for its tile of envs, so the tile's slab rows
@@ -1123,8 +1125,8 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
   // paying one cold-miss latency per pair, one after the other
   for (int j = 0; j < 2 * a.base.cfg.n_entities; j += 8) prefetch_l1(a.base.st.pos + 2 * env_base + j);
   for (int j = 0; j < a.base.cfg.n_entities; j += 8) prefetch_l1(a.base.st.rot + env_base + j);
-  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * PAIR_CHUNK);
-  for (int k = blockIdx.y * PAIR_CHUNK; k < k_end; ++k) {
+  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * a.chunk);
+  for (int k = blockIdx.y * a.chunk; k < k_end; ++k) {
     const long idx = (long)k * B + env;
     const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
     const EntG ga = load_ent(a.base, ia, env_base), gb = load_ent(a.base, ib, env_base);
@@ -1197,84 +1199,88 @@ struct ObsArgs {
   int32_t rows, width, batch_dim, n_entities;
 };
 
-DEVI float obs_source(const ObsArgs& a, int code, long env) {
+// A source decoded once per thread: base pointer of the field + offset, and the env pitch.
+struct ObsSrc {
+  const float* p;
+  unsigned pitch;
+};
+DEVI ObsSrc obs_decode(const ObsArgs& a, int code) {
   const int field = code >> 24, off = code & 0xFFFFFF;
-  const size_t E = (size_t)a.n_entities;
+  const unsigned E = (unsigned)a.n_entities;
+  ObsSrc s;
   switch (field) {
-    case VMAS_OBS_POS: return a.st.pos[(size_t)env * 2 * E + off];
-    case VMAS_OBS_VEL: return a.st.vel[(size_t)env * 2 * E + off];
-    case VMAS_OBS_ROT: return a.st.rot[(size_t)env * E + off];
-    default: return a.st.ang_vel[(size_t)env * E + off];
+    case VMAS_OBS_POS: s.p = a.st.pos + off; s.pitch = 2 * E; break;
+    case VMAS_OBS_VEL: s.p = a.st.vel + off; s.pitch = 2 * E; break;
+    case VMAS_OBS_ROT: s.p = a.st.rot + off; s.pitch = E; break;
+    default: s.p = a.st.ang_vel + off; s.pitch = E; break;
   }
+  return s;
 }
 
-DEVI float obs_column(const ObsArgs& a, int4 c, long env) {
-  float v = obs_source(a, c.y, env);
-  if (c.x == VMAS_OBS_DIFF) {
-    v = v - obs_source(a, c.z, env);
-  } else if (c.x == VMAS_OBS_REMAINDER) {  // torch.remainder: sign follows the modulus
-    const float m = __int_as_float(c.w);
-    float r = fmodf(v, m);
-    if (r != 0.f && (signbit(m) != signbit(r))) r = r + m;
-    v = r;
-  }
-  return v;
+__device__ __noinline__ float obs_remainder(float v, float m) {  // torch.remainder: sign follows the modulus
+  float r = fmodf(v, m);
+  if (r != 0.f && (signbit(m) != signbit(r))) r = r + m;
+  return r;
 }
 
-// Block = OBS_TILE consecutive envs of one observation row (blockIdx.y).  Phase 1: lanes are
-// envs and each warp walks a slice of the columns, so the column's op / source are uniform across
-// the warp (no divergence; the env tile's slab rows are fetched once and re-read from L1) and the
-// value goes to a shared-memory tile.  Phase 2: the tile is contiguous in the output
-// ([row][env][col]), so it is streamed out with fully coalesced stores, skipping SKIP columns.
-constexpr int OBS_TILE = 64;
+// blockIdx.y = observation row.  threadIdx.x = a group of VEC adjacent columns, threadIdx.y = env
+// lane: a thread keeps its column group and walks OBS_ENVS_PER_THREAD envs, so the column table is
+// decoded once per thread (pointers + pitches in registers) and the inner loop is a handful of
+// loads, at most one subtraction per column and one vector store; consecutive lanes write
+// consecutive pieces of an env's row.
+constexpr int OBS_ENVS_PER_THREAD = 8;
 
+template <int VEC>
 __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
-  extern __shared__ int4 s_cols[];                                  // [width]
-  const int F = a.width, pitch = F | 1;                             // odd pitch: conflict-free
-  float* tile = reinterpret_cast<float*>(s_cols + F);               // [OBS_TILE][pitch]
+  const int groups = a.width / VEC;
+  const int g = threadIdx.x;
+  if (g >= groups) return;
   const int row = blockIdx.y;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const long env0 = (long)blockIdx.x * OBS_TILE;
-  const size_t E = (size_t)a.n_entities;
-  // the tile's slab rows are contiguous: ask for them now, while the column table is on its way
-  {
-    const long n_env = min((long)OBS_TILE, (long)a.batch_dim - env0);
-    const size_t lines2 = (size_t)n_env * 2 * E / 32 + 1, lines1 = (size_t)n_env * E / 32 + 1;
-    for (size_t l = tid; l < lines2; l += 256) {
-      prefetch_l1(a.st.pos + (size_t)env0 * 2 * E + 32 * l);
-      prefetch_l1(a.st.vel + (size_t)env0 * 2 * E + 32 * l);
-    }
-    for (size_t l = tid; l < lines1; l += 256) {
-      prefetch_l1(a.st.rot + (size_t)env0 * E + 32 * l);
-      prefetch_l1(a.st.ang_vel + (size_t)env0 * E + 32 * l);
-    }
-  }
-  for (int c = tid; c < F; c += 256) s_cols[c] = __ldg(reinterpret_cast<const int4*>(a.cols) + (size_t)row * F + c);
-  __syncthreads();
+  const int4* table = reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + g * VEC;
+  int op[VEC];
+  ObsSrc sa[VEC], sb[VEC];
+  float par[VEC];
+  bool any = false, all = true;
 #pragma unroll
-  for (int half = 0; half < OBS_TILE / 32; ++half) {
-    const int e = half * 32 + threadIdx.x;
-    const long env = env0 + e;
-    if (env < a.batch_dim) {
-      for (int c = threadIdx.y; c < F; c += 8) {
-        const int4 col = s_cols[c];
-        if (col.x == VMAS_OBS_SKIP) continue;  // warp-uniform
-        tile[e * pitch + c] = obs_column(a, col, env);
+  for (int k = 0; k < VEC; ++k) {
+    const int4 c = __ldg(table + k);
+    op[k] = c.x;
+    sa[k] = obs_decode(a, c.y);
+    sb[k] = obs_decode(a, c.z);
+    par[k] = __int_as_float(c.w);
+    any |= c.x != VMAS_OBS_SKIP;
+    all &= c.x != VMAS_OBS_SKIP;
+  }
+  if (!any) return;  // columns owned by another producer (LIDAR, the scenario)
+  const unsigned env0 = blockIdx.x * (blockDim.y * OBS_ENVS_PER_THREAD) + threadIdx.y;
+  float* out = a.out + ((size_t)row * a.batch_dim) * a.width + g * VEC;
+#pragma unroll 2
+  for (int i = 0; i < OBS_ENVS_PER_THREAD; ++i) {
+    const unsigned env = env0 + i * blockDim.y;
+    if (env >= (unsigned)a.batch_dim) break;
+    float v[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v[k] = 0.f;
+      if (op[k] != VMAS_OBS_SKIP) {
+        v[k] = sa[k].p[(size_t)env * sa[k].pitch];
+        if (op[k] == VMAS_OBS_DIFF) v[k] = v[k] - sb[k].p[(size_t)env * sb[k].pitch];
+        if (op[k] == VMAS_OBS_REMAINDER) v[k] = obs_remainder(v[k], par[k]);
       }
     }
-  }
-  __syncthreads();
-  const long n_env = min((long)OBS_TILE, (long)a.batch_dim - env0);
-  float* dst = a.out + ((size_t)row * a.batch_dim + env0) * F;
-  int e = tid / F, c = tid - e * F;
-  const int de = 256 / F, dc = 256 - de * F;
-  for (long i = tid; i < n_env * F; i += 256) {
-    if (s_cols[c].x != VMAS_OBS_SKIP) dst[i] = tile[e * pitch + c];
-    e += de;
-    c += dc;
-    if (c >= F) {
-      c -= F;
-      ++e;
+    float* dst = out + (size_t)env * a.width;
+    if (all) {
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+      } else {
+        dst[0] = v[0];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (op[k] != VMAS_OBS_SKIP) dst[k] = v[k];
     }
   }
 }
@@ -1429,9 +1435,8 @@ static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
 }
 
 static int launch_broad_phase(const StepArgs& args, cudaStream_t stream) {
-  const int threads = 256;
-  const long blocks = ((long)args.cfg.batch_dim + threads - 1) / threads;
-  broad_phase_kernel<<<(unsigned)blocks, threads, args.mask_words * sizeof(uint32_t), stream>>>(args);
+  const long blocks = ((long)args.cfg.batch_dim + 31) / 32;
+  broad_phase_kernel<<<(unsigned)blocks, dim3(32, BROAD_SLICES), args.mask_words * sizeof(uint32_t), stream>>>(args);
   CUDA_OK(cudaGetLastError());
   return 1;
 }
@@ -1692,11 +1697,22 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   a.batch_dim = cfg->batch_dim;
   a.n_entities = cfg->n_entities;
   if (n_rows > 65535) return fail("more than 65535 observation rows%s");
-  const size_t smem = (size_t)width * sizeof(int4) + (size_t)OBS_TILE * (width | 1) * sizeof(float);
-  if (smem > 48 * 1024) return fail("observation rows wider than 140 columns are not supported%s");
-  const dim3 block(32, 8);
-  const dim3 grid((unsigned)((cfg->batch_dim + OBS_TILE - 1) / OBS_TILE), (unsigned)n_rows);
-  gather_observations_kernel<<<grid, block, smem, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  // vector width: the widest that divides the row (and keeps every store aligned)
+  const int vec = (width % 4 == 0 && ((uintptr_t)out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)out % 8 == 0)) ? 2 : 1;
+  const int groups = width / vec;
+  if (groups > 256) return fail("observation rows wider than 1024 columns are not supported%s");
+  const unsigned bx = (unsigned)groups, by = 256 / bx;
+  const dim3 block(bx, by);
+  const unsigned envs_per_block = by * OBS_ENVS_PER_THREAD;
+  const dim3 grid((unsigned)((cfg->batch_dim + envs_per_block - 1) / envs_per_block), (unsigned)n_rows);
+  if (vec == 4) {
+    gather_observations_kernel<4><<<grid, block, 0, stream>>>(a);
+  } else if (vec == 2) {
+    gather_observations_kernel<2><<<grid, block, 0, stream>>>(a);
+  } else {
+    gather_observations_kernel<1><<<grid, block, 0, stream>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
 }
@@ -1718,7 +1734,10 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   a.pairs = pairs;
   a.n_pairs = n_pairs;
   const int threads = 128;
-  const int chunks = (n_pairs + PAIR_CHUNK - 1) / PAIR_CHUNK;
+  // small batches: one pair per thread (more warps to hide latency); large ones: PAIR_CHUNK pairs
+  // per thread so a tile's slab rows are re-read from L1
+  a.chunk = ((long)cfg->batch_dim * n_pairs <= (1L << 19)) ? 1 : PAIR_CHUNK;
+  const int chunks = (n_pairs + a.chunk - 1) / a.chunk;
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
   pair_query_batched_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);

@@ -511,7 +511,10 @@ class Environment(TorchVectorizedObject):
             else:
                 small.setdefault(head.dtype, []).extend(ids)
         for dtype, ids in small.items():
-            packs.append((torch.cat([leaves[i].reshape(-1) for i in ids]), ids))
+            if len(ids) == 1 and leaves[ids[0]].is_contiguous():
+                packs.append((leaves[ids[0]].reshape(-1), ids))  # nothing to gather: no copy node
+            else:
+                packs.append((torch.cat([leaves[i].reshape(-1) for i in ids]), ids))
         self._graph_out_spec = spec
         self._graph_out_shapes = [tuple(t.shape) for t in leaves]
         self._graph_out_packs = packs
