@@ -1199,23 +1199,11 @@ struct ObsArgs {
   int32_t rows, width, batch_dim, n_entities;
 };
 
-// A source decoded once per thread: base pointer of the field + offset, and the env pitch.
+// A source decoded once per thread: where the field's tile starts in shared memory, the element
+// offset inside an env's row, and the row pitch.
 struct ObsSrc {
-  const float* p;
-  unsigned pitch;
+  unsigned base, pitch;
 };
-DEVI ObsSrc obs_decode(const ObsArgs& a, int code) {
-  const int field = code >> 24, off = code & 0xFFFFFF;
-  const unsigned E = (unsigned)a.n_entities;
-  ObsSrc s;
-  switch (field) {
-    case VMAS_OBS_POS: s.p = a.st.pos + off; s.pitch = 2 * E; break;
-    case VMAS_OBS_VEL: s.p = a.st.vel + off; s.pitch = 2 * E; break;
-    case VMAS_OBS_ROT: s.p = a.st.rot + off; s.pitch = E; break;
-    default: s.p = a.st.ang_vel + off; s.pitch = E; break;
-  }
-  return s;
-}
 
 __device__ __noinline__ float obs_remainder(float v, float m) {  // torch.remainder: sign follows the modulus
   float r = fmodf(v, m);
@@ -1223,18 +1211,50 @@ __device__ __noinline__ float obs_remainder(float v, float m) {  // torch.remain
   return r;
 }
 
-// blockIdx.y = observation row.  threadIdx.x = a group of VEC adjacent columns, threadIdx.y = env
-// lane: a thread keeps its column group and walks OBS_ENVS_PER_THREAD envs, so the column table is
-// decoded once per thread (pointers + pitches in registers) and the inner loop is a handful of
-// loads, at most one subtraction per column and one vector store; consecutive lanes write
-// consecutive pieces of an env's row.
-constexpr int OBS_ENVS_PER_THREAD = 8;
-
+// blockIdx.y = observation row, blockIdx.x = a tile of `tile_envs` consecutive envs.
+// (1) The tile's slab rows (pos, vel, rot, ang_vel: four contiguous global ranges) are copied to
+//     shared memory with coalesced vector loads — reading the scattered columns straight from
+//     global memory costs a 32-byte sector per 4-byte value.
+// (2) threadIdx.x = a group of VEC adjacent columns, threadIdx.y = env lane: a thread decodes its
+//     columns once (shared-memory offsets in registers) and walks the tile's envs; per env a
+//     handful of shared-memory loads, at most one subtraction per column and one vector store;
+//     consecutive lanes write consecutive pieces of an env's output row.
 template <int VEC>
-__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a) {
+__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a, const int tile_envs) {
+  extern __shared__ float4 s_state4[];
+  float* s_state = reinterpret_cast<float*>(s_state4);
+  const unsigned E = (unsigned)a.n_entities;
+  const long env0 = (long)blockIdx.x * tile_envs;
+  const unsigned n_env = (unsigned)min((long)tile_envs, (long)a.batch_dim - env0);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_threads = blockDim.x * blockDim.y;
+  // field f occupies s_state[base_f, base_f + tile_envs * pitch_f); bases are multiples of 4 floats
+  const unsigned pitch_f[4] = {2 * E, 2 * E, E, E};
+  unsigned base_f[4];
+  {
+    unsigned at = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      base_f[f] = at;
+      at += ((unsigned)tile_envs * pitch_f[f] + 3u) & ~3u;
+    }
+  }
+  const float* src_f[4] = {a.st.pos, a.st.vel, a.st.rot, a.st.ang_vel};
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const float* src = src_f[f] + (size_t)env0 * pitch_f[f];  // 16-byte aligned: env0 * pitch is a multiple of 4
+    const unsigned n = n_env * pitch_f[f];
+    for (unsigned i = 4 * tid; i < n; i += 4 * n_threads) {
+      if (i + 4 <= n) {
+        *reinterpret_cast<float4*>(s_state + base_f[f] + i) = *reinterpret_cast<const float4*>(src + i);
+      } else {
+        for (unsigned k = i; k < n; ++k) s_state[base_f[f] + k] = src[k];
+      }
+    }
+  }
+  __syncthreads();
+
   const int groups = a.width / VEC;
   const int g = threadIdx.x;
-  if (g >= groups) return;
   const int row = blockIdx.y;
   const int4* table = reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + g * VEC;
   int op[VEC];
@@ -1245,30 +1265,29 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
   for (int k = 0; k < VEC; ++k) {
     const int4 c = __ldg(table + k);
     op[k] = c.x;
-    sa[k] = obs_decode(a, c.y);
-    sb[k] = obs_decode(a, c.z);
+    const int fa = (c.y >> 24) & 3, fb = (c.z >> 24) & 3;
+    sa[k].base = base_f[fa] + (unsigned)(c.y & 0xFFFFFF);
+    sa[k].pitch = pitch_f[fa];
+    sb[k].base = base_f[fb] + (unsigned)(c.z & 0xFFFFFF);
+    sb[k].pitch = pitch_f[fb];
     par[k] = __int_as_float(c.w);
     any |= c.x != VMAS_OBS_SKIP;
     all &= c.x != VMAS_OBS_SKIP;
   }
-  if (!any) return;  // columns owned by another producer (LIDAR, the scenario)
-  const unsigned env0 = blockIdx.x * (blockDim.y * OBS_ENVS_PER_THREAD) + threadIdx.y;
-  float* out = a.out + ((size_t)row * a.batch_dim) * a.width + g * VEC;
-#pragma unroll 2
-  for (int i = 0; i < OBS_ENVS_PER_THREAD; ++i) {
-    const unsigned env = env0 + i * blockDim.y;
-    if (env >= (unsigned)a.batch_dim) break;
+  if (g >= groups || !any) return;  // columns owned by another producer (LIDAR, the scenario)
+  float* out = a.out + ((size_t)row * a.batch_dim + env0) * a.width + g * VEC;
+  for (unsigned e = threadIdx.y; e < n_env; e += blockDim.y) {
     float v[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       v[k] = 0.f;
       if (op[k] != VMAS_OBS_SKIP) {
-        v[k] = sa[k].p[(size_t)env * sa[k].pitch];
-        if (op[k] == VMAS_OBS_DIFF) v[k] = v[k] - sb[k].p[(size_t)env * sb[k].pitch];
+        v[k] = s_state[sa[k].base + e * sa[k].pitch];
+        if (op[k] == VMAS_OBS_DIFF) v[k] = v[k] - s_state[sb[k].base + e * sb[k].pitch];
         if (op[k] == VMAS_OBS_REMAINDER) v[k] = obs_remainder(v[k], par[k]);
       }
     }
-    float* dst = out + (size_t)env * a.width;
+    float* dst = out + (size_t)e * a.width;
     if (all) {
       if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -1704,14 +1723,19 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   if (groups > 256) return fail("observation rows wider than 1024 columns are not supported%s");
   const unsigned bx = (unsigned)groups, by = 256 / bx;
   const dim3 block(bx, by);
-  const unsigned envs_per_block = by * OBS_ENVS_PER_THREAD;
-  const dim3 grid((unsigned)((cfg->batch_dim + envs_per_block - 1) / envs_per_block), (unsigned)n_rows);
+  // tile: a multiple of 4 envs (keeps every field's tile 16-byte aligned) whose state fits 32 KB
+  const size_t per_env = 6u * (size_t)cfg->n_entities * sizeof(float);
+  int tile = 128;
+  while (tile > 4 && tile * per_env + 64 > 32 * 1024) tile /= 2;
+  if (tile * per_env + 64 > 48 * 1024) return fail("worlds with more than ~500 entities are not supported here%s");
+  const size_t smem = tile * per_env + 64;
+  const dim3 grid((unsigned)((cfg->batch_dim + tile - 1) / tile), (unsigned)n_rows);
   if (vec == 4) {
-    gather_observations_kernel<4><<<grid, block, 0, stream>>>(a);
+    gather_observations_kernel<4><<<grid, block, smem, stream>>>(a, tile);
   } else if (vec == 2) {
-    gather_observations_kernel<2><<<grid, block, 0, stream>>>(a);
+    gather_observations_kernel<2><<<grid, block, smem, stream>>>(a, tile);
   } else {
-    gather_observations_kernel<1><<<grid, block, 0, stream>>>(a);
+    gather_observations_kernel<1><<<grid, block, smem, stream>>>(a, tile);
   }
   CUDA_OK(cudaGetLastError());
   return 1;
@@ -1734,9 +1758,9 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   a.pairs = pairs;
   a.n_pairs = n_pairs;
   const int threads = 128;
-  // small batches: one pair per thread (more warps to hide latency); large ones: PAIR_CHUNK pairs
-  // per thread so a tile's slab rows are re-read from L1
-  a.chunk = ((long)cfg->batch_dim * n_pairs <= (1L << 19)) ? 1 : PAIR_CHUNK;
+  // a few pairs: one per thread (more warps to hide latency); many: PAIR_CHUNK per thread so a
+  // tile's slab rows are fetched once and re-read from L1
+  a.chunk = n_pairs <= 4 ? 1 : PAIR_CHUNK;
   const int chunks = (n_pairs + a.chunk - 1) / a.chunk;
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
