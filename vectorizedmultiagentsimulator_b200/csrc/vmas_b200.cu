@@ -1228,29 +1228,34 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
   const unsigned n_env = (unsigned)min((long)tile_envs, (long)a.batch_dim - env0);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_threads = blockDim.x * blockDim.y;
   // field f occupies s_state[base_f, base_f + tile_envs * pitch_f); bases are multiples of 4 floats
-  const unsigned pitch_f[4] = {2 * E, 2 * E, E, E};
-  unsigned base_f[4];
-  {
-    unsigned at = 0;
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      base_f[f] = at;
-      at += ((unsigned)tile_envs * pitch_f[f] + 3u) & ~3u;
-    }
-  }
-  const float* src_f[4] = {a.st.pos, a.st.vel, a.st.rot, a.st.ang_vel};
-#pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    const float* src = src_f[f] + (size_t)env0 * pitch_f[f];  // 16-byte aligned: env0 * pitch is a multiple of 4
-    const unsigned n = n_env * pitch_f[f];
+  // (scalars, not arrays: dynamically indexed arrays would live in local memory)
+  const unsigned T = (unsigned)tile_envs;
+  const unsigned base_vel = (T * 2 * E + 3u) & ~3u;
+  const unsigned base_rot = base_vel + ((T * 2 * E + 3u) & ~3u);
+  const unsigned base_w = base_rot + ((T * E + 3u) & ~3u);
+  auto stage = [&](const float* field, unsigned pitch, unsigned base) {
+    const float* src = field + (size_t)env0 * pitch;  // 16-byte aligned: env0 * pitch is a multiple of 4
+    const unsigned n = n_env * pitch;
     for (unsigned i = 4 * tid; i < n; i += 4 * n_threads) {
       if (i + 4 <= n) {
-        *reinterpret_cast<float4*>(s_state + base_f[f] + i) = *reinterpret_cast<const float4*>(src + i);
+        *reinterpret_cast<float4*>(s_state + base + i) = *reinterpret_cast<const float4*>(src + i);
       } else {
-        for (unsigned k = i; k < n; ++k) s_state[base_f[f] + k] = src[k];
+        for (unsigned k = i; k < n; ++k) s_state[base + k] = src[k];
       }
     }
-  }
+  };
+  stage(a.st.pos, 2 * E, 0u);
+  stage(a.st.vel, 2 * E, base_vel);
+  stage(a.st.rot, E, base_rot);
+  stage(a.st.ang_vel, E, base_w);
+  auto decode = [&](int code) {
+    const int field = (code >> 24) & 3;
+    const unsigned off = (unsigned)(code & 0xFFFFFF);
+    ObsSrc r;
+    r.base = off + (field == VMAS_OBS_POS ? 0u : field == VMAS_OBS_VEL ? base_vel : field == VMAS_OBS_ROT ? base_rot : base_w);
+    r.pitch = field <= VMAS_OBS_VEL ? 2 * E : E;
+    return r;
+  };
   __syncthreads();
 
   const int groups = a.width / VEC;
@@ -1265,11 +1270,8 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
   for (int k = 0; k < VEC; ++k) {
     const int4 c = __ldg(table + k);
     op[k] = c.x;
-    const int fa = (c.y >> 24) & 3, fb = (c.z >> 24) & 3;
-    sa[k].base = base_f[fa] + (unsigned)(c.y & 0xFFFFFF);
-    sa[k].pitch = pitch_f[fa];
-    sb[k].base = base_f[fb] + (unsigned)(c.z & 0xFFFFFF);
-    sb[k].pitch = pitch_f[fb];
+    sa[k] = decode(c.y);
+    sb[k] = decode(c.z);
     par[k] = __int_as_float(c.w);
     any |= c.x != VMAS_OBS_SKIP;
     all &= c.x != VMAS_OBS_SKIP;
