@@ -162,6 +162,8 @@ int vmas_b200_cast_rays(const VmasWorldConfig* cfg, const VmasPlanTables* tb, co
  *                scenarios/navigation.py:260 feeds to the policy) instead of the distance
  */
 #define VMAS_RAYS_RANGE_MINUS_DISTANCE 1
+/* the caller guarantees every entity in `targets` is a sphere: a kernel without box / line code */
+#define VMAS_RAYS_SPHERE_TARGETS 2
 int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                                 int32_t n_sensors, const int32_t* src, const int32_t* target_off,
                                 const int32_t* targets, const float* angles, const float* max_range,
@@ -205,7 +207,10 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
  * K entity pairs in one launch: mode 0 = World.get_distance (fp32), 1 = World.is_overlapping
  * (uint8), 2 = distance between the two centres (fp32; the quantity World.collides thresholds,
  * ref core.py:2797-2799).   pairs: device int32[K, 2];  out: [K, B].
+ * `mode | VMAS_QUERY_SPHERES`: the caller guarantees every entity named in `pairs` is a sphere;
+ * the launch then uses a kernel without the box / line closest-point code (same results).
  */
+#define VMAS_QUERY_SPHERES 0x100
 int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                                  const int32_t* pairs, int32_t n_pairs, int32_t mode, void* out,
                                  void* cuda_stream);

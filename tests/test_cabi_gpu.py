@@ -323,6 +323,13 @@ def test_batched_lidar_equals_per_sensor_launches(name):
         B = desc.batch_dim
         out = torch.empty(len(recs), B, n_rays, device=device)
         _native.cast_rays_batched(lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, out)
+        from vectorizedmultiagentsimulator_b200.simulator import plan as P
+
+        if all(int(tables.ent_i32[t, 0]) == P.SHAPE_SPHERE for t in flat):
+            hinted = torch.empty_like(out)  # the sphere-only kernel must return the same bits
+            _native.cast_rays_batched(lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, hinted,
+                                      flags=_native.RAYS_SPHERE_TARGETS)
+            assert torch.equal(hinted, out), f"{name} step {step}: sphere-only LIDAR kernel differs"
         for q, r in enumerate(recs):
             one = torch.empty(B, n_rays, device=device)
             t = torch.tensor(r["targets"], dtype=torch.int32, device=device)
@@ -471,3 +478,27 @@ def test_distance_shaping_equals_torch_expressions():
     rew2 = torch.empty(K, B, device=device)
     _native.distance_shaping(lib, dt, slab, pairs, factor, prev2, None, rew2)
     assert torch.equal(rew2, rew) and torch.equal(prev2, prev)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sphere_only_pair_kernel_equals_general_kernel(name):
+    """The VMAS_QUERY_SPHERES fast path returns the bits of the general kernel."""
+    from vectorizedmultiagentsimulator_b200.simulator import plan as P
+
+    fix, desc, tables = load(name)
+    spheres = [i for i in range(desc.n_entities) if int(tables.ent_i32[i, 0]) == P.SHAPE_SPHERE]
+    if len(spheres) < 2:
+        pytest.skip("fewer than two spheres")
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    dt = _device_tables(tables, {}, device)
+    slab = _Slab(fix["final_state"], device)
+    B = desc.batch_dim
+    pair_list = [(a, b) for i, a in enumerate(spheres) for b in spheres[i + 1 :]][:40] + [(spheres[0], spheres[0])]
+    pairs = torch.tensor(pair_list, dtype=torch.int32, device=device)
+    for mode, dtype in ((0, torch.float32), (1, torch.bool), (2, torch.float32)):
+        general = torch.empty(len(pair_list), B, dtype=dtype, device=device)
+        fast = torch.empty_like(general)
+        _native.pair_query_batched(lib, dt, slab, pairs, mode, general)
+        _native.pair_query_batched(lib, dt, slab, pairs, mode | _native.QUERY_SPHERES, fast)
+        assert torch.equal(general, fast), f"{name} mode {mode}"

@@ -499,6 +499,8 @@ def distance_shaping(lib, dt: DeviceTables, slab, pairs, factor: float, prev, di
 
 
 RAYS_RANGE_MINUS_DISTANCE = 1
+RAYS_SPHERE_TARGETS = 2
+QUERY_SPHERES = 0x100
 OBS_SKIP, OBS_COPY, OBS_DIFF, OBS_REMAINDER = 0, 1, 2, 3
 OBS_POS, OBS_VEL, OBS_ROT, OBS_ANG_VEL = 0, 1, 2, 3
 

@@ -213,6 +213,10 @@ class CudaBackend(PlanRuntime):
         return out
 
     # -- batched sensors / queries (one launch for many sensors or pairs) ---------------------------
+    def _all_spheres(self, entity_indices) -> bool:
+        shapes = self.tables.ent_i32[:, 0]
+        return all(int(shapes[i]) == P.SHAPE_SPHERE for i in entity_indices)
+
     def lidar_measure_many(self, sensors) -> Tensor:
         """``[Q, B, R]`` ranges of ``Q`` LIDARs with the same number of rays, in one launch."""
         self.refresh()
@@ -234,12 +238,13 @@ class CudaBackend(PlanRuntime):
                 torch.stack([s._angles[0] for s in sensors]).to(self.device, torch.float32).contiguous(),
                 torch.tensor([float(s._max_range) for s in sensors], dtype=torch.float32, device=self.device),
                 n_rays.pop(),
+                self._native.RAYS_SPHERE_TARGETS if self._all_spheres(flat) else 0,
             )
             self._ray_cache[key] = pack
-        src, off, flat, angles, ranges, n_rays = pack
+        src, off, flat, angles, ranges, n_rays, flags = pack
         out = torch.empty(len(sensors), self.world.batch_dim, n_rays, dtype=torch.float32, device=self.device)
         self._native.cast_rays_batched(
-            self.lib, self._dev_tables, self.world.slab, src, off, flat, angles, ranges, n_rays, out
+            self.lib, self._dev_tables, self.world.slab, src, off, flat, angles, ranges, n_rays, out, flags=flags
         )
         self.launches += 1
         return out
@@ -272,7 +277,8 @@ class CudaBackend(PlanRuntime):
                     torch.tensor([float(s._max_range) for s in sensors], dtype=torch.float32, device=self.device),
                     n_rays.pop(),
                     torch.tensor([r * B * F + c for r, c, _, _ in lidars], dtype=torch.int64, device=self.device),
-                    self._native.RAYS_RANGE_MINUS_DISTANCE if lidars[0][3] else 0,
+                    (self._native.RAYS_RANGE_MINUS_DISTANCE if lidars[0][3] else 0)
+                    | (self._native.RAYS_SPHERE_TARGETS if self._all_spheres(flat) else 0),
                 )
             plan.device_cache[id(self)] = dev
         out = torch.empty(plan.n_rows, B, F, dtype=torch.float32, device=self.device)
@@ -313,16 +319,20 @@ class CudaBackend(PlanRuntime):
     def pair_query_many(self, pairs, mode: int) -> Tensor:
         """``[K, B]``: mode 0 distances, 1 overlaps (bool), 2 centre distances, one launch."""
         self.refresh()
-        key = ("pairs",) + tuple((id(a), id(b)) for a, b in pairs)
-        idx = self._ray_cache.get(key)
-        if idx is None:
+        key = ("pairs+hint",) + tuple((id(a), id(b)) for a, b in pairs)
+        cached = self._ray_cache.get(key)
+        if cached is None:
+            from .simulator.core import Sphere
+
             idx = torch.tensor(
                 [[self.index_of(a), self.index_of(b)] for a, b in pairs], dtype=torch.int32, device=self.device
             )
-            self._ray_cache[key] = idx
+            spheres = all(isinstance(e.shape, Sphere) for pair in pairs for e in pair)
+            cached = self._ray_cache[key] = (idx, self._native.QUERY_SPHERES if spheres else 0)
+        idx, hint = cached
         dtype = torch.bool if mode == 1 else torch.float32
         out = torch.empty(len(pairs), self.world.batch_dim, dtype=dtype, device=self.device)
-        self._native.pair_query_batched(self.lib, self._dev_tables, self.world.slab, idx, mode, out)
+        self._native.pair_query_batched(self.lib, self._dev_tables, self.world.slab, idx, mode | hint, out)
         self.launches += 1
         return out
 

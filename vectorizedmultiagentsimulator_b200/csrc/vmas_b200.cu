@@ -806,25 +806,27 @@ struct RayArgs {
   float max_range;
 };
 
+// ref core.py:1414-1490
+DEVI float ray_vs_sphere(V2 o, float dc, float ds, V2 c, float radius, float max_range) {
+  const float half = max_range / 2.f;
+  V2 line_pos = mk(o.x + dc * half, o.y + ds * half);
+  V2 u = c - o;
+  if (!((u.x * dc + u.y * ds) > 0.f)) return max_range;  // behind the sensor
+  V2 closest = closest_point_carrier(line_pos, dc, ds, c);
+  float dn = norm2(c - closest);
+  if (!(dn < radius)) return max_range;  // the carrier passes the sphere by
+  float aa = radius * radius - dn * dn;
+  float m = sqrtf(aa > 0.f ? aa : 1e-8f);
+  return norm2(closest - o) - m;
+}
+
 DEVI float ray_vs_entity(const RayArgs& a, V2 o, float ang, float dc, float ds, int t, size_t env_base) {
   const int shape = __ldg(a.tb.ent_i32 + t * 4);
   const float* ef = a.tb.ent_f32 + (size_t)t * VMAS_EF_COLS;
   const float2 tp = reinterpret_cast<const float2*>(a.st.pos)[env_base + t];
   const V2 c = mk(tp.x, tp.y);
   const float max_range = a.max_range;
-  if (shape == VMAS_SHAPE_SPHERE) {
-    const float radius = __ldg(ef + VMAS_EF_D0);
-    const float half = max_range / 2.f;
-    V2 line_pos = mk(o.x + dc * half, o.y + ds * half);
-    V2 u = c - o;
-    if (!((u.x * dc + u.y * ds) > 0.f)) return max_range;  // behind the sensor
-    V2 closest = closest_point_carrier(line_pos, dc, ds, c);
-    float dn = norm2(c - closest);
-    if (!(dn < radius)) return max_range;  // the carrier passes the sphere by
-    float aa = radius * radius - dn * dn;
-    float m = sqrtf(aa > 0.f ? aa : 1e-8f);
-    return norm2(closest - o) - m;
-  }
+  if (shape == VMAS_SHAPE_SPHERE) return ray_vs_sphere(o, dc, ds, c, __ldg(ef + VMAS_EF_D0), max_range);
   const float trot = a.st.rot[env_base + t];
   if (shape == VMAS_SHAPE_BOX) {
     const float L = __ldg(ef + VMAS_EF_D0), Wd = __ldg(ef + VMAS_EF_D1);
@@ -923,6 +925,8 @@ struct RayBatchArgs {
 // formulation bit for bit (the reach test is an exact early-out, see ray_target_in_reach).
 constexpr int RAY_MASK_WORDS = 2, RAY_MASK_BITS = 32 * RAY_MASK_WORDS;
 
+// SPHERES: the caller's VMAS_RAYS_SPHERE_TARGETS hint — no box / line code in the kernel.
+template <bool SPHERES>
 __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchArgs a) {
   extern __shared__ uint32_t s_reach[];  // [blockDim.y][RAY_MASK_WORDS]
   const int R = a.base.n_rays;
@@ -980,8 +984,29 @@ __global__ void __launch_bounds__(256) cast_rays_batched_kernel(const RayBatchAr
         for (int w = 0; w < RAY_MASK_WORDS; ++w) {
           for (uint32_t rest = bits[w]; rest; rest &= rest - 1) {
             const int t = __ldg(a.all_targets + lo + 32 * w + __ffs(rest) - 1);
-            d = tmin(d, ray_vs_entity(s, o, ang, dc, ds, t, env_base));
+            if constexpr (SPHERES) {
+              const float2 tp = reinterpret_cast<const float2*>(s.st.pos)[env_base + t];
+              const float radius = __ldg(s.tb.ent_f32 + (size_t)t * VMAS_EF_COLS + VMAS_EF_D0);
+              d = tmin(d, ray_vs_sphere(o, dc, ds, mk(tp.x, tp.y), radius, s.max_range));
+            } else {
+              d = tmin(d, ray_vs_entity(s, o, ang, dc, ds, t, env_base));
+            }
           }
+        }
+      } else if constexpr (SPHERES) {  // more targets than mask bits: reach test per ray
+        const V2 o = mk(op.x, op.y);
+        float ds = 0.f, dc = 0.f;
+        bool have_dir = false;
+        for (int i = 0; i < n_targets; ++i) {
+          const int t = __ldg(a.all_targets + lo + i);
+          if (!ray_target_in_reach(s, o, t, env_base)) continue;
+          if (!have_dir) {
+            sincosf(ang, &ds, &dc);
+            have_dir = true;
+          }
+          const float2 tp = reinterpret_cast<const float2*>(s.st.pos)[env_base + t];
+          const float radius = __ldg(s.tb.ent_f32 + (size_t)t * VMAS_EF_COLS + VMAS_EF_D0);
+          d = tmin(d, ray_vs_sphere(o, dc, ds, mk(tp.x, tp.y), radius, s.max_range));
         }
       } else {
         d = cast_one_ray(s, ang, n_targets, [&](int i) { return __ldg(a.all_targets + lo + i); }, env_base);
@@ -1115,6 +1140,35 @@ struct PairBatchArgs {
 // are fetched from L2 once and re-read from L1 for the other pairs (one thread per (pair, env)
 // made every pair re-fetch 32 strided sectors per warp).  Stores are coalesced over envs.
 constexpr int PAIR_CHUNK = 8;
+
+// Sphere-only pair batches (the caller's VMAS_QUERY_SPHERES hint): a few instructions per pair and a
+// tiny code footprint — the general kernel drags the box / line closest-point code along.
+__global__ void __launch_bounds__(128) pair_query_spheres_kernel(const PairBatchArgs a) {
+  const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long B = a.base.cfg.batch_dim;
+  if (env >= B) return;
+  const float2* row = reinterpret_cast<const float2*>(a.base.st.pos) + (size_t)env * a.base.cfg.n_entities;
+  for (int j = 0; j < a.base.cfg.n_entities; j += 4) prefetch_l1(row + j);
+  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * a.chunk);
+  for (int k = blockIdx.y * a.chunk; k < k_end; ++k) {
+    const long idx = (long)k * B + env;
+    const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
+    const float2 pa = row[ia], pb = row[ib];
+    const float centre = norm2(pa.x - pb.x, pa.y - pb.y);
+    if (a.base.mode == 2) {
+      static_cast<float*>(a.base.out)[idx] = centre;
+    } else {
+      const float ra = __ldg(a.base.tb.ent_f32 + (size_t)ia * VMAS_EF_COLS + VMAS_EF_D0);
+      const float rb = __ldg(a.base.tb.ent_f32 + (size_t)ib * VMAS_EF_COLS + VMAS_EF_D0);
+      const float d = (centre - ra) - rb;  // ref core.py:1826-1828: (|pa - pb| - ra) - rb
+      if (a.base.mode == 0) {
+        static_cast<float*>(a.base.out)[idx] = d;
+      } else {
+        static_cast<uint8_t*>(a.base.out)[idx] = d < 0.f ? 1 : 0;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatchArgs a) {
   const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1698,8 +1752,12 @@ int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables
   const unsigned bx = (unsigned)(n_rays < 256 ? n_rays : 256), by = 256 / bx;
   const dim3 block(bx, by);
   const dim3 grid((unsigned)((cfg->batch_dim + by - 1) / by), (unsigned)n_sensors);
-  cast_rays_batched_kernel<<<grid, block, by * RAY_MASK_WORDS * sizeof(uint32_t),
-                             static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  const size_t smem = by * RAY_MASK_WORDS * sizeof(uint32_t);
+  if (flags & VMAS_RAYS_SPHERE_TARGETS) {
+    cast_rays_batched_kernel<true><<<grid, block, smem, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  } else {
+    cast_rays_batched_kernel<false><<<grid, block, smem, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
 }
@@ -1748,6 +1806,8 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
                                  void* cuda_stream) {
   if (check_common(cfg, tb, st) < 0) return -1;
   if (!pairs || !out || n_pairs <= 0) return fail("bad pair batch%s");
+  const bool spheres = mode & VMAS_QUERY_SPHERES;
+  mode &= ~VMAS_QUERY_SPHERES;
   if (mode < 0 || mode > 2) return fail("unknown pair query mode%s");
   PairBatchArgs a;
   a.base.cfg = *cfg;
@@ -1766,7 +1826,11 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   const int chunks = (n_pairs + a.chunk - 1) / a.chunk;
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
-  pair_query_batched_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  if (spheres) {
+    pair_query_spheres_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  } else {
+    pair_query_batched_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
 }
