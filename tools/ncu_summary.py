@@ -19,3 +19,6 @@ for r in rows[2:]:
     for w in WANT:
         if w in hdr:
             i = hdr.index(w); print(f'  {w:75s} {r[i]:>16s} {units[i]}')
+    for i, w in enumerate(hdr):  # warp-state breakdown (names differ between ncu versions)
+        if 'issue_stalled' in w and w.endswith('per_issue_active.ratio'):
+            print(f'  {w:75s} {r[i]:>16s} {units[i]}')

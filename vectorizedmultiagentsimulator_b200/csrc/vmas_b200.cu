@@ -1141,6 +1141,13 @@ struct PairBatchArgs {
 // made every pair re-fetch 32 strided sectors per warp).  Stores are coalesced over envs.
 constexpr int PAIR_CHUNK = 8;
 
+// Pairs evaluated by one thread: up to PAIR_CHUNK (the tile's slab rows are fetched once and re-read
+// from L1), fewer when the batch is small so that at least ~64 Ki threads are in flight.
+static int pairs_per_thread(long batch_dim, int n_pairs) {
+  const long c = batch_dim * n_pairs / 65536;
+  return (int)(c < 1 ? 1 : c > PAIR_CHUNK ? PAIR_CHUNK : c);
+}
+
 // Sphere-only pair batches (the caller's VMAS_QUERY_SPHERES hint): a few instructions per pair and a
 // tiny code footprint — the general kernel drags the box / line closest-point code along.
 __global__ void __launch_bounds__(128) pair_query_spheres_kernel(const PairBatchArgs a) {
@@ -1214,7 +1221,7 @@ struct ShapingArgs {
   float* dist;           // [K, B] or null
   float* rew;            // [K, B]
   float factor;
-  int32_t n_pairs, n_entities, batch_dim;
+  int32_t n_pairs, n_entities, batch_dim, chunk;
 };
 
 __global__ void __launch_bounds__(128) distance_shaping_kernel(const ShapingArgs a) {
@@ -1222,8 +1229,8 @@ __global__ void __launch_bounds__(128) distance_shaping_kernel(const ShapingArgs
   if (env >= a.batch_dim) return;
   const float2* row = reinterpret_cast<const float2*>(a.pos) + (size_t)env * a.n_entities;
   for (int j = 0; j < a.n_entities; j += 4) prefetch_l1(row + j);
-  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * PAIR_CHUNK);
-  for (int k = blockIdx.y * PAIR_CHUNK; k < k_end; ++k) {
+  const int k_end = min(a.n_pairs, (int)(blockIdx.y + 1) * a.chunk);
+  for (int k = blockIdx.y * a.chunk; k < k_end; ++k) {
     const size_t idx = (size_t)k * a.batch_dim + env;
     const float2 pa = row[__ldg(a.pairs + 2 * k)], pb = row[__ldg(a.pairs + 2 * k + 1)];
     const float d = norm2(pa.x - pb.x, pa.y - pb.y);
@@ -1820,9 +1827,7 @@ int vmas_b200_pair_query_batched(const VmasWorldConfig* cfg, const VmasPlanTable
   a.pairs = pairs;
   a.n_pairs = n_pairs;
   const int threads = 128;
-  // a few pairs: one per thread (more warps to hide latency); many: PAIR_CHUNK per thread so a
-  // tile's slab rows are fetched once and re-read from L1
-  a.chunk = n_pairs <= 4 ? 1 : PAIR_CHUNK;
+  a.chunk = pairs_per_thread(cfg->batch_dim, n_pairs);
   const int chunks = (n_pairs + a.chunk - 1) / a.chunk;
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
@@ -1851,7 +1856,8 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
   a.n_entities = cfg->n_entities;
   a.batch_dim = cfg->batch_dim;
   const int threads = 128;
-  const int chunks = (n_pairs + PAIR_CHUNK - 1) / PAIR_CHUNK;
+  a.chunk = pairs_per_thread(cfg->batch_dim, n_pairs);
+  const int chunks = (n_pairs + a.chunk - 1) / a.chunk;
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
   distance_shaping_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
