@@ -241,6 +241,9 @@ def main_b200(args):
     import torch.distributed as dist
 
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, in front of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
