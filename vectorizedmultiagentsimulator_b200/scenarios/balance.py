@@ -16,7 +16,7 @@ from ..simulator.utils import Color, ScenarioUtils
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
-        self._obs_plan = self._rew_consts = self._package_on_goal = None
+        self._obs_plan = self._obs_all = self._rew_consts = self._package_on_goal = None
         self.n_agents = kwargs.pop("n_agents", 3)
         self.package_mass = kwargs.pop("package_mass", 5)
         self.random_package_pos_on_line = kwargs.pop("random_package_pos_on_line", True)
@@ -173,7 +173,10 @@ class Scenario(BaseScenario):
         agents = self.world.agents
         if agent is agents[0] or getattr(self, "_obs_all", None) is None:
             self._obs_all = self._observe_all()
-        return self._obs_all[agents.index(agent)]
+        row = self._obs_all[agents.index(agent)]
+        if agent is agents[-1]:
+            self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+        return row
 
     def done(self):
         on_goal, self._package_on_goal = getattr(self, "_package_on_goal", None), None

@@ -18,6 +18,7 @@ from ..simulator.utils import Color, ScenarioUtils, Y
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
+        self._batch = self._obs_all = None  # caches of the batched callbacks belong to one world
         n_agents = kwargs.pop("n_agents", 4)
         n_obstacles = kwargs.pop("n_obstacles", 5)
         self._min_dist_between_entities = kwargs.pop("min_dist_between_entities", 0.15)
@@ -103,7 +104,7 @@ class Scenario(BaseScenario):
     def _batch_setup(self):
         world = self.world
         cache = getattr(self, "_batch", None)
-        if cache is not None and cache["version"] == world._plan_version:
+        if cache is not None and cache["world"] is world and cache["version"] == world._plan_version:
             return cache
         agents, policy, ents = world.agents, world.policy_agents, world.entities
         dev = world.device
@@ -126,6 +127,7 @@ class Scenario(BaseScenario):
             [[pair_row[(id(agents[i]), id(agents[j]))] for j in range(n) if j != i] for i in range(1, n)], device=dev
         )
         cache = dict(
+            world=world,
             version=world._plan_version,
             a0=a0,
             n=n,
@@ -171,7 +173,10 @@ class Scenario(BaseScenario):
                     [[O.pos(a), O.vel(a), O.rel_pos(a, self._target), O.lidar(a.sensors[0])] for a in policy]
                 )
             self._obs_all = world.observe(plan)
-        return self._obs_all[policy.index(agent)]
+        row = self._obs_all[policy.index(agent)]
+        if agent is policy[-1]:
+            self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+        return row
 
     def info(self, agent: Agent) -> Dict[str, Tensor]:
         return {"agent_collision_rew": agent.collision_rew, "agent_distance_rew": agent.dist_rew}

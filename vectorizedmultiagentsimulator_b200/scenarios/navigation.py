@@ -29,6 +29,7 @@ _PALETTE = [
 
 class Scenario(BaseScenario):
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
+        self._batch = self._obs_all = None  # caches of the batched callbacks belong to one world
         self.plot_grid = False
         self.n_agents = kwargs.pop("n_agents", 4)
         self.collisions = kwargs.pop("collisions", True)
@@ -136,7 +137,7 @@ class Scenario(BaseScenario):
     def _batch_setup(self):
         world = self.world
         cache = getattr(self, "_batch", None)
-        if cache is not None and cache["version"] == world._plan_version:
+        if cache is not None and cache["world"] is world and cache["version"] == world._plan_version:
             return cache
         agents, ents = world.agents, world.entities
         dev = world.device
@@ -148,6 +149,7 @@ class Scenario(BaseScenario):
             incidence[agents.index(a), k] = 1.0
             incidence[agents.index(b), k] = 1.0
         cache = dict(
+            world=world,
             version=world._plan_version,
             a0=a0,
             n=len(agents),
@@ -219,7 +221,10 @@ class Scenario(BaseScenario):
                     ]
                 )
             self._obs_all = self.world.observe(plan)  # [A, B, 18]: one gather + one LIDAR launch
-        return self._obs_all[agents.index(agent)]
+        row = self._obs_all[agents.index(agent)]
+        if agent is agents[-1]:
+            self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+        return row
 
     def _done_batched(self):
         c = self._batch_setup()

@@ -148,7 +148,10 @@ class Scenario(BaseScenario):
             for package, flag in zip(self.packages, self._on_goal_terms):
                 block[:, :, plan.column_of(0, flag)] = package.on_goal  # bool -> 0. / 1., every agent
             self._obs_all = block
-        return self._obs_all[agents.index(agent)]
+        row = self._obs_all[agents.index(agent)]
+        if agent is agents[-1]:
+            self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+        return row
 
     def done(self):
         return torch.stack([p.on_goal for p in self.packages], dim=1).all(dim=-1)
