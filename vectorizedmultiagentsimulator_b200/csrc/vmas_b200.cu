@@ -1079,6 +1079,48 @@ DEVI bool box_sphere_overlap(const QueryArgs& q, const EntG& box, const EntG& sp
   return (d_s_b < d_cp_b) || (d_s_cp < dist_min);
 }
 
+// Exact early-out for is_overlapping: true only if the two shapes are separated by clearly more
+// than the overlap threshold (sphere radii / LINE_MIN_DIST, ref core.py:1907-1969), so the answer
+// is "no" without any closest-point arithmetic.  Conservative tests (bounding circles; for boxes
+// the other shape's extent in the box frame) with a 1e-3 margin that dwarfs fp32 rounding.
+DEVI bool overlap_impossible(const EntG& ga, const EntG& gb) {
+  const float M = 1e-3f;
+  const int sa = ga.shape, sb = gb.shape;
+  if (sa == VMAS_SHAPE_SPHERE && sb == VMAS_SHAPE_SPHERE) return false;  // one norm: nothing to save
+  if (sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_BOX) {
+    const float ra = 0.5f * norm2(ga.d0, ga.d1), rb = 0.5f * norm2(gb.d0, gb.d1);
+    const float lim = ra + rb + LINE_MIN_DIST_F + M;
+    const V2 d = ga.p - gb.p;
+    return d.x * d.x + d.y * d.y > lim * lim;
+  }
+  if (sa == VMAS_SHAPE_BOX || sb == VMAS_SHAPE_BOX) {
+    const EntG& box = sa == VMAS_SHAPE_BOX ? ga : gb;
+    const EntG& other = sa == VMAS_SHAPE_BOX ? gb : ga;
+    float sn, cs;
+    sincosf(box.rot, &sn, &cs);
+    const V2 d = other.p - box.p;
+    const float lx = d.x * cs + d.y * sn, ly = d.y * cs - d.x * sn;  // other's centre in the box frame
+    float ex, ey, reach;
+    if (other.shape == VMAS_SHAPE_SPHERE) {
+      ex = ey = 0.f;
+      reach = other.d0 + LINE_MIN_DIST_F + M;
+    } else {  // line: half-length projected on the box axes
+      float so, co;
+      sincosf(other.rot, &so, &co);
+      const float half = other.d0 / 2.f;
+      ex = half * fabsf(co * cs + so * sn);
+      ey = half * fabsf(so * cs - co * sn);
+      reach = LINE_MIN_DIST_F + M;
+    }
+    return fabsf(lx) - ex > box.d0 / 2.f + reach || fabsf(ly) - ey > box.d1 / 2.f + reach;
+  }
+  // line - sphere, line - line: bounding circles
+  const float ra = sa == VMAS_SHAPE_LINE ? ga.d0 / 2.f : ga.d0, rb = sb == VMAS_SHAPE_LINE ? gb.d0 / 2.f : gb.d0;
+  const float lim = ra + rb + LINE_MIN_DIST_F + M;
+  const V2 d = ga.p - gb.p;
+  return d.x * d.x + d.y * d.y > lim * lim;
+}
+
 // ref core.py:1822-1905
 DEVI float pair_distance(const QueryArgs& q, const EntG& ga, const EntG& gb, int ia, int ib) {
   const int sa = ga.shape, sb = gb.shape;
@@ -1117,10 +1159,12 @@ __global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
     static_cast<float*>(q.out)[env] = pair_distance(q, ga, gb, q.a, q.b);
     return;
   }
-  bool over;
+  bool over = false;
   const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
                           (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
-  if (box_sphere) {
+  if (overlap_impossible(ga, gb)) {
+    over = false;
+  } else if (box_sphere) {
     const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
     over = box_sphere_overlap(q, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? q.b : q.a);
   } else {
@@ -1196,10 +1240,12 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
     } else if (a.base.mode == 2) {
       static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
     } else {
-      bool over;
+      bool over = false;
       const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
                               (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
-      if (box_sphere) {
+      if (overlap_impossible(ga, gb)) {
+        over = false;
+      } else if (box_sphere) {
         const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
         over = box_sphere_overlap(a.base, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
       } else {
