@@ -320,19 +320,19 @@ def main_b200(args):
     host_actions = pregenerate_actions(env, W + K, seed=101 + rank, device=device, pin=True)
     act_dev = [torch.empty_like(a, device=device) for a in host_actions[0]]
     obs0, rew0, done0, _ = env.step(dev_actions[0])
-    host_obs = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in obs0]
-    host_rew = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in rew0]
+    # the step's results are read back with one device->host copy per kind (observations of all
+    # agents, rewards of all agents, done): the per-agent tensors are stacked on the device first
+    host_obs = torch.empty((len(obs0),) + tuple(obs0[0].shape), dtype=obs0[0].dtype).pin_memory()
+    host_rew = torch.empty((len(rew0),) + tuple(rew0[0].shape), dtype=rew0[0].dtype).pin_memory()
     host_done = torch.empty(done0.shape, dtype=done0.dtype).pin_memory()
     h2d_bytes = sum(a.numel() * a.element_size() for a in host_actions[0])
-    d2h_bytes = sum(t.numel() * t.element_size() for t in host_obs + host_rew + [host_done])
+    d2h_bytes = sum(t.numel() * t.element_size() for t in (host_obs, host_rew, host_done))
 
     def e2e_step(i):
         # pinned host actions go straight into Environment.step (it copies them to the device)
         obs, rews, dones, _ = env.step(host_actions[W + i])
-        for dst, src in zip(host_obs, obs):
-            dst.copy_(src, non_blocking=True)
-        for dst, src in zip(host_rew, rews):
-            dst.copy_(src, non_blocking=True)
+        host_obs.copy_(torch.stack(obs), non_blocking=True)
+        host_rew.copy_(torch.stack(rews), non_blocking=True)
         host_done.copy_(dones, non_blocking=True)
 
     for t in range(3):
