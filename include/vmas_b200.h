@@ -260,6 +260,60 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
 int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                           uint32_t* mask, void* cuda_stream);
 
+/*
+ * Device-side episode reset.  Env selection, for both calls:
+ *   env_index >= 0            that env only (Environment.reset_at(i), ref environment.py:229-252)
+ *   env_index < 0, mask NULL  every env      (Environment.reset,     ref environment.py:204-227)
+ *   env_index < 0, mask       every env with env_mask[env] != 0 (device uint8[B]) — a batched
+ *                             reset of the envs that are done, which the reference does one
+ *                             reset_at() at a time
+ *
+ * vmas_b200_reset_state: World.reset(env_index) (ref core.py:1179-1181 -> EntityState._reset
+ * core.py:286-296, 371-383): zeroes pos, vel, rot, ang_vel of every entity and force, torque of
+ * every agent in the selected envs, one launch.  `reset_count` (device int32[B] or NULL) is the
+ * per-env episode number; it is incremented for the selected envs.
+ */
+int vmas_b200_reset_state(const VmasWorldConfig* cfg, const VmasState* st, int32_t env_index,
+                          const uint8_t* env_mask, int32_t* reset_count, void* cuda_stream);
+
+/*
+ * ScenarioUtils.spawn_entities_randomly / find_random_pos_for_entity (ref utils.py:241-319):
+ * per selected env, draws `n_spawn` positions one after the other, each uniform in
+ * [x_lo, x_hi] x [y_lo, y_hi] and re-drawn until it is at least `min_dist` away from every
+ * occupied point (the listed slab entities, the extra `occupied` points, and the positions drawn
+ * earlier in this call).  One thread per env, no host synchronisation (the reference loops in
+ * python with one torch.any() sync per attempt).
+ *
+ * Random numbers are Philox4x32-10 with counter (env, reset_count[env], stream_id << 16 | i,
+ * attempt / 2) and key `seed`: the position of draw i of an env is independent of which other
+ * envs are selected in the launch (masked reset == one reset_at per env, bit for bit), and
+ * oracle/reset.py reproduces it on the CPU.  A draw that still overlaps after `max_tries`
+ * attempts keeps its last proposal and `*status` is incremented (the reference would keep looping).
+ */
+#define VMAS_MAX_SPAWN 64
+typedef struct VmasSpawn {
+  int32_t n_spawn;
+  int32_t entity[VMAS_MAX_SPAWN];          /* slab entity that receives draw i, or -1: only written to `out` */
+  int32_t n_occupied_entities;
+  int32_t occupied_entity[VMAS_MAX_SPAWN]; /* slab entities (already placed) to keep away from */
+  const float* occupied;                   /* device fp32 [., n_occupied, 2] further occupied points, or NULL */
+  int32_t n_occupied;
+  int32_t max_tries;                       /* attempts per draw (> 0) */
+  int64_t occupied_env_stride;             /* elements between consecutive envs of `occupied`; 0: shared by all envs */
+  float* out;                              /* device fp32 [B, n_spawn, 2] or NULL: the positions drawn (selected envs only) */
+  float min_dist, x_lo, x_hi, y_lo, y_hi;
+  int32_t env_index;
+  const uint8_t* env_mask;
+  uint64_t seed;
+  uint32_t stream_id;                      /* which spawn call of the reset this is (< 65536) */
+  uint32_t reserved;
+  const int32_t* reset_count;              /* device int32[B] or NULL (= 0) */
+  int32_t* status;                         /* device int32[1] or NULL */
+} VmasSpawn;
+
+int vmas_b200_spawn_entities(const VmasWorldConfig* cfg, const VmasState* st, const VmasSpawn* spawn,
+                             void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

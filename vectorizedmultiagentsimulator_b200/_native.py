@@ -28,6 +28,7 @@ GENERATED = os.path.join(CSRC, "generated", "specializations.cuh")
 HEADERS = [
     os.path.join(CSRC, "geometry.cuh"),
     os.path.join(CSRC, "spec_kernel.cuh"),
+    os.path.join(CSRC, "reset.cuh"),
     os.path.join(INCLUDE, "vmas_b200.h"),
     GENERATED,
 ]
@@ -153,6 +154,37 @@ class AgentActionsC(C.Structure):
     ]
 
 
+MAX_SPAWN = 64
+
+
+class SpawnC(C.Structure):
+    """``VmasSpawn`` (include/vmas_b200.h)."""
+
+    _fields_ = [
+        ("n_spawn", C.c_int32),
+        ("entity", C.c_int32 * MAX_SPAWN),
+        ("n_occupied_entities", C.c_int32),
+        ("occupied_entity", C.c_int32 * MAX_SPAWN),
+        ("occupied", C.c_void_p),
+        ("n_occupied", C.c_int32),
+        ("max_tries", C.c_int32),
+        ("occupied_env_stride", C.c_int64),
+        ("out", C.c_void_p),
+        ("min_dist", C.c_float),
+        ("x_lo", C.c_float),
+        ("x_hi", C.c_float),
+        ("y_lo", C.c_float),
+        ("y_hi", C.c_float),
+        ("env_index", C.c_int32),
+        ("env_mask", C.c_void_p),
+        ("seed", C.c_uint64),
+        ("stream_id", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("reset_count", C.c_void_p),
+        ("status", C.c_void_p),
+    ]
+
+
 EXPORTS = [
     "vmas_b200_abi_version",
     "vmas_b200_last_error",
@@ -171,6 +203,8 @@ EXPORTS = [
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
     "vmas_b200_distance_shaping",
+    "vmas_b200_reset_state",
+    "vmas_b200_spawn_entities",
 ]
 
 _lib = None
@@ -225,6 +259,8 @@ def load():
     lib.vmas_b200_ingest_actions.argtypes = [
         p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
+    lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     for name in EXPORTS[2:]:
@@ -520,4 +556,23 @@ def pair_query_batched(lib, dt: DeviceTables, slab, pairs, mode: int, out) -> in
         C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), pairs.data_ptr(), int(pairs.shape[0]), mode, out.data_ptr(),
         _stream(dt.device),
     )
+    return _check(lib, rc)
+
+
+def reset_state(lib, dt: DeviceTables, slab, env_index, env_mask, reset_count) -> int:
+    """Zero the state rows of the selected envs (``env_index`` int or None, ``env_mask`` uint8/bool
+    ``[B]`` or None) and bump their episode counters (``reset_count`` int32 ``[B]`` or None)."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_reset_state(
+        C.byref(dt.cfg), C.byref(st), -1 if env_index is None else int(env_index),
+        None if env_mask is None else env_mask.data_ptr(),
+        None if reset_count is None else reset_count.data_ptr(), _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def spawn_entities(lib, dt: DeviceTables, slab, spawn: SpawnC) -> int:
+    """``spawn``: a filled ``SpawnC`` (device pointers as integers)."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_spawn_entities(C.byref(dt.cfg), C.byref(st), C.byref(spawn), _stream(dt.device))
     return _check(lib, rc)

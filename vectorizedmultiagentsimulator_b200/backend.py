@@ -367,6 +367,88 @@ class CudaBackend(PlanRuntime):
             self._native.ingest_actions(self.lib, self._dev_tables, self.world.slab, chunk, hi - lo, clamp, bad_flag)
             self.launches += 1
 
+    # -- episode reset (device side) ------------------------------------------------
+    @staticmethod
+    def _selection(env_index):
+        """``None`` / int / bool tensor ``[B]``  ->  (env_index or None, uint8 mask view or None)."""
+        if env_index is None:
+            return None, None
+        if isinstance(env_index, Tensor):
+            if env_index.dtype != torch.bool or env_index.dim() != 1:
+                raise TypeError("a tensor env selection must be a 1-D bool mask over the envs")
+            return None, env_index.contiguous().view(torch.uint8)
+        return int(env_index), None
+
+    def reset_state(self, env_index, reset_count: Optional[Tensor]) -> None:
+        """``World.reset(env_index)`` in one launch: zero the state rows of the selected envs and bump
+        their episode counters (ref core.py:1179-1181, 286-296)."""
+        self.refresh()
+        index, mask = self._selection(env_index)
+        if mask is not None:
+            assert mask.shape[0] == self.world.batch_dim and mask.device == self.device
+        self._native.reset_state(self.lib, self._dev_tables, self.world.slab, index, mask, reset_count)
+        self.launches += 1
+
+    def spawn(
+        self,
+        entities,
+        env_index,
+        min_dist: float,
+        x_bounds,
+        y_bounds,
+        seed: int,
+        stream_id: int,
+        reset_count: Optional[Tensor],
+        status: Optional[Tensor],
+        occupied: Optional[Tensor] = None,
+        occupied_entities=(),
+        want_positions: bool = False,
+        max_tries: int = 1 << 16,
+    ) -> Optional[Tensor]:
+        """Rejection-sampled respawn (ref utils.py:241-319) of up to ``MAX_SPAWN`` positions per
+        selected env in one launch.  ``entities``: ``Entity`` objects (their slab rows are written)
+        or ``None`` entries (position only returned).  ``occupied``: fp32 ``[B or 1, K, 2]``.
+        Returns the drawn positions ``[B, n, 2]`` when ``want_positions`` (rows of unselected envs
+        are zero), else ``None``."""
+        self.refresh()
+        n = len(entities)
+        assert 0 < n <= self._native.MAX_SPAWN and len(occupied_entities) <= self._native.MAX_SPAWN
+        index, mask = self._selection(env_index)
+        sp = self._native.SpawnC()
+        sp.n_spawn = n
+        for i, e in enumerate(entities):
+            sp.entity[i] = -1 if e is None else self.index_of(e)
+        sp.n_occupied_entities = len(occupied_entities)
+        for i, e in enumerate(occupied_entities):
+            sp.occupied_entity[i] = self.index_of(e)
+        B = self.world.batch_dim
+        if occupied is not None and occupied.shape[1] > 0:
+            occupied = occupied.to(device=self.device, dtype=torch.float32).contiguous()
+            assert occupied.dim() == 3 and occupied.shape[2] == 2 and occupied.shape[0] in (1, B)
+            sp.occupied = occupied.data_ptr()
+            sp.n_occupied = occupied.shape[1]
+            # a [1, K, 2] block is shared by all envs (for a single env index it is that env's rows)
+            sp.occupied_env_stride = occupied.shape[1] * 2 if (occupied.shape[0] == B and index is None) else 0
+            if index is not None and occupied.shape[0] == B and B > 1:
+                sp.occupied = occupied[index].data_ptr()
+        out = None
+        if want_positions:
+            out = torch.zeros(B, n, 2, dtype=torch.float32, device=self.device)
+            sp.out = out.data_ptr()
+        sp.min_dist = float(min_dist)
+        sp.x_lo, sp.x_hi = float(x_bounds[0]), float(x_bounds[1])
+        sp.y_lo, sp.y_hi = float(y_bounds[0]), float(y_bounds[1])
+        sp.env_index = -1 if index is None else index
+        sp.env_mask = None if mask is None else mask.data_ptr()
+        sp.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        sp.stream_id = int(stream_id) & 0xFFFF
+        sp.reset_count = None if reset_count is None else reset_count.data_ptr()
+        sp.status = None if status is None else status.data_ptr()
+        sp.max_tries = int(max_tries)
+        self._native.spawn_entities(self.lib, self._dev_tables, self.world.slab, sp)
+        self.launches += 1
+        return out
+
     # -- queries -----------------------------------------------------------------------------
     def pair_distance(self, a, b) -> Tensor:
         ia, ib = self.index_of(a), self.index_of(b)

@@ -1912,3 +1912,5 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
 }
 
 }  // extern "C"
+
+#include "reset.cuh"  // device-side episode reset: vmas_b200_reset_state, vmas_b200_spawn_entities

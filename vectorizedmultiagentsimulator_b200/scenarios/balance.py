@@ -15,6 +15,8 @@ from ..simulator.utils import Color, ScenarioUtils
 
 
 class Scenario(BaseScenario):
+    supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._obs_plan = self._obs_all = self._rew_consts = self._package_on_goal = None
         self.n_agents = kwargs.pop("n_agents", 3)
@@ -72,7 +74,7 @@ class Scenario(BaseScenario):
 
     def reset_world_at(self, env_index: int = None):
         world = self.world
-        n = 1 if env_index is not None else world.batch_dim
+        n = 1 if isinstance(env_index, int) else world.batch_dim  # None / bool mask: a row per env
         half = self.line_length / 2
         r_pkg = self.package.shape.radius
         dev = dict(device=world.device, dtype=torch.float32)

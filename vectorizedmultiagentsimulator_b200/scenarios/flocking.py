@@ -17,6 +17,8 @@ from ..simulator.utils import Color, ScenarioUtils, Y
 
 
 class Scenario(BaseScenario):
+    supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._batch = self._obs_all = None  # caches of the batched callbacks belong to one world
         n_agents = kwargs.pop("n_agents", 4)
@@ -83,7 +85,7 @@ class Scenario(BaseScenario):
 
     def reset_world_at(self, env_index: int = None):
         world = self.world
-        n = 1 if env_index is not None else world.batch_dim
+        n = 1 if isinstance(env_index, int) else world.batch_dim  # None / bool mask: a row per env
         target_pos = torch.zeros((n, world.dim_p), device=world.device, dtype=torch.float32)
         target_pos[:, Y] = -self.y_dim
         self._target.set_pos(target_pos, batch_index=env_index)

@@ -28,6 +28,8 @@ _PALETTE = [
 
 
 class Scenario(BaseScenario):
+    supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._batch = self._obs_all = None  # caches of the batched callbacks belong to one world
         self.plot_grid = False
@@ -102,7 +104,7 @@ class Scenario(BaseScenario):
             world.agents, world, env_index, self.min_distance_between_entities, xb, yb
         )
         occupied = torch.stack([a.state.pos for a in world.agents], dim=1)
-        if env_index is not None:
+        if isinstance(env_index, int):  # None / bool mask: a row per env
             occupied = occupied[env_index].unsqueeze(0)
         goal_positions = []
         for _ in world.agents:

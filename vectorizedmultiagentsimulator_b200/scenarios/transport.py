@@ -15,6 +15,8 @@ from ..simulator.utils import Color, ScenarioUtils
 
 
 class Scenario(BaseScenario):
+    supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._obs_plan = self._obs_all = self._shaping_block = self._zero = None
         n_agents = kwargs.pop("n_agents", 4)
@@ -76,7 +78,7 @@ class Scenario(BaseScenario):
             y_bounds=bounds,
         )
         occupied = torch.stack([a.state.pos for a in world.agents], dim=1)
-        if env_index is not None:
+        if isinstance(env_index, int):  # None / bool mask: a row per env
             occupied = occupied[env_index].unsqueeze(0)
         goal = world.landmarks[0]
         ScenarioUtils.spawn_entities_randomly(

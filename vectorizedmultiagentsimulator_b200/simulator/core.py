@@ -17,6 +17,7 @@ Reference behaviour each piece stands in for is cited inline as ``ref core.py:<l
 from __future__ import annotations
 
 import math
+import os
 from abc import ABC, abstractmethod
 from typing import Callable, List, Optional, Sequence, Tuple, Union
 
@@ -174,6 +175,22 @@ class Line(Shape):
         return anchor[X] * self.length / 2, 0.0
 
 
+def _zero_rows(t: Tensor, env_index) -> None:
+    """``t[env_index] = 0`` for ``None`` (all rows), an int, or a ``[B]`` bool mask (no host sync)."""
+    if env_index is None:
+        t.zero_()
+    elif isinstance(env_index, Tensor):
+        t.masked_fill_(env_index.view(-1, *([1] * (t.dim() - 1))), 0.0)
+    else:
+        t[env_index] = 0.0
+
+
+def _write_rows(dst: Tensor, new: Tensor, mask: Tensor) -> None:
+    """``dst[mask] = new[mask]`` for a ``[B]`` bool mask without a host sync; ``new`` is a full
+    ``[B, ...]`` tensor or broadcastable to one."""
+    dst.copy_(torch.where(mask.view(-1, *([1] * (dst.dim() - 1))), new, dst))
+
+
 # ----------------------------------------------------------------------------------------
 # State containers (ref core.py:206-410).  Fields are views into the world's StateSlab
 # once the entity has been packed; before that they are standalone [B, k] tensors.
@@ -214,12 +231,8 @@ class _SlabFields(TorchVectorizedObject):
     def _reset(self, env_index):
         for name in self._NAMES:
             t = self._fields.get(name)
-            if t is None:
-                continue
-            if env_index is None:
-                t.zero_()
-            else:
-                t[env_index] = 0.0
+            if t is not None:
+                _zero_rows(t, env_index)
 
     def zero_grad(self):
         # The CUDA path is forward-only; nothing carries a graph.
@@ -605,6 +618,10 @@ class Entity(TorchVectorizedObject, Observable, ABC):
                 setattr(self.state, name, new)
             else:
                 setattr(self.state, name, new.repeat(self.batch_dim, 1))
+        elif isinstance(batch_index, Tensor) and batch_index.dtype == torch.bool:
+            # extension: a [B] bool mask selects the envs; `new` holds a row for every env (or
+            # broadcasts), rows of unselected envs are ignored
+            _write_rows(getattr(self.state, name), new, batch_index)
         else:
             getattr(self.state, name)[batch_index] = new
         self.notify_observers()
@@ -945,6 +962,10 @@ class World(TorchVectorizedObject):
         self._plan_version = 0
         self._backend = None
         self._factory_at_init = type(self)._backend_factory
+        # device-side reset bookkeeping
+        self._reset_count: Optional[Tensor] = None
+        self._spawn_status: Optional[Tensor] = None
+        self._spawn_calls = 0
 
     # -- construction -------------------------------------------------------------------
     def add_agent(self, agent: Agent):
@@ -1013,9 +1034,112 @@ class World(TorchVectorizedObject):
         return self._backend
 
     # -- bulk operations ---------------------------------------------------------------------
+    #: device-side reset (``vmas_b200_reset_state`` / ``vmas_b200_spawn_entities``) for CUDA worlds;
+    #: ``VMAS_B200_DEVICE_RESET=0`` keeps the reference's torch formulation (same results for the
+    #: state zeroing; the respawn then draws from torch's generator instead of the kernel's stream)
+    device_reset_enabled = os.environ.get("VMAS_B200_DEVICE_RESET", "1") != "0"
+
+    @property
+    def uses_device_reset(self) -> bool:
+        return (
+            type(self).device_reset_enabled
+            and self._factory_at_init is None
+            and type(self)._backend_factory is None
+            and torch.device(self._device).type == "cuda"
+        )
+
+    @property
+    def reset_count(self) -> Tensor:
+        """``[B]`` int32: how many times each env has been reset (its episode number); part of the
+        respawn kernel's random-number counter."""
+        if self._reset_count is None or self._reset_count.device.type != torch.device(self._device).type:
+            self._reset_count = torch.zeros(self._batch_dim, dtype=torch.int32, device=self._device)
+        return self._reset_count
+
     def reset(self, env_index):
+        """Zero the state of every entity in the selected envs (ref core.py:1179-1181).
+
+        ``env_index``: ``None`` (all envs), an int (the reference's ``reset_at``), or — an extension —
+        a ``[B]`` bool tensor flagging the envs to reset, handled without a host sync.
+        """
+        self._spawn_calls = 0
+        if self.uses_device_reset:
+            self._ensure_slab()
+            self._get_backend().reset_state(env_index, self.reset_count)
+            if self._dim_c > 0:
+                for a in self._agents:
+                    if a.state.c is not None:
+                        _zero_rows(a.state.c, env_index)
+            return
         for e in self.entities:
             e._reset(env_index)
+        if isinstance(env_index, Tensor):
+            self.reset_count.add_(env_index.to(torch.int32))
+        elif env_index is None:
+            self.reset_count.add_(1)
+        else:
+            self.reset_count[env_index] += 1
+
+    def spawn_positions(
+        self,
+        entities,
+        env_index,
+        min_dist: float,
+        x_bounds,
+        y_bounds,
+        occupied_positions: Optional[Tensor] = None,
+        occupied_entities=(),
+        want_positions: bool = False,
+        max_tries: int = 1 << 16,
+    ) -> Optional[Tensor]:
+        """Device-side ``ScenarioUtils.spawn_entities_randomly`` (ref utils.py:241-319): places
+        ``entities`` (``None`` entries: only draw a position) in the selected envs, each at least
+        ``min_dist`` from the occupied points, the ``occupied_entities`` and the ones placed before
+        it.  At most ``MAX_SPAWN`` positions per launch; longer lists are chained.
+
+        The random stream is keyed by ``torch.initial_seed()`` (what ``Environment.seed`` sets), the
+        env, its episode number (:attr:`reset_count`) and the position of the call within the reset.
+        """
+        assert self.uses_device_reset, "spawn_positions needs a CUDA world (device-side reset)"
+        backend = self._get_backend()
+        if self._spawn_status is None:
+            self._spawn_status = torch.zeros(1, dtype=torch.int32, device=self._device)
+        entities, occupied_entities = list(entities), list(occupied_entities)
+        chunk_size = backend._native.MAX_SPAWN
+        assert len(occupied_entities) <= chunk_size, f"at most {chunk_size} occupied entities per spawn call"
+        outs = []
+        for lo in range(0, len(entities), chunk_size):
+            chunk = entities[lo : lo + chunk_size]
+            out = backend.spawn(
+                chunk,
+                env_index,
+                min_dist,
+                x_bounds,
+                y_bounds,
+                seed=torch.initial_seed(),
+                stream_id=self._spawn_calls,
+                reset_count=self.reset_count,
+                status=self._spawn_status,
+                occupied=occupied_positions,
+                occupied_entities=occupied_entities,
+                want_positions=want_positions or lo + chunk_size < len(entities),
+                max_tries=max_tries,
+            )
+            self._spawn_calls += 1
+            if out is not None:
+                outs.append(out)
+                if lo + chunk_size < len(entities):  # later chunks keep away from this one
+                    occupied_positions = out if occupied_positions is None else torch.cat(
+                        [occupied_positions.expand(out.shape[0], -1, -1), out], dim=1
+                    )
+        if not want_positions:
+            return None
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+    def spawn_failures(self) -> int:
+        """Number of (env, call) pairs whose rejection sampling ran out of attempts so far (the
+        reference would still be looping).  Reads a device counter: one host sync."""
+        return 0 if self._spawn_status is None else int(self._spawn_status.item())
 
     def zero_grad(self):
         return

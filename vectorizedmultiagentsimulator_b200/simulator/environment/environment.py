@@ -172,7 +172,13 @@ class Environment(TorchVectorizedObject):
         return_info: bool = False,
         return_dones: bool = False,
     ):
-        """Resets env ``index``; returns observations for all agents (all envs)."""
+        """Resets env ``index``; returns observations for all agents (all envs).
+
+        Extension of the reference API: ``index`` may be a ``[num_envs]`` bool tensor (e.g. the
+        ``dones`` of the last step); every flagged env is reset in one pass on the device, without
+        a host sync, where the reference needs one ``reset_at(i)`` per finished env.  Needs a
+        scenario with ``supports_masked_reset``.
+        """
         return self._reset_at(index, return_observations, return_info, return_dones)
 
     @_seeded
@@ -231,9 +237,21 @@ class Environment(TorchVectorizedObject):
         return result[0] if result and len(result) == 1 else result
 
     def _reset_at(self, index, return_observations=True, return_info=False, return_dones=False):
-        self._check_batch_index(index)
-        self.scenario.env_reset_world_at(index)
-        self.steps[index] = 0
+        if isinstance(index, Tensor):
+            if index.dtype != torch.bool or index.shape != (self.num_envs,):
+                raise ValueError("a tensor passed to reset_at must be a [num_envs] bool mask")
+            if not self.scenario.supports_masked_reset:
+                raise NotImplementedError(
+                    f"{type(self.scenario).__name__}.reset_world_at takes an env index; resetting by mask "
+                    "needs a scenario with supports_masked_reset = True"
+                )
+            index = index.to(self.device)
+            self.scenario.env_reset_world_at(index)
+            self.steps.masked_fill_(index, 0)
+        else:
+            self._check_batch_index(index)
+            self.scenario.env_reset_world_at(index)
+            self.steps[index] = 0
         result = self._get_from_scenario(
             get_observations=return_observations,
             get_infos=return_info,

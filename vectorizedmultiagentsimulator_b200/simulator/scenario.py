@@ -23,6 +23,11 @@ from .utils import (
 
 
 class BaseScenario(ABC):
+    #: True when ``reset_world_at`` also accepts a ``[B]`` bool tensor flagging the envs to reset
+    #: (``Environment.reset_at(mask)``: every finished env in one pass, no host sync).  The scenarios
+    #: shipped with this package do; scenario files written for the reference take an int or None.
+    supports_masked_reset = False
+
     def __init__(self):
         self._world = None
         # rendering knobs are kept so scenario files that set them still load
@@ -50,7 +55,7 @@ class BaseScenario(ABC):
 
         The first call binds ``owner.<name>``; later calls write into the existing tensor so its
         address never changes — the rule that makes a scenario replayable as a CUDA graph.
-        With ``env_index`` only that env's row is written.
+        With ``env_index`` (an int, or a ``[B]`` bool mask) only those envs' rows are written.
         """
         cur = getattr(owner, name, None)
         if not isinstance(cur, Tensor) or cur.shape != value.shape or cur.dtype != value.dtype:
@@ -58,6 +63,8 @@ class BaseScenario(ABC):
             return getattr(owner, name)
         if env_index is None:
             cur.copy_(value)
+        elif isinstance(env_index, Tensor):  # [B] bool mask of the envs being reset: no host sync
+            cur.copy_(torch.where(env_index.view(-1, *([1] * (cur.dim() - 1))), value, cur))
         else:
             cur[env_index] = value[env_index]
         return cur

@@ -173,7 +173,16 @@ class ScenarioUtils:
         occupied_positions: Tensor = None,
         disable_warn: bool = False,
     ):
-        n = world.batch_dim if env_index is None else 1
+        if getattr(world, "uses_device_reset", False):
+            # CUDA world: every entity of the call in one kernel launch, no host sync
+            entities = list(entities)
+            world.spawn_positions(
+                entities, env_index, min_dist_between_entities, x_bounds, y_bounds, occupied_positions
+            )
+            for entity in entities:
+                entity.notify_observers()
+            return
+        n = world.batch_dim if not isinstance(env_index, int) else 1
         if occupied_positions is None:
             occupied_positions = torch.zeros((n, 0, world.dim_p), device=world.device)
         for entity in entities:
@@ -204,7 +213,13 @@ class ScenarioUtils:
         Draw order (x then y, one ``uniform_`` each per attempt) follows the reference so a
         CPU world seeded the same way spawns the same layout.
         """
-        n = world.batch_dim if env_index is None else 1
+        if getattr(world, "uses_device_reset", False):
+            out = world.spawn_positions(
+                [None], env_index, min_dist_between_entities, x_bounds, y_bounds, occupied_positions,
+                want_positions=True,
+            )
+            return out[env_index].unsqueeze(0) if isinstance(env_index, int) else out
+        n = world.batch_dim if not isinstance(env_index, int) else 1
         pos = None
         tries = 0
         while True:
