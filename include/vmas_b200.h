@@ -284,8 +284,8 @@ int vmas_b200_reset_state(const VmasWorldConfig* cfg, const VmasState* st, int32
  * earlier in this call).  One thread per env, no host synchronisation (the reference loops in
  * python with one torch.any() sync per attempt).
  *
- * Random numbers are Philox4x32-10 with counter (env, reset_count[env], stream_id << 16 | i,
- * attempt / 2) and key `seed`: the position of draw i of an env is independent of which other
+ * Random numbers are Philox4x32-10 with counter (env, reset_count[env], stream_id,
+ * i << 26 | attempt / 2) and key `seed`: the position of draw i of an env is independent of which other
  * envs are selected in the launch (masked reset == one reset_at per env, bit for bit), and
  * oracle/reset.py reproduces it on the CPU.  A draw that still overlaps after `max_tries`
  * attempts keeps its last proposal and `*status` is incremented (the reference would keep looping).
@@ -298,14 +298,14 @@ typedef struct VmasSpawn {
   int32_t occupied_entity[VMAS_MAX_SPAWN]; /* slab entities (already placed) to keep away from */
   const float* occupied;                   /* device fp32 [., n_occupied, 2] further occupied points, or NULL */
   int32_t n_occupied;
-  int32_t max_tries;                       /* attempts per draw (> 0) */
+  int32_t max_tries;                       /* attempts per draw, in [1, 2^27] */
   int64_t occupied_env_stride;             /* elements between consecutive envs of `occupied`; 0: shared by all envs */
   float* out;                              /* device fp32 [B, n_spawn, 2] or NULL: the positions drawn (selected envs only) */
   float min_dist, x_lo, x_hi, y_lo, y_hi;
   int32_t env_index;
   const uint8_t* env_mask;
   uint64_t seed;
-  uint32_t stream_id;                      /* which spawn call of the reset this is (< 65536) */
+  uint32_t stream_id;                      /* which spawn call since the env's last reset this is */
   uint32_t reserved;
   const int32_t* reset_count;              /* device int32[B] or NULL (= 0) */
   int32_t* status;                         /* device int32[1] or NULL */

@@ -96,7 +96,7 @@ def spawn_entities(
     occupied: Optional[np.ndarray] = None,
     env_index: Optional[int] = None,
     env_mask=None,
-    max_tries: int = 1 << 20,
+    max_tries: int = 1 << 16,
 ):
     """Places ``len(entities)`` positions per selected env; ``pos`` (fp32 ``[B, E, 2]``) is updated
     in place for entries ``>= 0`` of ``entities``.
@@ -106,6 +106,7 @@ def spawn_entities(
     ``max_tries``.  ``occupied``: fp32 ``[B, K, 2]`` or ``[1, K, 2]`` (shared by all envs).
     """
     assert pos.dtype == np.float32 and pos.ndim == 3 and pos.shape[2] == 2
+    assert 0 < len(entities) <= 64 and 0 < max_tries <= 1 << 27
     B = pos.shape[0]
     envs = selected_envs(B, env_index, env_mask)
     n_spawn = len(entities)
@@ -129,14 +130,16 @@ def spawn_entities(
     exhausted = np.zeros(envs.size, dtype=bool)
     placed = np.zeros((envs.size, n_spawn, 2), dtype=np.float32)
     for i in range(n_spawn):
-        slot = np.uint32(((stream_id << 16) | i) & 0xFFFFFFFF)
+        slot = i << 26  # n_spawn <= 64, max_tries <= 2**27
         pending = np.ones(envs.size, dtype=bool)
         cur = np.zeros((envs.size, 2), dtype=np.float32)
         tries = 0
         r = None
         while pending.any():
             if tries % 2 == 0:
-                r = philox4x32_10((envs.astype(np.uint32), episode, slot, np.uint32(tries // 2)), key)
+                r = philox4x32_10(
+                    (envs.astype(np.uint32), episode, np.uint32(stream_id & 0xFFFFFFFF), np.uint32(slot | (tries // 2))), key
+                )
             bx, by = (r[2], r[3]) if tries % 2 else (r[0], r[1])
             prop = np.stack([_uniform(bx, x_lo, span_x), _uniform(by, y_lo, span_y)], axis=-1)
             cur[pending] = prop[pending]

@@ -10,8 +10,8 @@
 // host round trips, for all envs, one env, or the envs flagged in a device mask.
 //
 // Random numbers: Philox4x32-10 (Salmon et al., SC'11 — the generator family torch uses on
-// CUDA), counter-based: counter = (env, episode number of that env, stream << 16 | draw slot,
-// attempt block), key = seed.  A position therefore depends only on (seed, env, how often that
+// CUDA), counter-based: counter = (env, episode number of that env, spawn call number, draw slot
+// << 26 | attempt block), key = seed.  A position therefore depends only on (seed, env, how often that
 // env has been reset, which spawn call of the reset, which entity, which attempt) and not on
 // which other envs are reset in the same launch: a masked reset of many envs equals resetting
 // them one at a time, bit for bit.  oracle/reset.py restates the same procedure in numpy.
@@ -110,11 +110,11 @@ __global__ void __launch_bounds__(128) spawn_entities_kernel(const SpawnArgs a) 
   float2 placed[VMAS_MAX_SPAWN];
   bool exhausted = false;
   for (int i = 0; i < sp.n_spawn; ++i) {
-    const uint32_t slot = (sp.stream_id << 16) | (uint32_t)i;
+    const uint32_t slot = (uint32_t)i << 26;  // n_spawn <= 64, max_tries <= 2^27
     float2 p = make_float2(0.f, 0.f);
     Philox4 r = {0u, 0u, 0u, 0u};
     for (int tries = 0;; ++tries) {
-      if ((tries & 1) == 0) r = philox4x32_10((uint32_t)env, episode, slot, (uint32_t)(tries >> 1), k0, k1);
+      if ((tries & 1) == 0) r = philox4x32_10((uint32_t)env, episode, sp.stream_id, slot | (uint32_t)(tries >> 1), k0, k1);
       p.x = uniform_in((tries & 1) ? r.z : r.x, sp.x_lo, span_x);
       p.y = uniform_in((tries & 1) ? r.w : r.y, sp.y_lo, span_y);
       bool ok = true;
@@ -181,7 +181,7 @@ int vmas_b200_spawn_entities(const VmasWorldConfig* cfg, const VmasState* st, co
     return fail("n_occupied_entities must be in [0, VMAS_MAX_SPAWN]%s");
   if (spawn->n_occupied < 0 || (spawn->n_occupied > 0 && !spawn->occupied)) return fail("occupied points missing%s");
   if (spawn->env_index >= cfg->batch_dim) return fail("env_index out of range%s");
-  if (spawn->max_tries <= 0) return fail("max_tries must be positive%s");
+  if (spawn->max_tries <= 0 || spawn->max_tries > (1 << 27)) return fail("max_tries must be in [1, 2^27]%s");
   if (!(spawn->x_hi >= spawn->x_lo) || !(spawn->y_hi >= spawn->y_lo)) return fail("empty spawn bounds%s");
   bool writes = spawn->out != nullptr;
   for (int i = 0; i < spawn->n_spawn; ++i) {
