@@ -36,7 +36,12 @@ class DecodingNative:
     def __init__(self):
         self.calls = []
 
-    def reset_state(self, lib, dt, slab, env_index, env_mask, reset_count):
+    class SlabHandle:  # the stand-in needs the slab itself, not its device pointers
+        def __init__(self, slab):
+            self.slab = slab
+
+    def reset_state(self, lib, handle, env_index, env_mask, reset_count):
+        slab = handle.slab
         B = slab.batch_dim
         mask = None if env_mask is None else _view(env_mask.data_ptr(), (B,), C.c_uint8, np.uint8)
         envs = torch.from_numpy(R.selected_envs(B, env_index, mask))
@@ -46,7 +51,8 @@ class DecodingNative:
             _view(reset_count.data_ptr(), (B,), C.c_int32, np.int32)[envs.numpy()] += 1
         return 1
 
-    def spawn_entities(self, lib, dt, slab, sp):
+    def spawn_entities(self, lib, handle, sp):
+        slab = handle.slab
         B = slab.batch_dim
         index = None if sp.env_index < 0 else sp.env_index
         mask = _view(sp.env_mask, (B,), C.c_uint8, np.uint8) if sp.env_mask else None
@@ -87,11 +93,13 @@ class HostPathBackend(OracleBackend):
     def __init__(self, world):
         super().__init__(world)
         self._native = DecodingNative()
-        self.lib = self._dev_tables = None
+        self.lib = None
         self.device = torch.device("cpu")
         self.launches = 0
 
     _selection = staticmethod(CudaBackend._selection)
+    _slab_handle = CudaBackend._slab_handle
+    _slab_index_of = CudaBackend._slab_index_of
     reset_state = CudaBackend.reset_state
     spawn = CudaBackend.spawn
 
@@ -183,3 +191,34 @@ def test_long_entity_lists_are_chained(device_reset_on_cpu):
     pts = torch.stack([e.state.pos for e in ents], dim=1)
     d = torch.cdist(pts, pts) + torch.eye(70) * 10
     assert float(d.min()) >= 0.05 - 1e-6  # the second launch kept away from the first one's draws
+
+
+@pytest.mark.reference
+@pytest.mark.timeout(600)
+def test_reference_scenario_files_reset_through_the_device_path(device_reset_on_cpu):
+    """Every UNMODIFIED scenario file of the reference: construction (first reset), ``reset_at(i)``
+    and ``reset()`` through the device-reset marshalling — whatever arguments they hand to
+    ``ScenarioUtils`` (occupied blocks per env or shared, goals drawn without an entity, respawns
+    in the middle of an episode) must be accepted, and resetting must not need the compiled plan
+    (``joint_passage``'s collision filter reads state its first reset creates)."""
+    import os
+
+    import vectorizedmultiagentsimulator_b200 as b200
+    from conftest import REFERENCE_DIR
+    from dropin_runner import scenario_file
+
+    names = []
+    for _, _, files in os.walk(os.path.join(REFERENCE_DIR, "vmas", "scenarios")):
+        names += [f[:-3] for f in files if f.endswith(".py") and f != "__init__.py"]
+    assert len(names) >= 40
+    spawning = 0
+    for name in sorted(names):
+        env = b200.make_env(scenario_file(name), num_envs=5, device="cpu", seed=0)
+        env.step(env.get_random_actions())
+        env.reset_at(3)
+        env.step(env.get_random_actions())
+        env.reset()
+        assert env.world.spawn_failures() == 0, name
+        assert env.world.reset_count.tolist() == [2, 2, 2, 3, 2], name
+        spawning += bool(env.world._get_backend()._native.calls)
+    assert spawning >= 8  # the scenarios that place entities with ScenarioUtils

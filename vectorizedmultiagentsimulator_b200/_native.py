@@ -559,20 +559,37 @@ def pair_query_batched(lib, dt: DeviceTables, slab, pairs, mode: int, out) -> in
     return _check(lib, rc)
 
 
-def reset_state(lib, dt: DeviceTables, slab, env_index, env_mask, reset_count) -> int:
-    """Zero the state rows of the selected envs (``env_index`` int or None, ``env_mask`` uint8/bool
+class SlabHandle:
+    """What the reset entry points need of a world: its sizes and the slab's device pointers.  Unlike
+    :class:`DeviceTables` it does not need the compiled plan, so a world can be reset before its
+    collision structure is final (scenario collision filters may read state the first reset creates)."""
+
+    def __init__(self, slab):
+        for t in slab.tensors():
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.device.type == "cuda"
+        self.device = slab.pos.device
+        self.cfg = WorldConfig()
+        self.cfg.batch_dim = slab.batch_dim
+        self.cfg.n_entities = slab.n_entities
+        self.cfg.n_agents = slab.n_agents
+        self.st = StateC()
+        self.st.pos, self.st.vel, self.st.rot, self.st.ang_vel, self.st.force, self.st.torque = (
+            t.data_ptr() for t in slab.tensors()
+        )
+
+
+def reset_state(lib, handle: SlabHandle, env_index, env_mask, reset_count) -> int:
+    """Zero the state rows of the selected envs (``env_index`` int or None, ``env_mask`` uint8
     ``[B]`` or None) and bump their episode counters (``reset_count`` int32 ``[B]`` or None)."""
-    st = dt.state_struct(slab)
     rc = lib.vmas_b200_reset_state(
-        C.byref(dt.cfg), C.byref(st), -1 if env_index is None else int(env_index),
+        C.byref(handle.cfg), C.byref(handle.st), -1 if env_index is None else int(env_index),
         None if env_mask is None else env_mask.data_ptr(),
-        None if reset_count is None else reset_count.data_ptr(), _stream(dt.device),
+        None if reset_count is None else reset_count.data_ptr(), _stream(handle.device),
     )
     return _check(lib, rc)
 
 
-def spawn_entities(lib, dt: DeviceTables, slab, spawn: SpawnC) -> int:
+def spawn_entities(lib, handle: SlabHandle, spawn: SpawnC) -> int:
     """``spawn``: a filled ``SpawnC`` (device pointers as integers)."""
-    st = dt.state_struct(slab)
-    rc = lib.vmas_b200_spawn_entities(C.byref(dt.cfg), C.byref(st), C.byref(spawn), _stream(dt.device))
+    rc = lib.vmas_b200_spawn_entities(C.byref(handle.cfg), C.byref(handle.st), C.byref(spawn), _stream(handle.device))
     return _check(lib, rc)

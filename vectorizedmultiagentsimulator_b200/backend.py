@@ -379,14 +379,30 @@ class CudaBackend(PlanRuntime):
             return None, env_index.contiguous().view(torch.uint8)
         return int(env_index), None
 
+    def _slab_handle(self):
+        """Sizes + slab pointers for the reset entry points; they do not need the compiled plan (a
+        scenario's collision filters may depend on state that only its first reset creates)."""
+        slab = self.world.slab
+        cached = getattr(self, "_slab_handle_cache", None)
+        if cached is None or cached[0] is not slab:
+            index = {id(e): i for i, e in enumerate(self.world.entities)}
+            cached = self._slab_handle_cache = (slab, self._native.SlabHandle(slab), index)
+        return cached[1]
+
+    def _slab_index_of(self, entity) -> int:
+        self._slab_handle()
+        try:
+            return self._slab_handle_cache[2][id(entity)]
+        except KeyError:
+            raise RuntimeError(f"Entity '{entity.name}' does not belong to this world") from None
+
     def reset_state(self, env_index, reset_count: Optional[Tensor]) -> None:
         """``World.reset(env_index)`` in one launch: zero the state rows of the selected envs and bump
         their episode counters (ref core.py:1179-1181, 286-296)."""
-        self.refresh()
         index, mask = self._selection(env_index)
         if mask is not None:
             assert mask.shape[0] == self.world.batch_dim and mask.device == self.device
-        self._native.reset_state(self.lib, self._dev_tables, self.world.slab, index, mask, reset_count)
+        self._native.reset_state(self.lib, self._slab_handle(), index, mask, reset_count)
         self.launches += 1
 
     def spawn(
@@ -410,17 +426,16 @@ class CudaBackend(PlanRuntime):
         or ``None`` entries (position only returned).  ``occupied``: fp32 ``[B or 1, K, 2]``.
         Returns the drawn positions ``[B, n, 2]`` when ``want_positions`` (rows of unselected envs
         are zero), else ``None``."""
-        self.refresh()
         n = len(entities)
         assert 0 < n <= self._native.MAX_SPAWN and len(occupied_entities) <= self._native.MAX_SPAWN
         index, mask = self._selection(env_index)
         sp = self._native.SpawnC()
         sp.n_spawn = n
         for i, e in enumerate(entities):
-            sp.entity[i] = -1 if e is None else self.index_of(e)
+            sp.entity[i] = -1 if e is None else self._slab_index_of(e)
         sp.n_occupied_entities = len(occupied_entities)
         for i, e in enumerate(occupied_entities):
-            sp.occupied_entity[i] = self.index_of(e)
+            sp.occupied_entity[i] = self._slab_index_of(e)
         B = self.world.batch_dim
         if occupied is not None and occupied.shape[1] > 0:
             occupied = occupied.to(device=self.device, dtype=torch.float32).contiguous()
@@ -445,7 +460,7 @@ class CudaBackend(PlanRuntime):
         sp.reset_count = None if reset_count is None else reset_count.data_ptr()
         sp.status = None if status is None else status.data_ptr()
         sp.max_tries = int(max_tries)
-        self._native.spawn_entities(self.lib, self._dev_tables, self.world.slab, sp)
+        self._native.spawn_entities(self.lib, self._slab_handle(), sp)
         self.launches += 1
         return out
 
