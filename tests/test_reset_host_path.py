@@ -195,30 +195,27 @@ def test_long_entity_lists_are_chained(device_reset_on_cpu):
 
 @pytest.mark.reference
 @pytest.mark.timeout(600)
-def test_reference_scenario_files_reset_through_the_device_path(device_reset_on_cpu):
+def test_reference_scenario_files_reset_through_the_device_path():
     """Every UNMODIFIED scenario file of the reference: construction (first reset), ``reset_at(i)``
     and ``reset()`` through the device-reset marshalling — whatever arguments they hand to
     ``ScenarioUtils`` (occupied blocks per env or shared, goals drawn without an entity, respawns
     in the middle of an episode) must be accepted, and resetting must not need the compiled plan
-    (``joint_passage``'s collision filter reads state its first reset creates)."""
+    (``joint_passage``'s collision filter reads state its first reset creates).  Runs in its own
+    process: the scenario files import ``vmas``, which must resolve to this package's alias."""
+    import json
     import os
+    import subprocess
+    import sys
 
-    import vectorizedmultiagentsimulator_b200 as b200
-    from conftest import REFERENCE_DIR
-    from dropin_runner import scenario_file
-
-    names = []
-    for _, _, files in os.walk(os.path.join(REFERENCE_DIR, "vmas", "scenarios")):
-        names += [f[:-3] for f in files if f.endswith(".py") and f != "__init__.py"]
-    assert len(names) >= 40
-    spawning = 0
-    for name in sorted(names):
-        env = b200.make_env(scenario_file(name), num_envs=5, device="cpu", seed=0)
-        env.step(env.get_random_actions())
-        env.reset_at(3)
-        env.step(env.get_random_actions())
-        env.reset()
-        assert env.world.spawn_failures() == 0, name
-        assert env.world.reset_count.tolist() == [2, 2, 2, 3, 2], name
-        spawning += bool(env.world._get_backend()._native.calls)
-    assert spawning >= 8  # the scenarios that place entities with ScenarioUtils
+    here = os.path.dirname(os.path.abspath(__file__))
+    proc = subprocess.run(
+        [sys.executable, os.path.join(here, "reset_hostpath_runner.py")], capture_output=True, text=True, timeout=550
+    )
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    report = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert len(report) >= 40
+    failures = {k: v for k, v in report.items() if v.get("error")}
+    assert not failures, failures
+    for name, r in report.items():
+        assert r["spawn_failures"] == 0 and r["reset_count"] == [2, 2, 2, 3, 2], name
+    assert sum(r["spawn_calls"] > 0 for r in report.values()) >= 8  # the scenarios that use ScenarioUtils

@@ -37,29 +37,33 @@ def make_env(
     ``action_checks`` selects ``"sync"`` / ``"deferred"`` / ``"off"`` validation of the input
     actions (see ``Environment``).  Remaining ``kwargs`` go to ``Scenario.make_world``.
     """
-    if isinstance(scenario, str):
-        if not scenario.endswith(".py"):
-            scenario += ".py"
-        scenario = scenarios.load(scenario).Scenario()
-
     env = Environment(
-        scenario,
+        _as_scenario(scenario),
         num_envs=num_envs,
         device=device,
-        continuous_actions=continuous_actions,
         max_steps=max_steps,
         seed=seed,
-        dict_spaces=dict_spaces,
+        # how actions are read and outputs are laid out
+        continuous_actions=continuous_actions,
         multidiscrete_actions=multidiscrete_actions,
         clamp_actions=clamp_actions,
-        grad_enabled=grad_enabled,
+        dict_spaces=dict_spaces,
         terminated_truncated=terminated_truncated,
+        grad_enabled=grad_enabled,
+        # additions of this package
         cuda_graph=cuda_graph,
         action_checks=action_checks,
         **kwargs,
     )
-    if wrapper is not None and isinstance(wrapper, str):
-        wrapper = Wrapper[wrapper.upper()]
-    if wrapper_kwargs is None:
-        wrapper_kwargs = {}
-    return wrapper.get_env(env, **wrapper_kwargs) if wrapper is not None else env
+    if wrapper is None:
+        return env
+    adapter = Wrapper[wrapper.upper()] if isinstance(wrapper, str) else wrapper
+    return adapter.get_env(env, **(wrapper_kwargs or {}))
+
+
+def _as_scenario(scenario: Union[str, BaseScenario]) -> BaseScenario:
+    """A ``BaseScenario`` instance from a name, a file path or an instance."""
+    if isinstance(scenario, BaseScenario):
+        return scenario
+    file_name = scenario if scenario.endswith(".py") else scenario + ".py"
+    return scenarios.load(file_name).Scenario()
