@@ -284,7 +284,7 @@ int vmas_b200_reset_state(const VmasWorldConfig* cfg, const VmasState* st, int32
  * earlier in this call).  One thread per env, no host synchronisation (the reference loops in
  * python with one torch.any() sync per attempt).
  *
- * Random numbers are Philox4x32-10 with counter (env, reset_count[env], stream_id,
+ * Random numbers are Philox4x32-10 with counter (env_offset + env, reset_count[env], stream_id,
  * i << 26 | attempt / 2) and key `seed`: the position of draw i of an env is independent of which other
  * envs are selected in the launch (masked reset == one reset_at per env, bit for bit), and
  * oracle/reset.py reproduces it on the CPU.  A draw that still overlaps after `max_tries`
@@ -306,7 +306,9 @@ typedef struct VmasSpawn {
   const uint8_t* env_mask;
   uint64_t seed;
   uint32_t stream_id;                      /* which spawn call since the env's last reset this is */
-  uint32_t reserved;
+  uint32_t env_offset;                     /* index of this slab's env 0 in the whole job (batch_dim sharded over
+                                              GPUs): counters use env + env_offset, so a shard draws what the
+                                              unsharded job draws for the same envs */
   const int32_t* reset_count;              /* device int32[B] or NULL (= 0) */
   int32_t* status;                         /* device int32[1] or NULL */
 } VmasSpawn;

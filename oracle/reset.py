@@ -97,6 +97,7 @@ def spawn_entities(
     env_index: Optional[int] = None,
     env_mask=None,
     max_tries: int = 1 << 16,
+    env_offset: int = 0,
 ):
     """Places ``len(entities)`` positions per selected env; ``pos`` (fp32 ``[B, E, 2]``) is updated
     in place for entries ``>= 0`` of ``entities``.
@@ -104,6 +105,7 @@ def spawn_entities(
     Returns ``(out, exhausted)``: ``out`` fp32 ``[B, n_spawn, 2]`` holds the drawn positions in the
     rows of the selected envs (zeros elsewhere), ``exhausted`` counts the envs in which some draw hit
     ``max_tries``.  ``occupied``: fp32 ``[B, K, 2]`` or ``[1, K, 2]`` (shared by all envs).
+    ``env_offset``: index of env 0 in the whole job when ``pos`` is one shard of it.
     """
     assert pos.dtype == np.float32 and pos.ndim == 3 and pos.shape[2] == 2
     assert 0 < len(entities) <= 64 and 0 < max_tries <= 1 << 27
@@ -127,6 +129,7 @@ def spawn_entities(
             extra = occupied[envs]
         else:  # the same points for every env
             extra = np.broadcast_to(occupied[0], (envs.size,) + occupied.shape[1:])
+    global_env = ((envs + env_offset) & 0xFFFFFFFF).astype(np.uint32)  # the env's index in the whole (sharded) job
     exhausted = np.zeros(envs.size, dtype=bool)
     placed = np.zeros((envs.size, n_spawn, 2), dtype=np.float32)
     for i in range(n_spawn):
@@ -138,7 +141,7 @@ def spawn_entities(
         while pending.any():
             if tries % 2 == 0:
                 r = philox4x32_10(
-                    (envs.astype(np.uint32), episode, np.uint32(stream_id & 0xFFFFFFFF), np.uint32(slot | (tries // 2))), key
+                    (global_env, episode, np.uint32(stream_id & 0xFFFFFFFF), np.uint32(slot | (tries // 2))), key
                 )
             bx, by = (r[2], r[3]) if tries % 2 else (r[0], r[1])
             prop = np.stack([_uniform(bx, x_lo, span_x), _uniform(by, y_lo, span_y)], axis=-1)

@@ -37,3 +37,44 @@ def test_argument_validation_without_gpu():
     lib = _native.load()
     assert lib.vmas_b200_world_step(None, None, None, None, 1, None) < 0
     assert b"null" in lib.vmas_b200_last_error()
+
+
+def test_reset_entry_points_validate_their_arguments_without_gpu():
+    """vmas_b200_reset_state / vmas_b200_spawn_entities reject bad input before any CUDA call."""
+    lib = _native.load()
+    cfg = _native.WorldConfig()
+    cfg.batch_dim, cfg.n_entities, cfg.n_agents = 16, 4, 2
+    st = _native.StateC()
+    st.pos = st.vel = st.rot = st.ang_vel = st.force = st.torque = 0x1000  # never dereferenced on the host
+
+    def err():
+        return lib.vmas_b200_last_error().decode()
+
+    assert lib.vmas_b200_reset_state(None, None, -1, None, None, None) < 0 and "null" in err()
+    assert lib.vmas_b200_reset_state(ctypes.byref(cfg), ctypes.byref(st), 16, None, None, None) < 0
+    assert "env_index" in err()
+
+    def spawn(**kw):
+        sp = _native.SpawnC()
+        sp.n_spawn, sp.max_tries, sp.env_index = 2, 100, -1
+        sp.entity[0], sp.entity[1] = 0, 1
+        sp.x_lo, sp.x_hi, sp.y_lo, sp.y_hi, sp.min_dist = -1, 1, -1, 1, 0.1
+        for k, v in kw.items():
+            setattr(sp, k, v)
+        return lib.vmas_b200_spawn_entities(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(sp), None)
+
+    assert spawn(n_spawn=0) < 0 and "n_spawn" in err()
+    assert spawn(n_spawn=_native.MAX_SPAWN + 1) < 0 and "n_spawn" in err()
+    assert spawn(max_tries=0) < 0 and "max_tries" in err()
+    assert spawn(env_index=16) < 0 and "env_index" in err()
+    assert spawn(x_lo=2.0) < 0 and "bounds" in err()
+    assert spawn(n_occupied=3) < 0 and "occupied" in err()
+    sp = _native.SpawnC()
+    sp.n_spawn, sp.max_tries, sp.env_index = 1, 10, -1
+    sp.entity[0] = 9
+    sp.x_hi = sp.y_hi = 1.0
+    assert lib.vmas_b200_spawn_entities(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(sp), None) < 0
+    assert "out of range" in err()
+    sp.entity[0] = -1  # position only, but no `out` buffer either
+    assert lib.vmas_b200_spawn_entities(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(sp), None) < 0
+    assert "nothing to write" in err()

@@ -231,3 +231,19 @@ def test_masked_reset_between_graph_replays():
             for o_g, o_e in zip(graph.reset_at(mask), eager.reset_at(mask)):
                 assert torch.equal(o_g, o_e)
     assert graph.graph_replays > 0
+
+
+def test_shards_reset_like_the_unsharded_job():
+    """Two shard envs (``shard.make_shard_env``, here both on cuda:0) against the unsharded job."""
+    from vectorizedmultiagentsimulator_b200 import shard
+
+    total, kwargs = 1000, dict(n_agents=5)
+    full = shard.make_shard_env("flocking", total, 0, 1, DEV, seed=6, **kwargs)
+    mask = (torch.rand(total, generator=torch.Generator().manual_seed(0)) < 0.4).to(DEV)
+    full.reset_at(mask)
+    for rank in range(2):
+        lo, hi = shard.shard_bounds(total, rank, 2)
+        part = shard.make_shard_env("flocking", total, rank, 2, DEV, seed=6, **kwargs)
+        part.reset_at(mask[lo:hi])
+        for (k, got), want in zip(_slab(part).items(), _slab(full).values()):
+            assert torch.equal(got, want[lo:hi]), f"rank {rank}: {k}"

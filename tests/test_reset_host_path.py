@@ -76,6 +76,7 @@ class DecodingNative:
             env_index=index,
             env_mask=mask,
             max_tries=sp.max_tries,
+            env_offset=sp.env_offset,
         )
         slab.pos.copy_(torch.from_numpy(pos))
         if sp.out:
@@ -191,6 +192,28 @@ def test_long_entity_lists_are_chained(device_reset_on_cpu):
     pts = torch.stack([e.state.pos for e in ents], dim=1)
     d = torch.cdist(pts, pts) + torch.eye(70) * 10
     assert float(d.min()) >= 0.05 - 1e-6  # the second launch kept away from the first one's draws
+
+
+@pytest.mark.parametrize("name,kwargs", CASES[1:])
+def test_shards_reset_like_the_unsharded_job(device_reset_on_cpu, name, kwargs):
+    """``shard.make_shard_env``: a shard's layouts (initial and after a masked reset) are the matching
+    slice of the unsharded job's — what makes results independent of the number of GPUs."""
+    import vectorizedmultiagentsimulator_b200 as b200
+    from vectorizedmultiagentsimulator_b200 import shard
+
+    total = 22
+    full = shard.make_shard_env(name, total, 0, 1, "cpu", seed=6, **kwargs)
+    plain = b200.make_env(name, num_envs=total, device="cpu", seed=6, **kwargs)
+    assert torch.equal(full.world.slab.pos, plain.world.slab.pos)  # a job of one shard == a plain env
+    mask = torch.rand(total, generator=torch.Generator().manual_seed(0)) < 0.4
+    full.reset_at(mask)
+    for rank in range(3):
+        lo, hi = shard.shard_bounds(total, rank, 3)
+        part = shard.make_shard_env(name, total, rank, 3, "cpu", seed=6, **kwargs)
+        assert part.num_envs == hi - lo and part.world.env_offset == lo
+        part.reset_at(mask[lo:hi])
+        for (k, got), want in zip(_slab(part).items(), _slab(full).values()):
+            assert torch.equal(got, want[lo:hi]), f"{name} rank {rank}: {k}"
 
 
 @pytest.mark.reference

@@ -97,6 +97,19 @@ def test_masked_spawn_equals_one_env_at_a_time():
         assert np.array_equal(out_i[i], full[i])
 
 
+def test_env_offset_makes_shards_draw_what_the_whole_job_draws():
+    full = _spawn()[1]
+    lo = 100
+    pos = np.zeros((56, 7, 2), np.float32)
+    pos[:, 5] = (0.25, -0.25)
+    pos[:, 6] = (-0.5, 0.5)
+    out, _ = R.spawn_entities(
+        pos, [0, 1, 2, 3, -1], min_dist=0.3, x_bounds=(-1.0, 1.0), y_bounds=(-0.75, 0.75), seed=42,
+        occupied_entities=(5, 6), env_offset=lo,
+    )
+    assert np.array_equal(out, full[lo : lo + 56])
+
+
 def test_exhaustion_is_reported():
     # 4 points that keep 1.5 apart cannot fit in a unit square
     pos = np.zeros((8, 4, 2), np.float32)

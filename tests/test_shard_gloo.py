@@ -2,7 +2,9 @@
 
 Checks the shard arithmetic, that a sharded run equals the matching slice of an unsharded run
 (envs are independent; flocking is sphere-only so the batch-wide broad phase is result-neutral),
-and the max-/sum-over-ranks reductions bench.py relies on.
+and the max-/sum-over-ranks reductions bench.py relies on.  A second job runs the ranks through
+``shard.make_shard_env`` with the device-reset host path (the stand-in of test_reset_host_path.py):
+there the shards also *reset* like the unsharded job, so nothing has to be copied between them.
 """
 import os
 import sys
@@ -82,3 +84,54 @@ def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
         lo, hi, obs, rew = torch.load(os.path.join(str(tmp_path), f"shard{r}.pt"))
         assert torch.equal(obs, full_obs[lo:hi]), f"rank {r} observations differ from the unsharded run"
         assert torch.equal(rew, full_rew[lo:hi])
+
+
+def _self_contained_rollout(rank, world):
+    """make_shard_env -> steps -> masked reset -> steps, with the device-reset host path."""
+    from test_reset_host_path import HostPathBackend
+    from vectorizedmultiagentsimulator_b200.simulator.core import World
+
+    torch.set_num_threads(1)
+    World._backend_factory = staticmethod(lambda w: HostPathBackend(w))
+    World.uses_device_reset = property(lambda self: True)
+    lo, hi = shard.shard_bounds(TOTAL, rank, world)
+    env = shard.make_shard_env("flocking", TOTAL, rank, world, "cpu", seed=3, n_agents=3)
+    gen = torch.Generator().manual_seed(5)
+    done = torch.rand(TOTAL, generator=gen) < 0.5
+    out = None
+    for t in range(STEPS):
+        acts = [(torch.rand(TOTAL, 2, generator=gen) * 2 - 1)[lo:hi] for _ in env.agents]
+        out = env.step(acts)
+        if t == 1:
+            env.reset_at(done[lo:hi])
+    return lo, hi, torch.stack(out[0], 1), torch.stack(out[1], 1), env.world.slab.pos.clone()
+
+
+def _self_contained_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.save(_self_contained_rollout(rank, world), os.path.join(tmpdir, f"self{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gloo_ranks_reset_and_step_like_the_unsharded_job(tmp_path):
+    world, port = 2, 30500 + os.getpid() % 1000
+    mp.spawn(_self_contained_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vectorizedmultiagentsimulator_b200.simulator.core import World
+
+    saved = World._backend_factory, World.uses_device_reset
+    try:
+        _, _, full_obs, full_rew, full_pos = _self_contained_rollout(0, 1)
+    finally:
+        World._backend_factory, World.uses_device_reset = saved
+    for r in range(world):
+        lo, hi, obs, rew, pos = torch.load(os.path.join(str(tmp_path), f"self{r}.pt"))
+        assert torch.equal(pos, full_pos[lo:hi]), f"rank {r}: positions differ from the unsharded job"
+        assert torch.equal(obs, full_obs[lo:hi]) and torch.equal(rew, full_rew[lo:hi])

@@ -179,7 +179,7 @@ class SpawnC(C.Structure):
         ("env_mask", C.c_void_p),
         ("seed", C.c_uint64),
         ("stream_id", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("env_offset", C.c_uint32),
         ("reset_count", C.c_void_p),
         ("status", C.c_void_p),
     ]

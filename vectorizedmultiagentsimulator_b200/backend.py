@@ -457,6 +457,7 @@ class CudaBackend(PlanRuntime):
         sp.env_mask = None if mask is None else mask.data_ptr()
         sp.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         sp.stream_id = int(stream_id) & 0xFFFFFFFF
+        sp.env_offset = int(getattr(self.world, "env_offset", 0)) & 0xFFFFFFFF
         sp.reset_count = None if reset_count is None else reset_count.data_ptr()
         sp.status = None if status is None else status.data_ptr()
         sp.max_tries = int(max_tries)

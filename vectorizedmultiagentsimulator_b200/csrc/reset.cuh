@@ -10,8 +10,8 @@
 // host round trips, for all envs, one env, or the envs flagged in a device mask.
 //
 // Random numbers: Philox4x32-10 (Salmon et al., SC'11 — the generator family torch uses on
-// CUDA), counter-based: counter = (env, episode number of that env, spawn call number, draw slot
-// << 26 | attempt block), key = seed.  A position therefore depends only on (seed, env, how often that
+// CUDA), counter-based: counter = (env (+ the shard's offset in a multi-GPU job), episode number of
+// that env, spawn call number, draw slot << 26 | attempt block), key = seed.  A position therefore depends only on (seed, env, how often that
 // env has been reset, which spawn call of the reset, which entity, which attempt) and not on
 // which other envs are reset in the same launch: a masked reset of many envs equals resetting
 // them one at a time, bit for bit.  oracle/reset.py restates the same procedure in numpy.
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) spawn_entities_kernel(const SpawnArgs a) 
     float2 p = make_float2(0.f, 0.f);
     Philox4 r = {0u, 0u, 0u, 0u};
     for (int tries = 0;; ++tries) {
-      if ((tries & 1) == 0) r = philox4x32_10((uint32_t)env, episode, sp.stream_id, slot | (uint32_t)(tries >> 1), k0, k1);
+      if ((tries & 1) == 0) r = philox4x32_10((uint32_t)env + sp.env_offset, episode, sp.stream_id, slot | (uint32_t)(tries >> 1), k0, k1);
       p.x = uniform_in((tries & 1) ? r.z : r.x, sp.x_lo, span_x);
       p.y = uniform_in((tries & 1) ? r.w : r.y, sp.y_lo, span_y);
       bool ok = true;

@@ -53,3 +53,21 @@ def sum_over_ranks(value: float, device=None) -> float:
 def aggregate_throughput(local_units: float, local_seconds: float, device=None) -> float:
     """Whole-job units/s = sum of the units every rank processed / the slowest rank's time."""
     return sum_over_ranks(local_units, device) / max_over_ranks(local_seconds, device)
+
+
+def make_shard_env(scenario, total_envs: int, rank: int, world_size: int, device, seed: int = 0, **kwargs):
+    """This rank's shard of a job of ``total_envs`` envs: ``make_env`` with the shard's size, plus
+    the shard's position in the job (``world.env_offset``) so that every reset — including the one
+    that builds the initial state — places entities exactly where the unsharded job would place
+    them for the same envs (the respawn kernel numbers its random streams by global env index).
+    Scenarios that draw their reset from torch's generator instead (``balance``) still get
+    independent, reproducible shards, but not the unsharded job's layout.
+    """
+    from .make_env import make_env
+
+    lo, hi = shard_bounds(total_envs, rank, world_size)
+    env = make_env(scenario, num_envs=hi - lo, device=device, seed=seed, **kwargs)
+    env.world.env_offset = lo
+    env.world.reset_count.zero_()  # the construction-time reset above does not count as an episode
+    env.reset(seed=seed)
+    return env

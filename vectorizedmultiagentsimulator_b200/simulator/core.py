@@ -963,6 +963,10 @@ class World(TorchVectorizedObject):
         self._backend = None
         self._factory_at_init = type(self)._backend_factory
         # device-side reset bookkeeping
+        #: index of this world's env 0 in the whole job when ``batch_dim`` is one shard of a
+        #: multi-GPU job (``shard.make_shard_env``): the respawn kernel numbers its random streams by
+        #: global env, so a shard places entities exactly where the unsharded job would
+        self.env_offset = 0
         self._reset_count: Optional[Tensor] = None
         self._spawn_status: Optional[Tensor] = None
         self._spawn_calls = 0
