@@ -1,6 +1,7 @@
 """Times the substep kernel alone (both thread mappings) on a tiled golden state.
 
-    python tools/kernel_bench.py [scenario ...]        # on the GPU box
+    python tools/kernel_bench.py [scenario ...] [batch size ...]       # on the GPU box
+    KB_MAPPINGS=specialized VMAS_B200_LIB=tools/variants/lib_x.so python tools/kernel_bench.py balance
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +28,7 @@ for name in names:
         reps = max(1, B // desc.batch_dim)
         big = {k: v.repeat(reps, *([1] * (v.dim() - 1))) for k, v in state_in.items()}
         Bn = big["pos"].shape[0]
-        for mapping in ("specialized", "thread_per_env", "lanes_per_env"):
+        for mapping in os.environ.get("KB_MAPPINGS", "specialized,thread_per_env,lanes_per_env").split(","):
             old = desc.batch_dim
             desc.batch_dim = Bn
             try:

@@ -86,7 +86,7 @@ def emit_world(desc: P.WorldDescription, label: str) -> Tuple[str, str, int]:
     ef, ei = tables.ent_f32, tables.ent_i32
     lines = [f"// {label}: E={E} items={NI} substeps={desc.substeps}", f"struct {name} {{"]
     lines.append(f"  static constexpr int E = {E}, A = {desc.n_agents}, NI = {NI}, N_JOINTS = {tables.n_joints};")
-    lines.append(f"  static constexpr int MASK_WORDS = {(tables.n_masked + 31) // 32}, BLOCK = 64;")
+    lines.append(f"  static constexpr int MASK_WORDS = {(tables.n_masked + 31) // 32}, BLOCK = SPEC_BLOCK;")
     d = desc
     lines.append(
         "  static constexpr CfgC cfg = {"

@@ -277,7 +277,12 @@ __host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, in
   return m;
 }
 
-// SPEC_MIN_BLOCKS: resident blocks per SM the register allocator must leave room for (tuning knob)
+// Tuning knobs.  SPEC_BLOCK: threads (= envs) per block of the specialised kernels.
+// SPEC_MIN_BLOCKS: resident blocks per SM the register allocator must leave room for
+// (65536 / (SPEC_BLOCK * SPEC_MIN_BLOCKS) registers per thread at most).
+#ifndef SPEC_BLOCK
+#define SPEC_BLOCK 64
+#endif
 #ifndef SPEC_MIN_BLOCKS
 #define SPEC_MIN_BLOCKS 1
 #endif
