@@ -22,11 +22,16 @@ from .simulator import plan as P
 HERE = os.path.dirname(os.path.abspath(__file__))
 GENERATED = os.path.join(HERE, "csrc", "generated", "specializations.cuh")
 
-#: worlds that get an ahead-of-time specialisation: (scenario, kwargs)
-PRESETS: List[Tuple[str, Dict]] = [
+#: worlds that get an ahead-of-time specialisation: (scenario, kwargs[, tuning]).
+#: tuning["min_blocks"]: resident blocks per SM the register allocator leaves room for (default: the
+#: build's SPEC_MIN_BLOCKS = 8, i.e. <= 128 registers at 64 threads per block).  Measured per world
+#: on B200 (profiles/r1g_variant_bench.txt): stock transport runs 11 % faster at 1 Mi envs with 12
+#: (80 registers, 24 warps / SM) and the same at 32768; navigation loses 28 % there, balance and
+#: flocking gain 3-7 % at 1 Mi envs but lose 9-12 % at 32768, so they stay at the default.
+PRESETS: List[Tuple] = [
     ("balance", dict(n_agents=4)),  # BASELINE.json configs[0], [1]
     ("balance", dict()),
-    ("transport", dict(n_agents=4)),
+    ("transport", dict(n_agents=4), dict(min_blocks=12)),
     ("transport", dict(n_agents=4, n_lines=2, substeps=3)),  # BASELINE.json configs[2] variant
     ("navigation", dict(n_agents=8)),  # configs[3]
     ("navigation", dict()),
@@ -77,8 +82,9 @@ def _f(x) -> str:
     return s + "f"
 
 
-def emit_world(desc: P.WorldDescription, label: str) -> Tuple[str, str, int]:
+def emit_world(desc: P.WorldDescription, label: str, tuning: Dict = None) -> Tuple[str, str, int]:
     """C++ text of one world struct.  Returns (struct name, text, hash)."""
+    min_blocks = (tuning or {}).get("min_blocks", "SPEC_MIN_BLOCKS")
     tables = P.build_tables(desc)
     h = world_hash(desc)
     name = f"World_{h:016x}"
@@ -86,7 +92,10 @@ def emit_world(desc: P.WorldDescription, label: str) -> Tuple[str, str, int]:
     ef, ei = tables.ent_f32, tables.ent_i32
     lines = [f"// {label}: E={E} items={NI} substeps={desc.substeps}", f"struct {name} {{"]
     lines.append(f"  static constexpr int E = {E}, A = {desc.n_agents}, NI = {NI}, N_JOINTS = {tables.n_joints};")
-    lines.append(f"  static constexpr int MASK_WORDS = {(tables.n_masked + 31) // 32}, BLOCK = SPEC_BLOCK;")
+    lines.append(
+        f"  static constexpr int MASK_WORDS = {(tables.n_masked + 31) // 32}, BLOCK = SPEC_BLOCK, "
+        f"MIN_BLOCKS = {min_blocks};"
+    )
     d = desc
     lines.append(
         "  static constexpr CfgC cfg = {"
@@ -124,27 +133,27 @@ def emit_world(desc: P.WorldDescription, label: str) -> Tuple[str, str, int]:
     return name, "\n".join(lines), h
 
 
-def preset_descriptions() -> List[Tuple[str, P.WorldDescription]]:
+def preset_descriptions() -> List[Tuple[str, P.WorldDescription, Dict]]:
     """Builds every preset world on the CPU (construction only, no physics) and describes it."""
     import torch
 
     from . import scenarios
 
     out = []
-    for scenario, kwargs in PRESETS:
+    for scenario, kwargs, *tuning in PRESETS:
         sc = scenarios.load(scenario + ".py").Scenario()
         world = sc.env_make_world(1, torch.device("cpu"), **dict(kwargs))
         label = scenario + "(" + ", ".join(f"{k}={v}" for k, v in kwargs.items()) + ")"
-        out.append((label, P.describe_world(world)))
+        out.append((label, P.describe_world(world), tuning[0] if tuning else None))
     return out
 
 
 def generate(path: str = GENERATED) -> List[Tuple[str, int]]:
     worlds, seen = [], set()
-    for label, desc in preset_descriptions():
+    for label, desc, tuning in preset_descriptions():
         if not specializable(desc):
             continue
-        name, text, h = emit_world(desc, label)
+        name, text, h = emit_world(desc, label, tuning)
         if h in seen:
             continue
         seen.add(h)

@@ -288,7 +288,7 @@ __host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, in
 #endif
 
 template <class W>
-__global__ void __launch_bounds__(W::BLOCK, SPEC_MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
+__global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
   constexpr int E = W::E, NA = W::A, NI = W::NI, MW = W::MASK_WORDS;
     const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
 
