@@ -247,3 +247,54 @@ def test_shards_reset_like_the_unsharded_job():
         part.reset_at(mask[lo:hi])
         for (k, got), want in zip(_slab(part).items(), _slab(full).values()):
             assert torch.equal(got, want[lo:hi]), f"rank {rank}: {k}"
+
+
+def _staggered(name, kwargs, n_envs, **extra):
+    env = _make(name, kwargs, n_envs, max_steps=4, **extra)
+    env.steps.copy_((torch.arange(n_envs, dtype=torch.float32) % 4).to(DEV))  # episodes end at different steps
+    return env
+
+
+@pytest.mark.parametrize("name,kwargs", CASES[1:])  # balance draws its reset from torch's generator
+def test_auto_reset_equals_step_then_reset_at_dones(name, kwargs):
+    n_envs = 200
+    auto = _staggered(name, kwargs, n_envs, auto_reset=True)
+    manual = _staggered(name, kwargs, n_envs)
+    gen = torch.Generator().manual_seed(1)
+    for t in range(9):
+        act = _actions(auto, gen)
+        got = auto.step([a.clone() for a in act])
+        want = manual.step([a.clone() for a in act])
+        want_obs = manual.reset_at(want[2])
+        for g, w in zip(got[0] + got[1] + [got[2]], want_obs + want[1] + [want[2]]):
+            assert torch.equal(g, w), f"{name} step {t}"
+        assert torch.equal(auto.steps, manual.steps)
+    assert int(auto.world.reset_count.min()) >= 3 and auto.world.spawn_failures() == 0
+
+
+@pytest.mark.parametrize("name,kwargs", CASES)
+def test_auto_reset_inside_the_step_graph(name, kwargs):
+    """Graph mode captures the reset kernels with the step; replays must equal the eager env.
+    (balance: the reset draws come from torch's generator, so only the step outputs that do not
+    depend on the new layout are compared.)"""
+    n_envs = 128
+    eager = _staggered(name, kwargs, n_envs, auto_reset=True)
+    graph = _staggered(name, kwargs, n_envs, auto_reset=True, cuda_graph=True)
+    gen = torch.Generator().manual_seed(3)
+    for t in range(10):
+        act = _actions(eager, gen)
+        want = eager.step([a.clone() for a in act])
+        got = graph.step([a.clone() for a in act])
+        assert torch.equal(got[2], want[2]), f"{name} step {t}: dones"
+        assert torch.equal(graph.steps, eager.steps)
+        if name != "balance":
+            for g, w in zip(got[0] + got[1], want[0] + want[1]):
+                assert torch.equal(g, w), f"{name} step {t}"
+        else:
+            assert all(torch.isfinite(o).all() for o in got[0])
+            sync_to = {k: v for k, v in eager.world.slab.state_dict().items()}
+            graph.world.slab.load_state_dict(sync_to)  # keep the two balance envs in lock-step
+            graph.scenario.global_shaping.copy_(eager.scenario.global_shaping)
+    assert graph._graph is not None and graph.graph_replays >= 6
+    assert torch.equal(graph.world.reset_count, eager.world.reset_count)
+    assert int(graph.world.reset_count.min()) >= 3

@@ -195,6 +195,55 @@ def test_long_entity_lists_are_chained(device_reset_on_cpu):
 
 
 @pytest.mark.parametrize("name,kwargs", CASES[1:])
+@pytest.mark.parametrize("terminated_truncated", [False, True])
+def test_auto_reset_equals_step_then_reset_at_dones(device_reset_on_cpu, name, kwargs, terminated_truncated):
+    """``auto_reset=True``: the step's rewards / dones, then the observations ``reset_at(dones)`` would
+    return.  Episodes end at different times (staggered step counters against ``max_steps``)."""
+    import vectorizedmultiagentsimulator_b200 as b200
+
+    n = 12
+    opts = dict(num_envs=n, device="cpu", seed=8, max_steps=4, terminated_truncated=terminated_truncated, **kwargs)
+    auto = b200.make_env(name, auto_reset=True, **opts)
+    manual = b200.make_env(name, **opts)
+    stagger = torch.arange(n, dtype=torch.float32) % 4
+    auto.steps.copy_(stagger)
+    manual.steps.copy_(stagger)
+    gen = torch.Generator().manual_seed(1)
+    finished_total = 0
+    for t in range(9):
+        act = [torch.rand(n, 2, generator=gen) * 2 - 1 for _ in auto.agents]
+        got = auto.step([a.clone() for a in act])
+        want = manual.step([a.clone() for a in act])
+        finished = (want[2] | want[3]) if terminated_truncated else want[2]
+        finished_total += int(finished.sum())
+        want_obs = manual.reset_at(finished)
+        for g, w in zip(got[0], want_obs):
+            assert torch.equal(g, w), f"{name} step {t}: observations"
+        for g, w in zip(got[1], want[1]):
+            assert torch.equal(g, w), f"{name} step {t}: rewards"
+        for k in range(2, 4 if terminated_truncated else 3):
+            assert torch.equal(got[k], want[k]), f"{name} step {t}: dones"
+        assert torch.equal(auto.steps, manual.steps)
+        for x, y in zip(_slab(auto).values(), _slab(manual).values()):
+            assert torch.equal(x, y)
+    assert finished_total >= 2 * n  # every env ended at least two episodes
+    assert auto.world.reset_count.min() >= 3
+
+
+def test_auto_reset_needs_a_mask_capable_scenario():
+    import vectorizedmultiagentsimulator_b200 as b200
+    from oracle.backend import use_oracle
+    from vectorizedmultiagentsimulator_b200.scenarios import balance
+
+    class IndexOnly(balance.Scenario):
+        supports_masked_reset = False
+
+    with use_oracle():
+        with pytest.raises(NotImplementedError):
+            b200.make_env(IndexOnly(), num_envs=4, device="cpu", seed=0, n_agents=3, auto_reset=True)
+
+
+@pytest.mark.parametrize("name,kwargs", CASES[1:])
 def test_shards_reset_like_the_unsharded_job(device_reset_on_cpu, name, kwargs):
     """``shard.make_shard_env``: a shard's layouts (initial and after a masked reset) are the matching
     slice of the unsharded job's — what makes results independent of the number of GPUs."""

@@ -25,6 +25,7 @@ def make_env(
     wrapper_kwargs: Optional[dict] = None,
     cuda_graph: bool = False,
     action_checks: Optional[str] = None,
+    auto_reset: bool = False,
     **kwargs,
 ):
     """Create a vectorised environment.
@@ -35,7 +36,8 @@ def make_env(
     ``BaseScenario`` instance.  ``device`` defaults to ``"cuda"``: the physics only runs there.
     ``cuda_graph=True`` replays one captured CUDA graph per ``step`` (graph-safe scenarios only),
     ``action_checks`` selects ``"sync"`` / ``"deferred"`` / ``"off"`` validation of the input
-    actions (see ``Environment``).  Remaining ``kwargs`` go to ``Scenario.make_world``.
+    actions, ``auto_reset=True`` resets finished envs on the device inside ``step`` (see
+    ``Environment``).  Remaining ``kwargs`` go to ``Scenario.make_world``.
     """
     env = Environment(
         _as_scenario(scenario),
@@ -53,6 +55,7 @@ def make_env(
         # additions of this package
         cuda_graph=cuda_graph,
         action_checks=action_checks,
+        auto_reset=auto_reset,
         **kwargs,
     )
     if wrapper is None:

@@ -91,27 +91,37 @@ class Scenario(BaseScenario):
         spread = (-half + r_pkg, half - r_pkg) if self.random_package_pos_on_line else (0.0, 0.0)
         package_rel = torch.cat([self._uniform(n, *spread), torch.full((n, 1), r_pkg, **dev)], dim=1)
 
-        span = self.line_length - self.agent_radius
+        offsets, floor_pos = self._reset_constants()
         for i, agent in enumerate(world.agents):
-            offset = torch.tensor(
-                [-span / 2 + i * span / (self.n_agents - 1), -self.agent_radius * 2], **dev
-            )
-            agent.set_pos(line_pos + offset, batch_index=env_index)
+            agent.set_pos(line_pos + offsets[i], batch_index=env_index)
 
         self.line.set_pos(line_pos, batch_index=env_index)
         self.package.goal.set_pos(goal_pos, batch_index=env_index)
         self.line.set_rot(torch.zeros(1, **dev), batch_index=env_index)
         self.package.set_pos(line_pos + package_rel, batch_index=env_index)
-        self.floor.set_pos(
-            torch.tensor(
-                [0, -world.y_semidim - self.floor.shape.width / 2 - self.agent_radius],
-                device=world.device,
-            ),
-            batch_index=env_index,
-        )
+        self.floor.set_pos(floor_pos, batch_index=env_index)
         self.compute_on_the_ground()
         dist = torch.linalg.vector_norm(self.package.state.pos - self.package.goal.state.pos, dim=1)
         self.keep(self, "global_shaping", dist * self.shaping_factor, env_index)
+
+    def _reset_constants(self):
+        """Agent offsets under the line ``[A, 2]`` and the floor position ``[2]``, uploaded once per
+        device (a ``torch.tensor([...], device=cuda)`` per reset is a synchronous host copy, which
+        also cannot be captured in a CUDA graph — ``auto_reset`` in graph mode resets inside one)."""
+        world = self.world
+        cached = getattr(self, "_reset_consts", None)
+        if cached is None or cached[0].device != world.slab.pos.device:
+            span = self.line_length - self.agent_radius
+            offsets = torch.tensor(
+                [[-span / 2 + i * span / (self.n_agents - 1), -self.agent_radius * 2] for i in range(self.n_agents)],
+                device=world.device,
+                dtype=torch.float32,
+            )
+            floor_pos = torch.tensor(
+                [0, -world.y_semidim - self.floor.shape.width / 2 - self.agent_radius], device=world.device
+            )
+            cached = self._reset_consts = (offsets, floor_pos)
+        return cached
 
     def compute_on_the_ground(self):
         # the three overlap tests of a step (two here, one in done()) in one launch

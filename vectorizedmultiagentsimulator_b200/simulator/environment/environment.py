@@ -9,6 +9,10 @@ with one ``[num_envs, ...]`` tensor per policy agent).  What differs is undernea
   next call, instead of forcing two host syncs per agent per step (ref environment.py:621,
   651-653).  ``"sync"`` reproduces the reference timing of the asserts, ``"off"`` skips them;
 * ``grad_enabled=True`` is rejected: the kernels are forward-only;
+* ``auto_reset=True`` (extension) resets every env a step finishes inside that step, on the device:
+  ``rewards / dones / infos`` describe the step that ended the episode, ``obs`` of a finished env is
+  the first observation of its next episode — what ``obs = env.reset_at(dones)`` after the step
+  would return, without the host in the loop (and, in graph mode, inside the captured graph);
 * ``cuda_graph=True`` captures one whole ``step`` (action decoding → dynamics → physics kernels →
   scenario reward / observation / done / info) into a CUDA graph after two eager warm-up steps
   and replays it afterwards: no Python, no per-kernel launch latency.  It requires a
@@ -97,6 +101,7 @@ class Environment(TorchVectorizedObject):
         terminated_truncated: bool = False,
         action_checks: Optional[str] = None,
         cuda_graph: bool = False,
+        auto_reset: bool = False,
         **kwargs,
     ):
         if multidiscrete_actions:
@@ -132,6 +137,12 @@ class Environment(TorchVectorizedObject):
             if cuda_graph and self.device.type != "cuda":
                 raise ValueError("cuda_graph=True needs a CUDA device")
             self.cuda_graph = cuda_graph
+            self.auto_reset = auto_reset
+            if auto_reset and not self.scenario.supports_masked_reset:
+                raise NotImplementedError(
+                    f"auto_reset=True needs a scenario whose reset_world_at accepts a bool mask "
+                    f"(supports_masked_reset); {type(self.scenario).__name__} takes an env index"
+                )
             self._graph = None
             self._graph_inputs = None
             self._graph_outputs = None
@@ -301,6 +312,10 @@ class Environment(TorchVectorizedObject):
         torch.manual_seed(seed)
         np.random.seed(seed)
         random.seed(seed)
+        if getattr(self, "auto_reset", False) and getattr(self, "_graph", None) is not None:
+            # the captured step contains the respawn kernel, whose Philox key is the seed: capture again
+            self._graph = None
+            self._graph_warmup_left = 1
         return [seed]
 
     def _normalize_actions(self, actions) -> List[Tensor]:
@@ -436,9 +451,24 @@ class Environment(TorchVectorizedObject):
         self.world.step()
         self.scenario.post_step()
         self.steps += 1
-        return self._get_from_scenario(
-            get_observations=True, get_infos=True, get_rewards=True, get_dones=True, clone=clone_outputs
+        if not self.auto_reset:
+            return self._get_from_scenario(
+                get_observations=True, get_infos=True, get_rewards=True, get_dones=True, clone=clone_outputs
+            )
+        # auto-reset: rewards / infos / dones describe the step that just ran; every env it finished
+        # is reset on the device (mask = dones, no host sync) and the observations are taken
+        # afterwards, so a finished env hands out the first observation of its next episode.  The
+        # first three are cloned before the reset touches anything they might alias.
+        rest = self._get_from_scenario(
+            get_observations=False, get_infos=True, get_rewards=True, get_dones=True, clone=True
         )
+        finished = (rest[1] | rest[2]) if self.terminated_truncated else rest[1]
+        self.scenario.env_reset_world_at(finished)
+        self.steps.masked_fill_(finished, 0)
+        obs = self._get_from_scenario(
+            get_observations=True, get_infos=False, get_rewards=False, get_dones=False, clone=clone_outputs
+        )
+        return obs + rest
 
     def _step_device(self, actions: List[Tensor], clone_outputs: bool = True):
         """The device-side work of one step."""
