@@ -8,30 +8,27 @@ import torch
 
 from .utils import Color
 
+_NO_RENDERING = "Rendering is outside the scope of the B200 hot-path build"
+
 
 class Sensor(ABC):
+    """Something mounted on an agent that is read with ``measure()`` (ref sensors.py:21-44).
+    ``agent`` is filled in by ``Agent.__init__`` when the sensor is handed to it."""
+
     def __init__(self, world):
         super().__init__()
         self._world = world
-        self._agent = None
-
-    @property
-    def agent(self):
-        return self._agent
-
-    @agent.setter
-    def agent(self, agent):
-        self._agent = agent
+        self.agent = None
 
     @abstractmethod
     def measure(self):
         raise NotImplementedError
 
-    def render(self, env_index: int = 0):
-        raise NotImplementedError("Rendering is outside the scope of the B200 hot-path build")
-
     def to(self, device: torch.device):
         raise NotImplementedError
+
+    def render(self, env_index: int = 0):
+        raise NotImplementedError(_NO_RENDERING)
 
 
 class Lidar(Sensor):
@@ -54,20 +51,21 @@ class Lidar(Sensor):
         render: bool = True,
     ):
         super().__init__(world)
-        full_circle = (angle_start - angle_end) % (torch.pi * 2) < 1e-5
-        sweep = torch.linspace(
-            angle_start, angle_end, n_rays + 1 if full_circle else n_rays, device=world.device
-        )[:n_rays]
-        self._angles = sweep.repeat(world.batch_dim, 1)
+        closes_the_circle = (angle_start - angle_end) % (torch.pi * 2) < 1e-5
+        n_points = n_rays + 1 if closes_the_circle else n_rays
+        sweep = torch.linspace(angle_start, angle_end, n_points, device=world.device)[:n_rays]
+        self._angles = sweep.repeat(world.batch_dim, 1)  # [B, n_rays], agent frame
         self._max_range = max_range
-        self._last_measurement = None
-        self._render = render
         self._entity_filter = entity_filter
-        self._render_color = render_color
-        self._alpha = alpha
+        self._last_measurement = None
+        # rendering options are carried for API compatibility only
+        self._render, self._render_color, self._alpha = render, render_color, alpha
 
-    def to(self, device: torch.device):
-        self._angles = self._angles.to(device)
+    def measure(self, vectorized: bool = True):
+        # ``vectorized`` is accepted for API compatibility: both values run the same kernel
+        # (the reference's per-ray python loop, sensors.py:102-113, has no counterpart here).
+        self._last_measurement = self._world._get_backend().lidar_measure(self)
+        return self._last_measurement
 
     @property
     def entity_filter(self):
@@ -76,25 +74,21 @@ class Lidar(Sensor):
     @entity_filter.setter
     def entity_filter(self, entity_filter: Callable):
         self._entity_filter = entity_filter
-        if self._world is not None:
+        if self._world is not None:  # the set of entities the rays can hit is part of the compiled plan
             self._world._invalidate_plan()
 
+    def to(self, device: torch.device):
+        self._angles = self._angles.to(device)
+
+    # -- rendering attributes (kept so scenario files that read them still load) -------------------
     @property
     def render_color(self):
-        if isinstance(self._render_color, Color):
-            return self._render_color.value
-        return self._render_color
+        colour = self._render_color
+        return colour.value if isinstance(colour, Color) else colour
 
     @property
     def alpha(self):
         return self._alpha
-
-    def measure(self, vectorized: bool = True):
-        # ``vectorized`` is accepted for API compatibility: both values run the same kernel
-        # (the reference's per-ray python loop, sensors.py:102-113, has no counterpart here).
-        measurement = self._world._get_backend().lidar_measure(self)
-        self._last_measurement = measurement
-        return measurement
 
     def set_render(self, render: bool):
         self._render = render
