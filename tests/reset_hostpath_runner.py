@@ -27,6 +27,12 @@ for name in sorted(names):
         env = b200.make_env(scenario_file(name), num_envs=5, device="cpu", seed=0)
         env.step(env.get_random_actions())
         env.reset_at(3)
+        for agent in env.world.agents:  # what Agent._reset clears besides the slab rows
+            if agent.action.u is not None:
+                assert not agent.action.u[3].any(), "action.u of the reset env"
+            state = getattr(agent.dynamics, "drone_state", None)
+            if state is not None:
+                assert not state[3].any() and state[0].any(), "dynamics state of the reset env"
         env.step(env.get_random_actions())
         env.reset()
         report[name] = dict(

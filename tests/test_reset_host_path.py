@@ -153,6 +153,8 @@ def test_masked_reset_equals_one_reset_at_per_env(device_reset_on_cpu, name, kwa
     if spawns_everything:
         assert all(torch.equal(x, y) for x, y in zip(obs_a, obs_b))
     assert float(after_a["vel"][mask].abs().max()) == 0.0
+    for agent in a.world.policy_agents:  # the action buffers are cleared like Agent._reset does
+        assert not agent.action.u[mask].any() and agent.action.u[~mask].any()
     assert a.world.reset_count.tolist() == [1 + int(m) for m in mask.tolist()]
     assert a.world.spawn_failures() == 0
 

@@ -390,7 +390,7 @@ class Action(TorchVectorizedObject):
                 setattr(self, name, torch.zeros_like(t))
             else:
                 t = t.clone()
-                t[env_index] = 0.0
+                _zero_rows(t, env_index)  # an int, or a [B] bool mask (no host sync)
                 setattr(self, name, t)
 
     def zero_grad(self):
@@ -1070,10 +1070,13 @@ class World(TorchVectorizedObject):
         if self.uses_device_reset:
             self._ensure_slab()
             self._get_backend().reset_state(env_index, self.reset_count)
-            if self._dim_c > 0:
-                for a in self._agents:
-                    if a.state.c is not None:
-                        _zero_rows(a.state.c, env_index)
+            # what Agent._reset does besides zeroing the slab rows: the action buffers, the
+            # dynamics model's own state (e.g. Drone) and the communication state
+            for a in self._agents:
+                a.action._reset(env_index)
+                a.dynamics.reset(env_index)
+                if self._dim_c > 0 and a.state.c is not None:
+                    _zero_rows(a.state.c, env_index)
             return
         for e in self.entities:
             e._reset(env_index)
