@@ -287,29 +287,10 @@ __host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, in
 #define SPEC_MIN_BLOCKS 1
 #endif
 
+// One env, all of `a.n_substeps` substeps, state in the calling thread's registers.
 template <class W>
-__global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
-  constexpr int E = W::E, NA = W::A, NI = W::NI, MW = W::MASK_WORDS;
-    const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
-
-  uint32_t mask_words[MW > 0 ? MW : 1];
-  if constexpr (MW > 0) {
-    __shared__ uint32_t s_mask[MW];
-    if (a.use_mask) {
-      for (int w = threadIdx.x; w < MW; w += W::BLOCK) s_mask[w] = a.mask[w];
-      __syncthreads();
-      if (threadIdx.x == 0) {  // the last block to have copied the mask clears it
-        __threadfence();
-        unsigned done = atomicAdd(&a.mask[MW], 1u);
-        if (done == gridDim.x - 1) {
-          for (int w = 0; w < MW; ++w) a.mask[w] = 0u;
-          a.mask[MW] = 0u;
-        }
-      }
-#pragma unroll
-      for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
-    }
-  }
+DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask_words)[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1]) {
+  constexpr int E = W::E, NA = W::A, NI = W::NI;
   // ---- load this env's rows with vector accesses -----------------------------------------------
   constexpr uint64_t ALL_POS = (2 * E >= 64) ? ~0ull : ((1ull << (2 * E)) - 1);
   constexpr uint64_t MOV2 = ent_cols<W>(VMAS_F_MOVABLE, 2);
@@ -496,6 +477,35 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(cons
   row_store<NA, T_ST>(a.st.torque + (size_t)env * NA, row_t);
 }
 
+#ifdef __CUDACC__
+template <class W>
+__global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
+  constexpr int MW = W::MASK_WORDS;
+  const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
+
+  // the block's copy of the broad-phase mask (ref core.py:2797-2801); the last block to have copied
+  // it clears it for the next substep (no memset node: CUDA-graph safe)
+  uint32_t mask_words[MW > 0 ? MW : 1];
+  if constexpr (MW > 0) {
+    __shared__ uint32_t s_mask[MW];
+    if (a.use_mask) {
+      for (int w = threadIdx.x; w < MW; w += W::BLOCK) s_mask[w] = a.mask[w];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned done = atomicAdd(&a.mask[MW], 1u);
+        if (done == gridDim.x - 1) {
+          for (int w = 0; w < MW; ++w) a.mask[w] = 0u;
+          a.mask[MW] = 0u;
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
+    }
+  }
+  spec_env_step<W>(a, env, mask_words);
+}
+
 // host-side launcher used by the registry in generated/specializations.cuh
 template <class W>
 static cudaError_t launch_spec(const SpecArgs& a, cudaStream_t stream) {
@@ -503,6 +513,7 @@ static cudaError_t launch_spec(const SpecArgs& a, cudaStream_t stream) {
   step_spec_kernel<W><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a);
   return cudaGetLastError();
 }
+#endif  // __CUDACC__
 
 struct SpecEntry {
   uint64_t hash;
