@@ -84,10 +84,15 @@ typedef struct VmasPlanTables {
   const float*   ent_gravity; /* [B, E, 2] per-env gravity of entities flagged VMAS_F_GRAVITY_ENV, or NULL
                                  (ref core.py:594-601, 2049-2052: Entity.gravity given as a tensor) */
   int32_t n_rounds;
-  int32_t group;              /* lanes per env: 1 = one thread per env (default), or 8, 16, 32 */
+  int32_t group;              /* lanes per env: 1 = one thread per env (default), or 8, 16, 32; with a
+                                 specialization: 1, or VMAS_GROUP_COOPERATIVE = the cooperative kernel
+                                 (the warps of a block share a tile of 32 envs: shorter dependency chains,
+                                 meant for batches that leave the GPU latency-bound) */
   int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */
   int32_t specialization;     /* index from vmas_b200_find_specialization(), or -1: generic kernels */
 } VmasPlanTables;
+
+#define VMAS_GROUP_COOPERATIVE (-8)
 
 /* The state slab.  DEVICE pointers. */
 typedef struct VmasState {

@@ -159,6 +159,35 @@ def test_thread_per_env_and_lanes_per_env_agree_bitwise(name):
                 assert torch.equal(outs[0].t[k], other.t[k]), f"{name} step {t} field {k} ({mapping})"
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_cooperative_kernel_agrees_bitwise(name):
+    """The small-batch cooperative kernel (warps share a tile of 32 envs; csrc/spec_coop_kernel.cuh)
+    against the thread-per-env specialised kernel: identical bits, every golden world that has a
+    specialisation, whole steps (all substeps, broad phase included) and a batch that is not a
+    multiple of the tile."""
+    fix, desc, tables = load(name)
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    if _native.DeviceTables(tables, None, device).mapping != "specialized":
+        pytest.skip("no ahead-of-time specialisation of this world")
+    for t, state_in, fixed_rot, _ in teacher_forced_steps(fix):
+        if t % 3:
+            continue
+        for rows in (None, 37):
+            state = state_in if rows is None else {k: (v[:rows] if torch.is_tensor(v) else v) for k, v in state_in.items()}
+            outs = []
+            for mapping in ("specialized", "cooperative"):
+                dt = _device_tables(tables, fixed_rot, device, mapping=mapping, ent_gravity=state.get("ent_gravity"))
+                assert dt.mapping == mapping
+                if rows is not None:
+                    dt.cfg.batch_dim = rows
+                slab = _Slab(state, device)
+                _native.world_step(lib, dt, slab)
+                outs.append(slab)
+            for k in STATE_KEYS:
+                assert torch.equal(outs[0].t[k], outs[1].t[k]), f"{name} step {t} field {k} rows {rows}"
+
+
 def test_config_worlds_have_specialised_kernels():
     lib = _native.load()
     assert lib.vmas_b200_num_specializations() >= 4

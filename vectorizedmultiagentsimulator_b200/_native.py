@@ -28,6 +28,7 @@ GENERATED = os.path.join(CSRC, "generated", "specializations.cuh")
 HEADERS = [
     os.path.join(CSRC, "geometry.cuh"),
     os.path.join(CSRC, "spec_kernel.cuh"),
+    os.path.join(CSRC, "spec_coop_kernel.cuh"),
     os.path.join(CSRC, "reset.cuh"),
     os.path.join(INCLUDE, "vmas_b200.h"),
     GENERATED,
@@ -155,6 +156,7 @@ class AgentActionsC(C.Structure):
 
 
 MAX_SPAWN = 64
+GROUP_COOPERATIVE = -8  # VMAS_GROUP_COOPERATIVE
 
 
 class SpawnC(C.Structure):
@@ -344,8 +346,11 @@ class DeviceTables:
         self.device = torch.device(device)
         desc = tables.desc
         mapping = mapping or os.environ.get("VMAS_B200_MAPPING", "auto")
-        assert mapping in ("auto", "specialized", "thread_per_env", "lanes_per_env"), mapping
+        assert mapping in ("auto", "specialized", "cooperative", "thread_per_env", "lanes_per_env"), mapping
         self.specialization = -1
+        cooperative = mapping == "cooperative"  # the specialised world's small-batch kernel (opt-in)
+        if cooperative:
+            mapping = "specialized"
         if mapping in ("auto", "specialized"):
             from . import codegen
 
@@ -356,9 +361,11 @@ class DeviceTables:
                 mapping = "thread_per_env"
             else:
                 mapping = "specialized"
+        if cooperative:
+            mapping = "cooperative"
         self.mapping = mapping
-        if mapping in ("thread_per_env", "specialized"):
-            self.group, self.ents_per_lane = 1, desc.n_entities
+        if mapping in ("thread_per_env", "specialized", "cooperative"):
+            self.group, self.ents_per_lane = (GROUP_COOPERATIVE if cooperative else 1), desc.n_entities
             sched = np.zeros((0, 1), np.int32)
         else:
             self.group, self.ents_per_lane = lane_layout(desc.n_entities)

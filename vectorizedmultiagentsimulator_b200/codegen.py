@@ -163,21 +163,28 @@ def generate(path: str = GENERATED) -> List[Tuple[str, int]]:
         "// constexpr world tables the specialised substep kernel (spec_kernel.cuh) is instantiated with.",
         "#pragma once",
         '#include "../spec_kernel.cuh"',
+        '#include "../spec_coop_kernel.cuh"',
         "",
         "namespace vmas {",
         "",
     ]
     for _, _, text, _, _ in worlds:
         parts += [text, ""]
+    parts.append("#ifdef __CUDACC__")
     parts.append("static const SpecEntry kSpecs[] = {")
     for label, name, _, h, desc in worlds:
         parts.append(
-            f'    {{0x{h:016x}ull, "{label}", {desc.n_entities}, {len(desc.items)}, &launch_spec<{name}>}},'
+            f'    {{0x{h:016x}ull, "{label}", {desc.n_entities}, {len(desc.items)}, &launch_spec<{name}>, '
+            f"&launch_coop<{name}>}},"
         )
     if not worlds:
-        parts.append('    {0ull, "", 0, 0, nullptr},')
+        parts.append('    {0ull, "", 0, 0, nullptr, nullptr},')
     parts.append("};")
     parts.append(f"static const int kNumSpecs = {len(worlds)};")
+    parts.append("#endif")
+    # the same worlds as a type list, for code that instantiates a template per world (tests/hostsim)
+    parts.append("#define VMAS_FOR_EACH_SPEC_WORLD(X) \\")
+    parts.append(" \\\n".join(f"  X({i}, {name}, 0x{h:016x}ull)" for i, (_, name, _, h, _) in enumerate(worlds)))
     parts += ["", "}  // namespace vmas", ""]
     text = "\n".join(parts)
     os.makedirs(os.path.dirname(path), exist_ok=True)

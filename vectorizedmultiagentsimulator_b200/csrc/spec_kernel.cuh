@@ -515,11 +515,14 @@ static cudaError_t launch_spec(const SpecArgs& a, cudaStream_t stream) {
 }
 #endif  // __CUDACC__
 
+#ifdef __CUDACC__
 struct SpecEntry {
   uint64_t hash;
   const char* name;
   int n_entities, n_items;
-  cudaError_t (*launch)(const SpecArgs&, cudaStream_t);
+  cudaError_t (*launch)(const SpecArgs&, cudaStream_t);       // one thread per env (step_spec_kernel)
+  cudaError_t (*launch_coop)(const SpecArgs&, cudaStream_t);  // warps share a tile of 32 envs (step_coop_kernel)
 };
+#endif
 
 }  // namespace vmas

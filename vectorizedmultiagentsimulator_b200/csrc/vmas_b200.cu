@@ -1543,7 +1543,12 @@ static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
   sa.use_mask = args.use_mask;
   sa.first_substep = args.first_substep;
   sa.n_substeps = args.n_substeps;
-  CUDA_OK(sp.launch(sa, stream));
+  // tb.group selects the thread mapping of a specialised world: 1 = one thread per env,
+  // VMAS_GROUP_COOPERATIVE = warps share a tile of 32 envs (small batches)
+  if (args.tb.group == VMAS_GROUP_COOPERATIVE)
+    CUDA_OK(sp.launch_coop(sa, stream));
+  else
+    CUDA_OK(sp.launch(sa, stream));
   return 1;
 }
 
