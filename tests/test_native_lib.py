@@ -78,3 +78,32 @@ def test_reset_entry_points_validate_their_arguments_without_gpu():
     sp.entity[0] = -1  # position only, but no `out` buffer either
     assert lib.vmas_b200_spawn_entities(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(sp), None) < 0
     assert "nothing to write" in err()
+
+
+def test_device_tables_build_for_every_mapping_on_cpu():
+    """The host-side table upload of each thread mapping (incl. the opt-in cooperative one) — what
+    runs before the first launch — without a GPU."""
+    import sys
+
+    import pytest
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import load
+
+    cpu = torch.device("cpu")
+    for name, specialised in (("balance", True), ("flocking", True), ("pollock", False)):
+        _, desc, tables = load(name)
+        auto = _native.DeviceTables(tables, None, cpu, mapping="auto")
+        assert auto.mapping == ("specialized" if specialised else "thread_per_env")
+        for mapping in ("thread_per_env", "lanes_per_env"):
+            dt = _native.DeviceTables(tables, None, cpu, mapping=mapping)
+            assert dt.mapping == mapping and dt.tb.specialization == -1 and dt.tb.group >= 1
+        for mapping, group in (("specialized", 1), ("cooperative", _native.GROUP_COOPERATIVE)):
+            if specialised:
+                dt = _native.DeviceTables(tables, None, cpu, mapping=mapping)
+                assert dt.mapping == mapping and dt.tb.group == group and dt.tb.specialization >= 0
+                assert dt.tb.specialization == auto.tb.specialization
+            else:
+                with pytest.raises(RuntimeError):
+                    _native.DeviceTables(tables, None, cpu, mapping=mapping)

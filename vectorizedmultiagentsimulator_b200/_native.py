@@ -377,7 +377,7 @@ class DeviceTables:
         self.item_i32 = up(tables.item_i32)
         self.inc_off = up(tables.inc_off)
         self.inc = up(tables.inc)
-        self.sched = up(sched if sched.size else np.full((1, self.group), -1, np.int32))
+        self.sched = up(sched if sched.size else np.full((1, max(self.group, 1)), -1, np.int32))
         self.masked_items = up(tables.masked_items)
         B = desc.batch_dim if world is None else world.batch_dim
         needs_rot = any(it["kind"] == P.K_JOINT and not it["rotate"] for it in desc.items)
