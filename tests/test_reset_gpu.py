@@ -168,7 +168,7 @@ def test_env_masked_reset(name, kwargs):
     env.step(_actions(env, gen))  # and the env keeps stepping
 
 
-@pytest.mark.parametrize("name,kwargs", CASES[1:])  # balance draws its reset from torch's generator
+@pytest.mark.parametrize("name,kwargs", CASES)
 def test_masked_reset_equals_one_reset_at_per_env(name, kwargs):
     n_envs = 96
     a, b = _make(name, kwargs, n_envs), _make(name, kwargs, n_envs)
@@ -255,7 +255,7 @@ def _staggered(name, kwargs, n_envs, **extra):
     return env
 
 
-@pytest.mark.parametrize("name,kwargs", CASES[1:])  # balance draws its reset from torch's generator
+@pytest.mark.parametrize("name,kwargs", CASES)
 def test_auto_reset_equals_step_then_reset_at_dones(name, kwargs):
     n_envs = 200
     auto = _staggered(name, kwargs, n_envs, auto_reset=True)
@@ -274,9 +274,7 @@ def test_auto_reset_equals_step_then_reset_at_dones(name, kwargs):
 
 @pytest.mark.parametrize("name,kwargs", CASES)
 def test_auto_reset_inside_the_step_graph(name, kwargs):
-    """Graph mode captures the reset kernels with the step; replays must equal the eager env.
-    (balance: the reset draws come from torch's generator, so only the step outputs that do not
-    depend on the new layout are compared.)"""
+    """Graph mode captures the reset kernels with the step; replays must equal the eager env."""
     n_envs = 128
     eager = _staggered(name, kwargs, n_envs, auto_reset=True)
     graph = _staggered(name, kwargs, n_envs, auto_reset=True, cuda_graph=True)
@@ -287,14 +285,8 @@ def test_auto_reset_inside_the_step_graph(name, kwargs):
         got = graph.step([a.clone() for a in act])
         assert torch.equal(got[2], want[2]), f"{name} step {t}: dones"
         assert torch.equal(graph.steps, eager.steps)
-        if name != "balance":
-            for g, w in zip(got[0] + got[1], want[0] + want[1]):
-                assert torch.equal(g, w), f"{name} step {t}"
-        else:
-            assert all(torch.isfinite(o).all() for o in got[0])
-            sync_to = {k: v for k, v in eager.world.slab.state_dict().items()}
-            graph.world.slab.load_state_dict(sync_to)  # keep the two balance envs in lock-step
-            graph.scenario.global_shaping.copy_(eager.scenario.global_shaping)
+        for g, w in zip(got[0] + got[1], want[0] + want[1]):
+            assert torch.equal(g, w), f"{name} step {t}"
     assert graph._graph is not None and graph.graph_replays >= 6
     assert torch.equal(graph.world.reset_count, eager.world.reset_count)
     assert int(graph.world.reset_count.min()) >= 3

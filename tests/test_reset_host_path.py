@@ -130,9 +130,7 @@ def test_masked_reset_equals_one_reset_at_per_env(device_reset_on_cpu, name, kwa
     n = 24
     a = b200.make_env(name, num_envs=n, device="cpu", seed=4, **kwargs)
     b = b200.make_env(name, num_envs=n, device="cpu", seed=4, **kwargs)
-    spawns_everything = name != "balance"  # balance draws its reset from torch's generator
-    if spawns_everything:
-        assert all(torch.equal(x, y) for x, y in zip(_slab(a).values(), _slab(b).values()))
+    assert all(torch.equal(x, y) for x, y in zip(_slab(a).values(), _slab(b).values()))  # same seed, same layout
     gen = torch.Generator().manual_seed(2)
     for _ in range(2):
         act = [torch.rand(n, 2, generator=gen) * 2 - 1 for _ in a.agents]
@@ -148,10 +146,8 @@ def test_masked_reset_equals_one_reset_at_per_env(device_reset_on_cpu, name, kwa
     after_a, after_b = _slab(a), _slab(b)
     for k in after_a:
         assert torch.equal(after_a[k][~mask], before[k][~mask]), f"{name}: {k} of an unflagged env changed"
-        if spawns_everything:
-            assert torch.equal(after_a[k], after_b[k]), f"{name}: {k}"
-    if spawns_everything:
-        assert all(torch.equal(x, y) for x, y in zip(obs_a, obs_b))
+        assert torch.equal(after_a[k], after_b[k]), f"{name}: {k}"
+    assert all(torch.equal(x, y) for x, y in zip(obs_a, obs_b))
     assert float(after_a["vel"][mask].abs().max()) == 0.0
     for agent in a.world.policy_agents:  # the action buffers are cleared like Agent._reset does
         assert not agent.action.u[mask].any() and agent.action.u[~mask].any()
@@ -196,7 +192,7 @@ def test_long_entity_lists_are_chained(device_reset_on_cpu):
     assert float(d.min()) >= 0.05 - 1e-6  # the second launch kept away from the first one's draws
 
 
-@pytest.mark.parametrize("name,kwargs", CASES[1:])
+@pytest.mark.parametrize("name,kwargs", CASES)
 @pytest.mark.parametrize("terminated_truncated", [False, True])
 def test_auto_reset_equals_step_then_reset_at_dones(device_reset_on_cpu, name, kwargs, terminated_truncated):
     """``auto_reset=True``: the step's rewards / dones, then the observations ``reset_at(dones)`` would
@@ -245,7 +241,7 @@ def test_auto_reset_needs_a_mask_capable_scenario():
             b200.make_env(IndexOnly(), num_envs=4, device="cpu", seed=0, n_agents=3, auto_reset=True)
 
 
-@pytest.mark.parametrize("name,kwargs", CASES[1:])
+@pytest.mark.parametrize("name,kwargs", CASES)
 def test_shards_reset_like_the_unsharded_job(device_reset_on_cpu, name, kwargs):
     """``shard.make_shard_env``: a shard's layouts (initial and after a masked reset) are the matching
     slice of the unsharded job's — what makes results independent of the number of GPUs."""

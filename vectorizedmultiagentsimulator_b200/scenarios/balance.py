@@ -72,6 +72,12 @@ class Scenario(BaseScenario):
     def _uniform(self, n, low, high):
         return torch.zeros((n, 1), device=self.world.device, dtype=torch.float32).uniform_(low, high)
 
+    def _draw(self, env_index, x_bounds, y_bounds):
+        """A uniform point per selected env from the device-side stream: ``[B, 2]`` (rows of unselected
+        envs are zero), or ``[1, 2]`` for an int ``env_index``."""
+        out = self.world.spawn_positions([None], env_index, 0.0, x_bounds, y_bounds, want_positions=True)[:, 0]
+        return out[env_index : env_index + 1] if isinstance(env_index, int) else out
+
     def reset_world_at(self, env_index: int = None):
         world = self.world
         n = 1 if isinstance(env_index, int) else world.batch_dim  # None / bool mask: a row per env
@@ -79,17 +85,20 @@ class Scenario(BaseScenario):
         r_pkg = self.package.shape.radius
         dev = dict(device=world.device, dtype=torch.float32)
 
-        # draw order matters for seed-for-seed equality with the reference
-        goal_pos = torch.cat([self._uniform(n, -1.0, 1.0), self._uniform(n, 0.0, world.y_semidim)], dim=1)
-        line_pos = torch.cat(
-            [
-                self._uniform(n, -1.0 + half, 1.0 - half),
-                torch.full((n, 1), -world.y_semidim + self.agent_radius * 2, **dev),
-            ],
-            dim=1,
-        )
+        line_y = -world.y_semidim + self.agent_radius * 2
         spread = (-half + r_pkg, half - r_pkg) if self.random_package_pos_on_line else (0.0, 0.0)
-        package_rel = torch.cat([self._uniform(n, *spread), torch.full((n, 1), r_pkg, **dev)], dim=1)
+        if world.uses_device_reset:
+            # CUDA: the three draws come from the respawn kernel's counter-based stream (a uniform point
+            # per env; a degenerate y range pins the coordinate), so a masked reset equals one
+            # reset_at per env and a shard draws what the unsharded job draws
+            goal_pos = self._draw(env_index, (-1.0, 1.0), (0.0, world.y_semidim))
+            line_pos = self._draw(env_index, (-1.0 + half, 1.0 - half), (line_y, line_y))
+            package_rel = self._draw(env_index, spread, (r_pkg, r_pkg))
+        else:
+            # draw order matters for seed-for-seed equality with the reference
+            goal_pos = torch.cat([self._uniform(n, -1.0, 1.0), self._uniform(n, 0.0, world.y_semidim)], dim=1)
+            line_pos = torch.cat([self._uniform(n, -1.0 + half, 1.0 - half), torch.full((n, 1), line_y, **dev)], dim=1)
+            package_rel = torch.cat([self._uniform(n, *spread), torch.full((n, 1), r_pkg, **dev)], dim=1)
 
         offsets, floor_pos = self._reset_constants()
         for i, agent in enumerate(world.agents):

@@ -60,8 +60,9 @@ def make_shard_env(scenario, total_envs: int, rank: int, world_size: int, device
     the shard's position in the job (``world.env_offset``) so that every reset — including the one
     that builds the initial state — places entities exactly where the unsharded job would place
     them for the same envs (the respawn kernel numbers its random streams by global env index).
-    Scenarios that draw their reset from torch's generator instead (``balance``) still get
-    independent, reproducible shards, but not the unsharded job's layout.
+    That holds for scenarios whose reset draws all come from ``ScenarioUtils`` / ``World.spawn_positions``
+    (the four shipped ones); draws taken from torch's generator are reproducible per shard but differ
+    from the unsharded job's.
     """
     from .make_env import make_env
 
