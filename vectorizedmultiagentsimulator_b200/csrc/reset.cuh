@@ -47,10 +47,20 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return r;
 }
 
-// 24 random bits -> [0, 1), then lo + u * (hi - lo) with separate roundings (file is -fmad=false)
+// The sampler's arithmetic is written with the explicitly rounded intrinsics: the result (and with it
+// every accept / reject decision) must not depend on the build's contraction or division / square-root
+// flags — oracle/reset.py reproduces it bit for bit, also for the VMAS_B200_ARITH=fast library.
+
+// 24 random bits -> [0, 1), then lo + u * span with separate roundings
 __device__ __forceinline__ float uniform_in(uint32_t bits, float lo, float span) {
-  const float u = (float)(bits >> 8) * 5.9604644775390625e-8f;  // 2^-24
-  return lo + u * span;
+  const float u = __fmul_rn((float)(bits >> 8), 5.9604644775390625e-8f);  // * 2^-24, exact
+  return __fadd_rn(lo, __fmul_rn(u, span));
+}
+
+// |p - q| < min_dist with sqrt(dx*dx + dy*dy), every operation rounded on its own (IEEE square root)
+__device__ __forceinline__ bool too_close(float2 p, float2 q, float min_dist) {
+  const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y);
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) < min_dist;
 }
 
 __device__ __forceinline__ bool env_selected(long env, int32_t env_index, const uint8_t* env_mask) {
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(128) spawn_entities_kernel(const SpawnArgs a) 
       sp.occupied ? reinterpret_cast<const float2*>(sp.occupied + (size_t)env * sp.occupied_env_stride) : nullptr;
   const uint32_t k0 = (uint32_t)sp.seed, k1 = (uint32_t)(sp.seed >> 32);
   const uint32_t episode = sp.reset_count ? (uint32_t)sp.reset_count[env] : 0u;
-  const float span_x = sp.x_hi - sp.x_lo, span_y = sp.y_hi - sp.y_lo;
+  const float span_x = __fsub_rn(sp.x_hi, sp.x_lo), span_y = __fsub_rn(sp.y_hi, sp.y_lo);
 
   float2 placed[VMAS_MAX_SPAWN];
   bool exhausted = false;
@@ -118,20 +128,9 @@ __global__ void __launch_bounds__(128) spawn_entities_kernel(const SpawnArgs a) 
       p.x = uniform_in((tries & 1) ? r.z : r.x, sp.x_lo, span_x);
       p.y = uniform_in((tries & 1) ? r.w : r.y, sp.y_lo, span_y);
       bool ok = true;
-      for (int j = 0; ok && j < sp.n_occupied_entities; ++j) {
-        const float2 q = row[sp.occupied_entity[j]];
-        const float dx = p.x - q.x, dy = p.y - q.y;
-        ok = !(sqrtf(dx * dx + dy * dy) < sp.min_dist);
-      }
-      for (int j = 0; ok && j < sp.n_occupied; ++j) {
-        const float2 q = extra[j];
-        const float dx = p.x - q.x, dy = p.y - q.y;
-        ok = !(sqrtf(dx * dx + dy * dy) < sp.min_dist);
-      }
-      for (int j = 0; ok && j < i; ++j) {
-        const float dx = p.x - placed[j].x, dy = p.y - placed[j].y;
-        ok = !(sqrtf(dx * dx + dy * dy) < sp.min_dist);
-      }
+      for (int j = 0; ok && j < sp.n_occupied_entities; ++j) ok = !too_close(p, row[sp.occupied_entity[j]], sp.min_dist);
+      for (int j = 0; ok && j < sp.n_occupied; ++j) ok = !too_close(p, extra[j], sp.min_dist);
+      for (int j = 0; ok && j < i; ++j) ok = !too_close(p, placed[j], sp.min_dist);
       if (ok) break;
       if (tries + 1 >= sp.max_tries) {  // keep the last proposal, tell the host
         exhausted = true;
