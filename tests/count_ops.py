@@ -1,14 +1,15 @@
 """Counts aten ops per phase of Environment.step on the CPU (oracle backend) — each op is one
-kernel launch on the GPU, so this is the launch budget of the scenario callbacks.
+kernel launch on the GPU, so this is the launch budget of the scenario callbacks.  A developer aid
+that lives under tests/ because it drives the CPU oracle (test infrastructure).
 
-    python tools/count_ops.py balance n_agents=4
+    python tests/count_ops.py balance n_agents=4
 """
 import collections
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import torch
 from torch.utils._python_dispatch import TorchDispatchMode
