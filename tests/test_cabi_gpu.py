@@ -15,7 +15,7 @@ perturbed by 1 ulp (measured live, per step and field; see DESIGN.md "parity env
 import pytest
 import torch
 
-from golden_util import STATE_KEYS, golden_names, load, teacher_forced_steps
+from golden_util import same_result, STATE_KEYS, golden_names, load, teacher_forced_steps
 from oracle import queries as Q
 from oracle import world_step as WS
 from vectorizedmultiagentsimulator_b200 import _native
@@ -132,7 +132,7 @@ def test_fused_substeps_equal_single_substep_launches(name):
     for s in range(desc.substeps):
         _native.world_substeps(lib, dt, split, s, 1)
     for k in STATE_KEYS:
-        assert torch.equal(fused.t[k], split.t[k])
+        assert same_result(fused.t[k], split.t[k])
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -156,7 +156,7 @@ def test_thread_per_env_and_lanes_per_env_agree_bitwise(name):
             outs.append(slab)
         for other, mapping in zip(outs[1:], mappings[1:]):
             for k in STATE_KEYS:
-                assert torch.equal(outs[0].t[k], other.t[k]), f"{name} step {t} field {k} ({mapping})"
+                assert same_result(outs[0].t[k], other.t[k]), f"{name} step {t} field {k} ({mapping})"
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -186,7 +186,7 @@ def test_cooperative_kernel_agrees_bitwise(name):
                 _native.world_step(lib, dt, slab)
                 outs.append(slab)
             for k in STATE_KEYS:
-                assert torch.equal(outs[0].t[k], outs[1].t[k]), f"{name} step {t} field {k} rows {rows}"
+                assert same_result(outs[0].t[k], outs[1].t[k]), f"{name} step {t} field {k} rows {rows}"
 
 
 def test_config_worlds_have_specialised_kernels():
@@ -271,7 +271,7 @@ def test_lidar_vs_reference_golden(name):
         world_angles = (rec["angles"] + st["rot"][:, rec["src"]].unsqueeze(-1)).to(device).contiguous()
         out2 = torch.empty_like(angles)
         _native.cast_rays(lib, dt, slab, rec["src"], targets, len(rec["targets"]), world_angles, None, rec["max_range"], out2)
-        assert torch.equal(out, out2)
+        assert same_result(out, out2)
     print(f"{name}: lidar max |err| {worst:.3e}")
 
 
@@ -359,13 +359,13 @@ def test_batched_lidar_equals_per_sensor_launches(name):
             hinted = torch.empty_like(out)  # the sphere-only kernel must return the same bits
             _native.cast_rays_batched(lib, dt, slab, src, target_off, targets, angles, max_range, n_rays, hinted,
                                       flags=_native.RAYS_SPHERE_TARGETS)
-            assert torch.equal(hinted, out), f"{name} step {step}: sphere-only LIDAR kernel differs"
+            assert same_result(hinted, out), f"{name} step {step}: sphere-only LIDAR kernel differs"
         for q, r in enumerate(recs):
             one = torch.empty(B, n_rays, device=device)
             t = torch.tensor(r["targets"], dtype=torch.int32, device=device)
             _native.cast_rays(lib, dt, slab, r["src"], t, len(r["targets"]), r["angles"].to(device).contiguous(),
                               r["src"], r["max_range"], one)
-            assert torch.equal(out[q], one), f"{name} step {step} sensor {q}"
+            assert same_result(out[q], one), f"{name} step {step} sensor {q}"
             ok, err = _close(out[q], r["out"], 1e-5)
             assert ok, f"{name} step {step} sensor {q}: max |err| {err}"
             checked += 1
@@ -396,7 +396,7 @@ def test_batched_pair_query_equals_per_pair_launches(name):
         o = torch.empty(B, dtype=torch.bool, device=device)
         _native.pair_query(lib, dt, slab, q["a"], q["b"], 0, d)
         _native.pair_query(lib, dt, slab, q["a"], q["b"], 1, o)
-        assert torch.equal(dist[k], d) and torch.equal(over[k], o), f"{name} pair {k}"
+        assert same_result(dist[k], d) and same_result(over[k], o), f"{name} pair {k}"
         want = torch.linalg.vector_norm(pos[:, q["a"]] - pos[:, q["b"]], dim=-1)
         assert torch.allclose(centre[k], want, rtol=1e-6, atol=1e-7)
 
@@ -531,4 +531,4 @@ def test_sphere_only_pair_kernel_equals_general_kernel(name):
         fast = torch.empty_like(general)
         _native.pair_query_batched(lib, dt, slab, pairs, mode, general)
         _native.pair_query_batched(lib, dt, slab, pairs, mode | _native.QUERY_SPHERES, fast)
-        assert torch.equal(general, fast), f"{name} mode {mode}"
+        assert same_result(general, fast), f"{name} mode {mode}"
