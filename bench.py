@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: BASELINE.json configs[1] — scenario ``balance``, 32768 envs per GPU, 4 agents,
+Workload (default): BASELINE.json configs[1] — scenario ``balance``, 32768 envs per GPU, 4 agents,
 continuous random actions pre-generated before the timed region (weak scaling: every rank
-steps its own independent shard of envs; no data-path collective).
+steps its own independent shard of envs; no data-path collective).  ``--config`` selects the
+other BASELINE configs (transport3, navigation, flocking = 262144 envs strong-scaled).
 
 One JSON line is printed by rank 0:
   value        whole-job env-steps/s, actions already resident in HBM
@@ -17,9 +18,10 @@ One JSON line is printed by rank 0:
 Timing: per-iteration CUDA events on the launching stream, summed; L2 is flushed (512 MiB
 memset) between iterations outside the brackets; max over ranks.
 
-``--impl reference`` times the CPU oracle port of the path (the reference is pure Python and
-does not travel to the GPU box; the oracle is bit-identical to it, see tests/) on all host
-threads, through the same Environment API.
+``--impl reference`` times the oracle port of the path (the reference is pure Python and does not
+travel to the GPU box; the port issues the same eager torch op chain and is bit-identical to it,
+see tests/) through the same Environment API: on the host cores (default), or with
+``--ref-device cuda`` on the GPU — the reference's own PyTorch-CUDA path.
 """
 import argparse
 import json
@@ -34,10 +36,45 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-SCENARIO = "balance"
-SCENARIO_KWARGS = dict(n_agents=4)
-ENVS_PER_GPU = 32768
 METRIC = "env-steps/sec"
+
+#: BASELINE.json configs[1..4].  ``envs``: per GPU (weak scaling) or of the whole job (strong scaling).
+CONFIGS = {
+    "balance": dict(scenario="balance", kwargs=dict(n_agents=4), envs=32768, scaling="weak", ref="BASELINE.json configs[1]"),
+    "transport3": dict(
+        scenario="transport", kwargs=dict(n_agents=4, n_lines=2, substeps=3), envs=16384, scaling="weak",
+        ref="BASELINE.json configs[2]: box + 2 line landmarks, 3 substeps",
+    ),
+    "navigation": dict(
+        scenario="navigation", kwargs=dict(n_agents=8), envs=8192, scaling="weak",
+        ref="BASELINE.json configs[3]: LIDAR, 12 rays per agent",
+    ),
+    "flocking": dict(
+        scenario="flocking", kwargs=dict(n_agents=5), envs=262144, scaling="strong",
+        ref="BASELINE.json configs[4]: 262144 envs sharded over the GPUs",
+    ),
+}
+
+
+def resolve_config(args, world):
+    """(cfg, envs of this rank's shard, envs of the whole job, scaling)."""
+    cfg = CONFIGS[args.config]
+    scaling = args.scaling or cfg["scaling"]
+    if scaling == "strong":
+        total = args.total_envs or (cfg["envs"] if cfg["scaling"] == "strong" else cfg["envs"] * 8)
+        assert total % world == 0, f"--total-envs {total} is not a multiple of {world} ranks"
+        return cfg, total // world, total, scaling
+    per_gpu = args.envs_per_gpu or (cfg["envs"] if cfg["scaling"] == "weak" else cfg["envs"] // 8)
+    return cfg, per_gpu, per_gpu * world, scaling
+
+
+def workload_string(cfg, per_gpu, total, world, scaling):
+    """The one description of the workload both arms print (the driver compares the strings)."""
+    kw = ", ".join(f"{k}={v}" for k, v in cfg["kwargs"].items())
+    return (
+        f"{cfg['scenario']}({kw}), {total} envs = {per_gpu} per GPU x {world} GPU(s) ({scaling} scaling), "
+        f"random continuous actions ({cfg['ref']})"
+    )
 
 
 # --------------------------------------------------------------------------------------------
@@ -47,7 +84,15 @@ def parse_args():
     p.add_argument("--steps", type=int, default=1000)
     p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    p.add_argument("--config", default="balance", choices=sorted(CONFIGS), help="BASELINE.json config (default: configs[1])")
+    p.add_argument("--envs-per-gpu", type=int, default=None, help="weak scaling: envs of every rank")
+    p.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: the config's own")
+    p.add_argument("--total-envs", type=int, default=None, help="strong scaling: envs of the whole job")
+    p.add_argument(
+        "--ref-device", default="cpu", choices=["cpu", "cuda"],
+        help="--impl reference: run the reference's eager torch op chain on the host cores (the reference arm) "
+        "or on the GPU (the north star's PyTorch-CUDA denominator)",
+    )
     p.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="keep L2 warm between iterations (not a bench value)")
@@ -159,52 +204,118 @@ def usable_cpus() -> int:
     return n
 
 
-def run_cpu_oracle_env(n_envs, max_steps, time_budget_s=20.0):
-    """Times the CPU oracle port behind the same Environment API on the host cores.
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
 
-    The intra-op thread count is calibrated first (one step each at a few candidates up to the
-    usable core count; eager torch on many tiny ops gets *slower* with too many threads), then
-    steps are timed until ``max_steps`` or ``time_budget_s``.
-    Returns (env_steps_per_s, seconds, steps, threads).
+
+def pin_to_gpu_numa(local: int):
+    """Restricts this rank to the host cores next to its GPU (the PCI device's ``local_cpulist``):
+    the per-step launch path is host work, and a rank scheduled on the far socket pays for it in
+    every CUDA-event bracket.  Returns a short description (for the JSON line) or None."""
+    try:
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+            capture_output=True, text=True, timeout=20,
+        ).stdout.strip().lower()
+        if not out:
+            return None
+        bus = out[-12:] if len(out) > 12 else out  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        near = _parse_cpulist(open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(near & allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cores local to GPU {local} ({bus})"
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def run_reference_env(cfg, n_envs, device, warmup, max_steps, time_budget_s):
+    """Times the oracle port — the reference's eager torch op chain behind the same Environment
+    API — on the host cores (``device="cpu"``: the reference arm) or on the GPU (``"cuda"``: the
+    reference's PyTorch-CUDA path, the north star's "10x" denominator).
+
+    CPU: the intra-op thread count is calibrated first (eager torch on many tiny ops gets *slower*
+    with too many threads; the sweep is returned).  Returns a dict.
     """
+    import contextlib
+
     import vectorizedmultiagentsimulator_b200 as b200
     from oracle.backend import use_oracle
 
+    on_gpu = device != "cpu"
     cores = usable_cpus()
-    candidates = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True) or [1]
-    torch.set_num_threads(candidates[-1])
-    with use_oracle():
-        env = b200.make_env(SCENARIO, num_envs=n_envs, device="cpu", seed=0, **SCENARIO_KWARGS)
-        actions = pregenerate_actions(env, 4, seed=1, device="cpu")
-        env.step(actions[0])  # warm-up (allocator, plan compile)
-        best, best_t = candidates[-1], float("inf")
-        for c in reversed(candidates):  # small thread counts first; stop when it gets worse
-            torch.set_num_threads(c)
-            t0 = time.perf_counter()
-            env.step(actions[1])
-            dt = time.perf_counter() - t0
-            if dt < best_t:
-                best, best_t = c, dt
-            elif dt > 1.5 * best_t:
-                break
-        torch.set_num_threads(best)
+    sweep = {}
+    # tensors the op chain creates from python scalars land on the device, as in the reference
+    # (it passes device=self.device everywhere)
+    scope = torch.device(device) if on_gpu else contextlib.nullcontext()
+    sync = (lambda: torch.cuda.synchronize()) if on_gpu else (lambda: None)
+    with use_oracle(allow_cuda=on_gpu), scope:
+        # action_checks="sync": the reference's asserts (two host syncs per agent and step)
+        env = b200.make_env(
+            cfg["scenario"], num_envs=n_envs, device=device, seed=0, action_checks="sync", **cfg["kwargs"]
+        )
+        actions = pregenerate_actions(env, 4, seed=1, device=device)
+        env.step(actions[0])  # allocator, plan compile
+        best = 1
+        if not on_gpu:
+            candidates = sorted({c for c in (cores, 64, 32, 16, 8, 4) if c <= cores}) or [1]
+            best, best_t = candidates[0], float("inf")
+            for c in candidates:  # small thread counts first; stop when it gets clearly worse
+                torch.set_num_threads(c)
+                env.step(actions[1])
+                t0 = time.perf_counter()
+                env.step(actions[2])
+                dt = time.perf_counter() - t0
+                sweep[c] = round(dt * 1e3, 2)
+                if dt < best_t:
+                    best, best_t = c, dt
+                elif dt > 1.5 * best_t:
+                    break
+            torch.set_num_threads(best)
+        for t in range(warmup):
+            env.step(actions[t % 4])
+        sync()
         steps, t0 = 0, time.perf_counter()
         while steps < max_steps:
             env.step(actions[steps % 4])
             steps += 1
             if time.perf_counter() - t0 > time_budget_s and steps >= 2:
                 break
+        sync()
         dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt, steps, best
+    return dict(value=n_envs * steps / dt, seconds=dt, steps=steps, threads=best, sweep_ms_per_step=sweep, cores=cores)
 
 
 def main_reference(args):
-    rank, world, _ = dist_info()
+    rank, world, local = dist_info()
     if rank != 0:
         return
-    n_envs = args.envs_per_gpu
-    # bounded sample: at most --steps env steps and ~60 s of CPU time
-    value, seconds, steps, cores = run_cpu_oracle_env(n_envs, max(1, args.steps), time_budget_s=60.0)
+    world = max(world, args.gpus) if world == 1 else world
+    cfg, per_gpu, total, scaling = resolve_config(args, world)
+    on_gpu = args.ref_device == "cuda"
+    device = f"cuda:{local}" if on_gpu else "cpu"
+    W = max(args.warmup, 3)
+    try:
+        # bounded sample: every step is the per-GPU share of the workload; at most --steps of them
+        r = run_reference_env(cfg, per_gpu, device, W, max(1, args.steps), time_budget_s=90.0)
+    except Exception as err:  # noqa: BLE001
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(err).__name__}: {err}"[:300]}), flush=True)
+        return
+    value, seconds, steps = r["value"], r["seconds"], r["steps"]
+    where = (
+        f"eager torch op chain on {torch.cuda.get_device_name(local)} (the reference's PyTorch-CUDA path)"
+        if on_gpu
+        else f"{r['threads']} intra-op threads (calibrated; ms per step by thread count: {r['sweep_ms_per_step']}) "
+        f"of {r['cores']} usable cores"
+    )
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -212,23 +323,26 @@ def main_reference(args):
         "unit": "env-steps/s",
         "n_gpus": args.gpus,
         "steps": steps,
-        "warmup": 2,
+        "warmup": args.warmup,
         "ms_per_step": 1e3 * seconds / steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": scaling,
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{SCENARIO} n_agents=4, {n_envs} envs, random continuous actions, CPU",
-            "note": "CPU oracle port of the reference path (bit-identical to the reference, tests/); the pure-Python reference does not travel to the GPU box",
+            "workload": workload_string(cfg, per_gpu, total, world, scaling),
+            "reference_device": args.ref_device,
+            "note": "oracle port of the reference path (the same eager torch op chain, bit-identical to the "
+            "reference on CPU, tests/test_oracle_vs_reference.py); the pure-Python reference does not travel "
+            "to the GPU box.  Each step is one GPU's share of the workload (env-steps/s does not depend on it)",
         },
         "cpu_baseline": {
             "value": value,
             "unit": "env-steps/s",
-            "cores": cores,
+            "cores": 0 if on_gpu else r["threads"],
             "kind": "port",
-            "sample": f"{steps} env steps of {n_envs} envs ({seconds:.1f} s), {cores} intra-op threads (calibrated) of {usable_cpus()} usable cores",
+            "sample": f"{steps} env steps of {per_gpu} envs ({seconds:.1f} s), {where}",
         },
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -240,6 +354,7 @@ def main_b200(args):
     rank, world, local = dist_info()
     import torch.distributed as dist
 
+    pinned = pin_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, in front of the one JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -249,16 +364,25 @@ def main_b200(args):
     device = torch.device("cuda", local)
 
     import vectorizedmultiagentsimulator_b200 as b200
+    from vectorizedmultiagentsimulator_b200 import _native as nat
+    from vectorizedmultiagentsimulator_b200 import shard
     from vectorizedmultiagentsimulator_b200.simulator import plan as P
 
-    B, K, W = args.envs_per_gpu, args.steps, max(args.warmup, 3)
-    env = b200.make_env(
-        SCENARIO, num_envs=B, device=device, seed=rank, cuda_graph=not args.no_graph, **SCENARIO_KWARGS
-    )
+    cfg, B, total, scaling = resolve_config(args, world)
+    K, W = args.steps, max(args.warmup, 3)
+    if scaling == "strong":
+        env = shard.make_shard_env(
+            cfg["scenario"], total, rank, world, device, seed=0, cuda_graph=not args.no_graph, **cfg["kwargs"]
+        )
+    else:
+        env = b200.make_env(
+            cfg["scenario"], num_envs=B, device=device, seed=rank, cuda_graph=not args.no_graph, **cfg["kwargs"]
+        )
     backend = env.world._get_backend()
     backend.refresh()
     desc = backend.tables.desc
     bytes_per_env_substep = P.algorithmic_bytes_per_env_substep(desc)
+    launches_per_step = desc.substeps if backend.tables.n_masked else 1  # substep-kernel launches per world.step
 
     flush = None if args.no_flush else torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -293,16 +417,28 @@ def main_b200(args):
         sampler.wait_first_sample()
     barrier()
     launches_before = backend.launches
-    backend.kernel_events = []
     wall0 = time.perf_counter()
     ms_total = timed_loop(lambda i: env.step(dev_actions[W + i]), K)
     wall = time.perf_counter() - wall0
-    kernel_pairs = backend.kernel_events
-    backend.kernel_events = None
     launches = backend.launches - launches_before
     barrier()
-    # (empty in graph mode: the step is one graph replay, no per-kernel events inside it)
-    kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in kernel_pairs) / len(kernel_pairs) if kernel_pairs else 0.0
+
+    # ---- the substep kernel inside Environment.step: the same env stepped eagerly once more (a
+    # graph replay has no per-kernel events), L2 flushed before each step; the kernel then runs
+    # behind the ingest / broad-phase kernels of its own step, i.e. with the slab L2-warm
+    graph_mode = env.cuda_graph
+    env.cuda_graph = False
+    backend.kernel_events = []
+    n_inside = min(K, 50)
+    for i in range(n_inside):
+        if flush is not None:
+            flush.zero_()
+        env.step(dev_actions[W + i])
+    torch.cuda.synchronize()
+    pairs = backend.kernel_events
+    backend.kernel_events = None
+    env.cuda_graph = graph_mode
+    kernel_in_step_ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs) if pairs else 0.0
 
     # ---- the substep kernel alone: world.step() back to back, L2 flushed before every launch.
     # The flush (~100 us on the GPU) lets the host queue the next launch ahead, so the event
@@ -313,43 +449,67 @@ def main_b200(args):
             flush.zero_()
         env.world.step()
     torch.cuda.synchronize()
-    kernel_ms = sum(a.elapsed_time(b) for a, b in backend.kernel_events) / K
+    kernel_ms = sum(a.elapsed_time(b) for a, b in backend.kernel_events) / max(1, len(backend.kernel_events))
     backend.kernel_events = None
 
     # ---- arm 2: end to end with host buffers --------------------------------------------------
+    # Software-pipelined like a training loop would: the results of step t-1 travel to pinned host
+    # memory on a copy stream while step t (action upload + kernels) runs.  Every bracket holds one
+    # action upload, one step and one complete result download (of the previous step; a final
+    # bracket drains the last one), so K steps' worth of each are inside the timed region.
     host_actions = pregenerate_actions(env, W + K, seed=101 + rank, device=device, pin=True)
-    act_dev = [torch.empty_like(a, device=device) for a in host_actions[0]]
     obs0, rew0, done0, _ = env.step(dev_actions[0])
-    # the step's results are read back with one device->host copy per kind (observations of all
-    # agents, rewards of all agents, done): the per-agent tensors are stacked on the device first
-    host_obs = torch.empty((len(obs0),) + tuple(obs0[0].shape), dtype=obs0[0].dtype).pin_memory()
-    host_rew = torch.empty((len(rew0),) + tuple(rew0[0].shape), dtype=rew0[0].dtype).pin_memory()
-    host_done = torch.empty(done0.shape, dtype=done0.dtype).pin_memory()
+    host_sets = [
+        (
+            torch.empty((len(obs0),) + tuple(obs0[0].shape), dtype=obs0[0].dtype).pin_memory(),
+            torch.empty((len(rew0),) + tuple(rew0[0].shape), dtype=rew0[0].dtype).pin_memory(),
+            torch.empty(done0.shape, dtype=done0.dtype).pin_memory(),
+        )
+        for _ in range(2)
+    ]
     h2d_bytes = sum(a.numel() * a.element_size() for a in host_actions[0])
-    d2h_bytes = sum(t.numel() * t.element_size() for t in (host_obs, host_rew, host_done))
+    d2h_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+    copy_stream = torch.cuda.Stream(device=device)
+    pending = [None]
+
+    def download(slot):
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(host_sets[slot], pending[0]):
+                dst.copy_(src, non_blocking=True)
 
     def e2e_step(i):
-        # pinned host actions go straight into Environment.step (it copies them to the device)
+        main = torch.cuda.current_stream()
+        if pending[0] is not None:
+            download(i & 1)
+        # pinned host actions go straight into Environment.step (it uploads them)
         obs, rews, dones, _ = env.step(host_actions[W + i])
-        host_obs.copy_(torch.stack(obs), non_blocking=True)
-        host_rew.copy_(torch.stack(rews), non_blocking=True)
-        host_done.copy_(dones, non_blocking=True)
+        fresh = (torch.stack(obs), torch.stack(rews), dones)
+        main.wait_stream(copy_stream)  # the bracket closes after the download it overlapped
+        pending[0] = fresh
+
+    def e2e_drain(_):
+        download(0)
+        torch.cuda.current_stream().wait_stream(copy_stream)
 
     for t in range(3):
         e2e_step(t - W)
     barrier()
-    ms_e2e = timed_loop(e2e_step, K)
+    ms_e2e = timed_loop(e2e_step, K) + timed_loop(e2e_drain, 1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     env.check_actions_now()
 
     # ---- reduce over ranks ---------------------------------------------------------------------
     stats = torch.tensor([ms_total, ms_e2e, kernel_ms, kernel_in_step_ms], dtype=torch.float64, device=device)
+    per_rank = [stats.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, stats)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, kernel_ms, kernel_in_step_ms = (float(x) for x in stats.tolist())
-    value = world * B * K / (ms_total * 1e-3)
-    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    value = total * K / (ms_total * 1e-3)
+    e2e_value = total * K / (ms_e2e * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -363,19 +523,21 @@ def main_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = bytes_per_env_substep * B  # one launch advances B envs by one substep (S=1 here)
+    # one launch advances B envs by one substep (worlds with line / box pairs) or by all S substeps
+    # (sphere-only worlds: the state stays in registers); bytes per launch = bytes x B either way
+    alg_bytes = bytes_per_env_substep * B
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj["%s_%s" % (SCENARIO, "_".join(f"{k}={v}" for k, v in SCENARIO_KWARGS.items()))][str(B)]
+        ent = tj["%s_%s" % (cfg["scenario"], "_".join(f"{k}={v}" for k, v in cfg["kwargs"].items()))][str(B)]
         traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
         traffic_src = ent["source"]
     except Exception:  # noqa: BLE001
         pass
     roofline = {
         "bound": "hbm",
-        "kernel": "substep kernel, mapping=%s" % backend._dev_tables.mapping,
+        "kernel": "substep kernel, mapping=%s, arithmetic=%s" % (backend._dev_tables.mapping, nat.ARITH),
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -385,16 +547,32 @@ def main_b200(args):
         "peak_source": peak_src,
         "bytes_per_launch": alg_bytes,
         "bytes_per_env_substep": bytes_per_env_substep,
+        "substep_launches_per_step": launches_per_step,
         "kernel_us": kernel_ms * 1e3,
         "kernel_us_inside_env_step": kernel_in_step_ms * 1e3 if kernel_in_step_ms else None,
-        "how": "CUDA events recorded by the library around the substep kernel; standalone world.step() loop, L2 flushed before each launch",
+        "frac_inside_env_step": (alg_bytes / (kernel_in_step_ms * 1e-3) / 1e9 / peak) if kernel_in_step_ms else None,
+        "how": "CUDA events recorded by the library around the substep kernel; kernel_us: standalone world.step() "
+        "loop, L2 flushed before each launch; kernel_us_inside_env_step: the benched env stepped eagerly "
+        "(Environment.step, L2 flushed before each step), the kernel running behind its step's ingest / broad-phase kernels",
+    }
+    # the whole Environment.step against the same peak: compulsory bytes of one step (slab traffic of
+    # every substep, the actions read, the observations / rewards / dones written) / ms_per_step
+    out_bytes = sum(t.numel() * t.element_size() for t in list(obs0) + list(rew0) + [done0])
+    step_bytes = bytes_per_env_substep * B * desc.substeps + h2d_bytes + out_bytes
+    roofline_step = {
+        "bytes_per_step": step_bytes,
+        "achieved": step_bytes / (ms_total / K * 1e-3) / 1e9,
+        "unit": "GB/s",
+        "frac": step_bytes / (ms_total / K * 1e-3) / 1e9 / peak,
+        "note": "Environment.step as a whole (graph replay): slab traffic of all substeps + actions in + "
+        "observations, rewards, dones out, over ms_per_step",
     }
 
     # ---- same kernel at a batch that is not launch/latency-bound: 1 Mi envs (state tiled) -----------------
     try:
         big_B = 1 << 20
-        reps = big_B // B
-        from vectorizedmultiagentsimulator_b200 import _native as nat
+        reps = max(1, big_B // B)
+        big_B = reps * B
 
         class _BigSlab:
             def __init__(self, slab):
@@ -418,13 +596,13 @@ def main_b200(args):
             times.append(ev[0].elapsed_time(ev[1]))
         times = sorted(times[2:])
         big_ms = times[len(times) // 2]
-        big_achieved = bytes_per_env_substep * big_B / (big_ms * 1e-3) / 1e9
+        big_achieved = bytes_per_env_substep * big_B * launches_per_step / (big_ms * 1e-3) / 1e9
         roofline["at_1Mi_envs"] = {
-            "kernel_us": big_ms * 1e3,
+            "kernel_us": big_ms * 1e3 / launches_per_step,
             "achieved": big_achieved,
             "frac": big_achieved / peak,
-            "note": "same kernel and state tiled to 1,048,576 envs (slab 365 MB > L2); the 32768-env launch "
-            "is 11.4 MB = 1.7 us of HBM time, below launch latency",
+            "note": f"same kernel and state tiled to {big_B} envs (slab > L2); at {B} envs the slab is "
+            f"{alg_bytes / 1e6:.1f} MB = {alg_bytes / peak / 1e3:.1f} us of HBM time, below launch latency",
         }
         del big, big_dt
     except Exception as err:  # noqa: BLE001
@@ -433,14 +611,15 @@ def main_b200(args):
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        v, seconds, cpu_steps, cores = run_cpu_oracle_env(B, args.cpu_steps or 200, time_budget_s=20.0)
+        r = run_reference_env(cfg, B, "cpu", 2, args.cpu_steps or 200, time_budget_s=20.0)
         cpu_baseline = {
-            "value": v,
+            "value": r["value"],
             "unit": "env-steps/s",
-            "cores": cores,
+            "cores": r["threads"],
             "kind": "port",
-            "sample": f"{cpu_steps} env steps of {B} envs ({seconds:.1f} s), CPU oracle port behind the same "
-            f"Environment API, {cores} intra-op threads (calibrated) of {usable_cpus()} usable cores",
+            "sample": f"{r['steps']} env steps of {B} envs ({r['seconds']:.1f} s), CPU oracle port behind the same "
+            f"Environment API, {r['threads']} intra-op threads (calibrated; ms per step by thread count: "
+            f"{r['sweep_ms_per_step']}) of {r['cores']} usable cores",
         }
 
     line = {
@@ -449,19 +628,23 @@ def main_b200(args):
         "unit": "env-steps/s",
         "n_gpus": world,
         "steps": K,
-        "warmup": W,
+        "warmup": args.warmup,
         "ms_per_step": ms_total / K,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": scaling,
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{SCENARIO} n_agents=4, {B} envs per GPU, 1 substep, random continuous actions (BASELINE.json configs[1])",
+            "workload": workload_string(cfg, B, total, world, scaling),
+            "substeps": desc.substeps,
+            "arithmetic": nat.ARITH,
             "timing": "sum of per-iteration CUDA-event brackets around Environment.step; max over ranks",
             "l2": "flushed between iterations (512 MiB memset outside the brackets)" if flush is not None else "NOT flushed",
             "api": "make_env(..., cuda_graph=%s); Environment.step" % (not args.no_graph),
+            "warmup_steps_run": W,
             "wall_ms_per_step_incl_flush": 1e3 * wall / K,
+            "host_affinity": pinned,
         },
         "clocks": clocks,
         "e2e": {
@@ -470,9 +653,14 @@ def main_b200(args):
             "h2d_bytes_per_step": h2d_bytes,
             "d2h_bytes_per_step": d2h_bytes,
             "ms_per_step": ms_e2e / K,
+            "how": "pinned host actions -> Environment.step -> observations, rewards, dones into pinned host "
+            "buffers; the download of step t-1 overlaps step t on a copy stream, inside the brackets",
         },
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_step": roofline_step,
+        "per_rank_ms_per_step": [float(r[0]) / K for r in per_rank],
+        "per_rank_e2e_ms_per_step": [float(r[1]) / K for r in per_rank],
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

@@ -20,7 +20,9 @@ from . import queries, world_step
 class OracleBackend(PlanRuntime):
     def __init__(self, world):
         super().__init__(world)
-        assert torch.device(world.device).type == "cpu", "the oracle is a CPU checker"
+        # a CPU checker; bench.py's reference arm may also run this same eager torch op chain on a
+        # CUDA device (`use_oracle(allow_cuda=True)`): the reference's PyTorch-CUDA path, timed
+        assert _ALLOW_CUDA or torch.device(world.device).type == "cpu", "the oracle is a CPU checker"
 
     def _state(self):
         slab = self.world.slab
@@ -113,11 +115,17 @@ class OracleBackend(PlanRuntime):
         return queries.distance_from_point(self.tables, slab.pos, slab.rot, self.index_of(entity), point)
 
 
+_ALLOW_CUDA = False
+
+
 @contextlib.contextmanager
-def use_oracle():
-    previous = World._backend_factory
+def use_oracle(allow_cuda: bool = False):
+    global _ALLOW_CUDA
+    previous, previous_allow = World._backend_factory, _ALLOW_CUDA
     World._backend_factory = OracleBackend
+    _ALLOW_CUDA = allow_cuda
     try:
         yield
     finally:
         World._backend_factory = previous
+        _ALLOW_CUDA = previous_allow
