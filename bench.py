@@ -173,12 +173,12 @@ class ClockSampler:
 
 def pregenerate_actions(env, steps, seed, device, pin=False):
     """[steps][n_agents] tensors of shape [B, action_size], U(-u_range, u_range), from a CPU generator."""
-    gen = torch.Generator().manual_seed(seed)
+    gen = torch.Generator(device="cpu").manual_seed(seed)
     out = []
     for _ in range(steps):
         per_agent = []
         for a in env.agents:
-            u = (torch.rand(env.num_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor.cpu()
+            u = (torch.rand(env.num_envs, a.action_size, generator=gen, device="cpu") * 2 - 1) * a.action.u_range_tensor.cpu()
             if pin:
                 u = u.pin_memory()
             else:

@@ -85,14 +85,14 @@ typedef struct VmasPlanTables {
                                  (ref core.py:594-601, 2049-2052: Entity.gravity given as a tensor) */
   int32_t n_rounds;
   int32_t group;              /* lanes per env: 1 = one thread per env (default), or 8, 16, 32; with a
-                                 specialization: 1, or VMAS_GROUP_COOPERATIVE = the cooperative kernel
-                                 (the warps of a block share a tile of 32 envs: shorter dependency chains,
-                                 meant for batches that leave the GPU latency-bound) */
+                                 specialization: 1, or VMAS_GROUP_TILE = the warp-tile kernel (a warp owns
+                                 32 envs; far tests per env, then the narrow phase of the near (item, env)
+                                 pairs compacted over the warp's lanes; see csrc/spec_tile_kernel.cuh) */
   int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */
   int32_t specialization;     /* index from vmas_b200_find_specialization(), or -1: generic kernels */
 } VmasPlanTables;
 
-#define VMAS_GROUP_COOPERATIVE (-8)
+#define VMAS_GROUP_TILE (-8)
 
 /* The state slab.  DEVICE pointers. */
 typedef struct VmasState {
@@ -110,6 +110,8 @@ const char* vmas_b200_last_error(void);
 int vmas_b200_num_specializations(void);
 int vmas_b200_find_specialization(uint64_t world_hash);
 const char* vmas_b200_specialization_name(int index);
+/* 1 if the specialization also has the warp-tile kernel (VmasPlanTables.group = VMAS_GROUP_TILE) */
+int vmas_b200_specialization_has_tile(int index);
 
 /*
  * One World.step(): S substeps of force accumulation -> contact/joint resolution ->

@@ -1,5 +1,5 @@
 // hostsim.cpp — TEST INFRASTRUCTURE: runs the device functions of the specialised substep kernels on
-// the CPU (g++, shim/cuda_runtime.h), one "thread" after the other, so the cooperative kernel's
+// the CPU (g++, shim/cuda_runtime.h), one "thread" after the other, so the tile kernel's
 // phase structure (who owns which entity / item, shared-memory rows, accumulation order) can be
 // checked bit for bit against the thread-per-env formulation without a GPU.  Not product code.
 #include <vector>
@@ -16,32 +16,65 @@ static void run_thread_per_env(const SpecArgs& a, const uint32_t* mask) {
   for (long env = 0; env < a.batch_dim; ++env) spec_env_step<W>(a, env, mask_words);
 }
 
-// the body of step_coop_kernel with every __syncthreads() turned into "finish the loop over threads"
+// the body of tile_warp_step (csrc/spec_tile_kernel.cuh) for one tile of 32 envs: the lanes of the warp one
+// after the other, every __syncwarp() turned into "finish the loop over the lanes"; the ballot-based
+// queue construction is restated as plain loops (same order: item-major, lane-minor within a kind)
 template <class W>
-static void run_cooperative(const SpecArgs& a, const uint32_t* mask) {
-  uint32_t mask_words[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1] = {0};
-  if (a.use_mask)
-    for (int w = 0; w < W::MASK_WORDS; ++w) mask_words[w] = mask[w];
-  std::vector<float> sm(CoopRows<W>::BYTES / sizeof(float));
-  const long blocks = ((long)a.batch_dim + COOP_LANES - 1) / COOP_LANES;
-  for (long block = 0; block < blocks; ++block) {
-    // poison the tile: a row that is read before its owner wrote it must show up as NaN
-    for (float& v : sm) v = NAN;
-    auto for_threads = [&](auto&& fn) {
-      for (int warp = 0; warp < COOP_WARPS; ++warp)
-        for (int lane = 0; lane < COOP_LANES; ++lane) {
-          const long env = block * COOP_LANES + lane;
-          if (env < a.batch_dim) fn(warp, lane, env);
+static void run_tile(const SpecArgs& a, const uint32_t* mask) {
+  using T = Tile<W>;
+  using L = TileLayout<W>;
+  if constexpr (L::SUPPORTED) {
+    uint32_t mask_words[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1] = {0};
+    if (a.use_mask)
+      for (int w = 0; w < W::MASK_WORDS; ++w) mask_words[w] = mask[w];
+    std::vector<float> sm(L::FLOATS);
+    std::vector<typename T::Lane> lanes(TILE_LANES);
+    const long tiles = ((long)a.batch_dim + TILE_LANES - 1) / TILE_LANES;
+    for (long tile = 0; tile < tiles; ++tile) {
+      // poison the tile: a row that is read before its owner wrote it must show up as NaN
+      for (float& v : sm) v = NAN;
+      auto env_of = [&](int lane) { return tile * TILE_LANES + lane; };
+      auto valid = [&](int lane) { return env_of(lane) < a.batch_dim; };
+      auto env_c = [&](int lane) { return valid(lane) ? env_of(lane) : (long)a.batch_dim - 1; };
+      for (int lane = 0; lane < TILE_LANES; ++lane) {
+        lanes[lane].rows.load_pos_rot(a, env_c(lane));
+        lanes[lane].rows.unpack_pos_rot(lanes[lane].r);
+      }
+      uint16_t* q = T::queue(sm.data());
+      for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
+        for (int lane = 0; lane < TILE_LANES; ++lane) {
+          T::p1(sm.data(), lane, lanes[lane], a, mask_words);
+          if (!valid(lane)) lanes[lane].near = 0;
         }
-    };
-    for_threads([&](int warp, int lane, long env) { Coop<W>::load(sm.data(), warp, lane, env, a); });
-    for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
-      for_threads([&](int warp, int lane, long) { Coop<W>::forces(sm.data(), warp, lane); });
-      for_threads([&](int warp, int lane, long env) { Coop<W>::items(sm.data(), warp, lane, env, a, mask_words); });
-      for_threads([&](int warp, int lane, long) { Coop<W>::integrate(sm.data(), warp, lane, sub); });
+        int cnt[TILE_N_KINDS] = {0};
+        for (int i = 0; i < W::NI; ++i) {
+          const int k = W::item[i].kind;
+          for (int lane = 0; lane < TILE_LANES; ++lane)
+            if ((lanes[lane].near >> i) & 1u) q[L::kind_base(k) + cnt[k]++] = (uint16_t)((i << 5) | lane);
+        }
+        static_for<TILE_N_KINDS>([&](auto ki) {
+          constexpr int K = decltype(ki)::value;
+          if constexpr (L::kind_count(K) > 0 && K != VMAS_K_JOINT) {
+            for (int idx = 0; idx < cnt[K]; ++idx) T::template narrow<K>(sm.data(), q[L::kind_base(K) + idx]);
+          }
+        });
+        for (int lane = 0; lane < TILE_LANES; ++lane) {
+          if (sub == a.first_substep) {
+            lanes[lane].rows.load_rest(a, env_c(lane));
+            lanes[lane].rows.unpack_rest(lanes[lane].r, lanes[lane].afx, lanes[lane].afy, lanes[lane].atq);
+          }
+          T::p3(sm.data(), lane, lanes[lane], sub);
+        }
+      }
+      for (int lane = 0; lane < TILE_LANES; ++lane)
+        if (valid(lane)) lanes[lane].rows.store(a, env_of(lane), lanes[lane].r, lanes[lane].afx, lanes[lane].afy, lanes[lane].atq);
     }
-    for_threads([&](int warp, int lane, long env) { Coop<W>::store(sm.data(), warp, lane, env, a); });
   }
+}
+
+template <class W>
+static int tile_supported() {
+  return TileLayout<W>::SUPPORTED ? 1 : 0;
 }
 
 extern "C" {
@@ -54,8 +87,8 @@ int hostsim_num_worlds(void) {
   return n;
 }
 
-// variant 0: one thread per env (spec_env_step); 1: cooperative (Coop<W> phases).  Returns 0, or -1
-// if no specialised world has this hash.
+// variant 0: one thread per env (spec_env_step); 1: warp tile (Tile<W> phases).  Returns 0, -1 if no
+// specialised world has this hash, -2 if the world has no tile kernel.
 int hostsim_step(uint64_t world_hash, int variant, int batch_dim, float* pos, float* vel, float* rot,
                  float* ang_vel, float* force, float* torque, const uint32_t* mask, int use_mask,
                  int first_substep, int n_substeps) {
@@ -70,7 +103,8 @@ int hostsim_step(uint64_t world_hash, int variant, int batch_dim, float* pos, fl
 #define TRY(i, W, h)                                  \
   if (world_hash == h) {                              \
     if (variant == 0) run_thread_per_env<W>(a, mask); \
-    else run_cooperative<W>(a, mask);                 \
+    else if (!tile_supported<W>()) return -2;         \
+    else run_tile<W>(a, mask);                        \
     return 0;                                         \
   }
   VMAS_FOR_EACH_SPEC_WORLD(TRY)

@@ -160,16 +160,17 @@ def test_thread_per_env_and_lanes_per_env_agree_bitwise(name):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cooperative_kernel_agrees_bitwise(name):
-    """The small-batch cooperative kernel (warps share a tile of 32 envs; csrc/spec_coop_kernel.cuh)
+def test_tile_kernel_agrees_bitwise(name):
+    """The warp-tile kernel (a warp owns 32 envs, compacted narrow phase; csrc/spec_tile_kernel.cuh)
     against the thread-per-env specialised kernel: identical bits, every golden world that has a
-    specialisation, whole steps (all substeps, broad phase included) and a batch that is not a
+    tile kernel, whole steps (all substeps, broad phase included) and a batch that is not a
     multiple of the tile."""
     fix, desc, tables = load(name)
     lib = _native.load()
     device = torch.device("cuda:0")
-    if _native.DeviceTables(tables, None, device).mapping != "specialized":
-        pytest.skip("no ahead-of-time specialisation of this world")
+    auto = _native.DeviceTables(tables, None, device)
+    if auto.specialization < 0 or not lib.vmas_b200_specialization_has_tile(auto.specialization):
+        pytest.skip("no tile kernel for this world")
     for t, state_in, fixed_rot, _ in teacher_forced_steps(fix):
         if t % 3:
             continue
@@ -177,7 +178,7 @@ def test_cooperative_kernel_agrees_bitwise(name):
         for rows in (None, n_envs - 5):  # the whole batch, and one whose last tile is not full
             state = state_in if rows is None else {k: (v[:rows] if torch.is_tensor(v) else v) for k, v in state_in.items()}
             outs = []
-            for mapping in ("specialized", "cooperative"):
+            for mapping in ("specialized", "tile"):
                 dt = _device_tables(tables, fixed_rot, device, mapping=mapping, ent_gravity=state.get("ent_gravity"))
                 assert dt.mapping == mapping
                 if rows is not None:
@@ -195,7 +196,7 @@ def test_config_worlds_have_specialised_kernels():
     for name in ("balance", "transport", "navigation", "flocking"):
         _, _, tables = load(name)
         dt = _native.DeviceTables(tables, None, torch.device("cuda:0"))
-        assert dt.mapping == "specialized", name
+        assert dt.mapping in ("specialized", "tile") and dt.specialization >= 0, name
 
 
 @pytest.mark.parametrize("mapping", ["thread_per_env", "lanes_per_env"])

@@ -81,7 +81,7 @@ def test_reset_entry_points_validate_their_arguments_without_gpu():
 
 
 def test_device_tables_build_for_every_mapping_on_cpu():
-    """The host-side table upload of each thread mapping (incl. the opt-in cooperative one) — what
+    """The host-side table upload of each thread mapping (incl. the warp-tile one) — what
     runs before the first launch — without a GPU."""
     import sys
 
@@ -95,11 +95,11 @@ def test_device_tables_build_for_every_mapping_on_cpu():
     for name, specialised in (("balance", True), ("flocking", True), ("pollock", False)):
         _, desc, tables = load(name)
         auto = _native.DeviceTables(tables, None, cpu, mapping="auto")
-        assert auto.mapping == ("specialized" if specialised else "thread_per_env")
+        assert auto.mapping == ((_native.DEFAULT_SPEC_MAPPING if specialised else "thread_per_env"))
         for mapping in ("thread_per_env", "lanes_per_env"):
             dt = _native.DeviceTables(tables, None, cpu, mapping=mapping)
             assert dt.mapping == mapping and dt.tb.specialization == -1 and dt.tb.group >= 1
-        for mapping, group in (("specialized", 1), ("cooperative", _native.GROUP_COOPERATIVE)):
+        for mapping, group in (("specialized", 1), ("tile", _native.GROUP_TILE)):
             if specialised:
                 dt = _native.DeviceTables(tables, None, cpu, mapping=mapping)
                 assert dt.mapping == mapping and dt.tb.group == group and dt.tb.specialization >= 0

@@ -42,7 +42,7 @@ GENERATED = os.path.join(CSRC, "generated", "specializations.cuh")
 HEADERS = [
     os.path.join(CSRC, "geometry.cuh"),
     os.path.join(CSRC, "spec_kernel.cuh"),
-    os.path.join(CSRC, "spec_coop_kernel.cuh"),
+    os.path.join(CSRC, "spec_tile_kernel.cuh"),
     os.path.join(CSRC, "reset.cuh"),
     os.path.join(INCLUDE, "vmas_b200.h"),
     GENERATED,
@@ -177,7 +177,9 @@ class AgentActionsC(C.Structure):
 
 
 MAX_SPAWN = 64
-GROUP_COOPERATIVE = -8  # VMAS_GROUP_COOPERATIVE
+GROUP_TILE = -8  # VMAS_GROUP_TILE
+#: what mapping="auto" picks for a specialised world that has both kernels
+DEFAULT_SPEC_MAPPING = os.environ.get("VMAS_B200_SPEC_MAPPING", "specialized")
 
 
 class SpawnC(C.Structure):
@@ -214,6 +216,7 @@ EXPORTS = [
     "vmas_b200_num_specializations",
     "vmas_b200_find_specialization",
     "vmas_b200_specialization_name",
+    "vmas_b200_specialization_has_tile",
     "vmas_b200_world_step",
     "vmas_b200_world_substeps",
     "vmas_b200_world_step_timed",
@@ -286,6 +289,7 @@ def load():
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
+    lib.vmas_b200_specialization_has_tile.argtypes = [C.c_int]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int
     lib.vmas_b200_specialization_name.restype = C.c_char_p
@@ -367,26 +371,29 @@ class DeviceTables:
         self.device = torch.device(device)
         desc = tables.desc
         mapping = mapping or os.environ.get("VMAS_B200_MAPPING", "auto")
-        assert mapping in ("auto", "specialized", "cooperative", "thread_per_env", "lanes_per_env"), mapping
+        assert mapping in ("auto", "specialized", "tile", "thread_per_env", "lanes_per_env"), mapping
         self.specialization = -1
-        cooperative = mapping == "cooperative"  # the specialised world's small-batch kernel (opt-in)
-        if cooperative:
-            mapping = "specialized"
-        if mapping in ("auto", "specialized"):
+        # specialised worlds have two kernels: "specialized" = one thread per env (step_spec_kernel),
+        # "tile" = a warp per 32 envs with the narrow phase compacted (step_tile_kernel; not for
+        # worlds with joints).  "auto" takes DEFAULT_SPEC_MAPPING where the world has it.
+        if mapping in ("auto", "specialized", "tile"):
             from . import codegen
 
-            self.specialization = load().vmas_b200_find_specialization(codegen.world_hash(desc))
+            lib = load()
+            self.specialization = lib.vmas_b200_find_specialization(codegen.world_hash(desc))
             if self.specialization < 0:
-                if mapping == "specialized":
+                if mapping != "auto":
                     raise RuntimeError("no ahead-of-time specialisation of this world in libvmas_b200.so")
                 mapping = "thread_per_env"
             else:
-                mapping = "specialized"
-        if cooperative:
-            mapping = "cooperative"
+                has_tile = bool(lib.vmas_b200_specialization_has_tile(self.specialization))
+                if mapping == "tile" and not has_tile:
+                    raise RuntimeError("this world's specialisation has no tile kernel (joints / too many work items)")
+                if mapping == "auto":
+                    mapping = "tile" if (has_tile and DEFAULT_SPEC_MAPPING == "tile") else "specialized"
         self.mapping = mapping
-        if mapping in ("thread_per_env", "specialized", "cooperative"):
-            self.group, self.ents_per_lane = (GROUP_COOPERATIVE if cooperative else 1), desc.n_entities
+        if mapping in ("thread_per_env", "specialized", "tile"):
+            self.group, self.ents_per_lane = (GROUP_TILE if mapping == "tile" else 1), desc.n_entities
             sched = np.zeros((0, 1), np.int32)
         else:
             self.group, self.ents_per_lane = lane_layout(desc.n_entities)

@@ -163,7 +163,7 @@ def generate(path: str = GENERATED) -> List[Tuple[str, int]]:
         "// constexpr world tables the specialised substep kernel (spec_kernel.cuh) is instantiated with.",
         "#pragma once",
         '#include "../spec_kernel.cuh"',
-        '#include "../spec_coop_kernel.cuh"',
+        '#include "../spec_tile_kernel.cuh"',
         "",
         "namespace vmas {",
         "",
@@ -175,10 +175,10 @@ def generate(path: str = GENERATED) -> List[Tuple[str, int]]:
     for label, name, _, h, desc in worlds:
         parts.append(
             f'    {{0x{h:016x}ull, "{label}", {desc.n_entities}, {len(desc.items)}, &launch_spec<{name}>, '
-            f"&launch_coop<{name}>}},"
+            f"&launch_tile<{name}>, TileLayout<{name}>::SUPPORTED}},"
         )
     if not worlds:
-        parts.append('    {0ull, "", 0, 0, nullptr, nullptr},')
+        parts.append('    {0ull, "", 0, 0, nullptr, nullptr, false},')
     parts.append("};")
     parts.append(f"static const int kNumSpecs = {len(worlds)};")
     parts.append("#endif")

@@ -30,10 +30,17 @@ DEVI float norm2(V2 v) { return norm2(v.x, v.y); }
 DEVI float dot2(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }           // (a*b).sum(-1)
 DEVI float cross2(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }         // ref utils.py:194-197
 DEVI float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }  // torch.sign
-// a / b for a positive divisor.  IEEE division takes a ~40-instruction slow path when the numerator
-// is zero (FCHK), which is the common case here (contact normals along an axis, resting bodies,
-// zero torque); (+-0) / b == +-0 for b > 0, so the numerator itself is the exact quotient.
-DEVI float div_pos(float a, float b) { return (a == 0.f && b > 0.f) ? a : a / b; }
+// a / b for a positive divisor.  IEEE division takes a ~100-instruction slow path when the numerator
+// is zero (FCHK fails), which is the common case here (contact normals along an axis, resting bodies,
+// zero torque) — and a select does not help: the compiler evaluates the division for every lane and
+// the lanes with a zero numerator still walk the slow path (measured: 14 % of the balance kernel's
+// warp-instructions, profiles/r2a_*).  So the division itself is given a harmless numerator (1) in
+// that case; (+-0) / b == +-0 for b > 0, so the numerator itself is the exact quotient.
+DEVI float div_pos(float a, float b) {
+  const bool zero = (a == 0.f && b > 0.f);
+  const float q = (zero ? 1.f : a) / b;
+  return zero ? a : q;
+}
 // rotate `v` by the angle whose (cos, sin) is (c, s)  (ref utils.py:176-191)
 DEVI V2 rot2(V2 v, float c, float s) { return mk(v.x * c - v.y * s, v.x * s + v.y * c); }
 

@@ -287,194 +287,245 @@ __host__ __device__ constexpr uint64_t agent_cols(int flag_all, int flag_any, in
 #define SPEC_MIN_BLOCKS 1
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// The per-entity statements of one substep, shared by every specialised mapping (thread per env,
+// warp tile): same statements, same order => same bits.
+// ---------------------------------------------------------------------------------------------
+// sin / cos of the entities whose orientation the geometry needs
+template <class W, int E>
+DEVI void spec_trig(EnvRegs<E>& r) {
+  static_for<E>([&](auto ei) {
+    constexpr int e = decltype(ei)::value;
+    constexpr EntC en = W::ent[e];
+    if constexpr (en.flags & VMAS_F_TRIG) {
+      sincosf(r.rot[e], &r.s[e], &r.c[e]);
+      if constexpr (en.shape == VMAS_SHAPE_BOX) sincosf(r.rot[e] + SPEC_HALF_PI_F, &r.s2[e], &r.c2[e]);
+    }
+  });
+}
+
+// action force / torque (clamped in place), friction, gravity of every entity -> r.Fx, r.Fy, r.T
+// (ref core.py:1995-2004, 2018-2102)
+template <class W, int E, int NAX>
+DEVI void spec_entity_forces(EnvRegs<E>& r, float (&afx)[NAX], float (&afy)[NAX], float (&atq)[NAX]) {
+  constexpr float sub_dt = W::cfg.sub_dt;
+  static_for<E>([&](auto ei) {
+    constexpr int e = decltype(ei)::value;
+    constexpr EntC en = W::ent[e];
+    float Fx = 0.f, Fy = 0.f, T = 0.f;
+    if constexpr (en.flags & VMAS_F_AGENT) {
+      constexpr int ai = en.agent;
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        if constexpr (en.flags & VMAS_F_MAX_F) {
+          const float n = norm2(afx[ai], afy[ai]);
+          if (n > en.max_f) {
+            afx[ai] = (afx[ai] / n) * en.max_f;
+            afy[ai] = (afy[ai] / n) * en.max_f;
+          }
+        }
+        if constexpr (en.flags & VMAS_F_F_RANGE) {
+          afx[ai] = fminf(fmaxf(afx[ai], -en.f_range), en.f_range);
+          afy[ai] = fminf(fmaxf(afy[ai], -en.f_range), en.f_range);
+        }
+        Fx = Fx + afx[ai];
+        Fy = Fy + afy[ai];
+      }
+      if constexpr (en.flags & VMAS_F_ROTATABLE) {
+        if constexpr (en.flags & VMAS_F_MAX_T) {
+          const float n = sqrtf(atq[ai] * atq[ai]);
+          if (n > en.max_t) atq[ai] = (atq[ai] / n) * en.max_t;
+        }
+        if constexpr (en.flags & VMAS_F_T_RANGE) atq[ai] = fminf(fmaxf(atq[ai], -en.t_range), en.t_range);
+        T = T + atq[ai];
+      }
+    }
+    if constexpr (en.flags & VMAS_F_LIN_FRIC) {
+      const float speed = norm2(r.vx[e], r.vy[e]);
+      if (speed != 0.f) {
+        const float cap = en.lin_fric * en.mass;
+        Fx = Fx + (-(r.vx[e] / speed)) * fminf(cap, (fabsf(r.vx[e]) / sub_dt) * en.mass);
+        Fy = Fy + (-(r.vy[e] / speed)) * fminf(cap, (fabsf(r.vy[e]) / sub_dt) * en.mass);
+      }
+    }
+    if constexpr (en.flags & VMAS_F_ANG_FRIC) {
+      const float speed = sqrtf(r.w[e] * r.w[e]);
+      if (speed != 0.f) {
+        const float cap = en.ang_fric * en.inertia;
+        T = T + (-(r.w[e] / speed)) * fminf(cap, (fabsf(r.w[e]) / sub_dt) * en.inertia);
+      }
+    }
+    if constexpr (en.flags & VMAS_F_MOVABLE) {
+      if constexpr (W::cfg.has_world_gravity) {
+        Fx = Fx + en.mass * W::cfg.gravity_x;
+        Fy = Fy + en.mass * W::cfg.gravity_y;
+      }
+      if constexpr (en.flags & VMAS_F_GRAVITY) {
+        Fx = Fx + en.mass * en.grav_x;
+        Fy = Fy + en.mass * en.grav_y;
+      }
+    }
+    r.Fx[e] = Fx;
+    r.Fy[e] = Fy;
+    r.T[e] = T;
+  });
+}
+
+// semi-implicit Euler of every entity (ref core.py:2862-2908); `sub` is the substep's index in the step
+template <class W, int E>
+DEVI void spec_integrate(EnvRegs<E>& r, const int sub) {
+  constexpr float sub_dt = W::cfg.sub_dt;
+  static_for<E>([&](auto ei) {
+    constexpr int e = decltype(ei)::value;
+    constexpr EntC en = W::ent[e];
+    if constexpr (en.flags & VMAS_F_MOVABLE) {
+      if (sub == 0) {
+        r.vx[e] = r.vx[e] * en.drag_mult;
+        r.vy[e] = r.vy[e] * en.drag_mult;
+      }
+      r.vx[e] = r.vx[e] + div_pos(r.Fx[e], en.mass) * sub_dt;
+      r.vy[e] = r.vy[e] + div_pos(r.Fy[e], en.mass) * sub_dt;
+      if constexpr (en.flags & VMAS_F_MAX_SPEED) {
+        const float n = norm2(r.vx[e], r.vy[e]);
+        if (n > en.max_speed) {
+          r.vx[e] = (r.vx[e] / n) * en.max_speed;
+          r.vy[e] = (r.vy[e] / n) * en.max_speed;
+        }
+      }
+      if constexpr (en.flags & VMAS_F_V_RANGE) {
+        r.vx[e] = fminf(fmaxf(r.vx[e], -en.v_range), en.v_range);
+        r.vy[e] = fminf(fmaxf(r.vy[e], -en.v_range), en.v_range);
+      }
+      r.px[e] = r.px[e] + r.vx[e] * sub_dt;
+      r.py[e] = r.py[e] + r.vy[e] * sub_dt;
+      if constexpr (W::cfg.has_x_semidim) r.px[e] = fminf(fmaxf(r.px[e], -W::cfg.x_semidim), W::cfg.x_semidim);
+      if constexpr (W::cfg.has_y_semidim) r.py[e] = fminf(fmaxf(r.py[e], -W::cfg.y_semidim), W::cfg.y_semidim);
+    }
+    if constexpr (en.flags & VMAS_F_ROTATABLE) {
+      if (sub == 0) r.w[e] = r.w[e] * en.drag_mult;
+      r.w[e] = r.w[e] + div_pos(r.T[e], en.inertia) * sub_dt;
+      r.rot[e] = r.rot[e] + r.w[e] * sub_dt;
+    }
+  });
+}
+
+// The rows of one env (pos, vel, rot, ang_vel, agent force, agent torque) and which vector chunks
+// of them are read / written: derived from the world's entity flags at compile time.
+template <class W>
+struct SpecRows {
+  static constexpr int E = W::E, NA = W::A;
+  static constexpr uint64_t ALL_POS = (2 * E >= 64) ? ~0ull : ((1ull << (2 * E)) - 1);
+  static constexpr uint64_t MOV2 = ent_cols<W>(VMAS_F_MOVABLE, 2);
+  static constexpr uint64_t ROT1 = ent_cols<W>(VMAS_F_ROTATABLE, 1);
+  static constexpr uint64_t F_DIRTY = agent_cols<W>(VMAS_F_MOVABLE, VMAS_F_MAX_F | VMAS_F_F_RANGE, 2);
+  static constexpr uint64_t T_DIRTY = agent_cols<W>(VMAS_F_ROTATABLE, VMAS_F_MAX_T | VMAS_F_T_RANGE, 1);
+  // a vector chunk that will be stored must have been loaded whole (it carries unchanged columns)
+  static constexpr uint64_t VEL_IO = chunk_closure(MOV2, 2 * E, RowVec<2 * E>::W);
+  static constexpr uint64_t ROT_ST = chunk_closure(ROT1, E, RowVec<E>::W);
+  static constexpr uint64_t ROT_LD = ROT_ST | ent_cols<W>(VMAS_F_TRIG | VMAS_F_ROTATABLE, 1);
+  static constexpr uint64_t F_ST = chunk_closure(F_DIRTY, 2 * NA, RowVec<2 * NA>::W);
+  static constexpr uint64_t T_ST = chunk_closure(T_DIRTY, NA, RowVec<NA>::W);
+  static constexpr uint64_t F_LD = F_ST | agent_cols<W>(VMAS_F_MOVABLE, 0, 2);
+  static constexpr uint64_t T_LD = T_ST | agent_cols<W>(VMAS_F_ROTATABLE, 0, 1);
+
+  float pos[2 * E], vel[2 * E], rot[E], w[E];
+  float f[NA > 0 ? 2 * NA : 1], t[NA > 0 ? NA : 1];
+
+  DEVI void load_pos_rot(const SpecArgs& a, const long env) {
+    row_load<2 * E, ALL_POS>(a.st.pos + (size_t)env * 2 * E, pos);
+    row_load<E, ROT_LD>(a.st.rot + (size_t)env * E, rot);
+  }
+  DEVI void load_rest(const SpecArgs& a, const long env) {
+    row_load<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, vel);
+    row_load<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, w);
+    row_load<2 * NA, F_LD>(a.st.force + (size_t)env * 2 * NA, f);
+    row_load<NA, T_LD>(a.st.torque + (size_t)env * NA, t);
+  }
+  // rows -> registers (pos, rot; trig caches and velocities zeroed)
+  DEVI void unpack_pos_rot(EnvRegs<E>& r) const {
+    static_for<E>([&](auto ei) {
+      constexpr int e = decltype(ei)::value;
+      constexpr EntC en = W::ent[e];
+      r.px[e] = pos[2 * e];
+      r.py[e] = pos[2 * e + 1];
+      r.rot[e] = (en.flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE)) ? rot[e] : 0.f;
+      r.vx[e] = r.vy[e] = r.w[e] = 0.f;
+      r.c[e] = r.s[e] = r.c2[e] = r.s2[e] = 0.f;
+    });
+  }
+  template <int NAX>
+  DEVI void unpack_rest(EnvRegs<E>& r, float (&afx)[NAX], float (&afy)[NAX], float (&atq)[NAX]) const {
+    static_for<E>([&](auto ei) {
+      constexpr int e = decltype(ei)::value;
+      constexpr EntC en = W::ent[e];
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        r.vx[e] = vel[2 * e];
+        r.vy[e] = vel[2 * e + 1];
+      }
+      if constexpr (en.flags & VMAS_F_ROTATABLE) r.w[e] = w[e];
+      if constexpr (en.flags & VMAS_F_AGENT) {
+        if constexpr (en.flags & VMAS_F_MOVABLE) {
+          afx[en.agent] = f[2 * en.agent];
+          afy[en.agent] = f[2 * en.agent + 1];
+        }
+        if constexpr (en.flags & VMAS_F_ROTATABLE) atq[en.agent] = t[en.agent];
+      }
+    });
+  }
+  // registers -> rows -> global: vector stores of the chunks that hold a changed column
+  template <int NAX>
+  DEVI void store(const SpecArgs& a, const long env, const EnvRegs<E>& r, const float (&afx)[NAX],
+                  const float (&afy)[NAX], const float (&atq)[NAX]) {
+    static_for<E>([&](auto ei) {
+      constexpr int e = decltype(ei)::value;
+      constexpr EntC en = W::ent[e];
+      if constexpr (en.flags & VMAS_F_MOVABLE) {
+        pos[2 * e] = r.px[e];
+        pos[2 * e + 1] = r.py[e];
+        vel[2 * e] = r.vx[e];
+        vel[2 * e + 1] = r.vy[e];
+      }
+      if constexpr (en.flags & VMAS_F_ROTATABLE) {
+        rot[e] = r.rot[e];
+        w[e] = r.w[e];
+      }
+      if constexpr (en.flags & VMAS_F_AGENT) {
+        if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE))) {
+          f[2 * en.agent] = afx[en.agent];
+          f[2 * en.agent + 1] = afy[en.agent];
+        }
+        if constexpr ((en.flags & VMAS_F_ROTATABLE) && (en.flags & (VMAS_F_MAX_T | VMAS_F_T_RANGE)))
+          t[en.agent] = atq[en.agent];
+      }
+    });
+    row_store<2 * E, VEL_IO>(a.st.pos + (size_t)env * 2 * E, pos);
+    row_store<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, vel);
+    row_store<E, ROT_ST>(a.st.rot + (size_t)env * E, rot);
+    row_store<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, w);
+    row_store<2 * NA, F_ST>(a.st.force + (size_t)env * 2 * NA, f);
+    row_store<NA, T_ST>(a.st.torque + (size_t)env * NA, t);
+  }
+};
+
 // One env, all of `a.n_substeps` substeps, state in the calling thread's registers.
 template <class W>
 DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask_words)[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1]) {
   constexpr int E = W::E, NA = W::A, NI = W::NI;
-  // ---- load this env's rows with vector accesses -----------------------------------------------
-  constexpr uint64_t ALL_POS = (2 * E >= 64) ? ~0ull : ((1ull << (2 * E)) - 1);
-  constexpr uint64_t MOV2 = ent_cols<W>(VMAS_F_MOVABLE, 2);
-  constexpr uint64_t ROT1 = ent_cols<W>(VMAS_F_ROTATABLE, 1);
-  constexpr uint64_t F_DIRTY = agent_cols<W>(VMAS_F_MOVABLE, VMAS_F_MAX_F | VMAS_F_F_RANGE, 2);
-  constexpr uint64_t T_DIRTY = agent_cols<W>(VMAS_F_ROTATABLE, VMAS_F_MAX_T | VMAS_F_T_RANGE, 1);
-  // a vector chunk that will be stored must have been loaded whole (it carries unchanged columns)
-  constexpr uint64_t VEL_IO = chunk_closure(MOV2, 2 * E, RowVec<2 * E>::W);
-  constexpr uint64_t ROT_ST = chunk_closure(ROT1, E, RowVec<E>::W);
-  constexpr uint64_t ROT_LD = ROT_ST | ent_cols<W>(VMAS_F_TRIG | VMAS_F_ROTATABLE, 1);
-  constexpr uint64_t F_ST = chunk_closure(F_DIRTY, 2 * NA, RowVec<2 * NA>::W);
-  constexpr uint64_t T_ST = chunk_closure(T_DIRTY, NA, RowVec<NA>::W);
-  constexpr uint64_t F_LD = F_ST | agent_cols<W>(VMAS_F_MOVABLE, 0, 2);
-  constexpr uint64_t T_LD = T_ST | agent_cols<W>(VMAS_F_ROTATABLE, 0, 1);
   if (env >= a.batch_dim) return;
-
-  float row_pos[2 * E], row_vel[2 * E], row_rot[E], row_w[E];
-  float row_f[NA > 0 ? 2 * NA : 1], row_t[NA > 0 ? NA : 1];
-  row_load<2 * E, ALL_POS>(a.st.pos + (size_t)env * 2 * E, row_pos);
-  row_load<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, row_vel);
-  row_load<E, ROT_LD>(a.st.rot + (size_t)env * E, row_rot);
-  row_load<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, row_w);
-  row_load<2 * NA, F_LD>(a.st.force + (size_t)env * 2 * NA, row_f);
-  row_load<NA, T_LD>(a.st.torque + (size_t)env * NA, row_t);
-
+  SpecRows<W> rows;
+  rows.load_pos_rot(a, env);
+  rows.load_rest(a, env);
   EnvRegs<E> r;
   float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
-
-  static_for<E>([&](auto ei) {
-    constexpr int e = decltype(ei)::value;
-    constexpr EntC en = W::ent[e];
-    r.px[e] = row_pos[2 * e];
-    r.py[e] = row_pos[2 * e + 1];
-    r.rot[e] = (en.flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE)) ? row_rot[e] : 0.f;
-    r.vx[e] = r.vy[e] = r.w[e] = 0.f;
-    r.c[e] = r.s[e] = r.c2[e] = r.s2[e] = 0.f;
-    if constexpr (en.flags & VMAS_F_MOVABLE) {
-      r.vx[e] = row_vel[2 * e];
-      r.vy[e] = row_vel[2 * e + 1];
-    }
-    if constexpr (en.flags & VMAS_F_ROTATABLE) r.w[e] = row_w[e];
-    if constexpr (en.flags & VMAS_F_AGENT) {
-      if constexpr (en.flags & VMAS_F_MOVABLE) {
-        afx[en.agent] = row_f[2 * en.agent];
-        afy[en.agent] = row_f[2 * en.agent + 1];
-      }
-      if constexpr (en.flags & VMAS_F_ROTATABLE) atq[en.agent] = row_t[en.agent];
-    }
-  });
-
-  constexpr float sub_dt = W::cfg.sub_dt;
+  rows.unpack_pos_rot(r);
+  rows.unpack_rest(r, afx, afy, atq);
   for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
-    // ---- per-entity forces (ref core.py:1995-2004) ------------------------------------------
-    static_for<E>([&](auto ei) {
-      constexpr int e = decltype(ei)::value;
-      constexpr EntC en = W::ent[e];
-      if constexpr (en.flags & VMAS_F_TRIG) {
-        sincosf(r.rot[e], &r.s[e], &r.c[e]);
-        if constexpr (en.shape == VMAS_SHAPE_BOX) sincosf(r.rot[e] + SPEC_HALF_PI_F, &r.s2[e], &r.c2[e]);
-      }
-      float Fx = 0.f, Fy = 0.f, T = 0.f;
-      if constexpr (en.flags & VMAS_F_AGENT) {
-        constexpr int ai = en.agent;
-        if constexpr (en.flags & VMAS_F_MOVABLE) {
-          if constexpr (en.flags & VMAS_F_MAX_F) {
-            const float n = norm2(afx[ai], afy[ai]);
-            if (n > en.max_f) {
-              afx[ai] = (afx[ai] / n) * en.max_f;
-              afy[ai] = (afy[ai] / n) * en.max_f;
-            }
-          }
-          if constexpr (en.flags & VMAS_F_F_RANGE) {
-            afx[ai] = fminf(fmaxf(afx[ai], -en.f_range), en.f_range);
-            afy[ai] = fminf(fmaxf(afy[ai], -en.f_range), en.f_range);
-          }
-          Fx = Fx + afx[ai];
-          Fy = Fy + afy[ai];
-        }
-        if constexpr (en.flags & VMAS_F_ROTATABLE) {
-          if constexpr (en.flags & VMAS_F_MAX_T) {
-            const float n = sqrtf(atq[ai] * atq[ai]);
-            if (n > en.max_t) atq[ai] = (atq[ai] / n) * en.max_t;
-          }
-          if constexpr (en.flags & VMAS_F_T_RANGE) atq[ai] = fminf(fmaxf(atq[ai], -en.t_range), en.t_range);
-          T = T + atq[ai];
-        }
-      }
-      if constexpr (en.flags & VMAS_F_LIN_FRIC) {
-        const float speed = norm2(r.vx[e], r.vy[e]);
-        if (speed != 0.f) {
-          const float cap = en.lin_fric * en.mass;
-          Fx = Fx + (-(r.vx[e] / speed)) * fminf(cap, (fabsf(r.vx[e]) / sub_dt) * en.mass);
-          Fy = Fy + (-(r.vy[e] / speed)) * fminf(cap, (fabsf(r.vy[e]) / sub_dt) * en.mass);
-        }
-      }
-      if constexpr (en.flags & VMAS_F_ANG_FRIC) {
-        const float speed = sqrtf(r.w[e] * r.w[e]);
-        if (speed != 0.f) {
-          const float cap = en.ang_fric * en.inertia;
-          T = T + (-(r.w[e] / speed)) * fminf(cap, (fabsf(r.w[e]) / sub_dt) * en.inertia);
-        }
-      }
-      if constexpr (en.flags & VMAS_F_MOVABLE) {
-        if constexpr (W::cfg.has_world_gravity) {
-          Fx = Fx + en.mass * W::cfg.gravity_x;
-          Fy = Fy + en.mass * W::cfg.gravity_y;
-        }
-        if constexpr (en.flags & VMAS_F_GRAVITY) {
-          Fx = Fx + en.mass * en.grav_x;
-          Fy = Fy + en.mass * en.grav_y;
-        }
-      }
-      r.Fx[e] = Fx;
-      r.Fy[e] = Fy;
-      r.T[e] = T;
-    });
-
-    // ---- joints and contacts, in accumulation order ---------------------------------------------
+    spec_trig<W>(r);
+    spec_entity_forces<W>(r, afx, afy, atq);
+    // joints and contacts, in accumulation order
     static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value>(r, a, env, mask_words); });
-
-    // ---- semi-implicit Euler (ref core.py:2862-2908) ----------------------------------------------
-    static_for<E>([&](auto ei) {
-      constexpr int e = decltype(ei)::value;
-      constexpr EntC en = W::ent[e];
-      if constexpr (en.flags & VMAS_F_MOVABLE) {
-        if (sub == 0) {
-          r.vx[e] = r.vx[e] * en.drag_mult;
-          r.vy[e] = r.vy[e] * en.drag_mult;
-        }
-        r.vx[e] = r.vx[e] + div_pos(r.Fx[e], en.mass) * sub_dt;
-        r.vy[e] = r.vy[e] + div_pos(r.Fy[e], en.mass) * sub_dt;
-        if constexpr (en.flags & VMAS_F_MAX_SPEED) {
-          const float n = norm2(r.vx[e], r.vy[e]);
-          if (n > en.max_speed) {
-            r.vx[e] = (r.vx[e] / n) * en.max_speed;
-            r.vy[e] = (r.vy[e] / n) * en.max_speed;
-          }
-        }
-        if constexpr (en.flags & VMAS_F_V_RANGE) {
-          r.vx[e] = fminf(fmaxf(r.vx[e], -en.v_range), en.v_range);
-          r.vy[e] = fminf(fmaxf(r.vy[e], -en.v_range), en.v_range);
-        }
-        r.px[e] = r.px[e] + r.vx[e] * sub_dt;
-        r.py[e] = r.py[e] + r.vy[e] * sub_dt;
-        if constexpr (W::cfg.has_x_semidim) r.px[e] = fminf(fmaxf(r.px[e], -W::cfg.x_semidim), W::cfg.x_semidim);
-        if constexpr (W::cfg.has_y_semidim) r.py[e] = fminf(fmaxf(r.py[e], -W::cfg.y_semidim), W::cfg.y_semidim);
-      }
-      if constexpr (en.flags & VMAS_F_ROTATABLE) {
-        if (sub == 0) r.w[e] = r.w[e] * en.drag_mult;
-        r.w[e] = r.w[e] + div_pos(r.T[e], en.inertia) * sub_dt;
-        r.rot[e] = r.rot[e] + r.w[e] * sub_dt;
-      }
-    });
+    spec_integrate<W>(r, sub);
   }
-
-  // ---- write-back: vector stores of the chunks that hold a changed column ---------------------------
-  static_for<E>([&](auto ei) {
-    constexpr int e = decltype(ei)::value;
-    constexpr EntC en = W::ent[e];
-    if constexpr (en.flags & VMAS_F_MOVABLE) {
-      row_pos[2 * e] = r.px[e];
-      row_pos[2 * e + 1] = r.py[e];
-      row_vel[2 * e] = r.vx[e];
-      row_vel[2 * e + 1] = r.vy[e];
-    }
-    if constexpr (en.flags & VMAS_F_ROTATABLE) {
-      row_rot[e] = r.rot[e];
-      row_w[e] = r.w[e];
-    }
-    if constexpr (en.flags & VMAS_F_AGENT) {
-      if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE))) {
-        row_f[2 * en.agent] = afx[en.agent];
-        row_f[2 * en.agent + 1] = afy[en.agent];
-      }
-      if constexpr ((en.flags & VMAS_F_ROTATABLE) && (en.flags & (VMAS_F_MAX_T | VMAS_F_T_RANGE)))
-        row_t[en.agent] = atq[en.agent];
-    }
-  });
-  row_store<2 * E, VEL_IO>(a.st.pos + (size_t)env * 2 * E, row_pos);
-  row_store<2 * E, VEL_IO>(a.st.vel + (size_t)env * 2 * E, row_vel);
-  row_store<E, ROT_ST>(a.st.rot + (size_t)env * E, row_rot);
-  row_store<E, ROT_ST>(a.st.ang_vel + (size_t)env * E, row_w);
-  row_store<2 * NA, F_ST>(a.st.force + (size_t)env * 2 * NA, row_f);
-  row_store<NA, T_ST>(a.st.torque + (size_t)env * NA, row_t);
+  rows.store(a, env, r, afx, afy, atq);
 }
 
 #ifdef __CUDACC__
@@ -521,7 +572,8 @@ struct SpecEntry {
   const char* name;
   int n_entities, n_items;
   cudaError_t (*launch)(const SpecArgs&, cudaStream_t);       // one thread per env (step_spec_kernel)
-  cudaError_t (*launch_coop)(const SpecArgs&, cudaStream_t);  // warps share a tile of 32 envs (step_coop_kernel)
+  cudaError_t (*launch_tile)(const SpecArgs&, cudaStream_t);  // a warp owns a tile of 32 envs, compacted narrow phase
+  bool has_tile;                                              // (step_tile_kernel; not for worlds with joints)
 };
 #endif
 

@@ -1544,10 +1544,11 @@ static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
   sa.first_substep = args.first_substep;
   sa.n_substeps = args.n_substeps;
   // tb.group selects the thread mapping of a specialised world: 1 = one thread per env,
-  // VMAS_GROUP_COOPERATIVE = warps share a tile of 32 envs (small batches)
-  if (args.tb.group == VMAS_GROUP_COOPERATIVE)
-    CUDA_OK(sp.launch_coop(sa, stream));
-  else
+  // VMAS_GROUP_TILE = a warp owns a tile of 32 envs and runs the narrow phase compacted
+  if (args.tb.group == VMAS_GROUP_TILE) {
+    if (!sp.has_tile) return fail("this specialization has no tile kernel (joints, or too many work items)%s");
+    CUDA_OK(sp.launch_tile(sa, stream));
+  } else
     CUDA_OK(sp.launch(sa, stream));
   return 1;
 }
@@ -1588,6 +1589,10 @@ int vmas_b200_find_specialization(uint64_t world_hash) {
   for (int i = 0; i < kNumSpecs; ++i)
     if (kSpecs[i].hash == world_hash) return i;
   return -1;
+}
+
+int vmas_b200_specialization_has_tile(int index) {
+  return (index >= 0 && index < kNumSpecs && kSpecs[index].has_tile) ? 1 : 0;
 }
 
 const char* vmas_b200_specialization_name(int index) {
