@@ -2,6 +2,8 @@
 // the CPU (g++, shim/cuda_runtime.h), one "thread" after the other, so the tile kernel's
 // phase structure (who owns which entity / item, shared-memory rows, accumulation order) can be
 // checked bit for bit against the thread-per-env formulation without a GPU.  Not product code.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "generated/specializations.cuh"
@@ -18,7 +20,8 @@ static void run_thread_per_env(const SpecArgs& a, const uint32_t* mask) {
 
 // the body of tile_warp_step (csrc/spec_tile_kernel.cuh) for one tile of 32 envs: the lanes of the warp one
 // after the other, every __syncwarp() turned into "finish the loop over the lanes"; the ballot-based
-// queue construction is restated as plain loops (same order: item-major, lane-minor within a kind)
+// appends (contact ring, geometry queues) are restated as plain loops in lane order, with the same
+// ring discipline (a full round of the force as soon as 32 contacts wait)
 template <class W>
 static void run_tile(const SpecArgs& a, const uint32_t* mask) {
   using T = Tile<W>;
@@ -42,22 +45,68 @@ static void run_tile(const SpecArgs& a, const uint32_t* mask) {
       }
       uint16_t* q = T::queue(sm.data());
       for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
+        uint64_t any = 0;
         for (int lane = 0; lane < TILE_LANES; ++lane) {
           T::p1(sm.data(), lane, lanes[lane], a, mask_words);
-          if (!valid(lane)) lanes[lane].near = 0;
+          if (!valid(lane)) lanes[lane].near = lanes[lane].hits = 0;
+          any |= lanes[lane].near;
         }
-        int cnt[TILE_N_KINDS] = {0};
-        for (int i = 0; i < W::NI; ++i) {
-          const int k = W::item[i].kind;
-          for (int lane = 0; lane < TILE_LANES; ++lane)
-            if ((lanes[lane].near >> i) & 1u) q[L::kind_base(k) + cnt[k]++] = (uint16_t)((i << 5) | lane);
-        }
-        static_for<TILE_N_KINDS>([&](auto ki) {
-          constexpr int K = decltype(ki)::value;
-          if constexpr (L::kind_count(K) > 0 && K != VMAS_K_JOINT) {
-            for (int idx = 0; idx < cnt[K]; ++idx) T::template narrow<K>(sm.data(), q[L::kind_base(K) + idx]);
+        int head = 0, tail = 0;
+        auto flush_full_rounds = [&]() {
+          while (tail - head >= TILE_LANES) {
+            for (int l = 0; l < TILE_LANES; ++l) T::contact_force(sm.data(), head + l);
+            head += TILE_LANES;
+          }
+        };
+        // direct kinds
+        static_for<W::NI>([&](auto ii) {
+          constexpr int I = decltype(ii)::value;
+          if constexpr (tile_kind_is_direct(W::item[I].kind)) {
+            if ((any >> I) & 1u) {
+              int appended = 0;
+              for (int lane = 0; lane < TILE_LANES; ++lane) {
+                TileContact c;
+                bool has = false;
+                if ((lanes[lane].near >> I) & 1u) has = T::template direct_contact<I>(lane, lanes[lane].r, c);
+                if (has) {
+                  lanes[lane].hits |= (uint64_t)1 << I;
+                  if (tail + appended - head >= TILE_RING) abort();  // the ring can never overflow
+                  T::ring_put(sm.data(), tail + appended++, c);
+                }
+              }
+              tail += appended;
+              flush_full_rounds();
+            }
           }
         });
+        // geometry kinds
+        if constexpr (L::HAS_GEOM) {
+          int cnt[TILE_N_KINDS] = {0};
+          for (int i = 0; i < W::NI; ++i) {
+            const int k = W::item[i].kind;
+            if (!tile_kind_is_geom(k)) continue;
+            for (int lane = 0; lane < TILE_LANES; ++lane)
+              if ((lanes[lane].near >> i) & 1u) q[L::geom_base(k) + cnt[k]++] = (uint16_t)((i << 5) | lane);
+          }
+          static_for<TILE_N_KINDS>([&](auto ki) {
+            constexpr int K = decltype(ki)::value;
+            if constexpr (tile_kind_is_geom(K) && L::kind_count(K) > 0) {
+              for (int base = 0; base < cnt[K]; base += TILE_LANES) {
+                int appended = 0;
+                for (int l = 0; l < TILE_LANES && base + l < cnt[K]; ++l) {
+                  TileContact c;
+                  if (T::template geom_contact<K>(sm.data(), q[L::geom_base(K) + base + l], c)) {
+                    if (tail + appended - head >= TILE_RING) abort();
+                    T::ring_put(sm.data(), tail + appended++, c);
+                  }
+                }
+                tail += appended;
+                flush_full_rounds();
+              }
+            }
+          });
+        }
+        for (int slot = head; slot < tail; ++slot) T::contact_force(sm.data(), slot);  // the last, partial round
         for (int lane = 0; lane < TILE_LANES; ++lane) {
           if (sub == a.first_substep) {
             lanes[lane].rows.load_rest(a, env_c(lane));

@@ -41,11 +41,21 @@ CASES = [
     ("wind_flocking", dict(), 16, 15),  # per-env gravity tensors (Entity.gravity as [B, 2])
     ("football", dict(), 8, 10),
     ("passage", dict(), 16, 15),
+    # crafted worlds (tests/crafted.py) for the branches no reference scenario takes
+    ("crafted_clamps", dict(), 33, 12),  # max_f / f_range / max_t / t_range, angular + linear friction
+    ("crafted_joints_apart", dict(), 16, 4),  # joints with anchors clearly apart (strict-tolerance joint test)
+    ("crafted_lonely", dict(), 1, 6),  # batch_dim = 1, no work item
+    ("crafted_crowd", dict(), 4, 6),  # 70 entities
 ]
 
 
 def record(vmas, name, kwargs, num_envs, steps):
-    env = vmas.make_env(name, num_envs=num_envs, device="cpu", seed=0, **kwargs)
+    scenario = name
+    if name.startswith("crafted_"):
+        import crafted
+
+        scenario = crafted.make_scenario("vmas", name[len("crafted_"):])
+    env = vmas.make_env(scenario, num_envs=num_envs, device="cpu", seed=0, **kwargs)
     world = env.world
     desc = P.describe_world(world)
     fix = dict(name=name, kwargs=kwargs, desc=desc.to_json(), steps=[], lidar=[], queries=[])

@@ -32,6 +32,12 @@ CASES = [
     ("joint_passage", dict(), 6, 10, 11),
     ("wheel", dict(), 8, 12, 12),
     ("wind_flocking", dict(), 8, 10, 13),
+    # crafted worlds (tests/crafted.py): action clamps, angular friction, joints with anchors apart,
+    # a one-env batch without work items, 70 entities — branches no reference scenario takes
+    ("crafted_clamps", dict(), 21, 15, 14),
+    ("crafted_joints_apart", dict(), 10, 5, 15),
+    ("crafted_lonely", dict(), 1, 5, 16),
+    ("crafted_crowd", dict(), 3, 5, 17),
 ]
 STATE = ("pos", "vel", "rot", "ang_vel")
 
@@ -39,7 +45,12 @@ STATE = ("pos", "vel", "rot", "ang_vel")
 @pytest.mark.parametrize("name,kwargs,num_envs,steps,seed", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
 def test_oracle_equals_live_reference_bit_for_bit(name, kwargs, num_envs, steps, seed):
     vmas = import_reference()
-    env = vmas.make_env(name, num_envs=num_envs, device="cpu", seed=seed, **kwargs)
+    scenario = name
+    if name.startswith("crafted_"):
+        import crafted
+
+        scenario = crafted.make_scenario("vmas", name[len("crafted_"):], seed=1000 + seed)
+    env = vmas.make_env(scenario, num_envs=num_envs, device="cpu", seed=seed, **kwargs)
     world = env.world
     desc = P.describe_world(world)  # the plan compiler reads the reference's own objects
     tables = P.build_tables(desc)

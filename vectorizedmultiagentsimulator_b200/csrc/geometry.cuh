@@ -270,8 +270,8 @@ __device__ __noinline__ V2 constraint_force_live(float dx, float dy, float d, fl
   return mk(div_pos(cc * dx, denom) * pen, div_pos(cc * dy, denom) * pen);
 }
 
-DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {
-  V2 delta = pa - pb;
+// The force from the separation vector delta = pa - pb (what constraint_force() forms first).
+DEVI V2 constraint_force_delta(V2 delta, float dmin, float c, float k, bool attractive) {
   // |delta|^2 exactly as norm2() forms it.  sqrt is monotone, so s > dmin^2 (1 + 2e-6) implies
   // sqrtf(s) > dmin: the common "far apart" case is decided without the square root.
   const float s = __fmaf_rn(delta.y, delta.y, __fmul_rn(delta.x, delta.x));
@@ -280,6 +280,16 @@ DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attrac
   if (d < 1e-6f) return mk(0.f, 0.f);
   if (attractive ? (d < dmin) : (d > dmin)) return mk(0.f, 0.f);
   return constraint_force_live(delta.x, delta.y, d, dmin, c, k, attractive ? -1.f : 1.f);
+}
+
+DEVI V2 constraint_force(V2 pa, V2 pb, float dmin, float c, float k, bool attractive) {
+  return constraint_force_delta(pa - pb, dmin, c, k, attractive);
+}
+
+// true iff a repulsive constraint_force_delta(delta, dmin, ...) gets past its first early-out
+DEVI bool contact_possible(V2 delta, float dmin) {
+  const float s = __fmaf_rn(delta.y, delta.y, __fmul_rn(delta.x, delta.x));
+  return !(s > dmin * dmin * 1.000002f);
 }
 
 }  // namespace vmas
