@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VMAS_B200_ABI_VERSION 1
+#define VMAS_B200_ABI_VERSION 2
 
 /* shape kinds (ent_i32[:,0]) */
 enum { VMAS_SHAPE_SPHERE = 0, VMAS_SHAPE_BOX = 1, VMAS_SHAPE_LINE = 2 };
@@ -90,6 +90,9 @@ typedef struct VmasPlanTables {
                                  pairs compacted over the warp's lanes; see csrc/spec_tile_kernel.cuh) */
   int32_t ents_per_lane;      /* 1, 2 or 4 (E <= group * ents_per_lane) */
   int32_t specialization;     /* index from vmas_b200_find_specialization(), or -1: generic kernels */
+  /* env scheduling of the specialised thread-per-env kernel (both optional, may be NULL): */
+  const int32_t* env_order;   /* [B] permutation: thread t steps env env_order[t] (vmas_b200_build_env_order) */
+  uint32_t* env_signature;    /* [B] out: bit (i & 31) set iff work item i produced a force in this step */
 } VmasPlanTables;
 
 #define VMAS_GROUP_TILE (-8)
@@ -98,6 +101,14 @@ typedef struct VmasPlanTables {
 typedef struct VmasState {
   float* pos; float* vel; float* rot; float* ang_vel; float* force; float* torque;
 } VmasState;
+
+/* One (source, destination, size) piece of vmas_b200_copy_buffers().  DEVICE pointers. */
+typedef struct VmasCopySegment {
+  const void* src;
+  void* dst;
+  size_t bytes;
+} VmasCopySegment;
+#define VMAS_MAX_COPY_SEGMENTS 8
 
 int vmas_b200_abi_version(void);
 const char* vmas_b200_last_error(void);
@@ -208,6 +219,29 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
 int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* pairs,
                                int32_t n_pairs, float factor, float* prev, float* dist, float* rew,
                                void* cuda_stream);
+
+/*
+ * Env scheduling.  Envs are independent, so WHICH thread steps an env is free; the thread-per-env
+ * kernel diverges when the 32 envs of a warp need different narrow-phase work (different contacts).
+ * Contacts persist over steps, so grouping envs by the signature the previous step recorded
+ * (VmasPlanTables.env_signature) makes a warp's envs take the same branches.  This builds the
+ * permutation: a counting sort of the envs by a 10-bit hash of their signature (ascending env index
+ * between 2048-env chunks, arbitrary within a chunk's bucket — results never depend on the order).
+ *   signature  device uint32[B];  order  device int32[B] (out);
+ *   workspace  device uint32[vmas_b200_env_order_workspace_words(B)]
+ * Three small launches; meant to be called every few steps, not every step.
+ */
+size_t vmas_b200_env_order_workspace_words(int32_t batch_dim);
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, uint32_t* workspace,
+                              void* cuda_stream);
+
+/*
+ * Copies up to VMAS_MAX_COPY_SEGMENTS device buffers in ONE kernel launch (an SM copy, not a copy
+ * engine: it does not queue behind a concurrent host download).  Used to hand out fresh copies of
+ * the outputs a captured Environment.step writes into static buffers (the reference returns new
+ * tensors from every step, ref environment/environment.py:254-309).
+ */
+int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cuda_stream);
 
 
 /*

@@ -144,6 +144,8 @@ int hostsim_step(uint64_t world_hash, int variant, int batch_dim, float* pos, fl
   SpecArgs a;
   a.st.pos = pos; a.st.vel = vel; a.st.rot = rot; a.st.ang_vel = ang_vel; a.st.force = force; a.st.torque = torque;
   a.joint_rot = nullptr;
+  a.order = nullptr;
+  a.sig = nullptr;
   a.mask = nullptr;
   a.batch_dim = batch_dim;
   a.use_mask = use_mask;

@@ -190,6 +190,45 @@ def test_tile_kernel_agrees_bitwise(name):
                 assert same_result(outs[0].t[k], outs[1].t[k]), f"{name} step {t} field {k} rows {rows}"
 
 
+@pytest.mark.parametrize("name", ["balance", "transport", "navigation", "flocking"])
+def test_env_scheduling_changes_no_bit(name):
+    """Scheduling the envs by contact signature (``vmas_b200_build_env_order``: thread t steps env
+    order[t]) must not change any env's result: same inputs stepped with the identity order and with
+    the order built from the recorded signatures, bit for bit; and the order is a permutation."""
+    fix, desc, tables = load(name)
+    lib = _native.load()
+    device = torch.device("cuda:0")
+    steps = list(teacher_forced_steps(fix))
+    # a batch of 4096 envs stitched from different golden steps (different contact patterns)
+    reps = 4096 // desc.batch_dim
+    picks = [steps[(7 * i) % len(steps)][1] for i in range(reps)]
+    state = {k: torch.cat([p[k] for p in picks]) for k in STATE_KEYS}
+    B = state["pos"].shape[0]
+    old = desc.batch_dim
+    desc.batch_dim = B
+    try:
+        dt = _native.DeviceTables(tables, None, device, mapping="specialized")
+    finally:
+        desc.batch_dim = old
+    assert dt.env_order is not None and dt.env_signature is not None
+    first = _Slab(state, device)
+    _native.world_step(lib, dt, first)  # identity order; records the signatures
+    assert _native.build_env_order(lib, dt) == 3
+    torch.cuda.synchronize()
+    order = dt.env_order.long()
+    assert torch.equal(torch.sort(order).values, torch.arange(B, device=device)), "not a permutation"
+    if bool((dt.env_signature != dt.env_signature[0]).any()):
+        assert not torch.equal(order, torch.arange(B, device=device)), "signatures differ but the order is the identity"
+    second = _Slab(state, device)
+    _native.world_step(lib, dt, second)
+    for k in STATE_KEYS:
+        assert torch.equal(first.t[k], second.t[k]), f"{name}: {k} changed under env scheduling"
+    # same signatures again: sorting an already grouped batch keeps it a permutation
+    _native.build_env_order(lib, dt)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.sort(dt.env_order.long()).values, torch.arange(B, device=device))
+
+
 def test_config_worlds_have_specialised_kernels():
     lib = _native.load()
     assert lib.vmas_b200_num_specializations() >= 4

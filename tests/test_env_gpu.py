@@ -63,6 +63,36 @@ def test_env_step_teacher_forced(name, kwargs):
     assert gpu.world._get_backend().launches > 0
 
 
+# BASELINE.json configs[1..4] at their full per-GPU batch sizes
+FULL_SIZE_CASES = [
+    ("balance", dict(n_agents=4), 32768),
+    ("transport", dict(n_agents=4, n_lines=2, substeps=3), 16384),
+    ("navigation", dict(n_agents=8), 8192),  # incl. the LIDAR readings in the observations
+    ("flocking", dict(n_agents=5), 32768),
+]
+
+
+@pytest.mark.parametrize("name,kwargs,n_envs", FULL_SIZE_CASES)
+def test_env_step_teacher_forced_at_baseline_batch_size(name, kwargs, n_envs):
+    """The same teacher-forced comparison at the batch sizes BASELINE.json quotes (not a tiled small
+    batch: every env has its own reset layout and its own actions), CUDA-graph mode like the bench."""
+    with use_oracle():
+        cpu = b200.make_env(name, num_envs=n_envs, device="cpu", seed=0, **kwargs)
+    gpu = b200.make_env(name, num_envs=n_envs, device="cuda", seed=0, cuda_graph=True, **kwargs)
+    gen = torch.Generator().manual_seed(13)
+    for t in range(4):  # two eager warm-up steps, the capture, one replay
+        sync_env(cpu, gpu)
+        actions = [
+            (torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor for a in cpu.agents
+        ]
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step([a.to("cuda") for a in actions])
+        _compare(got[0], want[0], f"{name} B={n_envs} step {t} obs", atol=1e-5)
+        _compare(got[1], want[1], f"{name} B={n_envs} step {t} rews", atol=2e-4)
+        _compare(got[2], want[2], f"{name} B={n_envs} step {t} dones", atol=0)
+    gpu.check_actions_now()
+
+
 @pytest.mark.parametrize("name,kwargs", CASES[:1] + CASES[3:])
 def test_env_free_rollout(name, kwargs):
     n_envs = 32
@@ -76,6 +106,61 @@ def test_env_free_rollout(name, kwargs):
         want = cpu.step([a.clone() for a in actions])
         got = gpu.step([a.to("cuda") for a in actions])
     _compare(got[0], want[0], f"{name} rollout obs", atol=1e-4)
+
+
+def test_stock_style_scenario_on_cuda():
+    """A scenario in the reference's own style (tests/stock_style.py: per-agent ``is_overlapping`` /
+    ``get_distance`` / ``Lidar.measure`` calls, ``torch.cat`` observations, boxes + a line + LIDAR) on
+    the CUDA backend against the CPU oracle env, which is bit-equal to the reference for this scenario
+    (tests/test_env_vs_reference.py).  Eager mode: boolean-mask indexing (``rew[mask] += c``) syncs with
+    the host, so stock code like this cannot be captured in a CUDA graph."""
+    import stock_style
+
+    n_envs = 48
+    with use_oracle():
+        cpu = b200.make_env(stock_style.make_scenario(), num_envs=n_envs, device="cpu", seed=0, n_agents=3)
+    gpu = b200.make_env(stock_style.make_scenario(), num_envs=n_envs, device="cuda", seed=0, n_agents=3)
+    gen = torch.Generator().manual_seed(5)
+    before = gpu.world._get_backend().launches
+    for t in range(10):
+        sync_env(cpu, gpu)
+        actions = [(torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) for a in cpu.agents]
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step([a.to("cuda") for a in actions])
+        _compare(got[0], want[0], f"stock_style step {t} obs", atol=1e-5)
+        _compare(got[1], want[1], f"stock_style step {t} rews", atol=1e-4)
+        _compare(got[2], want[2], f"stock_style step {t} dones", atol=0)
+        _compare(got[3], want[3], f"stock_style step {t} infos", atol=1e-4)
+    gpu.check_actions_now()
+    assert gpu.world._get_backend().launches > before  # queries, LIDAR and the step ran in libvmas_b200.so
+
+
+def test_env_scheduling_inside_environment_step(monkeypatch):
+    """Periodic env re-ordering (every 2 steps here) in eager and CUDA-graph mode against an env that
+    never re-orders: identical observations / rewards / dones."""
+    from vectorizedmultiagentsimulator_b200 import _native
+
+    n_envs = 2048
+    monkeypatch.setattr(_native, "ENV_REORDER_EVERY", 0)
+    plain = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, n_agents=4)
+    plain.step(plain.get_random_actions())  # builds its device tables without an order table
+    assert plain.world._get_backend()._dev_tables.env_order is None
+    monkeypatch.setattr(_native, "ENV_REORDER_EVERY", 2)
+    envs = [b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, n_agents=4, cuda_graph=g) for g in (False, True)]
+    for env in envs:
+        sync_env(plain, env)
+    gen = torch.Generator().manual_seed(3)
+    for t in range(9):
+        actions = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1).cuda() for _ in plain.agents]
+        want = plain.step([a.clone() for a in actions])
+        for env in envs:
+            got = env.step([a.clone() for a in actions])
+            for g, w in zip(flatten(got[:3]), flatten(want[:3])):
+                assert torch.equal(g, w), f"step {t}: re-ordered env differs"
+    for env in envs:
+        dt = env.world._get_backend()._dev_tables
+        assert dt.env_order is not None
+        assert torch.equal(torch.sort(dt.env_order.long()).values, torch.arange(n_envs, device="cuda"))
 
 
 def test_reset_at_and_state_views_on_gpu():

@@ -64,6 +64,30 @@ def test_rollout_matches_reference(name, kwargs, continuous):
                 _assert_same(mine.reset_at(2), ref.reset_at(2), f"{name} reset_at obs", tol=1e-6)
 
 
+def test_stock_style_scenario_matches_reference():
+    """tests/stock_style.py — per-agent is_overlapping / get_distance / Lidar.measure callbacks as the
+    reference's scenario files write them — built once from the reference's modules and once from this
+    package's: identical roll-outs (this is the CPU half of the pin; tests/test_env_gpu.py steps the
+    same scenario on the CUDA backend against the oracle env)."""
+    vmas = import_reference()
+    import stock_style
+    import vectorizedmultiagentsimulator_b200 as b200
+
+    n_envs = 10
+    ref = vmas.make_env(stock_style.make_scenario("vmas"), num_envs=n_envs, device="cpu", seed=1, n_agents=3)
+    with use_oracle():
+        mine = b200.make_env(stock_style.make_scenario(), num_envs=n_envs, device="cpu", seed=1, n_agents=3)
+        gen = torch.Generator().manual_seed(2)
+        for t in range(10):
+            actions = [(torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) for a in ref.agents]
+            want = ref.step([a.clone() for a in actions])
+            got = mine.step([a.clone() for a in actions])
+            for part, label in zip(range(4), ("obs", "rews", "dones", "infos")):
+                _assert_same(got[part], want[part], f"stock_style step {t} {label}", tol=0.0)
+            if t == 4:
+                _assert_same(mine.reset_at(3), ref.reset_at(3), "stock_style reset_at obs", tol=0.0)
+
+
 def test_spaces_and_random_actions_match_reference():
     vmas = import_reference()
     import vectorizedmultiagentsimulator_b200 as b200

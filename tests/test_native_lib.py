@@ -25,10 +25,10 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = _native.load()
-    assert lib.vmas_b200_abi_version() == 1
+    assert lib.vmas_b200_abi_version() == 2
     # 10 int32 + 9 float
     assert ctypes.sizeof(_native.WorldConfig) == 19 * 4
-    assert ctypes.sizeof(_native.PlanTablesC) == 10 * 8 + 4 * 4
+    assert ctypes.sizeof(_native.PlanTablesC) == 10 * 8 + 4 * 4 + 2 * 8  # + env_order, env_signature (ABI 2)
     assert ctypes.sizeof(_native.StateC) == 6 * 8
 
 

@@ -29,16 +29,26 @@ for name in names:
         big = {k: v.repeat(reps, *([1] * (v.dim() - 1))) for k, v in state_in.items()}
         Bn = big["pos"].shape[0]
         for mapping in os.environ.get("KB_MAPPINGS", "specialized,thread_per_env,lanes_per_env").split(","):
+            # "specialized_ordered": the thread-per-env kernel with its envs scheduled by contact signature
+            ordered = mapping.endswith("_ordered")
             old = desc.batch_dim
             desc.batch_dim = Bn
             try:
-                dt = _native.DeviceTables(tables, None, dev, mapping=mapping)
+                dt = _native.DeviceTables(tables, None, dev, mapping=mapping.replace("_ordered", ""))
             except RuntimeError:
                 desc.batch_dim = old
                 continue
             desc.batch_dim = old
             slab = _Slab(big, dev)
             saved = {k: slab.t[k].clone() for k in STATE_KEYS}
+            if ordered:
+                if dt.env_order is None:
+                    continue
+                _native.world_step(lib, dt, slab)  # records the signatures of this state
+                _native.build_env_order(lib, dt)
+                torch.cuda.synchronize()
+                order = dt.env_order.long()
+                assert torch.equal(torch.sort(order).values, torch.arange(Bn, device=dev)), "order is not a permutation"
             times = []
             for it in range(12):
                 for k in STATE_KEYS:

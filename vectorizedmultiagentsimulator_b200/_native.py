@@ -145,6 +145,8 @@ class PlanTablesC(C.Structure):
         ("group", C.c_int32),
         ("ents_per_lane", C.c_int32),
         ("specialization", C.c_int32),
+        ("env_order", C.c_void_p),
+        ("env_signature", C.c_void_p),
     ]
 
 
@@ -178,6 +180,10 @@ class AgentActionsC(C.Structure):
 
 MAX_SPAWN = 64
 GROUP_TILE = -8  # VMAS_GROUP_TILE
+#: env scheduling of the specialised thread-per-env kernel: the envs are re-sorted by their contact
+#: signature every this many World.step calls (0 = off: thread t always steps env t)
+ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "16"))
+ENV_REORDER_MIN_BATCH = 1024  # below this there is nothing to gain from grouping
 #: what mapping="auto" picks for a specialised world that has both kernels
 DEFAULT_SPEC_MAPPING = os.environ.get("VMAS_B200_SPEC_MAPPING", "specialized")
 
@@ -229,6 +235,9 @@ EXPORTS = [
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
     "vmas_b200_distance_shaping",
+    "vmas_b200_copy_buffers",
+    "vmas_b200_env_order_workspace_words",
+    "vmas_b200_build_env_order",
     "vmas_b200_reset_state",
     "vmas_b200_spawn_entities",
 ]
@@ -287,28 +296,46 @@ def load():
     ]
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
+    lib.vmas_b200_copy_buffers.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.vmas_b200_env_order_workspace_words.argtypes = [C.c_int32]
+    lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     lib.vmas_b200_specialization_has_tile.argtypes = [C.c_int]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int
     lib.vmas_b200_specialization_name.restype = C.c_char_p
-    if lib.vmas_b200_abi_version() != 1:
+    lib.vmas_b200_env_order_workspace_words.restype = C.c_size_t
+    if lib.vmas_b200_abi_version() != 2:
         raise RuntimeError("libvmas_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib
 
 
+_restore_device = None  # the caller's current device while a launch on another GPU is in flight
+
+
 def _check(lib, rc: int) -> int:
+    """Every launch wrapper ends here: error check, and the caller's current CUDA device is put back
+    if ``_stream`` had to switch it (a world on cuda:1 must not leave the process on cuda:1)."""
+    global _restore_device
+    if _restore_device is not None:
+        torch.cuda.set_device(_restore_device)
+        _restore_device = None
     if rc < 0:
         raise RuntimeError(f"vmas_b200: {lib.vmas_b200_last_error().decode()}")
     return rc
 
 
 def _stream(device) -> int:
-    # kernels launch on the calling thread's current device: make it the world's device
+    # kernels launch on the calling thread's current device: make it the world's device for the
+    # duration of the call (``_check`` restores the caller's)
+    global _restore_device
     index = device.index
-    if torch.cuda.current_device() != index:
+    current = torch.cuda.current_device()
+    if current != index:
+        if _restore_device is None:
+            _restore_device = current
         torch.cuda.set_device(device)
     return _raw_stream(index)
 
@@ -446,6 +473,14 @@ class DeviceTables:
         tb.group = self.group
         tb.ents_per_lane = self.ents_per_lane
         tb.specialization = self.specialization
+        # env scheduling (specialised thread-per-env kernel only): identity order until the first
+        # re-ordering, so a captured CUDA graph already reads the table it will keep reading
+        self.env_order = self.env_signature = self._order_workspace = None
+        if self.mapping == "specialized" and ENV_REORDER_EVERY > 0 and B >= ENV_REORDER_MIN_BATCH:
+            self.env_order = torch.arange(B, dtype=torch.int32, device=self.device)
+            self.env_signature = torch.zeros(B, dtype=torch.int32, device=self.device)
+            tb.env_order = self.env_order.data_ptr()
+            tb.env_signature = self.env_signature.data_ptr()
         self.tb = tb
         self._state_key = None
         self._state_ref = None
@@ -488,6 +523,20 @@ def world_step(lib, dt: DeviceTables, slab, exact_broad_phase: bool = True, even
             C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), dt.mask.data_ptr(), int(exact_broad_phase),
             _stream(dt.device), events[0].cuda_event, events[1].cuda_event,
         )
+    return _check(lib, rc)
+
+
+def build_env_order(lib, dt: DeviceTables) -> int:
+    """Re-sorts ``dt.env_order`` by the contact signatures the last step recorded (3 launches)."""
+    if dt.env_order is None:
+        return 0
+    B = int(dt.env_order.shape[0])
+    if dt._order_workspace is None:
+        words = int(lib.vmas_b200_env_order_workspace_words(B))
+        dt._order_workspace = torch.empty(max(words, 1), dtype=torch.int32, device=dt.device)
+    rc = lib.vmas_b200_build_env_order(
+        dt.env_signature.data_ptr(), B, dt.env_order.data_ptr(), dt._order_workspace.data_ptr(), _stream(dt.device)
+    )
     return _check(lib, rc)
 
 
@@ -557,6 +606,26 @@ def cast_rays_batched(
         _stream(dt.device),
     )
     return _check(lib, rc)
+
+
+class CopySegmentC(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_size_t)]
+
+
+MAX_COPY_SEGMENTS = 8
+
+
+def copy_buffers(lib, device, pairs) -> int:
+    """``pairs``: [(src tensor, dst tensor)] of equal byte size, contiguous, on ``device``: one launch
+    per ``MAX_COPY_SEGMENTS`` of them."""
+    n = 0
+    for lo in range(0, len(pairs), MAX_COPY_SEGMENTS):
+        chunk = pairs[lo : lo + MAX_COPY_SEGMENTS]
+        segs = (CopySegmentC * len(chunk))()
+        for seg, (src, dst) in zip(segs, chunk):
+            seg.src, seg.dst, seg.bytes = src.data_ptr(), dst.data_ptr(), src.numel() * src.element_size()
+        n += _check(lib, lib.vmas_b200_copy_buffers(segs, len(chunk), _stream(device)))
+    return n
 
 
 def distance_shaping(lib, dt: DeviceTables, slab, pairs, factor: float, prev, dist, rew) -> int:

@@ -167,6 +167,20 @@ class CudaBackend(PlanRuntime):
         self.launches += self._native.world_step(
             self.lib, self._dev_tables, slab, exact_broad_phase=self.world.exact_broad_phase, events=events
         )
+        if not torch.cuda.is_current_stream_capturing():
+            self.after_step()  # (a graph replay calls it itself: Environment._step_graphed)
+
+    def after_step(self):
+        """Host-side bookkeeping after a World.step ran (eagerly or as part of a graph replay): every
+        ``ENV_REORDER_EVERY`` steps the envs are re-sorted by the contact signature the substep kernel
+        recorded, so that the threads of a warp step envs that take the same branches."""
+        dt = self._dev_tables
+        if dt is None or dt.env_order is None:
+            return
+        self._steps_since_reorder = getattr(self, "_steps_since_reorder", 0) + 1
+        if self._steps_since_reorder >= self._native.ENV_REORDER_EVERY:
+            self._steps_since_reorder = 0
+            self.launches += self._native.build_env_order(self.lib, dt)
 
     def _targets_tensor(self, entity, entity_filter) -> Tuple[int, Tensor]:
         src = self.index_of(entity)

@@ -44,6 +44,10 @@ struct SpecArgs {
   int use_mask;
   int first_substep;
   int n_substeps;
+  // env scheduling (optional, see vmas_b200_build_env_order): thread t steps env order[t]; every env
+  // records which of its work items produced a force (bit I & 31) for the next re-ordering
+  const int32_t* order;  // [B] permutation of the envs, or null: thread t steps env t
+  uint32_t* sig;         // [B] out, or null
 };
 
 template <class F, int... I>
@@ -92,7 +96,7 @@ DEVI BoxG spec_box(const EnvRegs<E>& r) {
 // One work item, fully resolved at compile time; accumulates into the env's force registers in
 // the reference's order (ref core.py:2191-2199).
 template <class W, int I, int E>
-DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* mask_words) {
+DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* mask_words, uint32_t& sig) {
   constexpr ItemC it = W::item[I];
   constexpr int A = it.a, B = it.b;
   constexpr EntC ea = W::ent[A], eb = W::ent[B];
@@ -185,6 +189,9 @@ DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* 
     }
   }
 
+  if constexpr (it.kind != VMAS_K_JOINT) {
+    if (f.x != 0.f || f.y != 0.f) sig |= 1u << (I & 31);  // this env took the contact branch of item I
+  }
   if constexpr (ea.flags & VMAS_F_MOVABLE) {
     r.Fx[A] = r.Fx[A] + f.x;
     r.Fy[A] = r.Fy[A] + f.y;
@@ -518,21 +525,23 @@ DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask
   float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
   rows.unpack_pos_rot(r);
   rows.unpack_rest(r, afx, afy, atq);
+  uint32_t sig = 0;
   for (int sub = a.first_substep; sub < a.first_substep + a.n_substeps; ++sub) {
     spec_trig<W>(r);
     spec_entity_forces<W>(r, afx, afy, atq);
     // joints and contacts, in accumulation order
-    static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value>(r, a, env, mask_words); });
+    static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value>(r, a, env, mask_words, sig); });
     spec_integrate<W>(r, sub);
   }
   rows.store(a, env, r, afx, afy, atq);
+  if (a.sig) a.sig[env] = (a.first_substep == 0 ? 0u : a.sig[env]) | sig;  // OR over the substeps of a step
 }
 
 #ifdef __CUDACC__
 template <class W>
 __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
   constexpr int MW = W::MASK_WORDS;
-  const long env = (long)blockIdx.x * W::BLOCK + threadIdx.x;
+  const long tid = (long)blockIdx.x * W::BLOCK + threadIdx.x;
 
   // the block's copy of the broad-phase mask (ref core.py:2797-2801); the last block to have copied
   // it clears it for the next substep (no memset node: CUDA-graph safe)
@@ -554,6 +563,9 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(cons
       for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
     }
   }
+  if (tid >= a.batch_dim) return;
+  // env scheduling: with an order table, neighbouring threads step envs with the same contact pattern
+  const long env = a.order ? (long)a.order[tid] : tid;
   spec_env_step<W>(a, env, mask_words);
 }
 

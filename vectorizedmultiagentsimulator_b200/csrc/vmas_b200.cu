@@ -1543,6 +1543,8 @@ static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
   sa.use_mask = args.use_mask;
   sa.first_substep = args.first_substep;
   sa.n_substeps = args.n_substeps;
+  sa.order = args.tb.env_order;
+  sa.sig = args.tb.env_signature;
   // tb.group selects the thread mapping of a specialised world: 1 = one thread per env,
   // VMAS_GROUP_TILE = a warp owns a tile of 32 envs and runs the narrow phase compacted
   if (args.tb.group == VMAS_GROUP_TILE) {
@@ -1566,6 +1568,78 @@ static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
   if (G == 32 && EPL == 2) return launch_step<32, 2>(args, stream);
   if (G == 32 && EPL == 4) return launch_step<32, 4>(args, stream);
   return fail("unsupported lane layout (group, ents_per_lane)%s");
+}
+
+// ---- env scheduling: counting sort of the envs by a hash of their contact signature ----------------
+constexpr int ORDER_BUCKETS = 1024, ORDER_CHUNK = 2048, ORDER_THREADS = 256;
+DEVI unsigned order_key(uint32_t sig) { return (sig * 0x9E3779B1u) >> 22; }  // 10 bits
+
+// counts[block][bucket] = envs of the block's chunk in the bucket
+__global__ void __launch_bounds__(ORDER_THREADS) order_hist_kernel(const uint32_t* __restrict__ sig, int B,
+                                                                   uint32_t* __restrict__ counts) {
+  __shared__ unsigned h[ORDER_BUCKETS];
+  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) h[k] = 0u;
+  __syncthreads();
+  const long base = (long)blockIdx.x * ORDER_CHUNK;
+  for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS)
+    if (base + i < B) atomicAdd(&h[order_key(sig[base + i])], 1u);
+  __syncthreads();
+  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) counts[(size_t)blockIdx.x * ORDER_BUCKETS + k] = h[k];
+}
+
+// one block, thread = bucket: counts[block][bucket] -> first output slot of (bucket, block)
+__global__ void __launch_bounds__(ORDER_BUCKETS) order_scan_kernel(uint32_t* counts, int n_blocks) {
+  __shared__ unsigned total[ORDER_BUCKETS];
+  const int k = threadIdx.x;
+  unsigned run = 0u;
+  for (int b = 0; b < n_blocks; ++b) {
+    const unsigned c = counts[(size_t)b * ORDER_BUCKETS + k];
+    counts[(size_t)b * ORDER_BUCKETS + k] = run;
+    run += c;
+  }
+  total[k] = run;
+  __syncthreads();
+  // exclusive scan of the bucket totals (Hillis-Steele over 1024 values)
+  for (int d = 1; d < ORDER_BUCKETS; d <<= 1) {
+    const unsigned v = k >= d ? total[k - d] : 0u;
+    __syncthreads();
+    total[k] += v;
+    __syncthreads();
+  }
+  const unsigned bucket_base = total[k] - run;
+  for (int b = 0; b < n_blocks; ++b) counts[(size_t)b * ORDER_BUCKETS + k] += bucket_base;
+}
+
+__global__ void __launch_bounds__(ORDER_THREADS) order_scatter_kernel(const uint32_t* __restrict__ sig, int B,
+                                                                      const uint32_t* __restrict__ counts,
+                                                                      int32_t* __restrict__ order) {
+  __shared__ unsigned off[ORDER_BUCKETS];
+  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) off[k] = counts[(size_t)blockIdx.x * ORDER_BUCKETS + k];
+  __syncthreads();
+  const long base = (long)blockIdx.x * ORDER_CHUNK;
+  for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS)
+    if (base + i < B) order[atomicAdd(&off[order_key(sig[base + i])], 1u)] = (int32_t)(base + i);
+}
+
+struct CopyArgs {
+  VmasCopySegment seg[VMAS_MAX_COPY_SEGMENTS];
+};
+
+// blockIdx.y = segment; grid-stride copy in 16-byte words when both ends are 16-byte aligned
+__global__ void __launch_bounds__(256) copy_buffers_kernel(const CopyArgs a) {
+  const VmasCopySegment s = a.seg[blockIdx.y];
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const char* src = static_cast<const char*>(s.src);
+  char* dst = static_cast<char*>(s.dst);
+  size_t done = 0;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const size_t words = s.bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = tid; i < words; i += stride) d4[i] = s4[i];
+    done = words * 16;
+  }
+  for (size_t i = done + tid; i < s.bytes; i += stride) dst[i] = src[i];
 }
 
 static int launch_broad_phase(const StepArgs& args, cudaStream_t stream) {
@@ -1917,6 +1991,47 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
   if (chunks > 65535) return fail("too many pairs in one batch%s");
   const dim3 grid((unsigned)((cfg->batch_dim + threads - 1) / threads), (unsigned)chunks);
   distance_shaping_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+size_t vmas_b200_env_order_workspace_words(int32_t batch_dim) {
+  const size_t blocks = batch_dim > 0 ? ((size_t)batch_dim + ORDER_CHUNK - 1) / ORDER_CHUNK : 0;
+  return blocks * ORDER_BUCKETS;
+}
+
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, uint32_t* workspace,
+                              void* cuda_stream) {
+  if (!signature || !order || !workspace) return fail("null argument%s");
+  if (batch_dim <= 0) return fail("empty batch%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const int blocks = (int)(((size_t)batch_dim + ORDER_CHUNK - 1) / ORDER_CHUNK);
+  order_hist_kernel<<<blocks, ORDER_THREADS, 0, stream>>>(signature, batch_dim, workspace);
+  order_scan_kernel<<<1, ORDER_BUCKETS, 0, stream>>>(workspace, blocks);
+  order_scatter_kernel<<<blocks, ORDER_THREADS, 0, stream>>>(signature, batch_dim, workspace, order);
+  CUDA_OK(cudaGetLastError());
+  return 3;
+}
+
+// ---- hand-out copy of a step's packed outputs ---------------------------------------------------
+// Environment.step in CUDA-graph mode hands out fresh copies of the buffers the graph writes.  One
+// kernel for all of them: cudaMemcpyAsync D2D runs on a copy engine, where it queues behind a
+// concurrent device->host download of the previous step's results (measured: the pipelined e2e loop
+// serialised completely); an SM copy does not.
+int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cuda_stream) {
+  if (!segs || n_segs <= 0 || n_segs > VMAS_MAX_COPY_SEGMENTS) return fail("1..VMAS_MAX_COPY_SEGMENTS segments expected%s");
+  CopyArgs a;
+  size_t largest = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    if (!segs[i].src || !segs[i].dst) return fail("null copy segment%s");
+    a.seg[i] = segs[i];
+    largest = segs[i].bytes > largest ? segs[i].bytes : largest;
+  }
+  if (largest == 0) return 1;
+  const int threads = 256;
+  size_t blocks = (largest / 16 + (size_t)threads * 4 - 1) / ((size_t)threads * 4);  // 4 x 16 B per thread
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  copy_buffers_kernel<<<dim3((unsigned)blocks, (unsigned)n_segs), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

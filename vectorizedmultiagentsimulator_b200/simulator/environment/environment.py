@@ -509,6 +509,7 @@ class Environment(TorchVectorizedObject):
         self.graph_replays += 1
         backend = world._get_backend()
         backend.launches += self._graph_launches
+        backend.after_step()  # periodic env re-ordering: eager launches between replays
         return self._unpack_graph_outputs()
 
     #: a run of adjacent output leaves at least this large is cloned straight from where the
@@ -584,10 +585,10 @@ class Environment(TorchVectorizedObject):
         fresh = [None] * len(self._graph_out_shapes)
         packs = self._graph_out_packs
         copies = [torch.empty_like(pack) for pack, _ in packs]
-        if len(packs) > 1:
-            torch._foreach_copy_(copies, [pack for pack, _ in packs])  # one launch for every pack
-        else:
-            copies[0].copy_(packs[0][0])
+        # one kernel for every pack (an SM copy: a cudaMemcpy D2D would queue on a copy engine behind
+        # a concurrent download of the previous step's results)
+        backend = self.world._get_backend()
+        backend.launches += backend._native.copy_buffers(backend.lib, backend.device, [(p, c) for (p, _), c in zip(packs, copies)])
         # leaves of equal shape that sit next to each other come out of ONE view + unbind
         for flat, (_, ids), layout in zip(copies, packs, self._graph_out_layouts):
             pieces = [flat] if len(layout) == 1 else flat.split_with_sizes([n * numel for n, _, numel in layout])
