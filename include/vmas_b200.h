@@ -121,6 +121,18 @@ const char* vmas_b200_last_error(void);
 int vmas_b200_num_specializations(void);
 int vmas_b200_find_specialization(uint64_t world_hash);
 const char* vmas_b200_specialization_name(int index);
+/*
+ * Run-time specialisation.  Any world can get the specialised kernels: the host generates the
+ * world's constexpr tables (codegen.emit_world), compiles csrc/spec_kernel.cuh for them into a small
+ * shared object (simulator/jit.py: nvcc for sm_100a, cached by world hash) and registers the object's
+ * launch functions here.  `launch` / `launch_tile`: addresses of
+ *     cudaError_t fn(const vmas::SpecArgs&, cudaStream_t)      (launch_tile may be NULL)
+ * `spec_args_bytes` = sizeof(vmas::SpecArgs) as the object was compiled (layout check).
+ * Returns the index for VmasPlanTables.specialization (the existing one if the hash is known).
+ */
+#define VMAS_MAX_RUNTIME_SPECS 256
+int vmas_b200_register_specialization(uint64_t world_hash, int32_t n_entities, int32_t n_items, void* launch,
+                                      void* launch_tile, int32_t spec_args_bytes);
 /* 1 if the specialization also has the warp-tile kernel (VmasPlanTables.group = VMAS_GROUP_TILE) */
 int vmas_b200_specialization_has_tile(int index);
 
@@ -225,15 +237,13 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
  * kernel diverges when the 32 envs of a warp need different narrow-phase work (different contacts).
  * Contacts persist over steps, so grouping envs by the signature the previous step recorded
  * (VmasPlanTables.env_signature) makes a warp's envs take the same branches.  This builds the
- * permutation: a counting sort of the envs by a 10-bit hash of their signature (ascending env index
- * between 2048-env chunks, arbitrary within a chunk's bucket — results never depend on the order).
- *   signature  device uint32[B];  order  device int32[B] (out);
- *   workspace  device uint32[vmas_b200_env_order_workspace_words(B)]
- * Three small launches; meant to be called every few steps, not every step.
+ * permutation: the envs of every chunk of 2048 consecutive envs sorted by (signature, env index) —
+ * chunk-local so that a warp's rows stay within a 128 KB window of each state array (a global sort
+ * makes the kernel memory-bound).  Results never depend on the order.
+ *   signature  device uint32[B];  order  device int32[B] (out)
+ * One launch; meant to be called every few steps, not every step.
  */
-size_t vmas_b200_env_order_workspace_words(int32_t batch_dim);
-int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, uint32_t* workspace,
-                              void* cuda_stream);
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, void* cuda_stream);
 
 /*
  * Copies up to VMAS_MAX_COPY_SEGMENTS device buffers in ONE kernel launch (an SM copy, not a copy

@@ -182,7 +182,7 @@ MAX_SPAWN = 64
 GROUP_TILE = -8  # VMAS_GROUP_TILE
 #: env scheduling of the specialised thread-per-env kernel: the envs are re-sorted by their contact
 #: signature every this many World.step calls (0 = off: thread t always steps env t)
-ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "16"))
+ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "8"))
 ENV_REORDER_MIN_BATCH = 1024  # below this there is nothing to gain from grouping
 #: what mapping="auto" picks for a specialised world that has both kernels
 DEFAULT_SPEC_MAPPING = os.environ.get("VMAS_B200_SPEC_MAPPING", "specialized")
@@ -223,6 +223,7 @@ EXPORTS = [
     "vmas_b200_find_specialization",
     "vmas_b200_specialization_name",
     "vmas_b200_specialization_has_tile",
+    "vmas_b200_register_specialization",
     "vmas_b200_world_step",
     "vmas_b200_world_substeps",
     "vmas_b200_world_step_timed",
@@ -236,7 +237,6 @@ EXPORTS = [
     "vmas_b200_gather_observations",
     "vmas_b200_distance_shaping",
     "vmas_b200_copy_buffers",
-    "vmas_b200_env_order_workspace_words",
     "vmas_b200_build_env_order",
     "vmas_b200_reset_state",
     "vmas_b200_spawn_entities",
@@ -297,15 +297,14 @@ def load():
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_copy_buffers.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
-    lib.vmas_b200_env_order_workspace_words.argtypes = [C.c_int32]
-    lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     lib.vmas_b200_specialization_has_tile.argtypes = [C.c_int]
+    lib.vmas_b200_register_specialization.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int
     lib.vmas_b200_specialization_name.restype = C.c_char_p
-    lib.vmas_b200_env_order_workspace_words.restype = C.c_size_t
     if lib.vmas_b200_abi_version() != 2:
         raise RuntimeError("libvmas_b200.so ABI version mismatch; rebuild it")
     _lib = lib
@@ -475,7 +474,7 @@ class DeviceTables:
         tb.specialization = self.specialization
         # env scheduling (specialised thread-per-env kernel only): identity order until the first
         # re-ordering, so a captured CUDA graph already reads the table it will keep reading
-        self.env_order = self.env_signature = self._order_workspace = None
+        self.env_order = self.env_signature = None
         if self.mapping == "specialized" and ENV_REORDER_EVERY > 0 and B >= ENV_REORDER_MIN_BATCH:
             self.env_order = torch.arange(B, dtype=torch.int32, device=self.device)
             self.env_signature = torch.zeros(B, dtype=torch.int32, device=self.device)
@@ -527,15 +526,11 @@ def world_step(lib, dt: DeviceTables, slab, exact_broad_phase: bool = True, even
 
 
 def build_env_order(lib, dt: DeviceTables) -> int:
-    """Re-sorts ``dt.env_order`` by the contact signatures the last step recorded (3 launches)."""
+    """Re-sorts ``dt.env_order`` by the contact signatures the last step recorded (one launch)."""
     if dt.env_order is None:
         return 0
-    B = int(dt.env_order.shape[0])
-    if dt._order_workspace is None:
-        words = int(lib.vmas_b200_env_order_workspace_words(B))
-        dt._order_workspace = torch.empty(max(words, 1), dtype=torch.int32, device=dt.device)
     rc = lib.vmas_b200_build_env_order(
-        dt.env_signature.data_ptr(), B, dt.env_order.data_ptr(), dt._order_workspace.data_ptr(), _stream(dt.device)
+        dt.env_signature.data_ptr(), int(dt.env_order.shape[0]), dt.env_order.data_ptr(), _stream(dt.device)
     )
     return _check(lib, rc)
 

@@ -128,6 +128,38 @@ class CudaBackend(PlanRuntime):
         self._dev_tables = self._native.DeviceTables(self.tables, self.world, self.device)
         self._fixed_rot_versions = {}
         self._ray_cache.clear()
+        # a world without an ahead-of-time specialisation gets one compiled at run time (jit.py); it
+        # steps on the generic kernels until the compiler is done (identical bits either way)
+        self._jit_job = None
+        if self._dev_tables.specialization < 0:
+            from . import jit
+
+            self._jit_job = jit.request(self.tables.desc)
+            self._adopt_jit()
+
+    def _adopt_jit(self, wait: bool = False):
+        """Switches to the run-time specialised kernels once their compilation has finished."""
+        job = self._jit_job
+        if job is None:
+            return
+        if wait:
+            job.done.wait()
+        if not job.done.is_set():
+            return
+        self._jit_job = None
+        if job.index >= 0:
+            self._dev_tables = self._native.DeviceTables(self.tables, self.world, self.device)
+            self._fixed_rot_versions = {}
+        elif job.error:
+            import warnings
+
+            warnings.warn(f"vmas_b200: run-time specialisation failed, staying on the generic kernels ({job.error})")
+
+    def wait_for_jit(self):
+        """Blocks until a pending run-time specialisation is in use (a CUDA-graph capture calls this: the
+        captured step must already contain the kernel it will keep replaying)."""
+        self.refresh()
+        self._adopt_jit(wait=True)
 
     def _sync_fixed_rotations(self):
         dt = self._dev_tables
@@ -157,6 +189,8 @@ class CudaBackend(PlanRuntime):
 
     def step(self):
         self.refresh()
+        if self._jit_job is not None:
+            self._adopt_jit()
         self._sync_fixed_rotations()
         self._sync_entity_gravity()
         slab = self.world.slab

@@ -1531,8 +1531,14 @@ static int dispatch_tpe(const StepArgs& args, cudaStream_t stream) {
   return r;
 }
 
+// specialisations compiled at run time (vmas_b200_register_specialization): indices kNumSpecs, ...
+static SpecEntry g_dyn_specs[VMAS_MAX_RUNTIME_SPECS];
+static int g_num_dyn_specs = 0;
+static int num_specs() { return kNumSpecs + g_num_dyn_specs; }
+static const SpecEntry& spec_at(int index) { return index < kNumSpecs ? kSpecs[index] : g_dyn_specs[index - kNumSpecs]; }
+
 static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
-  const SpecEntry& sp = kSpecs[args.tb.specialization];
+  const SpecEntry& sp = spec_at(args.tb.specialization);
   if (sp.n_entities != args.cfg.n_entities || sp.n_items != args.cfg.n_items)
     return fail("specialization does not match the world (stale index?)%s");
   SpecArgs sa;
@@ -1557,7 +1563,7 @@ static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
 
 static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
   if (args.tb.specialization >= 0) {
-    if (args.tb.specialization >= kNumSpecs) return fail("specialization index out of range%s");
+    if (args.tb.specialization >= num_specs()) return fail("specialization index out of range%s");
     return dispatch_spec(args, stream);
   }
   if (args.tb.group == 1) return dispatch_tpe(args, stream);
@@ -1570,55 +1576,37 @@ static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
   return fail("unsupported lane layout (group, ents_per_lane)%s");
 }
 
-// ---- env scheduling: counting sort of the envs by a hash of their contact signature ----------------
-constexpr int ORDER_BUCKETS = 1024, ORDER_CHUNK = 2048, ORDER_THREADS = 256;
-DEVI unsigned order_key(uint32_t sig) { return (sig * 0x9E3779B1u) >> 22; }  // 10 bits
+// ---- env scheduling: the envs of every 2048-env chunk sorted by their contact signature --------------
+// Chunk-local on purpose: a global sort scatters a warp's 32 envs over the whole slab (measured: DRAM
+// reads 2.3x the algorithmic bytes, the kernel turns memory-bound); within a chunk a warp's rows stay
+// inside a 128 KB window per array that the chunk's 64 warps consume together.  The key is the raw
+// signature (later = costlier items in the high bits), ties broken by env index: deterministic.
+constexpr int ORDER_CHUNK = 2048, ORDER_THREADS = 1024;
 
-// counts[block][bucket] = envs of the block's chunk in the bucket
-__global__ void __launch_bounds__(ORDER_THREADS) order_hist_kernel(const uint32_t* __restrict__ sig, int B,
-                                                                   uint32_t* __restrict__ counts) {
-  __shared__ unsigned h[ORDER_BUCKETS];
-  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) h[k] = 0u;
-  __syncthreads();
+__global__ void __launch_bounds__(ORDER_THREADS) order_sort_kernel(const uint32_t* __restrict__ sig, int B,
+                                                                   int32_t* __restrict__ order) {
+  __shared__ unsigned long long key[ORDER_CHUNK];
   const long base = (long)blockIdx.x * ORDER_CHUNK;
   for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS)
-    if (base + i < B) atomicAdd(&h[order_key(sig[base + i])], 1u);
+    key[i] = base + i < B ? ((unsigned long long)sig[base + i] << 11) | (unsigned)i : ~0ull;  // padding sorts last
   __syncthreads();
-  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) counts[(size_t)blockIdx.x * ORDER_BUCKETS + k] = h[k];
-}
-
-// one block, thread = bucket: counts[block][bucket] -> first output slot of (bucket, block)
-__global__ void __launch_bounds__(ORDER_BUCKETS) order_scan_kernel(uint32_t* counts, int n_blocks) {
-  __shared__ unsigned total[ORDER_BUCKETS];
-  const int k = threadIdx.x;
-  unsigned run = 0u;
-  for (int b = 0; b < n_blocks; ++b) {
-    const unsigned c = counts[(size_t)b * ORDER_BUCKETS + k];
-    counts[(size_t)b * ORDER_BUCKETS + k] = run;
-    run += c;
+  for (int k = 2; k <= ORDER_CHUNK; k <<= 1) {  // bitonic sort, ascending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS) {
+        const int partner = i ^ j;
+        if (partner > i) {
+          const unsigned long long a = key[i], b = key[partner];
+          if ((a > b) == ((i & k) == 0)) {
+            key[i] = b;
+            key[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
-  total[k] = run;
-  __syncthreads();
-  // exclusive scan of the bucket totals (Hillis-Steele over 1024 values)
-  for (int d = 1; d < ORDER_BUCKETS; d <<= 1) {
-    const unsigned v = k >= d ? total[k - d] : 0u;
-    __syncthreads();
-    total[k] += v;
-    __syncthreads();
-  }
-  const unsigned bucket_base = total[k] - run;
-  for (int b = 0; b < n_blocks; ++b) counts[(size_t)b * ORDER_BUCKETS + k] += bucket_base;
-}
-
-__global__ void __launch_bounds__(ORDER_THREADS) order_scatter_kernel(const uint32_t* __restrict__ sig, int B,
-                                                                      const uint32_t* __restrict__ counts,
-                                                                      int32_t* __restrict__ order) {
-  __shared__ unsigned off[ORDER_BUCKETS];
-  for (int k = threadIdx.x; k < ORDER_BUCKETS; k += ORDER_THREADS) off[k] = counts[(size_t)blockIdx.x * ORDER_BUCKETS + k];
-  __syncthreads();
-  const long base = (long)blockIdx.x * ORDER_CHUNK;
   for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS)
-    if (base + i < B) order[atomicAdd(&off[order_key(sig[base + i])], 1u)] = (int32_t)(base + i);
+    if (base + i < B) order[base + i] = (int32_t)(base + (long)(key[i] & 2047u));
 }
 
 struct CopyArgs {
@@ -1657,20 +1645,38 @@ extern "C" {
 
 int vmas_b200_abi_version(void) { return VMAS_B200_ABI_VERSION; }
 
-int vmas_b200_num_specializations(void) { return kNumSpecs; }
+int vmas_b200_num_specializations(void) { return num_specs(); }
 
 int vmas_b200_find_specialization(uint64_t world_hash) {
-  for (int i = 0; i < kNumSpecs; ++i)
-    if (kSpecs[i].hash == world_hash) return i;
+  for (int i = 0; i < num_specs(); ++i)
+    if (spec_at(i).hash == world_hash) return i;
   return -1;
 }
 
+int vmas_b200_register_specialization(uint64_t world_hash, int32_t n_entities, int32_t n_items, void* launch,
+                                      void* launch_tile, int32_t spec_args_bytes) {
+  if (!launch) return fail("null launch function%s");
+  if (spec_args_bytes != (int32_t)sizeof(SpecArgs)) return fail("SpecArgs layout mismatch: rebuild the specialisation%s");
+  const int have = vmas_b200_find_specialization(world_hash);
+  if (have >= 0) return have;
+  if (g_num_dyn_specs >= VMAS_MAX_RUNTIME_SPECS) return fail("too many run-time specialisations%s");
+  SpecEntry& e = g_dyn_specs[g_num_dyn_specs];
+  e.hash = world_hash;
+  e.name = "run-time specialisation";
+  e.n_entities = n_entities;
+  e.n_items = n_items;
+  e.launch = reinterpret_cast<cudaError_t (*)(const SpecArgs&, cudaStream_t)>(launch);
+  e.launch_tile = reinterpret_cast<cudaError_t (*)(const SpecArgs&, cudaStream_t)>(launch_tile);
+  e.has_tile = launch_tile != nullptr;
+  return kNumSpecs + g_num_dyn_specs++;
+}
+
 int vmas_b200_specialization_has_tile(int index) {
-  return (index >= 0 && index < kNumSpecs && kSpecs[index].has_tile) ? 1 : 0;
+  return (index >= 0 && index < num_specs() && spec_at(index).has_tile) ? 1 : 0;
 }
 
 const char* vmas_b200_specialization_name(int index) {
-  return (index >= 0 && index < kNumSpecs) ? kSpecs[index].name : "";
+  return (index >= 0 && index < num_specs()) ? spec_at(index).name : "";
 }
 
 const char* vmas_b200_last_error(void) { return g_last_error; }
@@ -1995,22 +2001,13 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
   return 1;
 }
 
-size_t vmas_b200_env_order_workspace_words(int32_t batch_dim) {
-  const size_t blocks = batch_dim > 0 ? ((size_t)batch_dim + ORDER_CHUNK - 1) / ORDER_CHUNK : 0;
-  return blocks * ORDER_BUCKETS;
-}
-
-int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, uint32_t* workspace,
-                              void* cuda_stream) {
-  if (!signature || !order || !workspace) return fail("null argument%s");
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, void* cuda_stream) {
+  if (!signature || !order) return fail("null argument%s");
   if (batch_dim <= 0) return fail("empty batch%s");
-  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const int blocks = (int)(((size_t)batch_dim + ORDER_CHUNK - 1) / ORDER_CHUNK);
-  order_hist_kernel<<<blocks, ORDER_THREADS, 0, stream>>>(signature, batch_dim, workspace);
-  order_scan_kernel<<<1, ORDER_BUCKETS, 0, stream>>>(workspace, blocks);
-  order_scatter_kernel<<<blocks, ORDER_THREADS, 0, stream>>>(signature, batch_dim, workspace, order);
+  order_sort_kernel<<<blocks, ORDER_THREADS, 0, static_cast<cudaStream_t>(cuda_stream)>>>(signature, batch_dim, order);
   CUDA_OK(cudaGetLastError());
-  return 3;
+  return 1;
 }
 
 // ---- hand-out copy of a step's packed outputs ---------------------------------------------------

@@ -1,0 +1,145 @@
+"""Run-time specialisation of the substep kernel for ANY world (ref core.py:1091-1177: arbitrary worlds
+are the reference's contract).
+
+``codegen.py`` pre-builds specialised kernels for a handful of preset worlds; every other world used
+to run on the generic table-driven kernels at 2-15x the time.  Here the same template
+(``csrc/spec_kernel.cuh``) is compiled for the world at hand when its plan is first uploaded: the
+world's constexpr tables are emitted (``codegen.emit_world``), ``nvcc`` builds a small shared object
+for sm_100a (a few seconds, in a background thread; cached on disk by world hash and arithmetic
+flags), and its launch functions are registered with the main library
+(``vmas_b200_register_specialization``).  Until the object is ready the world steps on the generic
+kernels; both produce identical bits (tests/test_cabi_gpu.py), so the switch is invisible.
+
+``VMAS_B200_JIT``: ``async`` (default) | ``block`` (wait for the compiler) | ``off``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import threading
+from typing import Dict, Optional
+
+from . import _native, codegen
+from .simulator import plan as P
+
+MODE = os.environ.get("VMAS_B200_JIT", "async")
+assert MODE in ("async", "block", "off"), MODE
+CACHE_DIR = os.environ.get("VMAS_B200_JIT_DIR") or os.path.join(_native.CSRC, "generated", "jit")
+
+_TEMPLATE = """// GENERATED at run time by vectorizedmultiagentsimulator_b200/jit.py — one world's specialised kernels.
+#include "spec_kernel.cuh"
+#include "spec_tile_kernel.cuh"
+
+namespace vmas {{
+
+{world}
+
+}}  // namespace vmas
+
+using W = vmas::{name};
+extern "C" {{
+cudaError_t vmas_jit_launch(const vmas::SpecArgs& a, cudaStream_t stream) {{ return vmas::launch_spec<W>(a, stream); }}
+cudaError_t vmas_jit_launch_tile(const vmas::SpecArgs& a, cudaStream_t stream) {{ return vmas::launch_tile<W>(a, stream); }}
+int vmas_jit_has_tile(void) {{ return vmas::TileLayout<W>::SUPPORTED ? 1 : 0; }}
+int vmas_jit_spec_args_bytes(void) {{ return (int)sizeof(vmas::SpecArgs); }}
+}}
+"""
+
+_lock = threading.Lock()
+_jobs: Dict[int, "Job"] = {}
+_keepalive = []  # loaded objects must outlive the registry entries that point into them
+
+
+def _source_stamp() -> str:
+    """Hash of the headers the object is compiled from: a header edit invalidates the cache."""
+    h = hashlib.sha1()
+    for name in ("geometry.cuh", "spec_kernel.cuh", "spec_tile_kernel.cuh"):
+        h.update(open(os.path.join(_native.CSRC, name), "rb").read())
+    h.update(open(os.path.join(_native.INCLUDE, "vmas_b200.h"), "rb").read())
+    return h.hexdigest()[:12]
+
+
+class Job:
+    """One world's compilation: ``index`` is the registered specialisation once ``done`` is set."""
+
+    def __init__(self, desc: P.WorldDescription):
+        self.hash = codegen.world_hash(desc)
+        self.desc = desc
+        self.done = threading.Event()
+        self.index = -1
+        self.error: Optional[str] = None
+        self.seconds = 0.0
+
+    def run(self):
+        import time
+
+        t0 = time.perf_counter()
+        try:
+            self.index = self._compile_and_register()
+        except Exception as err:  # noqa: BLE001  (stay on the generic kernels)
+            self.error = f"{type(err).__name__}: {err}"
+        self.seconds = time.perf_counter() - t0
+        self.done.set()
+
+    def _compile_and_register(self) -> int:
+        desc = self.desc
+        name, text, h = codegen.emit_world(desc, "run-time specialisation")
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        stem = os.path.join(CACHE_DIR, f"{h:016x}_{_native.ARITH}_{_source_stamp()}")
+        so = stem + ".so"
+        if not os.path.exists(so):
+            with open(stem + ".cu", "w") as fh:
+                fh.write(_TEMPLATE.format(world=text, name=name))
+            flags = _native.NVCC_FLAGS + _native.ARITH_FLAGS[_native.ARITH]
+            tmp = f"{so}.{os.getpid()}.tmp"
+            cmd = [_native._nvcc()] + flags + ["-I", _native.INCLUDE, "-I", _native.CSRC, "-o", tmp, stem + ".cu"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                raise RuntimeError(f"nvcc failed: {proc.stderr[-600:]}")
+            os.replace(tmp, so)  # atomic: concurrent processes (one per GPU) may race on the same world
+        obj = C.CDLL(so)
+        lib = _native.load()
+        launch = C.cast(obj.vmas_jit_launch, C.c_void_p)
+        tile = C.cast(obj.vmas_jit_launch_tile, C.c_void_p) if obj.vmas_jit_has_tile() else None
+        with _lock:
+            index = lib.vmas_b200_register_specialization(
+                C.c_uint64(h), desc.n_entities, len(desc.items), launch, tile, obj.vmas_jit_spec_args_bytes()
+            )
+            if index < 0:
+                raise RuntimeError(lib.vmas_b200_last_error().decode())
+            _keepalive.append(obj)
+        return index
+
+
+def available() -> bool:
+    if MODE == "off":
+        return False
+    try:
+        _native._nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def request(desc: P.WorldDescription) -> Optional[Job]:
+    """Starts (or finds) the compilation of ``desc``'s specialisation; None if the world cannot be
+    specialised (too large, per-env gravity tensors) or the JIT is off / has no compiler."""
+    if not available() or not codegen.specializable(desc):
+        return None
+    h = codegen.world_hash(desc)
+    with _lock:
+        job = _jobs.get(h)
+        if job is None:
+            job = _jobs[h] = Job(desc)
+            if MODE == "block":
+                start = job.run
+            else:
+                thread = threading.Thread(target=job.run, name=f"vmas-b200-jit-{h:016x}", daemon=True)
+                start = thread.start
+        else:
+            start = None
+    if start is not None:
+        start()
+    return job

@@ -11,13 +11,23 @@ class Wrapper(Enum):
     GYMNASIUM_VEC = 3
 
     def get_env(self, env: Environment, **kwargs):
-        # The gym / gymnasium / rllib adapters are thin list<->tensor shims over Environment and
-        # are outside the hot-path scope of this build; the reference's own
-        # adapters work unchanged on this Environment because its surface is identical.
-        raise NotImplementedError(
-            f"Wrapper {self.name} is not bundled: wrap the returned Environment with the "
-            "reference's adapter (its API is unchanged)"
-        )
+        """``make_env(..., wrapper=...)`` (ref vmas/simulator/environment/__init__.py:16-34)."""
+        if self is Wrapper.RLLIB:
+            # ray is not a dependency of this package and the adapter is a 250-line VectorEnv shim
+            # outside the physics path: fail up front, with the way out
+            raise ImportError(
+                "wrapper='rllib' is not bundled with vectorizedmultiagentsimulator_b200: wrap the Environment "
+                "returned by make_env(..., wrapper=None) in the reference's "
+                "vmas.simulator.environment.rllib.VectorEnvWrapper (the Environment API is the reference's)"
+            )
+        from . import gym_adapters
+
+        cls = {
+            Wrapper.GYM: gym_adapters.GymWrapper,
+            Wrapper.GYMNASIUM: gym_adapters.GymnasiumWrapper,
+            Wrapper.GYMNASIUM_VEC: gym_adapters.GymnasiumVectorizedWrapper,
+        }[self]
+        return cls(env, **kwargs)
 
 
 __all__ = ["Environment", "Wrapper"]

@@ -619,6 +619,7 @@ class Environment(TorchVectorizedObject):
             self._graph_inputs = [a.clone() for a in dev_actions]
         backend = self.world._get_backend()
         backend.refresh()
+        backend.wait_for_jit()  # a run-time specialisation still compiling: capture the kernel that stays
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         try:
