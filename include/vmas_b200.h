@@ -237,13 +237,16 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
  * kernel diverges when the 32 envs of a warp need different narrow-phase work (different contacts).
  * Contacts persist over steps, so grouping envs by the signature the previous step recorded
  * (VmasPlanTables.env_signature) makes a warp's envs take the same branches.  This builds the
- * permutation: the envs of every chunk of 2048 consecutive envs sorted by (signature, env index) —
- * chunk-local so that a warp's rows stay within a 128 KB window of each state array (a global sort
- * makes the kernel memory-bound).  Results never depend on the order.
+ * permutation: the envs of every chunk of `chunk` (256, 512, 1024 or 2048) consecutive envs sorted by
+ * (signature, env index) — chunk-local so that a warp's rows stay within a small window of each state
+ * array (a global sort makes the kernel memory-bound).  Results never depend on the order.
  *   signature  device uint32[B];  order  device int32[B] (out)
  * One launch; meant to be called every few steps, not every step.
  */
-int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, void* cuda_stream);
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, int32_t chunk,
+                              void* cuda_stream);
+/* cudaLimitMaxL2FetchGranularity of the current device (32 / 64 / 128 bytes); returns what the device reports. */
+int vmas_b200_set_l2_fetch_granularity(int32_t bytes);
 
 /*
  * Copies up to VMAS_MAX_COPY_SEGMENTS device buffers in ONE kernel launch (an SM copy, not a copy

@@ -14,6 +14,8 @@ from vectorizedmultiagentsimulator_b200.simulator import plan as P
 from test_cabi_gpu import _Slab
 
 lib = _native.load()
+if os.environ.get("VMAS_B200_L2_FETCH"):
+    print("# L2 fetch granularity:", lib.vmas_b200_set_l2_fetch_granularity(int(os.environ["VMAS_B200_L2_FETCH"])))
 dev = torch.device("cuda:0")
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)

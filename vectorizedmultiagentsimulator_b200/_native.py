@@ -184,6 +184,7 @@ GROUP_TILE = -8  # VMAS_GROUP_TILE
 #: signature every this many World.step calls (0 = off: thread t always steps env t)
 ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "8"))
 ENV_REORDER_MIN_BATCH = 1024  # below this there is nothing to gain from grouping
+ENV_REORDER_CHUNK = int(os.environ.get("VMAS_B200_ENV_REORDER_CHUNK", "2048"))  # envs sorted together
 #: what mapping="auto" picks for a specialised world that has both kernels
 DEFAULT_SPEC_MAPPING = os.environ.get("VMAS_B200_SPEC_MAPPING", "specialized")
 
@@ -238,6 +239,7 @@ EXPORTS = [
     "vmas_b200_distance_shaping",
     "vmas_b200_copy_buffers",
     "vmas_b200_build_env_order",
+    "vmas_b200_set_l2_fetch_granularity",
     "vmas_b200_reset_state",
     "vmas_b200_spawn_entities",
 ]
@@ -297,7 +299,8 @@ def load():
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_copy_buffers.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
-    lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.vmas_b200_set_l2_fetch_granularity.argtypes = [C.c_int32]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
     lib.vmas_b200_specialization_name.argtypes = [C.c_int]
     lib.vmas_b200_specialization_has_tile.argtypes = [C.c_int]
@@ -530,7 +533,8 @@ def build_env_order(lib, dt: DeviceTables) -> int:
     if dt.env_order is None:
         return 0
     rc = lib.vmas_b200_build_env_order(
-        dt.env_signature.data_ptr(), int(dt.env_order.shape[0]), dt.env_order.data_ptr(), _stream(dt.device)
+        dt.env_signature.data_ptr(), int(dt.env_order.shape[0]), dt.env_order.data_ptr(), ENV_REORDER_CHUNK,
+        _stream(dt.device),
     )
     return _check(lib, rc)
 

@@ -1581,10 +1581,10 @@ static int dispatch_step(const StepArgs& args, cudaStream_t stream) {
 // reads 2.3x the algorithmic bytes, the kernel turns memory-bound); within a chunk a warp's rows stay
 // inside a 128 KB window per array that the chunk's 64 warps consume together.  The key is the raw
 // signature (later = costlier items in the high bits), ties broken by env index: deterministic.
-constexpr int ORDER_CHUNK = 2048, ORDER_THREADS = 1024;
-
-__global__ void __launch_bounds__(ORDER_THREADS) order_sort_kernel(const uint32_t* __restrict__ sig, int B,
-                                                                   int32_t* __restrict__ order) {
+template <int ORDER_CHUNK>
+__global__ void __launch_bounds__(ORDER_CHUNK / 2) order_sort_kernel(const uint32_t* __restrict__ sig, int B,
+                                                                     int32_t* __restrict__ order) {
+  constexpr int ORDER_THREADS = ORDER_CHUNK / 2;
   __shared__ unsigned long long key[ORDER_CHUNK];
   const long base = (long)blockIdx.x * ORDER_CHUNK;
   for (int i = threadIdx.x; i < ORDER_CHUNK; i += ORDER_THREADS)
@@ -2001,13 +2001,29 @@ int vmas_b200_distance_shaping(const VmasWorldConfig* cfg, const VmasState* st, 
   return 1;
 }
 
-int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, void* cuda_stream) {
+int vmas_b200_build_env_order(const uint32_t* signature, int32_t batch_dim, int32_t* order, int32_t chunk,
+                              void* cuda_stream) {
   if (!signature || !order) return fail("null argument%s");
   if (batch_dim <= 0) return fail("empty batch%s");
-  const int blocks = (int)(((size_t)batch_dim + ORDER_CHUNK - 1) / ORDER_CHUNK);
-  order_sort_kernel<<<blocks, ORDER_THREADS, 0, static_cast<cudaStream_t>(cuda_stream)>>>(signature, batch_dim, order);
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const int blocks = (int)(((size_t)batch_dim + chunk - 1) / (chunk > 0 ? chunk : 1));
+  switch (chunk) {
+    case 256: order_sort_kernel<256><<<blocks, 128, 0, stream>>>(signature, batch_dim, order); break;
+    case 512: order_sort_kernel<512><<<blocks, 256, 0, stream>>>(signature, batch_dim, order); break;
+    case 1024: order_sort_kernel<1024><<<blocks, 512, 0, stream>>>(signature, batch_dim, order); break;
+    case 2048: order_sort_kernel<2048><<<blocks, 1024, 0, stream>>>(signature, batch_dim, order); break;
+    default: return fail("env order chunk must be 256, 512, 1024 or 2048%s");
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
+}
+
+int vmas_b200_set_l2_fetch_granularity(int32_t bytes) {
+  // 32, 64 or 128: how much the L2 fetches from DRAM on a sector miss (a device-wide hint)
+  CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  size_t got = 0;
+  CUDA_OK(cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity));
+  return (int)got;
 }
 
 // ---- hand-out copy of a step's packed outputs ---------------------------------------------------

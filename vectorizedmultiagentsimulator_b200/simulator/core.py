@@ -195,6 +195,9 @@ def _write_rows(dst: Tensor, new: Tensor, mask: Tensor) -> None:
 # State containers (ref core.py:206-410).  Fields are views into the world's StateSlab
 # once the entity has been packed; before that they are standalone [B, k] tensors.
 # ----------------------------------------------------------------------------------------
+_DEBUG_STATE_ALIASING = os.environ.get("VMAS_B200_DEBUG_STATE_ALIASING", "0") == "1"
+
+
 class _SlabFields(TorchVectorizedObject):
     _NAMES: Tuple[str, ...] = ()
 
@@ -203,7 +206,13 @@ class _SlabFields(TorchVectorizedObject):
         self._fields = {}
 
     def _get(self, name):
-        return self._fields.get(name)
+        value = self._fields.get(name)
+        if _DEBUG_STATE_ALIASING and value is not None:
+            # the reference hands out a tensor that the next step does not touch (it re-binds a new
+            # one); here state is a view into the slab.  Debug aid for drop-in scenarios that keep raw
+            # state tensors across a step without cloning: getters return copies.
+            return value.clone()
+        return value
 
     def _set(self, name, value: Tensor, same_shape_as: Optional[str] = None):
         assert (
@@ -969,6 +978,9 @@ class World(TorchVectorizedObject):
         self.env_offset = 0
         self._reset_count: Optional[Tensor] = None
         self._spawn_status: Optional[Tensor] = None
+        #: Philox key of the respawn kernel: set by Environment.seed() of the env that owns this world
+        #: (None: torch.initial_seed() at call time, e.g. for a World used without an Environment)
+        self.spawn_seed: Optional[int] = None
         self._spawn_calls = 0
 
     # -- construction -------------------------------------------------------------------
@@ -1123,7 +1135,7 @@ class World(TorchVectorizedObject):
                 min_dist,
                 x_bounds,
                 y_bounds,
-                seed=torch.initial_seed(),
+                seed=self.spawn_seed if self.spawn_seed is not None else torch.initial_seed(),
                 stream_id=self._spawn_calls,
                 reset_count=self.reset_count,
                 status=self._spawn_status,
@@ -1339,4 +1351,6 @@ class World(TorchVectorizedObject):
         self._slab = None
         self._slab_version = -1
         self._backend = None
+        self._spawn_status = None  # device-resident scratch of the respawn kernel: re-created on the new device
+        self._reset_count = None
         self._invalidate_plan()

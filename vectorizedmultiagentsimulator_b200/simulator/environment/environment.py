@@ -312,6 +312,10 @@ class Environment(TorchVectorizedObject):
         torch.manual_seed(seed)
         np.random.seed(seed)
         random.seed(seed)
+        if getattr(self, "world", None) is not None:
+            # the device-side respawn draws from a stream keyed by THIS env's seed, not by whatever
+            # env seeded torch's global generator last (the random state is shared by all envs)
+            self.world.spawn_seed = int(seed)
         if getattr(self, "auto_reset", False) and getattr(self, "_graph", None) is not None:
             # the captured step contains the respawn kernel, whose Philox key is the seed: capture again
             self._graph = None
