@@ -289,26 +289,54 @@ int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, 
  * `state.torque = u[:, 2]`).
  *   actions      device fp32 [B, action_size], contiguous
  *   u            device fp32 [B, action_size]: receives action * u_multiplier (agent.action.u)
- *   dynamics     0: holonomic (force <- u[0:2]), 1: holonomic with rotation (+ torque <- u[2]),
- *                -1: only fill `u` (another dynamics model consumes it afterwards)
+ *   dynamics     which action -> force / torque model runs in the same launch (VMAS_DYN_*):
+ *                  holonomic (force <- u[0:2]; ref dynamics/holonomic.py:14-15), with rotation (+ torque <- u[2];
+ *                  holonomic_with_rot.py), forward (u[0] along the heading; forward.py), rotation (torque <- u[0];
+ *                  roatation.py), differential drive (diff_drive.py:14-82), kinematic bicycle
+ *                  (kinematic_bicycle.py:14-111), drone (drone.py:17-166) — the last three integrate their ODE
+ *                  over dt (Euler or RK4) and back-solve the force / torque that realise the pose change under
+ *                  the world's semi-implicit Euler step (dynamics/common + each model's process_action);
+ *                  VMAS_DYN_NONE: only fill `u` (another model consumes it afterwards)
+ *   entity_index entity row of the agent in pos / vel / rot (forward and the kinematic models read them)
+ *   dyn_params   [0] dt  [1] mass  [2] moment of inertia  [3] 1 = RK4, 0 = Euler;
+ *                bicycle: [4] l_f  [5] l_r  [6] max steering angle;  drone: [4] I_xx  [5] I_yy  [6] I_zz  [7] g
+ *   dyn_state    drone only: device fp32 [B, 12] (roll pitch yaw | p q r | vx vy vz | x y z), updated in place
  *   bad_flag     device uint8[1] or NULL: set to 1 if any action is NaN or outside +-u_range
  *                (the reference asserts; here the host reads the flag back asynchronously)
  */
 #define VMAS_MAX_INGEST_AGENTS 16
 #define VMAS_MAX_ACTION_SIZE 8
+enum {
+  VMAS_DYN_NONE = -1, VMAS_DYN_HOLONOMIC = 0, VMAS_DYN_HOLONOMIC_ROT = 1, VMAS_DYN_FORWARD = 2, VMAS_DYN_ROTATION = 3,
+  VMAS_DYN_DIFF_DRIVE = 4, VMAS_DYN_BICYCLE = 5, VMAS_DYN_DRONE = 6
+};
 typedef struct VmasAgentActions {
   const float* actions;
   float* u;
   int32_t action_size;
   int32_t agent_index;   /* row in force / torque */
   int32_t dynamics;
-  int32_t reserved;
+  int32_t entity_index;  /* row in pos / vel / rot / ang_vel */
   float u_range[VMAS_MAX_ACTION_SIZE];
   float u_multiplier[VMAS_MAX_ACTION_SIZE];
+  float dyn_params[8];
+  float* dyn_state;
 } VmasAgentActions;
 
 int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
                              int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream);
+
+/*
+ * PID velocity controller (ref vmas/simulator/controllers/velocity_controller.py:113-125, process_force):
+ *     err = u - vel;  [accum += dt * err, clamped to +-windup;]  rate = Td * (err - prev) / dt;  prev <- err;
+ *     u <- gain * (err [+ accum / Ti] + rate) * mass                          (fp32, in this order, in place)
+ *   u      device fp32 [B, 2] (the agent's action, a velocity target on entry, a force on exit)
+ *   accum, prev  device fp32 [B, 2] controller state;  inv_ti = 1 / Ti or 0 (no integrator);
+ *   windup < 0: no anti-windup clamp
+ */
+int vmas_b200_velocity_controller(const VmasWorldConfig* cfg, const VmasState* st, int32_t entity, float* u,
+                                  float* accum, float* prev, float gain, float inv_ti, float td, float dt,
+                                  float windup, float mass, void* cuda_stream);
 
 /* The broad-phase pass alone: ORs bit i of `mask` if masked item i is within range in any env. */
 int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,

@@ -23,6 +23,9 @@ def _ns(root):
         Agent=core.Agent, Landmark=core.Landmark, World=core.World, Sphere=core.Sphere, Box=core.Box,
         Line=core.Line, BaseScenario=mod("scenario").BaseScenario, Joint=mod("joints").Joint,
         HolonomicWithRotation=mod("dynamics.holonomic_with_rot").HolonomicWithRotation,
+        DiffDrive=mod("dynamics.diff_drive").DiffDrive, KinematicBicycle=mod("dynamics.kinematic_bicycle").KinematicBicycle,
+        Drone=mod("dynamics.drone").Drone, Forward=mod("dynamics.forward").Forward,
+        Rotation=mod("dynamics.roatation").Rotation, Static=mod("dynamics.static").Static,
     )
 
 
@@ -86,6 +89,27 @@ def make_scenario(root, kind, seed=1234):
                 for j in self.joints:
                     world.add_joint(j)
                 self.spread = 0.35
+            elif kind == "dynamics_zoo":
+                # one agent per action -> force / torque model, no contacts in the way
+                world = World(batch_dim, device, substeps=1, drag=0.25)
+                zoo = [
+                    ("diff_rk4", ns["DiffDrive"](world, integration="rk4"), Sphere(0.05), dict(u_range=[1.0, 2.0], u_multiplier=[0.6, 1.0])),
+                    ("diff_euler", ns["DiffDrive"](world, integration="euler"), Box(0.12, 0.08), dict(u_range=[1.0, 2.0])),
+                    ("bicycle", ns["KinematicBicycle"](world, width=0.08, l_f=0.06, l_r=0.05, max_steering_angle=0.6),
+                     Box(0.12, 0.08), dict(u_range=[1.0, 1.0], u_multiplier=[0.8, 1.0])),
+                    ("bicycle_euler", ns["KinematicBicycle"](world, width=0.08, l_f=0.05, l_r=0.07, max_steering_angle=0.4,
+                                                             integration="euler"), Sphere(0.05), dict(u_range=[1.0, 1.0])),
+                    ("drone", ns["Drone"](world), Sphere(0.05), dict(u_range=[0.0001, 0.0001, 0.0001, 0.0001], mass=0.1)),
+                    ("forward", ns["Forward"](), Sphere(0.05), dict(u_range=[1.0])),
+                    ("rotation", ns["Rotation"](), Box(0.1, 0.06), dict(u_range=[0.02])),
+                    ("holo_rot", Rot(), Sphere(0.05), dict(u_range=[1.0, 1.0, 0.01])),
+                    ("static", ns["Static"](), Sphere(0.05), dict()),
+                ]
+                for name, dyn, shape, kw in zoo:
+                    world.add_agent(Agent(name=name, shape=shape, rotatable=True, collide=False, dynamics=dyn,
+                                          action_size=dyn.needed_action_size, **kw))
+                world.add_agent(Agent(name="holo", shape=Sphere(0.05), collide=False))
+                self.spread = 0.8
             elif kind == "lonely":
                 # no work item at all: one non-colliding agent
                 world = World(batch_dim, device, drag=0.25, angular_friction=0.05)
@@ -129,4 +153,4 @@ def make_scenario(root, kind, seed=1234):
     return Crafted()
 
 
-KINDS = ("clamps", "joints_apart", "lonely", "crowd")
+KINDS = ("clamps", "joints_apart", "lonely", "crowd", "dynamics_zoo")

@@ -163,6 +163,78 @@ def test_env_scheduling_inside_environment_step(monkeypatch):
         assert torch.equal(torch.sort(dt.env_order.long()).values, torch.arange(n_envs, device="cuda"))
 
 
+def test_device_side_dynamics_match_the_torch_formulation():
+    """DiffDrive / KinematicBicycle / Drone (RK4 and Euler), Forward, Rotation,
+    HolonomicWithRotation and Static run inside the ingest kernel on CUDA.  One agent per model
+    (tests/crafted.py "dynamics_zoo"), teacher-forced against the CPU env, whose torch formulation of
+    the models is bit-equal to the reference's (tests/test_env_vs_reference.py)."""
+    import crafted
+
+    root = "vectorizedmultiagentsimulator_b200"
+    n_envs = 96
+    with use_oracle():
+        cpu = b200.make_env(crafted.make_scenario(root, "dynamics_zoo"), num_envs=n_envs, device="cpu", seed=0)
+    gpu = b200.make_env(crafted.make_scenario(root, "dynamics_zoo"), num_envs=n_envs, device="cuda", seed=0)
+    assert gpu._fused_ingest_specs() is not None, "the fused ingest kernel must cover every model of the zoo"
+    drones = [(a.dynamics, b.dynamics) for a, b in zip(cpu.agents, gpu.agents) if hasattr(a.dynamics, "drone_state")]
+    assert drones
+    gen = torch.Generator().manual_seed(11)
+    launches = gpu.world._get_backend().launches
+    for t in range(10):
+        sync_env(cpu, gpu)
+        for src, dst in drones:
+            dst.drone_state = src.drone_state.to("cuda").clone()
+        actions = [(torch.rand(n_envs, a.action_size, generator=gen) * 2 - 1) * a.action.u_range_tensor for a in cpu.agents]
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step([a.to("cuda") for a in actions])
+        for k in ("force", "torque", "pos", "vel", "rot", "ang_vel"):
+            g, w = getattr(gpu.world.slab, k).cpu(), getattr(cpu.world.slab, k)
+            err = (g - w).abs()
+            assert bool((err <= 1e-5 + 1e-4 * w.abs()).all()), f"step {t} {k}: max |err| {float(err.max())}"
+        for src, dst in drones:
+            err = (dst.drone_state.cpu() - src.drone_state).abs()
+            assert bool((err <= 1e-5 + 1e-4 * src.drone_state.abs()).all()), f"step {t} drone state: {float(err.max())}"
+        for a, b in zip(cpu.agents, gpu.agents):  # the scaled actions, incl. the drone's in-place thrust offset
+            assert torch.allclose(b.action.u.cpu(), a.action.u, rtol=1e-6, atol=1e-7), f"step {t}: action.u of {a.name}"
+        _compare(got[0], want[0], f"dynamics_zoo step {t} obs", atol=1e-5)
+    gpu.check_actions_now()
+    assert gpu.world._get_backend().launches > launches
+
+
+@pytest.mark.parametrize("params,form,cutoff", [((2.0, 1.5, 0.02), "standard", 0.3), ((1.2, 0.0, 0.05), "standard", None), ((3.0, 2.0, 0.1), "parallel", None)])
+def test_velocity_controller_kernel_equals_the_torch_statements(params, form, cutoff):
+    """``VelocityController.process_force`` on CUDA is one kernel (ref controllers/velocity_controller.py:
+    113-125); it must reproduce the torch statements it replaces — same fp32 operations, same order."""
+    import warnings
+
+    from golden_util import same_result
+    from vectorizedmultiagentsimulator_b200.simulator.controllers.velocity_controller import VelocityController
+
+    env = b200.make_env("navigation", num_envs=257, device="cuda", seed=0, n_agents=2)
+    agent = env.world.agents[1]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fused, eager = (VelocityController(agent, env.world, params, form) for _ in range(2))
+    eager.use_kernel = False
+    for c in (fused, eager):
+        if cutoff is not None:
+            c.integrator_windup_cutoff = cutoff
+    gen = torch.Generator().manual_seed(1)
+    before = env.world._get_backend().launches
+    for t in range(6):
+        agent.set_vel((torch.rand(257, 2, generator=gen) - 0.5).cuda(), batch_index=None)
+        target = (torch.rand(257, 2, generator=gen) * 2 - 1).cuda()
+        agent.action.u = target.clone()
+        fused.process_force()
+        got = agent.action.u.clone()
+        agent.action.u = target.clone()
+        eager.process_force()
+        want = agent.action.u
+        assert same_result(got, want), f"iteration {t}: max |diff| {float((got - want).abs().max())}"
+        assert same_result(fused.accum_errs, eager.accum_errs) and same_result(fused.prev_err, eager.prev_err)
+    assert env.world._get_backend().launches == before + 6
+
+
 def test_reset_at_and_state_views_on_gpu():
     env = b200.make_env("transport", num_envs=8, device="cuda", seed=0, n_agents=3)
     agent = env.world.agents[0]

@@ -33,6 +33,7 @@ for name in names:
         for mapping in os.environ.get("KB_MAPPINGS", "specialized,thread_per_env,lanes_per_env").split(","):
             # "specialized_ordered": the thread-per-env kernel with its envs scheduled by contact signature
             ordered = mapping.endswith("_ordered")
+            _native.ENV_REORDER_EVERY = 8 if ordered else 0
             old = desc.batch_dim
             desc.batch_dim = Bn
             try:

@@ -172,17 +172,24 @@ class AgentActionsC(C.Structure):
         ("action_size", C.c_int32),
         ("agent_index", C.c_int32),
         ("dynamics", C.c_int32),
-        ("reserved", C.c_int32),
+        ("entity_index", C.c_int32),
         ("u_range", C.c_float * MAX_ACTION_SIZE),
         ("u_multiplier", C.c_float * MAX_ACTION_SIZE),
+        ("dyn_params", C.c_float * 8),
+        ("dyn_state", C.c_void_p),
     ]
+
+
+DYN_NONE, DYN_HOLONOMIC, DYN_HOLONOMIC_ROT, DYN_FORWARD, DYN_ROTATION, DYN_DIFF_DRIVE, DYN_BICYCLE, DYN_DRONE = -1, 0, 1, 2, 3, 4, 5, 6
 
 
 MAX_SPAWN = 64
 GROUP_TILE = -8  # VMAS_GROUP_TILE
 #: env scheduling of the specialised thread-per-env kernel: the envs are re-sorted by their contact
-#: signature every this many World.step calls (0 = off: thread t always steps env t)
-ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "8"))
+#: signature every this many World.step calls (0 = off: thread t always steps env t).  OFF by default:
+#: it halves the warp-instructions (1.8 k per 32 envs at 31 of 32 lanes active) but the scattered rows
+#: leave the kernel latency-bound — measured slower on real roll-out states (profiles/r2f_*)
+ENV_REORDER_EVERY = int(os.environ.get("VMAS_B200_ENV_REORDER_EVERY", "0"))
 ENV_REORDER_MIN_BATCH = 1024  # below this there is nothing to gain from grouping
 ENV_REORDER_CHUNK = int(os.environ.get("VMAS_B200_ENV_REORDER_CHUNK", "2048"))  # envs sorted together
 #: what mapping="auto" picks for a specialised world that has both kernels
@@ -233,6 +240,7 @@ EXPORTS = [
     "vmas_b200_point_query",
     "vmas_b200_broad_phase",
     "vmas_b200_ingest_actions",
+    "vmas_b200_velocity_controller",
     "vmas_b200_cast_rays_batched",
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
@@ -299,6 +307,10 @@ def load():
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_copy_buffers.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.vmas_b200_velocity_controller.argtypes = [
+        p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+        C.c_float, C.c_float, C.c_void_p,
+    ]
     lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.vmas_b200_set_l2_fetch_granularity.argtypes = [C.c_int32]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
@@ -603,6 +615,16 @@ def cast_rays_batched(
         targets.data_ptr(), angles.data_ptr(), max_range.data_ptr(), int(n_rays), out.data_ptr(),
         out_offsets.data_ptr() if out_offsets is not None else None, int(out_env_stride), int(flags),
         _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+def velocity_controller(lib, dt: DeviceTables, slab, entity: int, u, accum, prev, gain, inv_ti, td, step_dt, windup, mass) -> int:
+    """PID force from a velocity target, in place on ``u`` [B, 2] (see include/vmas_b200.h)."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_velocity_controller(
+        C.byref(dt.cfg), C.byref(st), int(entity), u.data_ptr(), accum.data_ptr(), prev.data_ptr(), float(gain),
+        float(inv_ti), float(td), float(step_dt), float(windup), float(mass), _stream(dt.device),
     )
     return _check(lib, rc)
 

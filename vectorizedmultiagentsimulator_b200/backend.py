@@ -394,11 +394,24 @@ class CudaBackend(PlanRuntime):
         if arr is None or len(arr) != n:
             arr = (self._native.AgentActionsC * n)()
             agent_row = {id(a): j for j, a in enumerate(self.world.agents)}
+            self._ingest_drones = []
             for c, (agent, dyn, u) in zip(arr, specs):
                 c.u = u.data_ptr()
                 c.action_size = agent.action_size
                 c.agent_index = agent_row[id(agent)]
                 c.dynamics = dyn
+                c.entity_index = self.index_of(agent)
+                if dyn >= self._native.DYN_DIFF_DRIVE:  # the kinematic models' parameters
+                    model = agent.dynamics
+                    params = [float(model.dt), float(agent.mass), float(agent.moment_of_inertia),
+                              1.0 if model.integration == "rk4" else 0.0, 0.0, 0.0, 0.0, 0.0]
+                    if dyn == self._native.DYN_BICYCLE:
+                        params[4:7] = [float(model.l_f), float(model.l_r), float(model.max_steering_angle)]
+                    elif dyn == self._native.DYN_DRONE:
+                        params[4:8] = [float(model.I_xx), float(model.I_yy), float(model.I_zz), float(model.g)]
+                        self._ingest_drones.append((c, model))
+                    for j, v in enumerate(params):
+                        c.dyn_params[j] = v
                 rng = agent.action.u_range_tensor.tolist()
                 mul = agent.action.u_multiplier_tensor.tolist()
                 for j in range(agent.action_size):
@@ -407,6 +420,8 @@ class CudaBackend(PlanRuntime):
             self._ingest_arr = arr
         for c, a in zip(arr, actions):
             c.actions = a.data_ptr()
+        for c, model in self._ingest_drones:  # a reset re-binds the drone's 12-state tensor
+            c.dyn_state = model.drone_state.data_ptr()
         for lo in range(0, n, self._native.MAX_INGEST_AGENTS):
             hi = min(n, lo + self._native.MAX_INGEST_AGENTS)
             chunk = (self._native.AgentActionsC * (hi - lo)).from_address(

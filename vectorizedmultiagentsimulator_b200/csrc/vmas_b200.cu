@@ -1418,14 +1418,76 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
 // ---------------------------------------------------------------------------------------------
 struct IngestArgs {
   VmasAgentActions ag[VMAS_MAX_INGEST_AGENTS];
-  float* force;
-  float* torque;
+  VmasState st;
   uint8_t* bad_flag;
+  int n_entities;      // E: row stride of pos / vel / rot / ang_vel
   int n_agents_total;  // A: row stride of force / torque
   int n;               // agents in this launch
   int batch_dim;
   int clamp;
 };
+
+// ---- the kinematic action models (ref dynamics/diff_drive.py, kinematic_bicycle.py, drone.py) ---------
+// Each integrates a small ODE over dt — classic RK4 or Euler, the reference's order of operations — to
+// get the pose change the command asks for.
+struct Pose3 {
+  float x, y, yaw;
+};
+DEVI Pose3 diff_drive_f(float heading, float v, float w) {
+  float s, c;
+  sincosf(heading, &s, &c);
+  Pose3 d = {v * c, v * s, w};
+  return d;
+}
+DEVI Pose3 bicycle_f(float yaw, float steering, float v, float l_f, float l_r) {
+  const float wheelbase = l_f + l_r;
+  const float slip = atan2f(tanf(steering) * l_r / wheelbase, 1.f);
+  float s, c;
+  sincosf(yaw + slip, &s, &c);
+  Pose3 d = {v * c, v * s, v / wheelbase * cosf(slip) * tanf(steering)};
+  return d;
+}
+template <class F>
+DEVI Pose3 integrate_pose(float yaw, float dt, bool rk4, F f) {
+  const Pose3 k1 = f(yaw);
+  if (!rk4) {
+    Pose3 e = {dt * k1.x, dt * k1.y, dt * k1.yaw};
+    return e;
+  }
+  const Pose3 k2 = f(yaw + dt * k1.yaw / 2.f);
+  const Pose3 k3 = f(yaw + dt * k2.yaw / 2.f);
+  const Pose3 k4 = f(yaw + dt * k3.yaw);
+  const float w = dt / 6.f;
+  Pose3 d = {w * (k1.x + 2.f * k2.x + 2.f * k3.x + k4.x), w * (k1.y + 2.f * k2.y + 2.f * k3.y + k4.y),
+             w * (k1.yaw + 2.f * k2.yaw + 2.f * k3.yaw + k4.yaw)};
+  return d;
+}
+
+struct Drone12 {
+  float v[12];
+};
+DEVI Drone12 drone_f(const Drone12& s, float thrust, float tx, float ty, float tz, float mass, float Ixx, float Iyy,
+                     float Izz, float g) {
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(s.v[0], &sr, &cr);
+  sincosf(s.v[1], &sp, &cp);
+  sincosf(s.v[2], &sy, &cy);
+  const float p = s.v[3], q = s.v[4], r = s.v[5];
+  Drone12 d;
+  d.v[0] = p;
+  d.v[1] = q;
+  d.v[2] = r;
+  d.v[3] = (tx - (Iyy - Izz) * q * r) / Ixx;
+  d.v[4] = (ty - (Izz - Ixx) * p * r) / Iyy;
+  d.v[5] = (tz - (Ixx - Iyy) * p * q) / Izz;
+  d.v[6] = (cr * sp * cy + sr * sy) * thrust / mass;
+  d.v[7] = (cr * sp * sy - sr * cy) * thrust / mass;
+  d.v[8] = (cr * cp) * thrust / mass - g;
+  d.v[9] = s.v[6];
+  d.v[10] = s.v[7];
+  d.v[11] = s.v[8];
+  return d;
+}
 
 __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1445,15 +1507,120 @@ __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a)
       if (a.clamp) v = fminf(fmaxf(v, -r), r);       // torch.clamp keeps NaN
       bad |= (v != v) || (fabsf(v) > r);
       u[j] = v * ag.u_multiplier[j];
-      ag.u[env * sz + j] = u[j];
     }
   }
   if (bad && a.bad_flag) *a.bad_flag = 1;
-  if (ag.dynamics >= 0) {
-    const size_t row = (size_t)env * a.n_agents_total + ag.agent_index;
-    reinterpret_cast<float2*>(a.force)[row] = make_float2(u[0], u[1]);
-    if (ag.dynamics == 1) a.torque[row] = u[2];
+  const int dyn = ag.dynamics;
+  const size_t row = (size_t)env * a.n_agents_total + ag.agent_index;
+  const size_t ent = (size_t)env * a.n_entities + ag.entity_index;
+  float2 force = make_float2(0.f, 0.f);
+  float torque = 0.f;
+  bool write_force = false, write_torque = false;
+  if (dyn == VMAS_DYN_HOLONOMIC || dyn == VMAS_DYN_HOLONOMIC_ROT) {
+    force = make_float2(u[0], u[1]);
+    write_force = true;
+    if (dyn == VMAS_DYN_HOLONOMIC_ROT) {
+      torque = u[2];
+      write_torque = true;
+    }
+  } else if (dyn == VMAS_DYN_FORWARD) {  // (u0, 0) rotated by the heading (ref dynamics/forward.py)
+    float s, c;
+    sincosf(a.st.rot[ent], &s, &c);
+    force = make_float2(u[0] * c - 0.f * s, u[0] * s + 0.f * c);
+    write_force = true;
+  } else if (dyn == VMAS_DYN_ROTATION) {
+    torque = u[0];
+    write_torque = true;
+  } else if (dyn >= VMAS_DYN_DIFF_DRIVE) {
+    const float dt = ag.dyn_params[0], mass = ag.dyn_params[1], inertia = ag.dyn_params[2];
+    const bool rk4 = ag.dyn_params[3] != 0.f;
+    const float yaw = a.st.rot[ent];
+    Pose3 d;
+    if (dyn == VMAS_DYN_DIFF_DRIVE) {
+      const float v = u[0], w = u[1];
+      d = integrate_pose(yaw, dt, rk4, [&](float h) { return diff_drive_f(h, v, w); });
+    } else if (dyn == VMAS_DYN_BICYCLE) {
+      const float l_f = ag.dyn_params[4], l_r = ag.dyn_params[5], lim = ag.dyn_params[6];
+      const float steer = fminf(fmaxf(u[1], -lim), lim), v = u[0];
+      d = integrate_pose(yaw, dt, rk4, [&](float h) { return bicycle_f(h, steer, v, l_f, l_r); });
+    } else {  // drone: thrust gets the hover feed-forward (in place on the action, as the reference does)
+      const float Ixx = ag.dyn_params[4], Iyy = ag.dyn_params[5], Izz = ag.dyn_params[6], g = ag.dyn_params[7];
+      u[0] = u[0] + mass * g;
+      const float thrust = u[0], tx = u[1], ty = u[2], tz = u[3];
+      float* ds = ag.dyn_state + (size_t)env * 12;
+      Drone12 s;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) s.v[j] = ds[j];
+      const float2 p = reinterpret_cast<const float2*>(a.st.pos)[ent];
+      s.v[9] = p.x;
+      s.v[10] = p.y;
+      s.v[2] = yaw;
+      auto f = [&](const Drone12& x) { return drone_f(x, thrust, tx, ty, tz, mass, Ixx, Iyy, Izz, g); };
+      auto axpy = [&](const Drone12& x, float h, const Drone12& kk) {
+        Drone12 o;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) o.v[j] = x.v[j] + h * kk.v[j] / 2.f;
+        return o;
+      };
+      Drone12 delta;
+      const Drone12 k1 = f(s);
+      if (!rk4) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) delta.v[j] = dt * k1.v[j];
+      } else {
+        const Drone12 k2 = f(axpy(s, dt, k1));
+        const Drone12 k3 = f(axpy(s, dt, k2));
+        Drone12 s4;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) s4.v[j] = s.v[j] + dt * k3.v[j];
+        const Drone12 k4 = f(s4);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) delta.v[j] = (dt / 6.f) * (k1.v[j] + 2.f * k2.v[j] + 2.f * k3.v[j] + k4.v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 12; ++j) ds[j] = s.v[j] + delta.v[j];
+      d.x = delta.v[6];
+      d.y = delta.v[7];
+      d.yaw = delta.v[5];
+    }
+    // the force / torque that realise the pose change under the world's integrator (dynamics/common)
+    const float2 vel = reinterpret_cast<const float2*>(a.st.vel)[ent];
+    const float w0 = a.st.ang_vel[ent];
+    const float dt2 = dt * dt;
+    force = make_float2(mass * ((d.x - vel.x * dt) / dt2), mass * ((d.y - vel.y * dt) / dt2));
+    torque = inertia * ((d.yaw - w0 * dt) / dt2);
+    write_force = write_torque = true;
   }
+#pragma unroll
+  for (int j = 0; j < VMAS_MAX_ACTION_SIZE; ++j)
+    if (j < sz) ag.u[env * sz + j] = u[j];
+  if (write_force) reinterpret_cast<float2*>(a.st.force)[row] = force;
+  if (write_torque) a.st.torque[row] = torque;
+}
+
+// PID velocity controller (ref controllers/velocity_controller.py:88-125): one thread per (env, axis)
+struct PidArgs {
+  const float* vel;
+  float *u, *accum, *prev;
+  int entity, n_entities, batch_dim;
+  float gain, inv_ti, td, dt, windup, mass;
+};
+__global__ void __launch_bounds__(256) velocity_controller_kernel(const PidArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)a.batch_dim * 2) return;
+  const long env = idx >> 1;
+  const int axis = (int)(idx & 1);
+  const float err = a.u[idx] - a.vel[((size_t)env * a.n_entities + a.entity) * 2 + axis];
+  float sum = err;
+  if (a.inv_ti != 0.f) {
+    float acc = a.accum[idx] + a.dt * err;
+    if (a.windup >= 0.f) acc = fminf(fmaxf(acc, -a.windup), a.windup);
+    a.accum[idx] = acc;
+    sum = sum + a.inv_ti * acc;
+  }
+  const float rate = a.td * (err - a.prev[idx]) / a.dt;
+  a.prev[idx] = err;
+  a.u[idx] = (a.gain * (sum + rate)) * a.mass;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1842,14 +2009,21 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
     if (!agents[i].actions || !agents[i].u) return fail("null action buffer%s");
     if (agents[i].action_size < 0 || agents[i].action_size > VMAS_MAX_ACTION_SIZE) return fail("action size > 8%s");
     if (agents[i].dynamics >= 0) {
+      static const int need[] = {2, 3, 1, 1, 2, 2, 4};
+      if (agents[i].dynamics > VMAS_DYN_DRONE) return fail("unknown dynamics code%s");
       if (!st->force || !st->torque) return fail("null force/torque pointer%s");
       if (agents[i].agent_index < 0 || agents[i].agent_index >= cfg->n_agents) return fail("agent index%s");
-      if (agents[i].action_size < (agents[i].dynamics == 1 ? 3 : 2)) return fail("action too small for dynamics%s");
+      if (agents[i].action_size < need[agents[i].dynamics]) return fail("action too small for dynamics%s");
+      if (agents[i].dynamics >= VMAS_DYN_FORWARD && agents[i].dynamics != VMAS_DYN_ROTATION) {
+        if (agents[i].entity_index < 0 || agents[i].entity_index >= cfg->n_entities) return fail("entity index%s");
+        if (!st->pos || !st->vel || !st->rot || !st->ang_vel) return fail("null state pointer%s");
+      }
+      if (agents[i].dynamics == VMAS_DYN_DRONE && !agents[i].dyn_state) return fail("drone without its state buffer%s");
     }
   }
-  a.force = st->force;
-  a.torque = st->torque;
+  a.st = *st;
   a.bad_flag = bad_flag;
+  a.n_entities = cfg->n_entities;
   a.n_agents_total = cfg->n_agents;
   a.n = n_agents;
   a.batch_dim = cfg->batch_dim;
@@ -1858,6 +2032,34 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
   const long total = (long)cfg->batch_dim * n_agents;
   ingest_actions_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
                           static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_velocity_controller(const VmasWorldConfig* cfg, const VmasState* st, int32_t entity, float* u,
+                                  float* accum, float* prev, float gain, float inv_ti, float td, float dt,
+                                  float windup, float mass, void* cuda_stream) {
+  if (!cfg || !st || !st->vel || !u || !accum || !prev) return fail("null argument%s");
+  if (entity < 0 || entity >= cfg->n_entities) return fail("entity index%s");
+  if (cfg->batch_dim <= 0 || !(dt > 0.f)) return fail("empty batch or dt <= 0%s");
+  PidArgs a;
+  a.vel = st->vel;
+  a.u = u;
+  a.accum = accum;
+  a.prev = prev;
+  a.entity = entity;
+  a.n_entities = cfg->n_entities;
+  a.batch_dim = cfg->batch_dim;
+  a.gain = gain;
+  a.inv_ti = inv_ti;
+  a.td = td;
+  a.dt = dt;
+  a.windup = windup;
+  a.mass = mass;
+  const int threads = 256;
+  const long total = (long)cfg->batch_dim * 2;
+  velocity_controller_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                               static_cast<cudaStream_t>(cuda_stream)>>>(a);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

@@ -16,6 +16,9 @@ from ..simulator.utils import Color, ScenarioUtils
 
 class Scenario(BaseScenario):
     supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+    #: observation() reads the world state only (nothing reward() / done() computed): the environment
+    #: may run it on a side stream next to the reward callbacks
+    observations_are_independent = True
 
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._obs_plan = self._obs_all = self._rew_consts = self._package_on_goal = None

@@ -18,6 +18,9 @@ from ..simulator.utils import Color, ScenarioUtils, Y
 
 class Scenario(BaseScenario):
     supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
+    #: observation() reads the world state only (nothing reward() / done() computed): the environment
+    #: may run it on a side stream next to the reward callbacks
+    observations_are_independent = True
 
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
         self._batch = self._obs_all = None  # caches of the batched callbacks belong to one world

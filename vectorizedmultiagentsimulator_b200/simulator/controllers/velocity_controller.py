@@ -2,8 +2,9 @@
 (API and arithmetic of ref vmas/simulator/controllers/velocity_controller.py:16-125).
 
 ``ctrl_params`` is ``[gain, integral time, derivative time]`` in ``"standard"`` form or
-``[kP, kI, kD]`` in ``"parallel"`` form (``Ti = kP / kI``, ``Td = kD / kP``).  Runs as host-side
-torch ops right before ``World.step``; it is not part of the CUDA hot path.
+``[kP, kI, kD]`` in ``"parallel"`` form (``Ti = kP / kI``, ``Td = kD / kP``).  On a CUDA world
+``process_force`` is one kernel launch (``vmas_b200_velocity_controller``: the same fp32 statements in
+the same order); elsewhere (the CPU oracle backend of the tests) the torch ops below.
 """
 from __future__ import annotations
 
@@ -65,7 +66,33 @@ class VelocityController:
         self.prev_err = err
         return rate
 
+    #: tests set this to False to run the torch statements on CUDA too (the kernel is compared with them)
+    use_kernel = True
+
+    def _process_force_cuda(self) -> bool:
+        """The fused path: needs a CUDA world on this package's backend and a contiguous [B, 2] action."""
+        world, agent = self.world, self.agent
+        backend = world._get_backend() if hasattr(world, "_get_backend") else None
+        u = agent.action.u
+        if (
+            not self.use_kernel or backend is None or not hasattr(backend, "lib") or u is None or u.device.type != "cuda"
+            or u.dim() != 2 or u.shape[1] != 2 or not u.is_contiguous() or u.dtype != torch.float32
+        ):
+            return False
+        self.accum_errs = self.accum_errs.to(world.device).contiguous()
+        self.prev_err = self.prev_err.to(world.device).contiguous()
+        backend.refresh()
+        cutoff = getattr(self, "integrator_windup_cutoff", None)
+        backend.launches += backend._native.velocity_controller(
+            backend.lib, backend._dev_tables, world.slab, backend.index_of(agent), u, self.accum_errs, self.prev_err,
+            self.ctrl_gain, (1.0 / self.integralTs) if self.use_integrator else 0.0, self.derivativeTs, self.dt,
+            -1.0 if cutoff is None else cutoff, agent.mass,
+        )
+        return True
+
     def process_force(self):
+        if self._process_force_cuda():
+            return
         self.accum_errs = self.accum_errs.to(self.world.device)
         self.prev_err = self.prev_err.to(self.world.device)
         err = self.agent.action.u - self.agent.state.vel

@@ -82,6 +82,17 @@ def _seeded(method):
     return wrapper
 
 
+def _leaves(x):
+    if isinstance(x, Tensor):
+        yield x
+    elif isinstance(x, dict):
+        for v in x.values():
+            yield from _leaves(v)
+    elif isinstance(x, (list, tuple)):
+        for v in x:
+            yield from _leaves(v)
+
+
 class Environment(TorchVectorizedObject):
     metadata = {"render.modes": ["human", "rgb_array"], "runtime.vectorized": True}
     vmas_random_state = [torch.random.get_rng_state(), np.random.get_state(), random.getstate()]
@@ -292,9 +303,30 @@ class Environment(TorchVectorizedObject):
                     out.append(value)
             return out
 
+        # A scenario whose observations read nothing but the world state (it says so:
+        # ``observations_are_independent``) has them computed on a side stream, next to the reward /
+        # info / done callbacks instead of behind them: the step's kernels are small and mostly
+        # latency-bound at RL batch sizes, so the two chains overlap (in a captured CUDA graph they become
+        # parallel branches).  Everything joins again before the results are handed out.
+        fork = (
+            get_observations
+            and (get_rewards or get_infos or get_dones)
+            and self.device.type == "cuda"
+            and getattr(self.scenario, "observations_are_independent", False)
+        )
+        obs = None
+        if fork:
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_obs_stream", None) is None:
+                self._obs_stream = torch.cuda.Stream(device=self.device)
+            side = self._obs_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                obs = collect(lambda a: _rc(self.scenario.observation(a)))
         # order matters: scenarios cache shared terms while computing agent 0's reward
         rewards = collect(lambda a: _c(self.scenario.reward(a))) if get_rewards else None
-        obs = collect(lambda a: _rc(self.scenario.observation(a))) if get_observations else None
+        if get_observations and not fork:
+            obs = collect(lambda a: _rc(self.scenario.observation(a)))
         infos = collect(lambda a: _rc(self.scenario.info(a))) if get_infos else None
         if self.terminated_truncated:
             terminated = truncated = None
@@ -304,6 +336,11 @@ class Environment(TorchVectorizedObject):
         else:
             dones = self._done(clone) if get_dones else None
             result = [obs, rewards, dones, infos]
+        if fork:
+            main.wait_stream(side)
+            if not torch.cuda.is_current_stream_capturing():
+                for leaf in _leaves(obs):  # allocated on the side stream, used by the caller on this one
+                    leaf.record_stream(main)
         return [data for data in result if data is not None]
 
     def _seed(self, seed=None):
@@ -381,15 +418,25 @@ class Environment(TorchVectorizedObject):
         """[(agent, dynamics code, u buffer)] if the fused action-ingest kernel reproduces what
         ``_set_action`` + ``env_process_action`` would do for every policy agent, else None.
 
-        That holds for continuous, noise-free, non-communicating agents with (rotating) holonomic
-        dynamics in scenarios that do not override ``process_action``.
+        That holds for continuous, noise-free, non-communicating agents whose dynamics model the kernel
+        implements (holonomic, holonomic with rotation, forward, rotation, static, differential drive,
+        kinematic bicycle, drone) in scenarios that do not override ``process_action``.
         """
         version = self.world._plan_version
         cached = getattr(self, "_ingest_cache", None)
         if cached is not None and cached[0] == version:
             return cached[1]
-        from ..dynamics.holonomic import Holonomic
-        from ..dynamics.holonomic_with_rot import HolonomicWithRotation
+        from ... import _native as N
+        from ..dynamics.basic import Forward, Holonomic, HolonomicWithRotation, Rotation, Static
+        from ..dynamics.diff_drive import DiffDrive
+        from ..dynamics.drone import Drone
+        from ..dynamics.kinematic_bicycle import KinematicBicycle
+
+        codes = {
+            Holonomic: N.DYN_HOLONOMIC, HolonomicWithRotation: N.DYN_HOLONOMIC_ROT, Forward: N.DYN_FORWARD,
+            Rotation: N.DYN_ROTATION, Static: N.DYN_NONE, DiffDrive: N.DYN_DIFF_DRIVE,
+            KinematicBicycle: N.DYN_BICYCLE, Drone: N.DYN_DRONE,
+        }
 
         specs = None
         ok = (
@@ -404,7 +451,7 @@ class Environment(TorchVectorizedObject):
             for agent in self.agents:
                 noise = agent.action.u_noise
                 noisy = (max(noise) if isinstance(noise, Sequence) else noise) > 0
-                dyn = {Holonomic: 0, HolonomicWithRotation: 1}.get(type(agent.dynamics))
+                dyn = codes.get(type(agent.dynamics))  # exact types: a subclass may override process_action
                 if noisy or dyn is None or self._comm_dims(agent) > 0 or not (0 < agent.action_size <= 8):
                     specs = None
                     break

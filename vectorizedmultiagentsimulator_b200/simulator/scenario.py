@@ -27,6 +27,11 @@ class BaseScenario(ABC):
     #: (``Environment.reset_at(mask)``: every finished env in one pass, no host sync).  The scenarios
     #: shipped with this package do; scenario files written for the reference take an int or None.
     supports_masked_reset = False
+    #: True if ``observation()`` depends on the world state only — not on anything ``reward()``, ``info()`` or
+    #: ``done()`` compute or cache.  The CUDA environment then evaluates the observations on a second
+    #: stream, concurrently with the reward callbacks (off by default: third-party scenarios often share
+    #: cached terms between the callbacks)
+    observations_are_independent = False
 
     def __init__(self):
         self._world = None
