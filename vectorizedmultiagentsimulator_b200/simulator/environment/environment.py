@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 import random
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -80,6 +81,9 @@ def _seeded(method):
     wrapper.__name__ = method.__name__
     wrapper.__doc__ = method.__doc__
     return wrapper
+
+
+_FORK_OBSERVATIONS = os.environ.get("VMAS_B200_FORK_OBS", "1") != "0"
 
 
 def _leaves(x):
@@ -313,6 +317,7 @@ class Environment(TorchVectorizedObject):
             and (get_rewards or get_infos or get_dones)
             and self.device.type == "cuda"
             and getattr(self.scenario, "observations_are_independent", False)
+            and _FORK_OBSERVATIONS
         )
         obs = None
         if fork:
@@ -452,7 +457,8 @@ class Environment(TorchVectorizedObject):
                 noise = agent.action.u_noise
                 noisy = (max(noise) if isinstance(noise, Sequence) else noise) > 0
                 dyn = codes.get(type(agent.dynamics))  # exact types: a subclass may override process_action
-                if noisy or dyn is None or self._comm_dims(agent) > 0 or not (0 < agent.action_size <= 8):
+                size_ok = 0 < agent.action_size <= 8 or (agent.action_size == 0 and dyn == N.DYN_NONE)
+                if noisy or dyn is None or self._comm_dims(agent) > 0 or not size_ok:
                     specs = None
                     break
                 u = torch.zeros(self.num_envs, agent.action_size, device=self.device, dtype=torch.float32)
@@ -463,7 +469,7 @@ class Environment(TorchVectorizedObject):
     def _fused_ingest_applies(self, actions: List[Tensor]) -> bool:
         return self._fused_ingest_specs() is not None and all(
             a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions
-        )
+        )  # (an agent without action components — Static dynamics — hands in a [B, 0] tensor)
 
     def _apply_actions(self, actions: List[Tensor], fused: Optional[bool] = None) -> bool:
         """Decodes the policy agents' actions into ``agent.action.u`` and slab forces.  Returns
@@ -481,7 +487,9 @@ class Environment(TorchVectorizedObject):
                 msg = "an action is NaN or outside its agent's u_range"
                 if msg not in self._bad_action_messages:
                     self._bad_action_messages.append(msg)
-            self.world._get_backend().ingest_actions(actions, specs, self.clamp_action, flag)
+            # agents without action components (Static dynamics) have nothing to ingest
+            live = [(a, s) for a, s in zip(actions, specs) if s[0].action_size > 0]
+            self.world._get_backend().ingest_actions([a for a, _ in live], [s for _, s in live], self.clamp_action, flag)
             for agent, _, u in specs:
                 if agent.action._u is not u:  # the u buffers are static: bind them once
                     agent.action.u = u
