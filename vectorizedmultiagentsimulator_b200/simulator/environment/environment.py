@@ -83,7 +83,9 @@ def _seeded(method):
     return wrapper
 
 
-_FORK_OBSERVATIONS = os.environ.get("VMAS_B200_FORK_OBS", "1") != "0"
+# opt-in (VMAS_B200_FORK_OBS=1): measured 5-8 % SLOWER on balance / navigation / flocking at the BASELINE
+# batch sizes (profiles/r2h_fork_ab.txt) — the branches of the captured graph do not start together
+_FORK_OBSERVATIONS = os.environ.get("VMAS_B200_FORK_OBS", "0") == "1"
 
 
 def _leaves(x):
@@ -307,11 +309,10 @@ class Environment(TorchVectorizedObject):
                     out.append(value)
             return out
 
-        # A scenario whose observations read nothing but the world state (it says so:
-        # ``observations_are_independent``) has them computed on a side stream, next to the reward /
-        # info / done callbacks instead of behind them: the step's kernels are small and mostly
-        # latency-bound at RL batch sizes, so the two chains overlap (in a captured CUDA graph they become
-        # parallel branches).  Everything joins again before the results are handed out.
+        # Experiment, off by default: a scenario whose observations read nothing but the world state (it
+        # says so: ``observations_are_independent``) can have them computed on a side stream, next to the
+        # reward / info / done callbacks instead of behind them (parallel branches of the captured graph).
+        # Everything joins again before the results are handed out.
         fork = (
             get_observations
             and (get_rewards or get_infos or get_dones)
