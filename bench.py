@@ -508,7 +508,7 @@ def main_b200(args):
         download(0)
         torch.cuda.current_stream().wait_stream(copy_stream)
 
-    for t in range(8):
+    for t in range(min(8, W + K)):
         e2e_step(t - W)
     barrier()
     ms_e2e = timed_loop(e2e_step, K) + timed_loop(e2e_drain, 1)
