@@ -190,7 +190,8 @@ DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* 
   }
 
   if constexpr (it.kind != VMAS_K_JOINT) {
-    if (f.x != 0.f || f.y != 0.f) sig |= 1u << (I & 31);  // this env took the contact branch of item I
+    // (only when env scheduling is on: a.sig is a kernel parameter, the test is warp-uniform)
+    if (a.sig && (f.x != 0.f || f.y != 0.f)) sig |= 1u << (I & 31);  // this env took the contact branch of item I
   }
   if constexpr (ea.flags & VMAS_F_MOVABLE) {
     r.Fx[A] = r.Fx[A] + f.x;
