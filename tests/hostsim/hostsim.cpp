@@ -138,6 +138,10 @@ int hostsim_num_worlds(void) {
 
 // variant 0: one thread per env (spec_env_step); 1: warp tile (Tile<W> phases).  Returns 0, -1 if no
 // specialised world has this hash, -2 if the world has no tile kernel.
+static uint32_t* g_sig_out = nullptr;
+// the next hostsim_step (variant 0) also records every env's contact signature into `sig` (uint32[B])
+void hostsim_record_signatures(uint32_t* sig) { g_sig_out = sig; }
+
 int hostsim_step(uint64_t world_hash, int variant, int batch_dim, float* pos, float* vel, float* rot,
                  float* ang_vel, float* force, float* torque, const uint32_t* mask, int use_mask,
                  int first_substep, int n_substeps) {
@@ -145,7 +149,8 @@ int hostsim_step(uint64_t world_hash, int variant, int batch_dim, float* pos, fl
   a.st.pos = pos; a.st.vel = vel; a.st.rot = rot; a.st.ang_vel = ang_vel; a.st.force = force; a.st.torque = torque;
   a.joint_rot = nullptr;
   a.order = nullptr;
-  a.sig = nullptr;
+  a.sig = g_sig_out;
+  g_sig_out = nullptr;
   a.mask = nullptr;
   a.batch_dim = batch_dim;
   a.use_mask = use_mask;
