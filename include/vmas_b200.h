@@ -287,7 +287,7 @@ int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, 
  * `u = action * u_multiplier`) and the Holonomic / HolonomicWithRotation dynamics
  * (ref dynamics/holonomic.py:14-15, holonomic_with_rot.py: `state.force = u[:, :2]`,
  * `state.torque = u[:, 2]`).
- *   actions      device fp32 [B, action_size], contiguous
+ *   actions      device fp32 [B, action_size], contiguous (discrete spaces: int64, see action_kind)
  *   u            device fp32 [B, action_size]: receives action * u_multiplier (agent.action.u)
  *   dynamics     which action -> force / torque model runs in the same launch (VMAS_DYN_*):
  *                  holonomic (force <- u[0:2]; ref dynamics/holonomic.py:14-15), with rotation (+ torque <- u[2];
@@ -321,7 +321,15 @@ typedef struct VmasAgentActions {
   float u_multiplier[VMAS_MAX_ACTION_SIZE];
   float dyn_params[8];
   float* dyn_state;
+  /* discrete action spaces (ref environment/environment.py:656-706): `actions` is then device int64 —
+   * [B, 1] holding the flat index of the cartesian product of the components (VMAS_ACT_DISCRETE) or
+   * [B, action_size] with one index per component (VMAS_ACT_MULTIDISCRETE); component j has nvec[j]
+   * choices and decodes to  u_j = (k / (n - 1)) * (2 u_range_j) - u_range_j  with the reference's
+   * re-ordering for odd n (index 0 = "no force").  An index outside [0, n) raises `bad_flag`. */
+  int32_t action_kind;   /* VMAS_ACT_CONTINUOUS (0) | VMAS_ACT_DISCRETE | VMAS_ACT_MULTIDISCRETE */
+  int32_t nvec[VMAS_MAX_ACTION_SIZE];
 } VmasAgentActions;
+enum { VMAS_ACT_CONTINUOUS = 0, VMAS_ACT_DISCRETE = 1, VMAS_ACT_MULTIDISCRETE = 2 };
 
 int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
                              int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream);

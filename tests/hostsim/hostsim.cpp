@@ -15,7 +15,10 @@ static void run_thread_per_env(const SpecArgs& a, const uint32_t* mask) {
   uint32_t mask_words[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1] = {0};
   if (a.use_mask)
     for (int w = 0; w < W::MASK_WORDS; ++w) mask_words[w] = mask[w];
-  for (long env = 0; env < a.batch_dim; ++env) spec_env_step<W>(a, env, mask_words);
+  if (a.sig)
+    for (long env = 0; env < a.batch_dim; ++env) spec_env_step<W, true>(a, env, mask_words);
+  else
+    for (long env = 0; env < a.batch_dim; ++env) spec_env_step<W, false>(a, env, mask_words);
 }
 
 // the body of tile_warp_step (csrc/spec_tile_kernel.cuh) for one tile of 32 envs: the lanes of the warp one

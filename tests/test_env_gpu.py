@@ -237,6 +237,40 @@ def test_velocity_controller_kernel_equals_the_torch_statements(params, form, cu
     assert env.world._get_backend().launches == before + 6
 
 
+@pytest.mark.parametrize("multidiscrete", [False, True])
+@pytest.mark.parametrize("name,kwargs", [("balance", dict(n_agents=3)), ("navigation", dict(n_agents=4))])
+def test_discrete_actions_decoded_on_the_device(name, kwargs, multidiscrete):
+    """Discrete and multi-discrete action spaces (ref environment.py:656-706) go through the fused ingest
+    kernel too: flat index -> per-component index -> force level, incl. the odd-n re-ordering.  Teacher-forced
+    against the CPU env (whose torch decoding is bit-equal to the reference's, tests/test_env_vs_reference.py)."""
+    n_envs = 128
+    opts = dict(continuous_actions=False, multidiscrete_actions=multidiscrete, **kwargs)
+    with use_oracle():
+        cpu = b200.make_env(name, num_envs=n_envs, device="cpu", seed=0, **opts)
+    gpu = b200.make_env(name, num_envs=n_envs, device="cuda", seed=0, **opts)
+    gen = torch.Generator().manual_seed(21)
+    for t in range(6):
+        sync_env(cpu, gpu)
+        if multidiscrete:
+            actions = [torch.stack([torch.randint(0, n, (n_envs,), generator=gen) for n in a.discrete_action_nvec], dim=-1) for a in cpu.agents]
+        else:
+            actions = [torch.randint(0, 9, (n_envs, 1), generator=gen) for _ in cpu.agents]
+        gpu_actions = [a.cuda() for a in actions]
+        assert gpu._fused_ingest_applies(gpu_actions), "discrete actions must take the fused ingest kernel"
+        want = cpu.step([a.clone() for a in actions])
+        got = gpu.step(gpu_actions)
+        for a_cpu, a_gpu in zip(cpu.agents, gpu.agents):
+            assert torch.equal(a_gpu.action.u.cpu(), a_cpu.action.u), f"step {t}: decoded action of {a_cpu.name}"
+        _compare(got[0], want[0], f"{name} discrete step {t} obs", atol=1e-5)
+        _compare(got[1], want[1], f"{name} discrete step {t} rews", atol=2e-4)
+    gpu.check_actions_now()
+    bad = [torch.full((n_envs, a.action_size if multidiscrete else 1), 99, dtype=torch.int64, device="cuda") for a in gpu.agents]
+    gpu.step(bad)  # out of range: flagged on the device, raised by the deferred check
+    torch.cuda.synchronize()
+    with pytest.raises(AssertionError):
+        gpu.check_actions_now()
+
+
 def test_reset_at_and_state_views_on_gpu():
     env = b200.make_env("transport", num_envs=8, device="cuda", seed=0, n_agents=3)
     agent = env.world.agents[0]

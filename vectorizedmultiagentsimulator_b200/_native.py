@@ -177,7 +177,12 @@ class AgentActionsC(C.Structure):
         ("u_multiplier", C.c_float * MAX_ACTION_SIZE),
         ("dyn_params", C.c_float * 8),
         ("dyn_state", C.c_void_p),
+        ("action_kind", C.c_int32),
+        ("nvec", C.c_int32 * MAX_ACTION_SIZE),
     ]
+
+
+ACT_CONTINUOUS, ACT_DISCRETE, ACT_MULTIDISCRETE = 0, 1, 2
 
 
 DYN_NONE, DYN_HOLONOMIC, DYN_HOLONOMIC_ROT, DYN_FORWARD, DYN_ROTATION, DYN_DIFF_DRIVE, DYN_BICYCLE, DYN_DRONE = -1, 0, 1, 2, 3, 4, 5, 6

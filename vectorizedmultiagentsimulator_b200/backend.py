@@ -385,13 +385,14 @@ class CudaBackend(PlanRuntime):
         return out
 
     # -- action ingestion ----------------------------------------------------------------------
-    def ingest_actions(self, actions, specs, clamp: bool, bad_flag) -> None:
+    def ingest_actions(self, actions, specs, clamp: bool, bad_flag, action_kind=None) -> None:
         """One launch: validate + scale the policy actions and write ``agent.action.u`` and the
         force / torque rows of the slab.  ``specs``: [(agent, dynamics code, u buffer)]."""
         self.refresh()
         n = len(specs)
         arr = getattr(self, "_ingest_arr", None)
-        if arr is None or len(arr) != n:
+        if arr is None or len(arr) != n or getattr(self, "_ingest_kind", None) != action_kind:
+            self._ingest_kind = action_kind
             arr = (self._native.AgentActionsC * n)()
             agent_row = {id(a): j for j, a in enumerate(self.world.agents)}
             self._ingest_drones = []
@@ -401,6 +402,11 @@ class CudaBackend(PlanRuntime):
                 c.agent_index = agent_row[id(agent)]
                 c.dynamics = dyn
                 c.entity_index = self.index_of(agent)
+                c.action_kind = self._native.ACT_CONTINUOUS
+                if action_kind is not None and action_kind != self._native.ACT_CONTINUOUS:
+                    c.action_kind = action_kind
+                    for j, n in enumerate(agent.discrete_action_nvec):
+                        c.nvec[j] = int(n)
                 if dyn >= self._native.DYN_DIFF_DRIVE:  # the kinematic models' parameters
                     model = agent.dynamics
                     params = [float(model.dt), float(agent.mass), float(agent.moment_of_inertia),

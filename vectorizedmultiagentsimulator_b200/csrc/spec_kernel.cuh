@@ -95,7 +95,8 @@ DEVI BoxG spec_box(const EnvRegs<E>& r) {
 
 // One work item, fully resolved at compile time; accumulates into the env's force registers in
 // the reference's order (ref core.py:2191-2199).
-template <class W, int I, int E>
+// TRACK: also record in `sig` whether the item produced a force (env scheduling; off in the default kernel)
+template <class W, int I, bool TRACK, int E>
 DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* mask_words, uint32_t& sig) {
   constexpr ItemC it = W::item[I];
   constexpr int A = it.a, B = it.b;
@@ -189,9 +190,8 @@ DEVI void spec_item(EnvRegs<E>& r, const SpecArgs& a, long env, const uint32_t* 
     }
   }
 
-  if constexpr (it.kind != VMAS_K_JOINT) {
-    // (only when env scheduling is on: a.sig is a kernel parameter, the test is warp-uniform)
-    if (a.sig && (f.x != 0.f || f.y != 0.f)) sig |= 1u << (I & 31);  // this env took the contact branch of item I
+  if constexpr (TRACK && it.kind != VMAS_K_JOINT) {
+    if (f.x != 0.f || f.y != 0.f) sig |= 1u << (I & 31);  // this env took the contact branch of item I
   }
   if constexpr (ea.flags & VMAS_F_MOVABLE) {
     r.Fx[A] = r.Fx[A] + f.x;
@@ -515,7 +515,7 @@ struct SpecRows {
 };
 
 // One env, all of `a.n_substeps` substeps, state in the calling thread's registers.
-template <class W>
+template <class W, bool TRACK = false>
 DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask_words)[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1]) {
   constexpr int E = W::E, NA = W::A, NI = W::NI;
   if (env >= a.batch_dim) return;
@@ -531,15 +531,19 @@ DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask
     spec_trig<W>(r);
     spec_entity_forces<W>(r, afx, afy, atq);
     // joints and contacts, in accumulation order
-    static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value>(r, a, env, mask_words, sig); });
+    static_for<NI>([&](auto ii) { spec_item<W, decltype(ii)::value, TRACK>(r, a, env, mask_words, sig); });
     spec_integrate<W>(r, sub);
   }
   rows.store(a, env, r, afx, afy, atq);
-  if (a.sig) a.sig[env] = (a.first_substep == 0 ? 0u : a.sig[env]) | sig;  // OR over the substeps of a step
+  if constexpr (TRACK) {
+    if (a.sig) a.sig[env] = (a.first_substep == 0 ? 0u : a.sig[env]) | sig;  // OR over the substeps of a step
+  }
 }
 
 #ifdef __CUDACC__
-template <class W>
+// SCHED: the env-scheduling variant (thread t steps env order[t], signatures recorded); the default
+// kernel carries none of that code
+template <class W, bool SCHED = false>
 __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(const SpecArgs a) {
   constexpr int MW = W::MASK_WORDS;
   const long tid = (long)blockIdx.x * W::BLOCK + threadIdx.x;
@@ -565,16 +569,23 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(cons
     }
   }
   if (tid >= a.batch_dim) return;
-  // env scheduling: with an order table, neighbouring threads step envs with the same contact pattern
-  const long env = a.order ? (long)a.order[tid] : tid;
-  spec_env_step<W>(a, env, mask_words);
+  if constexpr (SCHED) {
+    // env scheduling: with an order table, neighbouring threads step envs with the same contact pattern
+    const long env = a.order ? (long)a.order[tid] : tid;
+    spec_env_step<W, true>(a, env, mask_words);
+  } else {
+    spec_env_step<W, false>(a, tid, mask_words);
+  }
 }
 
 // host-side launcher used by the registry in generated/specializations.cuh
 template <class W>
 static cudaError_t launch_spec(const SpecArgs& a, cudaStream_t stream) {
   const long blocks = ((long)a.batch_dim + W::BLOCK - 1) / W::BLOCK;
-  step_spec_kernel<W><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a);
+  if (a.order || a.sig)
+    step_spec_kernel<W, true><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a);
+  else
+    step_spec_kernel<W, false><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a);
   return cudaGetLastError();
 }
 #endif  // __CUDACC__

@@ -1498,15 +1498,44 @@ __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a)
   const int sz = ag.action_size;
   float u[VMAS_MAX_ACTION_SIZE];
   bool bad = false;
+  if (ag.action_kind == VMAS_ACT_CONTINUOUS) {
 #pragma unroll
-  for (int j = 0; j < VMAS_MAX_ACTION_SIZE; ++j) {
-    u[j] = 0.f;
-    if (j < sz) {
-      float v = ag.actions[env * sz + j];
-      const float r = ag.u_range[j];
-      if (a.clamp) v = fminf(fmaxf(v, -r), r);       // torch.clamp keeps NaN
-      bad |= (v != v) || (fabsf(v) > r);
-      u[j] = v * ag.u_multiplier[j];
+    for (int j = 0; j < VMAS_MAX_ACTION_SIZE; ++j) {
+      u[j] = 0.f;
+      if (j < sz) {
+        float v = ag.actions[env * sz + j];
+        const float r = ag.u_range[j];
+        if (a.clamp) v = fminf(fmaxf(v, -r), r);       // torch.clamp keeps NaN
+        bad |= (v != v) || (fabsf(v) > r);
+        u[j] = v * ag.u_multiplier[j];
+      }
+    }
+  } else {  // discrete / multi-discrete indices (ref environment.py:656-706)
+    const long long* idx_in = reinterpret_cast<const long long*>(ag.actions);
+    long long flat = ag.action_kind == VMAS_ACT_DISCRETE ? idx_in[env] : 0;
+#pragma unroll
+    for (int j = 0; j < VMAS_MAX_ACTION_SIZE; ++j) {
+      u[j] = 0.f;
+      if (j < sz) {
+        const long long n = ag.nvec[j];
+        long long k;
+        if (ag.action_kind == VMAS_ACT_DISCRETE) {  // unravel the flat index of the cartesian product
+          long long stride = 1;
+          for (int m = j + 1; m < sz; ++m) stride *= ag.nvec[m];
+          k = flat / stride;
+          flat = flat % stride;
+        } else {
+          k = idx_in[env * sz + j];
+        }
+        bad |= k < 0 || k >= n;
+        if (n % 2 != 0) {  // odd n: index 0 means "no force"; indices 1 .. n/2 shift down by one
+          if (k == 0) k = n / 2;
+          else if (k <= n / 2) k = k - 1;
+        }
+        const float r = ag.u_range[j];
+        const float v = ((float)k / (float)(n - 1)) * (2.f * r) - r;
+        u[j] = v * ag.u_multiplier[j];
+      }
     }
   }
   if (bad && a.bad_flag) *a.bad_flag = 1;

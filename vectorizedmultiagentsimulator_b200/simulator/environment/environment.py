@@ -447,7 +447,6 @@ class Environment(TorchVectorizedObject):
         specs = None
         ok = (
             self.device.type == "cuda"
-            and self.continuous_actions
             and self.action_checks != "sync"
             and type(self.scenario).process_action is BaseScenario.process_action
             and self.n_agents > 0
@@ -467,10 +466,23 @@ class Environment(TorchVectorizedObject):
         self._ingest_cache = (version, specs)
         return specs
 
+    def _ingest_dtype(self):
+        """What the fused ingest kernel reads: fp32 actions, or int64 indices in discrete spaces."""
+        return torch.float32 if self.continuous_actions else torch.int64
+
     def _fused_ingest_applies(self, actions: List[Tensor]) -> bool:
-        return self._fused_ingest_specs() is not None and all(
-            a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions
-        )  # (an agent without action components — Static dynamics — hands in a [B, 0] tensor)
+        specs = self._fused_ingest_specs()
+        if specs is None:
+            return False
+        if self.continuous_actions:
+            # (an agent without action components — Static dynamics — hands in a [B, 0] tensor)
+            return all(a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions)
+        # discrete spaces: int64 indices, [B, 1] (flat index of the product) or [B, action_size] (multi-discrete)
+        return all(
+            a.dtype == torch.int64 and a.is_contiguous() and a.device.type == "cuda" and a.dim() == 2
+            and a.shape[1] == (s[0].action_size if self.multidiscrete_actions else 1)
+            for a, s in zip(actions, specs)
+        )
 
     def _apply_actions(self, actions: List[Tensor], fused: Optional[bool] = None) -> bool:
         """Decodes the policy agents' actions into ``agent.action.u`` and slab forces.  Returns
@@ -490,7 +502,14 @@ class Environment(TorchVectorizedObject):
                     self._bad_action_messages.append(msg)
             # agents without action components (Static dynamics) have nothing to ingest
             live = [(a, s) for a, s in zip(actions, specs) if s[0].action_size > 0]
-            self.world._get_backend().ingest_actions([a for a, _ in live], [s for _, s in live], self.clamp_action, flag)
+            N = self.world._get_backend()._native
+            kind = (
+                N.ACT_CONTINUOUS if self.continuous_actions
+                else (N.ACT_MULTIDISCRETE if self.multidiscrete_actions else N.ACT_DISCRETE)
+            )
+            self.world._get_backend().ingest_actions(
+                [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind
+            )
             for agent, _, u in specs:
                 if agent.action._u is not u:  # the u buffers are static: bind them once
                     agent.action.u = u
@@ -554,7 +573,7 @@ class Environment(TorchVectorizedObject):
             if not self._fused_ingest_applies(actions):
                 # pinned host tensors are uploaded asynchronously (stream-ordered before the kernel)
                 actions = [
-                    a.to(self.device, torch.float32, non_blocking=a.is_pinned() if a.device.type == "cpu" else False)
+                    a.to(self.device, self._ingest_dtype(), non_blocking=a.is_pinned() if a.device.type == "cpu" else False)
                     .contiguous()
                     for a in actions
                 ]
@@ -671,7 +690,7 @@ class Environment(TorchVectorizedObject):
         self._graph_action_layout = [(a.shape, a.dtype) for a in actions]
         dev_actions = [a.to(self.device) for a in actions]
         ingest_outside = self._fused_ingest_applies(
-            [a.to(torch.float32).contiguous() for a in dev_actions]
+            [a.to(self._ingest_dtype()).contiguous() for a in dev_actions]
         )
         if ingest_outside:
             self._graph_inputs = None
@@ -684,7 +703,7 @@ class Environment(TorchVectorizedObject):
         graph = torch.cuda.CUDAGraph()
         try:
             if ingest_outside:
-                self._apply_actions([a.to(torch.float32).contiguous() for a in dev_actions])
+                self._apply_actions([a.to(self._ingest_dtype()).contiguous() for a in dev_actions])
             before = backend.launches
             with torch.cuda.graph(graph):
                 # outputs stay un-cloned inside the graph; they are packed into flat buffers
