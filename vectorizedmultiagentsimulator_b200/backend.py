@@ -405,8 +405,8 @@ class CudaBackend(PlanRuntime):
                 c.action_kind = self._native.ACT_CONTINUOUS
                 if action_kind is not None and action_kind != self._native.ACT_CONTINUOUS:
                     c.action_kind = action_kind
-                    for j, n in enumerate(agent.discrete_action_nvec):
-                        c.nvec[j] = int(n)
+                    for j, choices in enumerate(agent.discrete_action_nvec):
+                        c.nvec[j] = int(choices)
                 if dyn >= self._native.DYN_DIFF_DRIVE:  # the kinematic models' parameters
                     model = agent.dynamics
                     params = [float(model.dt), float(agent.mass), float(agent.moment_of_inertia),
