@@ -223,6 +223,44 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
                                   int32_t n_rows, int32_t width, float* out, void* cuda_stream);
 
 /*
+ * Post-step program: the scenario's reward / done glue (distance and overlap queries, the distance-shaping
+ * pattern, elementwise operations on per-env scalars) as a short instruction list interpreted by one
+ * thread per env, launched TOGETHER with the observation gather (the blocks with blockIdx.y == n_rows run
+ * the program).  Replaces the chain of small torch kernels a scenario's reward() / done() issue every step
+ * (ref scenarios/balance.py:197-263).  Registers hold fp32 values, booleans are 0 / 1.
+ *   op               operands
+ *   OVERLAP / DISTANCE / CENTER_DISTANCE   dst <- query(entity arg & 0xFFFF, entity arg >> 16)
+ *   SHAPING          dst <- buffers[a][env] - d * imm;  dst + 1 <- d = |pos_a - pos_b|;  buffers[a][env] <- d * imm
+ *   LOAD_F32 / LOAD_BOOL   dst <- buffers[a][env]          CONST   dst <- imm
+ *   ADD SUB MUL MIN MAX OR AND LT LE   dst <- a op b       NEG NOT   dst <- op a
+ *   WHERE            dst <- a != 0 ? b : register (arg & 0xFF)
+ *   STORE_F32 / STORE_BOOL   buffers[b][env] <- a
+ * `columns`, `n_rows`, `width`, `obs_out`: as vmas_b200_gather_observations (or NULL / 0: program only).
+ */
+#define VMAS_PROG_MAX_INSTR 64
+#define VMAS_PROG_MAX_BUFFERS 16
+#define VMAS_PROG_REGS 32
+enum {
+  VMAS_OP_OVERLAP = 1, VMAS_OP_DISTANCE, VMAS_OP_CENTER_DISTANCE, VMAS_OP_SHAPING, VMAS_OP_LOAD_F32, VMAS_OP_LOAD_BOOL,
+  VMAS_OP_CONST, VMAS_OP_ADD, VMAS_OP_SUB, VMAS_OP_MUL, VMAS_OP_MIN, VMAS_OP_MAX, VMAS_OP_NEG, VMAS_OP_OR, VMAS_OP_AND,
+  VMAS_OP_NOT, VMAS_OP_LT, VMAS_OP_LE, VMAS_OP_WHERE, VMAS_OP_STORE_F32, VMAS_OP_STORE_BOOL
+};
+typedef struct VmasProgInstr {
+  uint8_t op, dst, a, b;
+  int32_t arg;
+  float imm;
+} VmasProgInstr;
+typedef struct VmasStepProgram {
+  int32_t n_instr;
+  int32_t reserved;
+  VmasProgInstr instr[VMAS_PROG_MAX_INSTR];
+  void* buffers[VMAS_PROG_MAX_BUFFERS];  /* device pointers: per-env fp32 or uint8 arrays [B] */
+} VmasStepProgram;
+int vmas_b200_post_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                        const VmasStepProgram* program, const int32_t* columns, int32_t n_rows, int32_t width,
+                        float* obs_out, void* cuda_stream);
+
+/*
  * Distance shaping for K entity pairs in one launch — the reward pattern of
  * scenarios/balance.py:197-214, navigation.py:203-216, transport.py:139-152:
  *     dist = |pos_a - pos_b|;  rew = prev - dist * factor;  prev <- dist * factor   (fp32, in this order)

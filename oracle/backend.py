@@ -84,6 +84,62 @@ class OracleBackend(PlanRuntime):
             rows.append(torch.cat(parts, dim=-1))
         return torch.stack(rows)
 
+    def run_program(self, prog, observe=None):
+        """CPU statement of a ``program.StepProgram``: the torch ops the instruction list stands for
+        (ref scenarios/balance.py:197-263: per-pair queries, the shaping pattern, elementwise glue)."""
+        from vectorizedmultiagentsimulator_b200.simulator import program as SP
+
+        regs = {}
+        for op, dst, a, b, arg, imm, entities in prog.instr:
+            if op == SP.OP_OVERLAP:
+                regs[dst] = self.pair_overlap(*entities)
+            elif op == SP.OP_DISTANCE:
+                regs[dst] = self.pair_distance(*entities)
+            elif op == SP.OP_CENTER_DISTANCE:
+                regs[dst] = torch.linalg.vector_norm(entities[0].state.pos - entities[1].state.pos, dim=-1)
+            elif op == SP.OP_SHAPING:
+                prev = prog.resolve(prog.buffers[a])
+                dist = torch.linalg.vector_norm(entities[0].state.pos - entities[1].state.pos, dim=-1)
+                shaping = dist * imm
+                regs[dst], regs[dst + 1] = prev - shaping, dist
+                prev.copy_(shaping)
+            elif op == SP.OP_LOAD_F32:
+                regs[dst] = prog.resolve(prog.buffers[a]).clone()
+            elif op == SP.OP_LOAD_BOOL:
+                regs[dst] = prog.resolve(prog.buffers[a]).to(torch.bool)
+            elif op == SP.OP_CONST:
+                regs[dst] = torch.tensor(imm, dtype=torch.float32)
+            elif op == SP.OP_ADD:
+                regs[dst] = regs[a] + regs[b]
+            elif op == SP.OP_SUB:
+                regs[dst] = regs[a] - regs[b]
+            elif op == SP.OP_MUL:
+                regs[dst] = regs[a] * regs[b]
+            elif op == SP.OP_MIN:
+                regs[dst] = torch.minimum(regs[a], regs[b])
+            elif op == SP.OP_MAX:
+                regs[dst] = torch.maximum(regs[a], regs[b])
+            elif op == SP.OP_NEG:
+                regs[dst] = -regs[a]
+            elif op == SP.OP_OR:
+                regs[dst] = regs[a].to(torch.bool) | regs[b].to(torch.bool)
+            elif op == SP.OP_AND:
+                regs[dst] = regs[a].to(torch.bool) & regs[b].to(torch.bool)
+            elif op == SP.OP_NOT:
+                regs[dst] = ~regs[a].to(torch.bool)
+            elif op == SP.OP_LT:
+                regs[dst] = regs[a] < regs[b]
+            elif op == SP.OP_LE:
+                regs[dst] = regs[a] <= regs[b]
+            elif op == SP.OP_WHERE:
+                regs[dst] = torch.where(regs[a].to(torch.bool), regs[b], regs[arg])
+            elif op in (SP.OP_STORE_F32, SP.OP_STORE_BOOL):
+                out = prog.resolve(prog.buffers[b])
+                out.copy_(regs[a].expand_as(out).to(out.dtype))
+            else:
+                raise ValueError(f"unknown program op {op}")
+        return self.observe(observe) if observe is not None else None
+
     def distance_shaping(self, pairs, factor, prev):
         """CPU statement of ``World.distance_shaping`` (ref scenarios/balance.py:197-214)."""
         dist = torch.stack([torch.linalg.vector_norm(a.state.pos - b.state.pos, dim=-1) for a, b in pairs])

@@ -250,6 +250,7 @@ EXPORTS = [
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
     "vmas_b200_distance_shaping",
+    "vmas_b200_post_step",
     "vmas_b200_copy_buffers",
     "vmas_b200_build_env_order",
     "vmas_b200_set_l2_fetch_granularity",
@@ -312,6 +313,9 @@ def load():
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
     lib.vmas_b200_copy_buffers.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.vmas_b200_post_step.argtypes = [
+        p_cfg, p_tb, p_st, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+    ]
     lib.vmas_b200_velocity_controller.argtypes = [
         p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
         C.c_float, C.c_float, C.c_void_p,
@@ -630,6 +634,33 @@ def velocity_controller(lib, dt: DeviceTables, slab, entity: int, u, accum, prev
     rc = lib.vmas_b200_velocity_controller(
         C.byref(dt.cfg), C.byref(st), int(entity), u.data_ptr(), accum.data_ptr(), prev.data_ptr(), float(gain),
         float(inv_ti), float(td), float(step_dt), float(windup), float(mass), _stream(dt.device),
+    )
+    return _check(lib, rc)
+
+
+PROG_MAX_INSTR, PROG_MAX_BUFFERS = 64, 16
+
+
+class ProgInstrC(C.Structure):
+    _fields_ = [("op", C.c_uint8), ("dst", C.c_uint8), ("a", C.c_uint8), ("b", C.c_uint8), ("arg", C.c_int32), ("imm", C.c_float)]
+
+
+class StepProgramC(C.Structure):
+    _fields_ = [
+        ("n_instr", C.c_int32),
+        ("reserved", C.c_int32),
+        ("instr", ProgInstrC * PROG_MAX_INSTR),
+        ("buffers", C.c_void_p * PROG_MAX_BUFFERS),
+    ]
+
+
+def post_step(lib, dt: DeviceTables, slab, program, columns, n_rows: int, width: int, out) -> int:
+    """The scenario's step program and (optionally) the observation gather in one launch."""
+    st = dt.state_struct(slab)
+    rc = lib.vmas_b200_post_step(
+        C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), C.byref(program) if program is not None else None,
+        None if columns is None else columns.data_ptr(), int(n_rows), int(width),
+        None if out is None else out.data_ptr(), _stream(dt.device),
     )
     return _check(lib, rc)
 

@@ -297,7 +297,36 @@ class CudaBackend(PlanRuntime):
         self.launches += 1
         return out
 
-    def observe(self, plan) -> Tensor:
+    def run_program(self, prog, observe=None) -> Optional[Tensor]:
+        """A ``program.StepProgram`` (the scenario's reward / done glue) in one launch, together with the
+        state-slab columns of the observation plan ``observe`` if one is given."""
+        self.refresh()
+        cached = prog.device_cache.get(id(self))
+        if cached is None or cached[0] != self._plan_version:
+            N = self._native
+            c = N.StepProgramC()
+            c.n_instr = len(prog.instr)
+            for k, (op, dst, a, b, arg, imm, entities) in enumerate(prog.instr):
+                if entities is not None:
+                    arg = self.index_of(entities[0]) | (self.index_of(entities[1]) << 16)
+                ins = c.instr[k]
+                ins.op, ins.dst, ins.a, ins.b, ins.arg, ins.imm = op, dst, a, b, arg, imm
+            cached = (self._plan_version, c)
+            prog.device_cache[id(self)] = cached
+        c = cached[1]
+        B = self.world.batch_dim
+        for slot, buf in enumerate(prog.buffers):
+            t = prog.resolve(buf)
+            assert t.device == self.device and t.is_contiguous() and t.shape == (B,), "program buffers are contiguous [B] tensors on the world's device"
+            assert t.dtype in (torch.float32, torch.bool, torch.uint8), "program buffers are fp32 or bool"
+            c.buffers[slot] = t.data_ptr()
+        if observe is not None:
+            return self.observe(observe, program=c)
+        self._native.post_step(self.lib, self._dev_tables, self.world.slab, c, None, 0, 0, None)
+        self.launches += 1
+        return None
+
+    def observe(self, plan, program=None) -> Tensor:
         """``[rows, B, width]`` observation block of an ``observe.ObservationPlan``: one launch
         for the state-slab columns, one for all LIDAR columns."""
         self.refresh()
@@ -330,7 +359,14 @@ class CudaBackend(PlanRuntime):
                 )
             plan.device_cache[id(self)] = dev
         out = torch.empty(plan.n_rows, B, F, dtype=torch.float32, device=self.device)
-        if dev["any_state"]:
+        if program is not None:
+            # the scenario's reward / done program rides in the same launch as the state-slab columns
+            self._native.post_step(
+                self.lib, self._dev_tables, self.world.slab, program, dev["cols"] if dev["any_state"] else None,
+                plan.n_rows, F, out,
+            )
+            self.launches += 1
+        elif dev["any_state"]:
             self._native.gather_observations(
                 self.lib, self._dev_tables, self.world.slab, dev["cols"], plan.n_rows, F, out
             )

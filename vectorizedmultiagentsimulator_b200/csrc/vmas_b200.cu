@@ -1221,6 +1221,18 @@ __global__ void __launch_bounds__(128) pair_query_spheres_kernel(const PairBatch
   }
 }
 
+// World.is_overlapping of one pair in one env (ref core.py:1907-1969)
+DEVI bool pair_overlap(const QueryArgs& q, const EntG& ga, const EntG& gb, int ia, int ib) {
+  const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
+                          (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
+  if (overlap_impossible(ga, gb)) return false;
+  if (box_sphere) {
+    const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
+    return box_sphere_overlap(q, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
+  }
+  return pair_distance(q, ga, gb, ia, ib) < 0.f;
+}
+
 __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatchArgs a) {
   const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long B = a.base.cfg.batch_dim;
@@ -1240,18 +1252,7 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
     } else if (a.base.mode == 2) {
       static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
     } else {
-      bool over = false;
-      const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
-                              (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
-      if (overlap_impossible(ga, gb)) {
-        over = false;
-      } else if (box_sphere) {
-        const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
-        over = box_sphere_overlap(a.base, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
-      } else {
-        over = pair_distance(a.base, ga, gb, ia, ib) < 0.f;
-      }
-      static_cast<uint8_t*>(a.base.out)[idx] = over ? 1 : 0;
+      static_cast<uint8_t*>(a.base.out)[idx] = pair_overlap(a.base, ga, gb, ia, ib) ? 1 : 0;
     }
   }
 }
@@ -1327,7 +1328,7 @@ __device__ __noinline__ float obs_remainder(float v, float m) {  // torch.remain
 //     handful of shared-memory loads, at most one subtraction per column and one vector store;
 //     consecutive lanes write consecutive pieces of an env's output row.
 template <int VEC>
-__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a, const int tile_envs) {
+DEVI void gather_observations_body(const ObsArgs& a, const int tile_envs, const int obs_row) {
   extern __shared__ float4 s_state4[];
   float* s_state = reinterpret_cast<float*>(s_state4);
   const unsigned E = (unsigned)a.n_entities;
@@ -1367,7 +1368,7 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
 
   const int groups = a.width / VEC;
   const int g = threadIdx.x;
-  const int row = blockIdx.y;
+  const int row = obs_row;
   const int4* table = reinterpret_cast<const int4*>(a.cols) + (size_t)row * a.width + g * VEC;
   int op[VEC];
   ObsSrc sa[VEC], sb[VEC];
@@ -1411,6 +1412,91 @@ __global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs 
         if (op[k] != VMAS_OBS_SKIP) dst[k] = v[k];
     }
   }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_observations_kernel(const ObsArgs a, const int tile_envs) {
+  gather_observations_body<VEC>(a, tile_envs, blockIdx.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-step program: the scenario's reward / done glue as ONE launch together with the observation
+// gather.  A scenario's callbacks are a handful of distance / overlap queries, the distance-shaping
+// pattern and a few elementwise operations on [B] tensors (ref scenarios/balance.py:197-263,
+// transport.py:139-190): in torch every one of them is a kernel launch of a few microseconds.  Here they
+// are a short instruction list interpreted by one thread per env (registers = per-env scalars, bools as
+// 0 / 1), in the blocks with blockIdx.y == obs.rows of a launch whose other blocks assemble the
+// observations (horizontal fusion: the two jobs do not depend on each other).
+// ---------------------------------------------------------------------------------------------
+struct ProgArgs {
+  QueryArgs base;  // cfg, plan tables, state
+  VmasStepProgram prog;
+};
+
+DEVI void post_step_program_body(const ProgArgs& p, const int tile_envs) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_threads = blockDim.x * blockDim.y;
+  const long B = p.base.cfg.batch_dim;
+  const long env_end = min(B, ((long)blockIdx.x + 1) * tile_envs);
+  for (long env = (long)blockIdx.x * tile_envs + tid; env < env_end; env += n_threads) {
+    const size_t env_base = (size_t)env * p.base.cfg.n_entities;
+    const float2* row = reinterpret_cast<const float2*>(p.base.st.pos) + env_base;
+    float r[VMAS_PROG_REGS];
+#pragma unroll
+    for (int i = 0; i < VMAS_PROG_REGS; ++i) r[i] = 0.f;
+    for (int pc = 0; pc < p.prog.n_instr; ++pc) {
+      const VmasProgInstr in = p.prog.instr[pc];
+      const int ia = in.arg & 0xFFFF, ib = (in.arg >> 16) & 0xFFFF;
+      switch (in.op) {
+        case VMAS_OP_OVERLAP: {
+          const EntG ga = load_ent(p.base, ia, env_base), gb = load_ent(p.base, ib, env_base);
+          r[in.dst] = pair_overlap(p.base, ga, gb, ia, ib) ? 1.f : 0.f;
+        } break;
+        case VMAS_OP_DISTANCE: {
+          const EntG ga = load_ent(p.base, ia, env_base), gb = load_ent(p.base, ib, env_base);
+          r[in.dst] = pair_distance(p.base, ga, gb, ia, ib);
+        } break;
+        case VMAS_OP_CENTER_DISTANCE: {
+          const float2 pa = row[ia], pb = row[ib];
+          r[in.dst] = norm2(pa.x - pb.x, pa.y - pb.y);
+        } break;
+        case VMAS_OP_SHAPING: {  // dist -> r[dst + 1]; rew = prev - dist * factor -> r[dst]; prev <- dist * factor
+          const float2 pa = row[ia], pb = row[ib];
+          const float d = norm2(pa.x - pb.x, pa.y - pb.y);
+          const float shaping = d * in.imm;
+          float* prev = static_cast<float*>(p.prog.buffers[in.a]) + env;
+          r[in.dst] = *prev - shaping;
+          r[in.dst + 1] = d;
+          *prev = shaping;
+        } break;
+        case VMAS_OP_LOAD_F32: r[in.dst] = static_cast<const float*>(p.prog.buffers[in.a])[env]; break;
+        case VMAS_OP_LOAD_BOOL: r[in.dst] = static_cast<const uint8_t*>(p.prog.buffers[in.a])[env] ? 1.f : 0.f; break;
+        case VMAS_OP_CONST: r[in.dst] = in.imm; break;
+        case VMAS_OP_ADD: r[in.dst] = r[in.a] + r[in.b]; break;
+        case VMAS_OP_SUB: r[in.dst] = r[in.a] - r[in.b]; break;
+        case VMAS_OP_MUL: r[in.dst] = r[in.a] * r[in.b]; break;
+        case VMAS_OP_MIN: r[in.dst] = fminf(r[in.a], r[in.b]); break;
+        case VMAS_OP_MAX: r[in.dst] = fmaxf(r[in.a], r[in.b]); break;
+        case VMAS_OP_NEG: r[in.dst] = -r[in.a]; break;
+        case VMAS_OP_OR: r[in.dst] = (r[in.a] != 0.f || r[in.b] != 0.f) ? 1.f : 0.f; break;
+        case VMAS_OP_AND: r[in.dst] = (r[in.a] != 0.f && r[in.b] != 0.f) ? 1.f : 0.f; break;
+        case VMAS_OP_NOT: r[in.dst] = r[in.a] != 0.f ? 0.f : 1.f; break;
+        case VMAS_OP_LT: r[in.dst] = r[in.a] < r[in.b] ? 1.f : 0.f; break;
+        case VMAS_OP_LE: r[in.dst] = r[in.a] <= r[in.b] ? 1.f : 0.f; break;
+        case VMAS_OP_WHERE: r[in.dst] = r[in.a] != 0.f ? r[in.b] : r[in.arg & 0xFF]; break;
+        case VMAS_OP_STORE_F32: static_cast<float*>(p.prog.buffers[in.b])[env] = r[in.a]; break;
+        case VMAS_OP_STORE_BOOL: static_cast<uint8_t*>(p.prog.buffers[in.b])[env] = r[in.a] != 0.f ? 1 : 0; break;
+        default: break;
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) post_step_kernel(const ObsArgs obs, const int tile_envs, const ProgArgs prog) {
+  if ((int)blockIdx.y < obs.rows)
+    gather_observations_body<VEC>(obs, tile_envs, blockIdx.y);
+  else
+    post_step_program_body(prog, tile_envs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2170,6 +2256,63 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
     gather_observations_kernel<2><<<grid, block, smem, stream>>>(a, tile);
   } else {
     gather_observations_kernel<1><<<grid, block, smem, stream>>>(a, tile);
+  }
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+int vmas_b200_post_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                        const VmasStepProgram* program, const int32_t* columns, int32_t n_rows, int32_t width,
+                        float* obs_out, void* cuda_stream) {
+  if (check_common(cfg, tb, st) < 0) return -1;
+  const bool has_prog = program && program->n_instr > 0, has_obs = columns && n_rows > 0;
+  if (!has_prog && !has_obs) return fail("neither a program nor observation rows%s");
+  if (has_prog && (program->n_instr > VMAS_PROG_MAX_INSTR)) return fail("program too long%s");
+  if (has_obs && (!obs_out || width <= 0 || n_rows > 65534)) return fail("bad observation block%s");
+  ProgArgs pa;
+  pa.base.cfg = *cfg;
+  pa.base.tb = *tb;
+  pa.base.st = *st;
+  pa.base.a = pa.base.b = pa.base.mode = 0;
+  pa.base.point = nullptr;
+  pa.base.out = nullptr;
+  pa.prog.n_instr = 0;
+  if (has_prog) {
+    pa.prog = *program;
+    for (int i = 0; i < program->n_instr; ++i) {
+      const VmasProgInstr& in = program->instr[i];
+      if (in.dst >= VMAS_PROG_REGS || in.a >= VMAS_PROG_REGS && in.op >= VMAS_OP_ADD && in.op <= VMAS_OP_WHERE)
+        return fail("program register out of range%s");
+      if (in.op == VMAS_OP_SHAPING && in.dst + 1 >= VMAS_PROG_REGS) return fail("program register out of range%s");
+    }
+  }
+  ObsArgs oa;
+  oa.st = *st;
+  oa.cols = columns;
+  oa.out = obs_out;
+  oa.rows = has_obs ? n_rows : 0;
+  oa.width = has_obs ? width : 4;
+  oa.batch_dim = cfg->batch_dim;
+  oa.n_entities = cfg->n_entities;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  int vec = 4;
+  if (has_obs) vec = (width % 4 == 0 && ((uintptr_t)obs_out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)obs_out % 8 == 0)) ? 2 : 1;
+  const int groups = oa.width / vec;
+  if (groups > 256 || groups < 1) return fail("observation rows wider than 1024 columns are not supported%s");
+  const unsigned bx = (unsigned)groups, by = 256 / bx;
+  const dim3 block(bx, by);
+  const size_t per_env = 6u * (size_t)cfg->n_entities * sizeof(float);
+  int tile = 128;
+  while (tile > 4 && tile * per_env + 64 > 32 * 1024) tile /= 2;
+  if (tile * per_env + 64 > 48 * 1024) return fail("worlds with more than ~500 entities are not supported here%s");
+  const size_t smem = tile * per_env + 64;
+  const dim3 grid((unsigned)((cfg->batch_dim + tile - 1) / tile), (unsigned)(oa.rows + (has_prog ? 1 : 0)));
+  if (vec == 4) {
+    post_step_kernel<4><<<grid, block, smem, stream>>>(oa, tile, pa);
+  } else if (vec == 2) {
+    post_step_kernel<2><<<grid, block, smem, stream>>>(oa, tile, pa);
+  } else {
+    post_step_kernel<1><<<grid, block, smem, stream>>>(oa, tile, pa);
   }
   CUDA_OK(cudaGetLastError());
   return 1;

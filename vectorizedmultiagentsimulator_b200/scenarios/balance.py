@@ -9,6 +9,7 @@ overlap tests are single kernel launches.
 import torch
 
 from ..simulator import observe as O
+from ..simulator.program import StepProgram
 from ..simulator.core import Agent, Box, Landmark, Line, Sphere, World
 from ..simulator.scenario import BaseScenario
 from ..simulator.utils import Color, ScenarioUtils
@@ -21,7 +22,7 @@ class Scenario(BaseScenario):
     observations_are_independent = True
 
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
-        self._obs_plan = self._obs_all = self._rew_consts = self._package_on_goal = None
+        self._obs_plan = self._obs_all = self._rew_consts = self._package_on_goal = self._program = None
         self.n_agents = kwargs.pop("n_agents", 3)
         self.package_mass = kwargs.pop("package_mass", 5)
         self.random_package_pos_on_line = kwargs.pop("random_package_pos_on_line", True)
@@ -83,6 +84,8 @@ class Scenario(BaseScenario):
 
     def reset_world_at(self, env_index: int = None):
         world = self.world
+        # whatever reward() of the running step cached describes the state before this reset
+        self._obs_all, self._obs_from_program, self._done_from_program = None, False, None
         n = 1 if isinstance(env_index, int) else world.batch_dim  # None / bool mask: a row per env
         half = self.line_length / 2
         r_pkg = self.package.shape.radius
@@ -144,34 +147,42 @@ class Scenario(BaseScenario):
         self._package_on_goal = overlaps[2]  # consumed by the next done()
 
     # -- per-step callbacks --------------------------------------------------------------------
+    def _step_program(self):
+        """reward(), done() and info() of a step as ONE launch (fused with the observation gather): the
+        three overlap tests, the shaping term and the glue between them (ref scenarios/balance.py:216-263)."""
+        prog = self._program
+        if prog is None or prog.world is not self.world:
+            p = StepProgram(self.world)
+            on_line = p.overlap(self.line, self.floor)
+            on_floor = p.overlap(self.package, self.floor)
+            on_goal = p.overlap(self.package, self.package.goal)
+            on_ground = p.logical_or(on_line, on_floor)
+            pos_rew, dist = p.shaping(self.package, self.package.goal, self.shaping_factor, prev=lambda: self.global_shaping)
+            ground_rew = p.where(on_ground, p.const(float(self.fall_reward)), p.const(0.0))
+            # outputs (fp32 block: shared reward, pos_rew, ground_rew, package distance; bool block: flags)
+            p.out_rew = p.store(p.add(ground_rew, pos_rew))
+            p.out_pos_rew = p.store(pos_rew)
+            p.out_ground_rew = p.store(ground_rew)
+            p.out_dist = p.store(dist)
+            p.out_on_ground = p.store(on_ground)
+            p.out_done = p.store(p.logical_or(on_ground, on_goal))
+            prog = self._program = p.finalize()
+        return prog
+
     def reward(self, agent: Agent):
         if agent is self.world.agents[0]:
-            self.compute_on_the_ground()
-            # |package - goal|, the shaping difference and the carried shaping term: one launch
-            dist, rew = self.world.distance_shaping(
-                [(self.package, self.package.goal)], self.shaping_factor, self.global_shaping.unsqueeze(0)
-            )
-            self.package_dist, self.pos_rew = dist[0], rew[0]
-            fall, zero = self._reward_constants()
-            self.ground_rew = torch.where(self.on_the_ground, fall, zero)
-            self._shared_rew = self.ground_rew + self.pos_rew  # the same for every agent
+            prog = self._step_program()
+            # the observations of the step ride in the same launch; observation() hands them out
+            self._obs_all = prog.run(observe=self._observation_plan())
+            self._obs_from_program = True
+            self.on_the_ground = prog.out_on_ground.tensor
+            self._done_from_program = prog.out_done.tensor
+            self.package_dist, self.pos_rew = prog.out_dist.tensor, prog.out_pos_rew.tensor
+            self.ground_rew = prog.out_ground_rew.tensor
+            self._shared_rew = prog.out_rew.tensor  # the same for every agent
         return self._shared_rew
 
-    def _reward_constants(self):
-        """Device-resident scalars (created once: no fill kernels inside the step)."""
-        consts = getattr(self, "_rew_consts", None)
-        if consts is None or consts[0].device != self.world.slab.pos.device:
-            dev = self.world.slab.pos.device
-            consts = self._rew_consts = (
-                torch.tensor(float(self.fall_reward), dtype=torch.float32, device=dev),
-                torch.tensor(0.0, dtype=torch.float32, device=dev),
-            )
-        return consts
-
-    def _observe_all(self):
-        """Observations of every agent, ``[A, B, 16]``, assembled by one kernel over the state
-        slab (same fp32 arithmetic as a per-agent ``torch.cat`` of the nine terms).  Agent-major:
-        each agent's ``[B, 16]`` observation is a contiguous slice."""
+    def _observation_plan(self):
         plan = getattr(self, "_obs_plan", None)
         if plan is None:
             package, line = self.package, self.line
@@ -191,18 +202,29 @@ class Scenario(BaseScenario):
                     for a in self.world.agents
                 ]
             )
-        return self.world.observe(plan)
+        return plan
+
+    def _observe_all(self):
+        """Observations of every agent, ``[A, B, 16]``, assembled by one kernel over the state
+        slab (same fp32 arithmetic as a per-agent ``torch.cat`` of the nine terms).  Agent-major:
+        each agent's ``[B, 16]`` observation is a contiguous slice."""
+        return self.world.observe(self._observation_plan())
 
     def observation(self, agent: Agent):
         agents = self.world.agents
-        if agent is agents[0] or getattr(self, "_obs_all", None) is None:
+        fresh = getattr(self, "_obs_from_program", False)  # reward() of this step already produced the block
+        if (agent is agents[0] and not fresh) or getattr(self, "_obs_all", None) is None:
             self._obs_all = self._observe_all()
         row = self._obs_all[agents.index(agent)]
         if agent is agents[-1]:
             self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+            self._obs_from_program = False
         return row
 
     def done(self):
+        from_program, self._done_from_program = getattr(self, "_done_from_program", None), None
+        if from_program is not None:  # reward() of this step computed it
+            return from_program
         on_goal, self._package_on_goal = getattr(self, "_package_on_goal", None), None
         if on_goal is None:  # no reward() / reset since the last done(): test the current state
             on_goal = self.world.is_overlapping(self.package, self.package.goal)
