@@ -369,8 +369,10 @@ typedef struct VmasAgentActions {
 } VmasAgentActions;
 enum { VMAS_ACT_CONTINUOUS = 0, VMAS_ACT_DISCRETE = 1, VMAS_ACT_MULTIDISCRETE = 2 };
 
+/* `steps`: device fp32 [B] or NULL — the environment's per-env step counter (ref environment.py:396,
+ * `self.steps += 1`), incremented here so that it does not cost a launch of its own. */
 int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
-                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream);
+                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, float* steps, void* cuda_stream);
 
 /*
  * PID velocity controller (ref vmas/simulator/controllers/velocity_controller.py:113-125, process_force):

@@ -22,7 +22,7 @@ class _Capture:
             if name.isupper() or name == "AgentActionsC":
                 setattr(self, name, getattr(_native, name))
 
-    def ingest_actions(self, lib, dt, slab, chunk, n, clamp, bad_flag):
+    def ingest_actions(self, lib, dt, slab, chunk, n, clamp, bad_flag, steps=None):
         self.calls.append([{f[0]: (list(getattr(chunk[i], f[0])) if hasattr(getattr(chunk[i], f[0]), "__len__") else getattr(chunk[i], f[0])) for f in _native.AgentActionsC._fields_} for i in range(n)])
         return 1
 

@@ -21,18 +21,17 @@ def _build(env, carried, flag, level):
     rew, dist = p.shaping(sc.package, sc.package.goal, 3.5, prev=carried)
     f, lvl = p.load(flag, is_bool=True), p.load(level)
     k = p.const(0.25)
-    outs = dict(
+    outs = dict(  # (16 buffers per program: 3 inputs + 13 outputs here)
         o1=p.store(o1), o2=p.store(o2), d1=p.store(d1), d2=p.store(d2), c1=p.store(c1), rew=p.store(rew), dist=p.store(dist),
         add=p.store(p.add(d1, k)), sub=p.store(p.sub(c1, lvl)), mul=p.store(p.mul(d2, lvl)), mn=p.store(p.minimum(d1, d2)),
-        mx=p.store(p.maximum(d1, d2)), neg=p.store(p.neg(c1)),
         lor=p.store(p.logical_or(o1, f)), land=p.store(p.logical_and(p.logical_not(o2), f)),
     )
-    # a second program for the remaining opcodes (16 buffers per program)
+    # a second program for the remaining opcodes
     q = StepProgram(w)
     e1, e2 = q.distance(a0, sc.line), q.center_distance(a0, a1)
     lvl2 = q.load(level)
     outs2 = dict(
-        lt=q.store(q.lt(e1, lvl2)), le=q.store(q.le(e2, e2)),
+        mx=q.store(q.maximum(e1, e2)), neg=q.store(q.neg(e2)), lt=q.store(q.lt(e1, lvl2)), le=q.store(q.le(e2, e2)),
         where=q.store(q.where(q.lt(e1, e2), e1, q.const(-1.0))), where_b=q.store(q.where(q.le(lvl2, e2), q.lt(e1, e2), q.le(e1, e2))),
     )
     return (p.finalize(), outs), (q.finalize(), outs2)

@@ -308,7 +308,7 @@ def load():
         p_cfg, p_tb, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
     ]
     lib.vmas_b200_ingest_actions.argtypes = [
-        p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+        p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p
     ]
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
@@ -602,12 +602,14 @@ def broad_phase(lib, dt: DeviceTables, slab) -> int:
     return _check(lib, rc)
 
 
-def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, bad_flag) -> int:
-    """``agents_c``: a ctypes array of AgentActionsC whose pointers are already filled in."""
+def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, bad_flag, steps=None) -> int:
+    """``agents_c``: a ctypes array of AgentActionsC whose pointers are already filled in; ``steps``: the
+    environment's fp32 ``[B]`` step counter to increment in the same launch, or None."""
     st = dt.state_struct(slab)
     rc = lib.vmas_b200_ingest_actions(
         C.byref(dt.cfg), C.byref(st), agents_c, n, int(clamp),
-        None if bad_flag is None else bad_flag.data_ptr(), _stream(dt.device),
+        None if bad_flag is None else bad_flag.data_ptr(), None if steps is None else steps.data_ptr(),
+        _stream(dt.device),
     )
     return _check(lib, rc)
 

@@ -421,7 +421,7 @@ class CudaBackend(PlanRuntime):
         return out
 
     # -- action ingestion ----------------------------------------------------------------------
-    def ingest_actions(self, actions, specs, clamp: bool, bad_flag, action_kind=None) -> None:
+    def ingest_actions(self, actions, specs, clamp: bool, bad_flag, action_kind=None, steps=None) -> None:
         """One launch: validate + scale the policy actions and write ``agent.action.u`` and the
         force / torque rows of the slab.  ``specs``: [(agent, dynamics code, u buffer)]."""
         self.refresh()
@@ -469,7 +469,10 @@ class CudaBackend(PlanRuntime):
             chunk = (self._native.AgentActionsC * (hi - lo)).from_address(
                 C.addressof(arr) + lo * C.sizeof(self._native.AgentActionsC)
             )
-            self._native.ingest_actions(self.lib, self._dev_tables, self.world.slab, chunk, hi - lo, clamp, bad_flag)
+            self._native.ingest_actions(
+                self.lib, self._dev_tables, self.world.slab, chunk, hi - lo, clamp, bad_flag,
+                steps=steps if lo == 0 else None,  # the step counter rides in the first launch
+            )
             self.launches += 1
 
     # -- episode reset (device side) ------------------------------------------------

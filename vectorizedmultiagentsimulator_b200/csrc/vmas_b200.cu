@@ -1440,6 +1440,10 @@ DEVI void post_step_program_body(const ProgArgs& p, const int tile_envs) {
   for (long env = (long)blockIdx.x * tile_envs + tid; env < env_end; env += n_threads) {
     const size_t env_base = (size_t)env * p.base.cfg.n_entities;
     const float2* row = reinterpret_cast<const float2*>(p.base.st.pos) + env_base;
+    // request the env's pos / rot rows up front: the queries below then hit L1 instead of paying one
+    // cold-miss latency each, one after the other
+    for (int j = 0; j < 2 * p.base.cfg.n_entities; j += 8) prefetch_l1(p.base.st.pos + 2 * env_base + j);
+    for (int j = 0; j < p.base.cfg.n_entities; j += 8) prefetch_l1(p.base.st.rot + env_base + j);
     float r[VMAS_PROG_REGS];
 #pragma unroll
     for (int i = 0; i < VMAS_PROG_REGS; ++i) r[i] = 0.f;
@@ -1491,12 +1495,15 @@ DEVI void post_step_program_body(const ProgArgs& p, const int tile_envs) {
   }
 }
 
+// blockIdx.y == 0 (when there is a program): the program blocks — scheduled first, because a program thread
+// is a chain of dependent queries (latency) that the bandwidth-bound gather blocks behind it can hide
 template <int VEC>
 __global__ void __launch_bounds__(256) post_step_kernel(const ObsArgs obs, const int tile_envs, const ProgArgs prog) {
-  if ((int)blockIdx.y < obs.rows)
-    gather_observations_body<VEC>(obs, tile_envs, blockIdx.y);
-  else
+  const int first_obs = prog.prog.n_instr > 0 ? 1 : 0;
+  if ((int)blockIdx.y < first_obs)
     post_step_program_body(prog, tile_envs);
+  else
+    gather_observations_body<VEC>(obs, tile_envs, (int)blockIdx.y - first_obs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1506,6 +1513,7 @@ struct IngestArgs {
   VmasAgentActions ag[VMAS_MAX_INGEST_AGENTS];
   VmasState st;
   uint8_t* bad_flag;
+  float* steps;        // [B] step counter of the environment, or null
   int n_entities;      // E: row stride of pos / vel / rot / ang_vel
   int n_agents_total;  // A: row stride of force / torque
   int n;               // agents in this launch
@@ -1625,6 +1633,7 @@ __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a)
     }
   }
   if (bad && a.bad_flag) *a.bad_flag = 1;
+  if (a.steps && k == 0) a.steps[env] = a.steps[env] + 1.f;
   const int dyn = ag.dynamics;
   const size_t row = (size_t)env * a.n_agents_total + ag.agent_index;
   const size_t ent = (size_t)env * a.n_entities + ag.entity_index;
@@ -2115,7 +2124,7 @@ int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, 
 }
 
 int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
-                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, void* cuda_stream) {
+                             int32_t n_agents, int32_t clamp, uint8_t* bad_flag, float* steps, void* cuda_stream) {
   if (!cfg || !st || !agents) return fail("null argument%s");
   if (n_agents <= 0 || n_agents > VMAS_MAX_INGEST_AGENTS) return fail("1..16 agents per ingest call%s");
   IngestArgs a;
@@ -2138,6 +2147,7 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
   }
   a.st = *st;
   a.bad_flag = bad_flag;
+  a.steps = steps;
   a.n_entities = cfg->n_entities;
   a.n_agents_total = cfg->n_agents;
   a.n = n_agents;

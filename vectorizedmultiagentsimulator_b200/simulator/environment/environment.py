@@ -507,9 +507,12 @@ class Environment(TorchVectorizedObject):
                 N.ACT_CONTINUOUS if self.continuous_actions
                 else (N.ACT_MULTIDISCRETE if self.multidiscrete_actions else N.ACT_DISCRETE)
             )
+            # the per-env step counter is incremented by the same launch (_finish_step then skips its add)
+            counter = self.steps if (self.steps.dtype == torch.float32 and self.steps.is_contiguous() and live) else None
             self.world._get_backend().ingest_actions(
-                [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind
+                [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind, steps=counter
             )
+            self._steps_counted = counter is not None
             for agent, _, u in specs:
                 if agent.action._u is not u:  # the u buffers are static: bind them once
                     agent.action.u = u
@@ -529,7 +532,10 @@ class Environment(TorchVectorizedObject):
         self.scenario.pre_step()
         self.world.step()
         self.scenario.post_step()
-        self.steps += 1
+        if fused_ingest and getattr(self, "_steps_counted", False):
+            self._steps_counted = False  # the ingest kernel already counted this step
+        else:
+            self.steps += 1
         if not self.auto_reset:
             return self._get_from_scenario(
                 get_observations=True, get_infos=True, get_rewards=True, get_dones=True, clone=clone_outputs
