@@ -108,7 +108,7 @@ typedef struct VmasCopySegment {
   void* dst;
   size_t bytes;
 } VmasCopySegment;
-#define VMAS_MAX_COPY_SEGMENTS 8
+#define VMAS_MAX_COPY_SEGMENTS 32
 
 int vmas_b200_abi_version(void);
 const char* vmas_b200_last_error(void);

@@ -671,7 +671,7 @@ class CopySegmentC(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_size_t)]
 
 
-MAX_COPY_SEGMENTS = 8
+MAX_COPY_SEGMENTS = 32
 
 
 def copy_buffers(lib, device, pairs) -> int:
@@ -685,6 +685,33 @@ def copy_buffers(lib, device, pairs) -> int:
             seg.src, seg.dst, seg.bytes = src.data_ptr(), dst.data_ptr(), src.numel() * src.element_size()
         n += _check(lib, lib.vmas_b200_copy_buffers(segs, len(chunk), _stream(device)))
     return n
+
+
+class CopyPlan:
+    """A fixed list of copies whose SOURCES never move (the buffers a captured step writes) into
+    destination blocks that are allocated anew every step: sources, sizes and destination offsets are
+    marshalled once, a run only adds the fresh base addresses."""
+
+    def __init__(self, items):
+        """``items``: [(source tensor (contiguous), destination block index, byte offset in that block)]."""
+        assert len(items) <= MAX_COPY_SEGMENTS, f"at most {MAX_COPY_SEGMENTS} copies per plan"
+        self.segs = (CopySegmentC * max(len(items), 1))()
+        self.where = []
+        self.keep = [src for src, _, _ in items]  # the sources stay alive as long as the plan
+        for seg, (src, block, offset) in zip(self.segs, items):
+            assert src.is_contiguous()
+            seg.src, seg.bytes = src.data_ptr(), src.numel() * src.element_size()
+            self.where.append((block, offset))
+        self.n = len(items)
+
+    def run(self, lib, device, bases) -> int:
+        """``bases[i]``: address of destination block ``i``.  One launch."""
+        if self.n == 0:
+            return 0
+        segs = self.segs
+        for k, (block, offset) in enumerate(self.where):
+            segs[k].dst = bases[block] + offset
+        return _check(lib, lib.vmas_b200_copy_buffers(segs, self.n, _stream(device)))
 
 
 def distance_shaping(lib, dt: DeviceTables, slab, pairs, factor: float, prev, dist, rew) -> int:

@@ -1904,21 +1904,25 @@ struct CopyArgs {
   VmasCopySegment seg[VMAS_MAX_COPY_SEGMENTS];
 };
 
-// blockIdx.y = segment; grid-stride copy in 16-byte words when both ends are 16-byte aligned
-__global__ void __launch_bounds__(256) copy_buffers_kernel(const CopyArgs a) {
-  const VmasCopySegment s = a.seg[blockIdx.y];
+// every block walks all segments (grid-stride inside each): no idle blocks when the segments differ in
+// size by orders of magnitude (an 8 MB observation block next to 128 KB reward rows); 16-byte words when
+// both ends are 16-byte aligned
+__global__ void __launch_bounds__(256) copy_buffers_kernel(const CopyArgs a, const int n_segs) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  const char* src = static_cast<const char*>(s.src);
-  char* dst = static_cast<char*>(s.dst);
-  size_t done = 0;
-  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
-    const size_t words = s.bytes / 16;
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (size_t i = tid; i < words; i += stride) d4[i] = s4[i];
-    done = words * 16;
+  for (int k = 0; k < n_segs; ++k) {
+    const VmasCopySegment s = a.seg[k];
+    const char* src = static_cast<const char*>(s.src);
+    char* dst = static_cast<char*>(s.dst);
+    size_t done = 0;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+      const size_t words = s.bytes / 16;
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (size_t i = tid; i < words; i += stride) d4[i] = s4[i];
+      done = words * 16;
+    }
+    for (size_t i = done + tid; i < s.bytes; i += stride) dst[i] = src[i];
   }
-  for (size_t i = done + tid; i < s.bytes; i += stride) dst[i] = src[i];
 }
 
 static int launch_broad_phase(const StepArgs& args, cudaStream_t stream) {
@@ -2418,17 +2422,17 @@ int vmas_b200_set_l2_fetch_granularity(int32_t bytes) {
 int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cuda_stream) {
   if (!segs || n_segs <= 0 || n_segs > VMAS_MAX_COPY_SEGMENTS) return fail("1..VMAS_MAX_COPY_SEGMENTS segments expected%s");
   CopyArgs a;
-  size_t largest = 0;
+  size_t total = 0;
   for (int i = 0; i < n_segs; ++i) {
     if (!segs[i].src || !segs[i].dst) return fail("null copy segment%s");
     a.seg[i] = segs[i];
-    largest = segs[i].bytes > largest ? segs[i].bytes : largest;
+    total += segs[i].bytes;
   }
-  if (largest == 0) return 1;
+  if (total == 0) return 1;
   const int threads = 256;
-  size_t blocks = (largest / 16 + (size_t)threads * 4 - 1) / ((size_t)threads * 4);  // 4 x 16 B per thread
+  size_t blocks = (total / 16 + (size_t)threads * 4 - 1) / ((size_t)threads * 4);  // ~4 x 16 B per thread
   blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-  copy_buffers_kernel<<<dim3((unsigned)blocks, (unsigned)n_segs), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  copy_buffers_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a, n_segs);
   CUDA_OK(cudaGetLastError());
   return 1;
 }

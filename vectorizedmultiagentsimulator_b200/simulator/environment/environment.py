@@ -602,7 +602,8 @@ class Environment(TorchVectorizedObject):
     PACK_ALONE_BYTES = 1 << 20
 
     def _pack_graph_outputs(self, outputs):
-        """(inside the capture) concatenates every output leaf into one flat buffer per dtype."""
+        """(inside the capture) lays the output leaves out as a few flat blocks — one per big contiguous
+        run, one per dtype for the small leaves — and prepares the copy that hands them out."""
         leaves = []
 
         def index(x):
@@ -644,11 +645,26 @@ class Environment(TorchVectorizedObject):
                 packs.append((head.as_strided((numel,), (1,)), ids))
             else:
                 small.setdefault(head.dtype, []).extend(ids)
+        # The small leaves of a dtype form one output block too, but nothing gathers them inside the graph:
+        # the hand-out copy reads every leaf where the scenario wrote it (sources[i] = the pieces of block
+        # i, in order).  A non-contiguous leaf is made contiguous by a copy node (rare: scenarios return
+        # fresh or [B]-row tensors).
+        sources = [[pack] for pack, _ in packs]
         for dtype, ids in small.items():
-            if len(ids) == 1 and leaves[ids[0]].is_contiguous():
-                packs.append((leaves[ids[0]].reshape(-1), ids))  # nothing to gather: no copy node
-            else:
-                packs.append((torch.cat([leaves[i].reshape(-1) for i in ids]), ids))
+            pieces = [leaves[i] if leaves[i].is_contiguous() else leaves[i].contiguous() for i in ids]
+            total = sum(t.numel() for t in pieces)
+            packs.append((None, ids))
+            sources.append([t.reshape(-1) for t in pieces])
+        self._graph_out_blocks = [(sum(t.numel() for t in pieces), pieces[0].dtype) for pieces in sources]
+        items, copies_per_block = [], []
+        for block, pieces in enumerate(sources):
+            offset = 0
+            for t in pieces:
+                if t.numel():
+                    items.append((t, block, offset))
+                offset += t.numel() * t.element_size()
+        N = self.world._get_backend()._native
+        self._graph_out_copy = [N.CopyPlan(items[lo : lo + N.MAX_COPY_SEGMENTS]) for lo in range(0, len(items), N.MAX_COPY_SEGMENTS)]
         self._graph_out_spec = spec
         self._graph_out_shapes = [tuple(t.shape) for t in leaves]
         self._graph_out_packs = packs
@@ -669,11 +685,14 @@ class Environment(TorchVectorizedObject):
         """Fresh output tensors: one clone per pack, then views (no further kernel launches)."""
         fresh = [None] * len(self._graph_out_shapes)
         packs = self._graph_out_packs
-        copies = [torch.empty_like(pack) for pack, _ in packs]
-        # one kernel for every pack (an SM copy: a cudaMemcpy D2D would queue on a copy engine behind
-        # a concurrent download of the previous step's results)
+        copies = [torch.empty(n, dtype=dtype, device=self.device) for n, dtype in self._graph_out_blocks]
+        # one kernel for every output block (an SM copy: a cudaMemcpy D2D would queue on a copy engine
+        # behind a concurrent download of the previous step's results); sources and sizes were marshalled
+        # at capture time, only the fresh destinations are filled in
         backend = self.world._get_backend()
-        backend.launches += backend._native.copy_buffers(backend.lib, backend.device, [(p, c) for (p, _), c in zip(packs, copies)])
+        bases = [c.data_ptr() for c in copies]
+        for plan in self._graph_out_copy:
+            backend.launches += plan.run(backend.lib, backend.device, bases)
         # leaves of equal shape that sit next to each other come out of ONE view + unbind
         for flat, (_, ids), layout in zip(copies, packs, self._graph_out_layouts):
             pieces = [flat] if len(layout) == 1 else flat.split_with_sizes([n * numel for n, _, numel in layout])
