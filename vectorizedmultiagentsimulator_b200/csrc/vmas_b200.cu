@@ -1498,7 +1498,7 @@ DEVI void post_step_program_body(const ProgArgs& p, const int tile_envs) {
 // blockIdx.y == 0 (when there is a program): the program blocks — scheduled first, because a program thread
 // is a chain of dependent queries (latency) that the bandwidth-bound gather blocks behind it can hide
 template <int VEC>
-__global__ void __launch_bounds__(256) post_step_kernel(const ObsArgs obs, const int tile_envs, const ProgArgs prog) {
+__global__ void __launch_bounds__(256, 5) post_step_kernel(const ObsArgs obs, const int tile_envs, const ProgArgs prog) {
   const int first_obs = prog.prog.n_instr > 0 ? 1 : 0;
   if ((int)blockIdx.y < first_obs)
     post_step_program_body(prog, tile_envs);

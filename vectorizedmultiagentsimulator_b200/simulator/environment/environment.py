@@ -484,7 +484,7 @@ class Environment(TorchVectorizedObject):
             for a, s in zip(actions, specs)
         )
 
-    def _apply_actions(self, actions: List[Tensor], fused: Optional[bool] = None) -> bool:
+    def _apply_actions(self, actions: List[Tensor], fused: Optional[bool] = None, count_step: bool = True) -> bool:
         """Decodes the policy agents' actions into ``agent.action.u`` and slab forces.  Returns
         True if the fused kernel did it (scripted agents are then still to be processed).
         ``fused``: the caller's answer to ``_fused_ingest_applies(actions)``, if it already asked."""
@@ -508,11 +508,12 @@ class Environment(TorchVectorizedObject):
                 else (N.ACT_MULTIDISCRETE if self.multidiscrete_actions else N.ACT_DISCRETE)
             )
             # the per-env step counter is incremented by the same launch (_finish_step then skips its add)
-            counter = self.steps if (self.steps.dtype == torch.float32 and self.steps.is_contiguous() and live) else None
+            counts = self.steps.dtype == torch.float32 and self.steps.is_contiguous() and bool(live)
+            counter = self.steps if (counts and count_step) else None
             self.world._get_backend().ingest_actions(
                 [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind, steps=counter
             )
-            self._steps_counted = counter is not None
+            self._steps_counted = counts  # (count_step=False: the caller's replay will count this step)
             for agent, _, u in specs:
                 if agent.action._u is not u:  # the u buffers are static: bind them once
                     agent.action.u = u
@@ -728,7 +729,8 @@ class Environment(TorchVectorizedObject):
         graph = torch.cuda.CUDAGraph()
         try:
             if ingest_outside:
-                self._apply_actions([a.to(self._ingest_dtype()).contiguous() for a in dev_actions])
+                # (binds the action buffers; the replay that follows the capture ingests — and counts — again)
+                self._apply_actions([a.to(self._ingest_dtype()).contiguous() for a in dev_actions], count_step=False)
             before = backend.launches
             with torch.cuda.graph(graph):
                 # outputs stay un-cloned inside the graph; they are packed into flat buffers
