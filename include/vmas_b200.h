@@ -386,6 +386,13 @@ int vmas_b200_velocity_controller(const VmasWorldConfig* cfg, const VmasState* s
                                   float* accum, float* prev, float gain, float inv_ti, float td, float dt,
                                   float windup, float mass, void* cuda_stream);
 
+/* The same plus the broad phase of the step's FIRST substep (vmas_b200_broad_phase into `mask`) in one
+ * launch; the following vmas_b200_world_step must then be told so (`exact_broad_phase` = 2).  Only valid
+ * when nothing moves an entity between the two calls. */
+int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                         const VmasAgentActions* agents, int32_t n_agents, int32_t clamp,
+                                         uint8_t* bad_flag, float* steps, uint32_t* mask, void* cuda_stream);
+
 /* The broad-phase pass alone: ORs bit i of `mask` if masked item i is within range in any env. */
 int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                           uint32_t* mask, void* cuda_stream);

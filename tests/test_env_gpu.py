@@ -271,6 +271,29 @@ def test_discrete_actions_decoded_on_the_device(name, kwargs, multidiscrete):
         gpu.check_actions_now()
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_broad_phase_in_the_ingest_launch_changes_no_bit(graph):
+    """The action ingest also builds the coming step's first broad-phase mask (one launch instead of two)
+    when nothing can move an entity in between; a scenario that overrides ``pre_step`` keeps the separate
+    launch.  Same roll-out either way, bit for bit (balance: line / box pairs obey the mask)."""
+    n_envs = 640
+    fused = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, n_agents=4, cuda_graph=graph)
+    plain = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, n_agents=4, cuda_graph=graph)
+    plain.scenario.__class__ = type("WithPreStep", (plain.scenario.__class__,), {"pre_step": lambda self: None})
+    sync_env(fused, plain)
+    gen = torch.Generator().manual_seed(17)
+    counts = []
+    for t in range(8):
+        actions = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1).cuda() for _ in fused.agents]
+        before = [e.world._get_backend().launches for e in (fused, plain)]
+        got = fused.step([a.clone() for a in actions])
+        want = plain.step([a.clone() for a in actions])
+        counts.append([e.world._get_backend().launches - b for e, b in zip((fused, plain), before)])
+        for g, w in zip(flatten(got[:3]), flatten(want[:3])):
+            assert torch.equal(g, w), f"step {t}"
+    assert all(c[1] == c[0] + 1 for c in counts[-3:]), counts  # the separate broad-phase launch
+
+
 def test_reset_at_and_state_views_on_gpu():
     env = b200.make_env("transport", num_envs=8, device="cuda", seed=0, n_agents=3)
     agent = env.world.agents[0]

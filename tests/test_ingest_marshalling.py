@@ -22,7 +22,7 @@ class _Capture:
             if name.isupper() or name == "AgentActionsC":
                 setattr(self, name, getattr(_native, name))
 
-    def ingest_actions(self, lib, dt, slab, chunk, n, clamp, bad_flag, steps=None):
+    def ingest_actions(self, lib, dt, slab, chunk, n, clamp, bad_flag, steps=None, broad_phase=False):
         self.calls.append([{f[0]: (list(getattr(chunk[i], f[0])) if hasattr(getattr(chunk[i], f[0]), "__len__") else getattr(chunk[i], f[0])) for f in _native.AgentActionsC._fields_} for i in range(n)])
         return 1
 
@@ -33,7 +33,7 @@ def _fake_backend(env):
     cap = _Capture()
     fake = types.SimpleNamespace(
         world=world, _native=cap, lib=None, _dev_tables=None, launches=0, refresh=lambda: None,
-        index_of=lambda agent: index[id(agent)],
+        index_of=lambda agent: index[id(agent)], tables=types.SimpleNamespace(n_masked=0),
     )
     return fake, cap
 

@@ -245,6 +245,7 @@ EXPORTS = [
     "vmas_b200_point_query",
     "vmas_b200_broad_phase",
     "vmas_b200_ingest_actions",
+    "vmas_b200_ingest_actions_broad_phase",
     "vmas_b200_velocity_controller",
     "vmas_b200_cast_rays_batched",
     "vmas_b200_pair_query_batched",
@@ -309,6 +310,9 @@ def load():
     ]
     lib.vmas_b200_ingest_actions.argtypes = [
         p_cfg, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p
+    ]
+    lib.vmas_b200_ingest_actions_broad_phase.argtypes = [
+        p_cfg, p_tb, p_st, C.POINTER(AgentActionsC), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     ]
     lib.vmas_b200_reset_state.argtypes = [p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vmas_b200_spawn_entities.argtypes = [p_cfg, p_st, C.POINTER(SpawnC), C.c_void_p]
@@ -602,10 +606,19 @@ def broad_phase(lib, dt: DeviceTables, slab) -> int:
     return _check(lib, rc)
 
 
-def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, bad_flag, steps=None) -> int:
+def ingest_actions(lib, dt: DeviceTables, slab, agents_c, n: int, clamp: bool, bad_flag, steps=None, broad_phase=False) -> int:
     """``agents_c``: a ctypes array of AgentActionsC whose pointers are already filled in; ``steps``: the
-    environment's fp32 ``[B]`` step counter to increment in the same launch, or None."""
+    environment's fp32 ``[B]`` step counter to increment in the same launch, or None; ``broad_phase``: also
+    build the broad-phase mask of the coming step's first substep (the next ``world_step`` is then called
+    with ``exact_broad_phase=2``)."""
     st = dt.state_struct(slab)
+    if broad_phase:
+        rc = lib.vmas_b200_ingest_actions_broad_phase(
+            C.byref(dt.cfg), C.byref(dt.tb), C.byref(st), agents_c, n, int(clamp),
+            None if bad_flag is None else bad_flag.data_ptr(), None if steps is None else steps.data_ptr(),
+            dt.mask.data_ptr(), _stream(dt.device),
+        )
+        return _check(lib, rc)
     rc = lib.vmas_b200_ingest_actions(
         C.byref(dt.cfg), C.byref(st), agents_c, n, int(clamp),
         None if bad_flag is None else bad_flag.data_ptr(), None if steps is None else steps.data_ptr(),

@@ -198,9 +198,10 @@ class CudaBackend(PlanRuntime):
         if self.kernel_events is not None:
             events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self.kernel_events.append(events)
-        self.launches += self._native.world_step(
-            self.lib, self._dev_tables, slab, exact_broad_phase=self.world.exact_broad_phase, events=events
-        )
+        # 2: the fused ingest launch of this step already built the first substep's broad-phase mask
+        mode = 2 if (getattr(self, "_mask_ready", False) and self.world.exact_broad_phase) else self.world.exact_broad_phase
+        self._mask_ready = False
+        self.launches += self._native.world_step(self.lib, self._dev_tables, slab, exact_broad_phase=mode, events=events)
         if not torch.cuda.is_current_stream_capturing():
             self.after_step()  # (a graph replay calls it itself: Environment._step_graphed)
 
@@ -421,10 +422,13 @@ class CudaBackend(PlanRuntime):
         return out
 
     # -- action ingestion ----------------------------------------------------------------------
-    def ingest_actions(self, actions, specs, clamp: bool, bad_flag, action_kind=None, steps=None) -> None:
+    def ingest_actions(self, actions, specs, clamp: bool, bad_flag, action_kind=None, steps=None, broad_phase=False) -> None:
         """One launch: validate + scale the policy actions and write ``agent.action.u`` and the
-        force / torque rows of the slab.  ``specs``: [(agent, dynamics code, u buffer)]."""
+        force / torque rows of the slab.  ``specs``: [(agent, dynamics code, u buffer)].
+        ``broad_phase``: the caller guarantees that nothing moves an entity before the coming
+        ``world.step()``; the launch then also builds that step's first broad-phase mask."""
         self.refresh()
+        broad_phase = bool(broad_phase and self.tables.n_masked > 0 and self.world.exact_broad_phase)
         n = len(specs)
         arr = getattr(self, "_ingest_arr", None)
         if arr is None or len(arr) != n or getattr(self, "_ingest_kind", None) != action_kind:
@@ -471,9 +475,11 @@ class CudaBackend(PlanRuntime):
             )
             self._native.ingest_actions(
                 self.lib, self._dev_tables, self.world.slab, chunk, hi - lo, clamp, bad_flag,
-                steps=steps if lo == 0 else None,  # the step counter rides in the first launch
+                steps=steps if lo == 0 else None,  # the step counter and the broad phase ride in the first launch
+                broad_phase=broad_phase and lo == 0,
             )
             self.launches += 1
+        self._mask_ready = broad_phase
 
     # -- episode reset (device side) ------------------------------------------------
     @staticmethod

@@ -760,13 +760,14 @@ DEVI void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :
 // of dependent loads per thread is short and there are B * BROAD_SLICES / 32 warps to hide it.
 constexpr int BROAD_SLICES = 8;
 
-__global__ void __launch_bounds__(32 * BROAD_SLICES) broad_phase_kernel(const StepArgs a) {
+// block (32, BROAD_SLICES); `block` = which 32-env tile this block handles
+DEVI void broad_phase_body(const StepArgs& a, const long block) {
   extern __shared__ uint32_t s_bits[];
   const int W = a.mask_words;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   for (int w = tid; w < W; w += 32 * BROAD_SLICES) s_bits[w] = 0u;
   __syncthreads();
-  const long env = (long)blockIdx.x * 32 + threadIdx.x;
+  const long env = block * 32 + threadIdx.x;
   const bool live = env < a.cfg.batch_dim;
   const int E = a.cfg.n_entities;
   const float2* pos = reinterpret_cast<const float2*>(a.st.pos) + (size_t)(live ? env : 0) * E;
@@ -786,6 +787,10 @@ __global__ void __launch_bounds__(32 * BROAD_SLICES) broad_phase_kernel(const St
     const uint32_t b = s_bits[w];
     if (b) atomicOr(&a.mask[w], b);
   }
+}
+
+__global__ void __launch_bounds__(32 * BROAD_SLICES) broad_phase_kernel(const StepArgs a) {
+  broad_phase_body(a, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1583,8 +1588,7 @@ DEVI Drone12 drone_f(const Drone12& s, float thrust, float tx, float ty, float t
   return d;
 }
 
-__global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+DEVI void ingest_actions_body(const IngestArgs& a, const long idx) {
   if (idx >= (long)a.batch_dim * a.n) return;
   const long env = idx / a.n;
   const int k = (int)(idx % a.n);
@@ -1720,6 +1724,21 @@ __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a)
     if (j < sz) ag.u[env * sz + j] = u[j];
   if (write_force) reinterpret_cast<float2*>(a.st.force)[row] = force;
   if (write_torque) a.st.torque[row] = torque;
+}
+
+__global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a) {
+  ingest_actions_body(a, (long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Action ingest and the first substep's broad phase in ONE launch (blocks [0, n_ingest) ingest, the rest
+// test the masked pairs): both only read what the previous step left, neither depends on the other, and
+// each is too small to fill the GPU on its own.  Block = (32, BROAD_SLICES) = 256 threads.
+static_assert(32 * BROAD_SLICES == 256, "the fused launch assumes 256-thread blocks");
+__global__ void __launch_bounds__(256) ingest_broad_kernel(const IngestArgs ia, const StepArgs sa, const int n_ingest) {
+  if ((int)blockIdx.x < n_ingest)
+    ingest_actions_body(ia, (long)blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x);
+  else
+    broad_phase_body(sa, (long)blockIdx.x - n_ingest);
 }
 
 // PID velocity controller (ref controllers/velocity_controller.py:88-125): one thread per (env, axis)
@@ -2008,9 +2027,12 @@ static int substeps_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, c
   for (int s = first_substep; s < first_substep + n_substeps; ++s) {
     args.first_substep = s;
     args.n_substeps = 1;
-    int r = launch_broad_phase(args, stream);
-    if (r < 0) return r;
-    launches += r;
+    int r = 0;
+    if (!(exact_broad_phase == 2 && s == first_substep)) {  // 2: the caller's fused ingest launch built this mask
+      r = launch_broad_phase(args, stream);
+      if (r < 0) return r;
+      launches += r;
+    }
     if (ev_begin && s == first_substep) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), stream));
     r = dispatch_step(args, stream);
     if (r < 0) return r;
@@ -2127,8 +2149,25 @@ int vmas_b200_point_query(const VmasWorldConfig* cfg, const VmasPlanTables* tb, 
   return 1;
 }
 
+static int ingest_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                       const VmasAgentActions* agents, int32_t n_agents, int32_t clamp, uint8_t* bad_flag, float* steps,
+                       uint32_t* mask, void* cuda_stream);
+
 int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, const VmasAgentActions* agents,
                              int32_t n_agents, int32_t clamp, uint8_t* bad_flag, float* steps, void* cuda_stream) {
+  return ingest_impl(cfg, nullptr, st, agents, n_agents, clamp, bad_flag, steps, nullptr, cuda_stream);
+}
+
+int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                                         const VmasAgentActions* agents, int32_t n_agents, int32_t clamp,
+                                         uint8_t* bad_flag, float* steps, uint32_t* mask, void* cuda_stream) {
+  if (!tb || !mask) return fail("null argument%s");
+  return ingest_impl(cfg, tb, st, agents, n_agents, clamp, bad_flag, steps, mask, cuda_stream);
+}
+
+static int ingest_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
+                       const VmasAgentActions* agents, int32_t n_agents, int32_t clamp, uint8_t* bad_flag, float* steps,
+                       uint32_t* mask, void* cuda_stream) {
   if (!cfg || !st || !agents) return fail("null argument%s");
   if (n_agents <= 0 || n_agents > VMAS_MAX_INGEST_AGENTS) return fail("1..16 agents per ingest call%s");
   IngestArgs a;
@@ -2159,8 +2198,24 @@ int vmas_b200_ingest_actions(const VmasWorldConfig* cfg, const VmasState* st, co
   a.clamp = clamp;
   const int threads = 256;
   const long total = (long)cfg->batch_dim * n_agents;
-  ingest_actions_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
-                          static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  const unsigned n_ingest = (unsigned)((total + threads - 1) / threads);
+  if (mask && cfg->n_masked > 0) {
+    if (!tb->masked_items || !tb->item_i32 || !tb->item_f32 || !st->pos) return fail("null broad-phase tables%s");
+    StepArgs sa;
+    sa.cfg = *cfg;
+    sa.tb = *tb;
+    sa.st = *st;
+    sa.mask = mask;
+    sa.mask_words = (cfg->n_masked + 31) / 32;
+    sa.use_mask = 1;
+    sa.first_substep = 0;
+    sa.n_substeps = 1;
+    const unsigned n_broad = (unsigned)(((long)cfg->batch_dim + 31) / 32);
+    ingest_broad_kernel<<<n_ingest + n_broad, dim3(32, BROAD_SLICES), sa.mask_words * sizeof(uint32_t),
+                          static_cast<cudaStream_t>(cuda_stream)>>>(a, sa, (int)n_ingest);
+  } else {
+    ingest_actions_kernel<<<n_ingest, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   return 1;
 }

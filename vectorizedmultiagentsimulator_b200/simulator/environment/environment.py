@@ -510,8 +510,13 @@ class Environment(TorchVectorizedObject):
             # the per-env step counter is incremented by the same launch (_finish_step then skips its add)
             counts = self.steps.dtype == torch.float32 and self.steps.is_contiguous() and bool(live)
             counter = self.steps if (counts and count_step) else None
+            # ... and so does the broad phase of the coming step, if nothing can move an entity in between
+            static_until_step = (
+                type(self.scenario).pre_step is BaseScenario.pre_step and not self.world.scripted_agents and bool(live)
+            )
             self.world._get_backend().ingest_actions(
-                [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind, steps=counter
+                [a for a, _ in live], [s for _, s in live], self.clamp_action, flag, action_kind=kind, steps=counter,
+                broad_phase=static_until_step,
             )
             self._steps_counted = counts  # (count_step=False: the caller's replay will count this step)
             for agent, _, u in specs:
@@ -595,6 +600,7 @@ class Environment(TorchVectorizedObject):
         self.graph_replays += 1
         backend = world._get_backend()
         backend.launches += self._graph_launches
+        backend._mask_ready = False  # (consumed by the substep kernel inside the replay)
         backend.after_step()  # periodic env re-ordering: eager launches between replays
         return self._unpack_graph_outputs()
 
