@@ -1588,6 +1588,9 @@ DEVI Drone12 drone_f(const Drone12& s, float thrust, float tx, float ty, float t
   return d;
 }
 
+// KIN: the launch has an agent with a kinematic model (diff drive / bicycle / drone); the lean
+// instantiation without that code needs half the registers, and most scenarios use it
+template <bool KIN>
 DEVI void ingest_actions_body(const IngestArgs& a, const long idx) {
   if (idx >= (long)a.batch_dim * a.n) return;
   const long env = idx / a.n;
@@ -1659,7 +1662,7 @@ DEVI void ingest_actions_body(const IngestArgs& a, const long idx) {
   } else if (dyn == VMAS_DYN_ROTATION) {
     torque = u[0];
     write_torque = true;
-  } else if (dyn >= VMAS_DYN_DIFF_DRIVE) {
+  } else if (KIN && dyn >= VMAS_DYN_DIFF_DRIVE) {
     const float dt = ag.dyn_params[0], mass = ag.dyn_params[1], inertia = ag.dyn_params[2];
     const bool rk4 = ag.dyn_params[3] != 0.f;
     const float yaw = a.st.rot[ent];
@@ -1726,17 +1729,19 @@ DEVI void ingest_actions_body(const IngestArgs& a, const long idx) {
   if (write_torque) a.st.torque[row] = torque;
 }
 
+template <bool KIN>
 __global__ void __launch_bounds__(256) ingest_actions_kernel(const IngestArgs a) {
-  ingest_actions_body(a, (long)blockIdx.x * blockDim.x + threadIdx.x);
+  ingest_actions_body<KIN>(a, (long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Action ingest and the first substep's broad phase in ONE launch (blocks [0, n_ingest) ingest, the rest
 // test the masked pairs): both only read what the previous step left, neither depends on the other, and
 // each is too small to fill the GPU on its own.  Block = (32, BROAD_SLICES) = 256 threads.
 static_assert(32 * BROAD_SLICES == 256, "the fused launch assumes 256-thread blocks");
+template <bool KIN>
 __global__ void __launch_bounds__(256) ingest_broad_kernel(const IngestArgs ia, const StepArgs sa, const int n_ingest) {
   if ((int)blockIdx.x < n_ingest)
-    ingest_actions_body(ia, (long)blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x);
+    ingest_actions_body<KIN>(ia, (long)blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x);
   else
     broad_phase_body(sa, (long)blockIdx.x - n_ingest);
 }
@@ -1921,27 +1926,28 @@ __global__ void __launch_bounds__(ORDER_CHUNK / 2) order_sort_kernel(const uint3
 
 struct CopyArgs {
   VmasCopySegment seg[VMAS_MAX_COPY_SEGMENTS];
+  int first_block[VMAS_MAX_COPY_SEGMENTS + 1];  // segment k is copied by blocks [first_block[k], first_block[k + 1])
 };
 
-// every block walks all segments (grid-stride inside each): no idle blocks when the segments differ in
-// size by orders of magnitude (an 8 MB observation block next to 128 KB reward rows); 16-byte words when
-// both ends are 16-byte aligned
+// Every segment gets a share of the blocks in proportion to its size (an 8 MB observation block next to
+// 128 KB reward rows); grid-stride inside the share; 16-byte words when both ends are 16-byte aligned.
 __global__ void __launch_bounds__(256) copy_buffers_kernel(const CopyArgs a, const int n_segs) {
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (int k = 0; k < n_segs; ++k) {
-    const VmasCopySegment s = a.seg[k];
-    const char* src = static_cast<const char*>(s.src);
-    char* dst = static_cast<char*>(s.dst);
-    size_t done = 0;
-    if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
-      const size_t words = s.bytes / 16;
-      const uint4* s4 = reinterpret_cast<const uint4*>(src);
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-      for (size_t i = tid; i < words; i += stride) d4[i] = s4[i];
-      done = words * 16;
-    }
-    for (size_t i = done + tid; i < s.bytes; i += stride) dst[i] = src[i];
+  int k = 0;
+  while (k + 1 < n_segs && (int)blockIdx.x >= a.first_block[k + 1]) ++k;
+  const VmasCopySegment s = a.seg[k];
+  const size_t n_blocks = (size_t)(a.first_block[k + 1] - a.first_block[k]);
+  const size_t tid = (size_t)(blockIdx.x - a.first_block[k]) * blockDim.x + threadIdx.x, stride = n_blocks * blockDim.x;
+  const char* src = static_cast<const char*>(s.src);
+  char* dst = static_cast<char*>(s.dst);
+  size_t done = 0;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const size_t words = s.bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = tid; i < words; i += stride) d4[i] = s4[i];
+    done = words * 16;
   }
+  for (size_t i = done + tid; i < s.bytes; i += stride) dst[i] = src[i];
 }
 
 static int launch_broad_phase(const StepArgs& args, cudaStream_t stream) {
@@ -2199,6 +2205,8 @@ static int ingest_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, con
   const int threads = 256;
   const long total = (long)cfg->batch_dim * n_agents;
   const unsigned n_ingest = (unsigned)((total + threads - 1) / threads);
+  bool kinematic = false;
+  for (int i = 0; i < n_agents; ++i) kinematic |= agents[i].dynamics >= VMAS_DYN_DIFF_DRIVE;
   if (mask && cfg->n_masked > 0) {
     if (!tb->masked_items || !tb->item_i32 || !tb->item_f32 || !st->pos) return fail("null broad-phase tables%s");
     StepArgs sa;
@@ -2211,10 +2219,17 @@ static int ingest_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, con
     sa.first_substep = 0;
     sa.n_substeps = 1;
     const unsigned n_broad = (unsigned)(((long)cfg->batch_dim + 31) / 32);
-    ingest_broad_kernel<<<n_ingest + n_broad, dim3(32, BROAD_SLICES), sa.mask_words * sizeof(uint32_t),
-                          static_cast<cudaStream_t>(cuda_stream)>>>(a, sa, (int)n_ingest);
+    const dim3 block(32, BROAD_SLICES);
+    const size_t smem = sa.mask_words * sizeof(uint32_t);
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (kinematic)
+      ingest_broad_kernel<true><<<n_ingest + n_broad, block, smem, stream>>>(a, sa, (int)n_ingest);
+    else
+      ingest_broad_kernel<false><<<n_ingest + n_broad, block, smem, stream>>>(a, sa, (int)n_ingest);
+  } else if (kinematic) {
+    ingest_actions_kernel<true><<<n_ingest, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   } else {
-    ingest_actions_kernel<<<n_ingest, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
+    ingest_actions_kernel<false><<<n_ingest, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   }
   CUDA_OK(cudaGetLastError());
   return 1;
@@ -2477,16 +2492,18 @@ int vmas_b200_set_l2_fetch_granularity(int32_t bytes) {
 int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cuda_stream) {
   if (!segs || n_segs <= 0 || n_segs > VMAS_MAX_COPY_SEGMENTS) return fail("1..VMAS_MAX_COPY_SEGMENTS segments expected%s");
   CopyArgs a;
-  size_t total = 0;
+  const int threads = 256;
+  const size_t per_block = (size_t)threads * 4 * 16;  // ~4 x 16 B per thread
+  int blocks = 0;
   for (int i = 0; i < n_segs; ++i) {
     if (!segs[i].src || !segs[i].dst) return fail("null copy segment%s");
     a.seg[i] = segs[i];
-    total += segs[i].bytes;
+    a.first_block[i] = blocks;
+    size_t want = (segs[i].bytes + per_block - 1) / per_block;
+    want = want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want);
+    blocks += (int)want;
   }
-  if (total == 0) return 1;
-  const int threads = 256;
-  size_t blocks = (total / 16 + (size_t)threads * 4 - 1) / ((size_t)threads * 4);  // ~4 x 16 B per thread
-  blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  a.first_block[n_segs] = blocks;
   copy_buffers_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a, n_segs);
   CUDA_OK(cudaGetLastError());
   return 1;
