@@ -74,6 +74,10 @@ def _close(got, want, atol=ATOL):
 
 @pytest.mark.parametrize("name", golden_names())
 def test_world_step_vs_reference_golden(name):
+    if _native.ARITH == "fast" and name == "crafted_clamps":
+        # the reason the fast-arithmetic build is opt-in: torques over a small moment of inertia land at 1.2x
+        # the tolerance (profiles/r2c_parity_fast.txt)
+        pytest.xfail("VMAS_B200_ARITH=fast leaves the 1e-4 contract on this world")
     fix, desc, tables = load(name)
     lib = _native.load()
     device = torch.device("cuda:0")
