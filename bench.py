@@ -425,6 +425,11 @@ def main_b200(args):
     wall0 = time.perf_counter()
     ms_total = timed_loop(lambda i: env.step(dev_actions[W + i]), K)
     wall = time.perf_counter() - wall0
+    brackets = sorted(timed_loop.last)
+    bracket_us = {
+        "min": round(1e3 * brackets[0], 1), "median": round(1e3 * brackets[len(brackets) // 2], 1),
+        "p90": round(1e3 * brackets[min(len(brackets) - 1, (9 * len(brackets)) // 10)], 1), "max": round(1e3 * brackets[-1], 1),
+    }
     launches = backend.launches - launches_before
     barrier()
 
@@ -675,6 +680,7 @@ def main_b200(args):
             "api": "make_env(..., cuda_graph=%s); Environment.step" % (not args.no_graph),
             "warmup_steps_run": W,
             "wall_ms_per_step_incl_flush": 1e3 * wall / K,
+            "bracket_us": bracket_us,
             "host_affinity": pinned,
         },
         "clocks": clocks,

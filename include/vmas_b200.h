@@ -393,6 +393,59 @@ int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasP
                                          const VmasAgentActions* agents, int32_t n_agents, int32_t clamp,
                                          uint8_t* bad_flag, float* steps, uint32_t* mask, void* cuda_stream);
 
+/*
+ * One Environment.step() of a set-up environment in ONE call (replaces the host side of ref
+ * environment/environment.py:254-309 once the step's work is known): in stream order
+ *   1. vmas_b200_ingest_actions[_broad_phase] on the caller's action tensors (n_agents > 0);
+ *   2. the step proper: either `graph_exec` (a cudaGraphExec_t holding the physics step and the scenario's
+ *      callbacks, captured by the caller) is launched, or — `graph_exec` NULL — vmas_b200_world_step followed
+ *      by vmas_b200_post_step (`program` / `columns` as there; both NULL: physics only) — or, with
+ *      `fused_kernel`, ONE launch doing both;
+ *   3. vmas_b200_copy_buffers handing results out: segment i is copied to out_blocks[seg_block[i]] +
+ *      (byte offset held in segs[i].dst), so that a caller allocating fresh result blocks every step only
+ *      fills in `out_blocks`.
+ * `ingest_mask` non-NULL: the ingest launch also builds the first substep's broad-phase mask (then
+ * `exact_broad_phase` must be 2 in direct mode, and the captured graph must have been captured that way).
+ * Returns the number of kernels this call launched itself (the graph's nodes are not counted).
+ */
+/*
+ * Registers a WHOLE-STEP kernel compiled at run time for one (world, step program, observation plan): the
+ * specialised substep kernel with the program and the observation rows as its epilogue (csrc/spec_kernel.cuh,
+ * step_fused_kernel; built by vectorizedmultiagentsimulator_b200/jit.py).  `launch`:
+ * cudaError_t (*)(const SpecArgs&, const EpiArgs&, cudaStream_t).  Returns a handle > 0 for
+ * VmasEnvStep.fused_kernel (the same key returns the same handle).
+ */
+int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch,
+                                   int32_t spec_args_bytes, int32_t epi_args_bytes);
+
+#define VMAS_MAX_OUT_BLOCKS 8
+typedef struct VmasEnvStep {
+  const VmasWorldConfig* cfg;
+  const VmasPlanTables* tb;
+  const VmasState* st;
+  /* 1 */
+  const VmasAgentActions* agents;
+  int32_t n_agents, clamp;
+  uint8_t* bad_flag;
+  float* steps;
+  uint32_t* ingest_mask;
+  /* 2 */
+  void* graph_exec;
+  uint32_t* mask;
+  int32_t exact_broad_phase;
+  int32_t fused_kernel;  /* > 0: a handle from vmas_b200_register_step_kernel (direct mode only) */
+  const VmasStepProgram* program;
+  const int32_t* columns;
+  int32_t n_rows, width;
+  float* obs_out;
+  /* 3 */
+  const VmasCopySegment* segs;
+  const int32_t* seg_block;
+  int32_t n_segs, n_out_blocks;
+  void* out_blocks[VMAS_MAX_OUT_BLOCKS];
+} VmasEnvStep;
+int vmas_b200_env_step(const VmasEnvStep* step, void* cuda_stream);
+
 /* The broad-phase pass alone: ORs bit i of `mask` if masked item i is within range in any env. */
 int vmas_b200_broad_phase(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                           uint32_t* mask, void* cuda_stream);

@@ -360,6 +360,8 @@ def test_cuda_graph_mode_is_bit_identical_to_eager(name, kwargs):
             graph.reset()
             sync_env(eager, graph)
     assert graph.graph_replays >= 6
+    # every shipped scenario's captured step goes through the one-call entry point (vmas_b200_env_step)
+    assert graph._one_call_state == "on", f"{name}: captured step not on vmas_b200_env_step"
     # outputs of one step must survive the next replay (they are clones of the static buffers)
     kept = [o.clone() for o in got[0]]
     graph.step([a.clone() for a in actions])
@@ -389,3 +391,53 @@ def test_graph_mode_outputs_are_freed_by_refcount():
     finally:
         gc.enable()
     assert after <= before + (1 << 16), f"graph-mode steps leak device memory: {before} -> {after} bytes"
+
+
+def test_a_graph_that_draws_device_random_numbers_stays_on_torchs_replay():
+    """vmas_b200_env_step launches the captured graph itself; torch's replay additionally advances the
+    philox offset of a graph that consumes device random numbers.  Such a graph must not be launched raw
+    (it would replay the same numbers): the first replay detects it."""
+    from vectorizedmultiagentsimulator_b200.scenarios.balance import Scenario as Balance
+
+    class NoisyBalance(Balance):
+        def observation(self, agent):
+            obs = super().observation(agent)
+            return obs + 0.01 * torch.randn_like(obs)
+
+    env = b200.make_env(NoisyBalance(), num_envs=64, device="cuda", seed=0, cuda_graph=True, n_agents=3)
+    env.reset()
+    seen = []
+    for _ in range(6):
+        obs = env.step(env.get_random_actions())[0]
+        seen.append(obs[0].clone())
+    assert env.graph_replays >= 3
+    assert env._one_call_state == "off"
+    noise = [(a - b).abs().max().item() for a, b in zip(seen[-2:], seen[-3:-1])]
+    assert all(n > 0 for n in noise)
+
+    quiet = b200.make_env("balance", num_envs=64, device="cuda", seed=0, cuda_graph=True, n_agents=3)
+    quiet.reset()
+    for _ in range(6):
+        quiet.step(quiet.get_random_actions())
+    assert quiet._one_call_state == "on"
+
+
+def test_one_call_step_can_be_switched_off_and_changes_no_bit(monkeypatch):
+    from vectorizedmultiagentsimulator_b200.simulator.environment import environment as E
+
+    envs = []
+    for flag in (True, False):
+        monkeypatch.setattr(E, "_ONE_CALL_STEP", flag)
+        env = b200.make_env("balance", num_envs=96, device="cuda", seed=0, cuda_graph=True, n_agents=4)
+        env.reset()
+        envs.append(env)
+    gen = torch.Generator().manual_seed(5)
+    for t in range(8):
+        actions = [(torch.rand(96, 2, generator=gen) * 2 - 1).cuda() for _ in range(4)]
+        a = envs[0].step([x.clone() for x in actions])
+        monkeypatch.setattr(E, "_ONE_CALL_STEP", False)
+        b = envs[1].step([x.clone() for x in actions])
+        for g, w in zip(flatten(a), flatten(b)):
+            assert torch.equal(g, w)
+    assert envs[0]._one_call_state == "on" and envs[1]._one_call_state == "off"
+    assert float(envs[0].steps[0]) == float(envs[1].steps[0]) == 8.0

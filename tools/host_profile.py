@@ -18,6 +18,14 @@ acts = [env.get_random_actions() for _ in range(16)]
 for i in range(50):
     env.step(acts[i % 16])
 torch.cuda.synchronize()
+import time
+for rep in range(3):
+    t0 = time.perf_counter()
+    for i in range(2000):
+        env.step(acts[i % 16])
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"# {name}: host wall per step (32 envs, no profiler): {(t1 - t0) / 2000 * 1e6:.1f} us")
 prof = cProfile.Profile()
 prof.enable()
 for i in range(2000):

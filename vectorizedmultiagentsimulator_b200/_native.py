@@ -253,6 +253,8 @@ EXPORTS = [
     "vmas_b200_distance_shaping",
     "vmas_b200_post_step",
     "vmas_b200_copy_buffers",
+    "vmas_b200_env_step",
+    "vmas_b200_register_step_kernel",
     "vmas_b200_build_env_order",
     "vmas_b200_set_l2_fetch_granularity",
     "vmas_b200_reset_state",
@@ -324,6 +326,8 @@ def load():
         p_cfg, p_st, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
         C.c_float, C.c_float, C.c_void_p,
     ]
+    lib.vmas_b200_env_step.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vmas_b200_register_step_kernel.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
     lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.vmas_b200_set_l2_fetch_granularity.argtypes = [C.c_int32]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
@@ -725,6 +729,68 @@ class CopyPlan:
         for k, (block, offset) in enumerate(self.where):
             segs[k].dst = bases[block] + offset
         return _check(lib, lib.vmas_b200_copy_buffers(segs, self.n, _stream(device)))
+
+
+MAX_OUT_BLOCKS = 8
+
+
+class EnvStepC(C.Structure):
+    _fields_ = [
+        ("cfg", C.c_void_p), ("tb", C.c_void_p), ("st", C.c_void_p),
+        ("agents", C.c_void_p), ("n_agents", C.c_int32), ("clamp", C.c_int32),
+        ("bad_flag", C.c_void_p), ("steps", C.c_void_p), ("ingest_mask", C.c_void_p),
+        ("graph_exec", C.c_void_p), ("mask", C.c_void_p), ("exact_broad_phase", C.c_int32), ("fused_kernel", C.c_int32),
+        ("program", C.c_void_p), ("columns", C.c_void_p), ("n_rows", C.c_int32), ("width", C.c_int32),
+        ("obs_out", C.c_void_p),
+        ("segs", C.c_void_p), ("seg_block", C.c_void_p), ("n_segs", C.c_int32), ("n_out_blocks", C.c_int32),
+        ("out_blocks", C.c_void_p * MAX_OUT_BLOCKS),
+    ]
+
+
+class EnvStepPlan:
+    """``vmas_b200_env_step`` with everything that does not change from step to step marshalled once:
+    a run fills in the action tensors' addresses and the fresh output blocks, then crosses the FFI once
+    (action ingest, the step itself — a captured graph or the library's own two launches — and the
+    hand-out copy)."""
+
+    def __init__(self, lib, dt: "DeviceTables", slab, agents_c, n_agents: int, clamp: bool, bad_flag, steps,
+                 ingest_broad_phase: bool, graph_exec: int, copy_items, n_out_blocks: int,
+                 program=None, columns=None, n_rows: int = 0, width: int = 0, obs_out=None, exact_broad_phase: int = 1):
+        assert len(copy_items) <= MAX_COPY_SEGMENTS and n_out_blocks <= MAX_OUT_BLOCKS and n_agents <= MAX_INGEST_AGENTS
+        self.lib, self.device = lib, dt.device
+        st = dt.state_struct(slab)
+        segs = (CopySegmentC * max(len(copy_items), 1))()
+        blocks = (C.c_int32 * max(len(copy_items), 1))()
+        for k, (src, block, offset) in enumerate(copy_items):
+            assert src.is_contiguous()
+            segs[k].src, segs[k].dst, segs[k].bytes = src.data_ptr(), offset, src.numel() * src.element_size()
+            blocks[k] = block
+        c = self.c = EnvStepC()
+        c.cfg, c.tb, c.st = C.addressof(dt.cfg), C.addressof(dt.tb), C.addressof(st)
+        c.agents = C.addressof(agents_c) if n_agents else None
+        c.n_agents, c.clamp = n_agents, int(clamp)
+        c.bad_flag = None if bad_flag is None else bad_flag.data_ptr()
+        c.steps = None if steps is None else steps.data_ptr()
+        c.ingest_mask = dt.mask.data_ptr() if ingest_broad_phase else None
+        c.graph_exec = graph_exec or None
+        c.mask, c.exact_broad_phase = dt.mask.data_ptr(), exact_broad_phase
+        c.program = None if program is None else C.addressof(program)
+        c.columns = None if columns is None else columns.data_ptr()
+        c.n_rows, c.width = n_rows, width
+        c.obs_out = None if obs_out is None else obs_out.data_ptr()
+        c.segs, c.seg_block = C.addressof(segs), C.addressof(blocks)
+        c.n_segs, c.n_out_blocks = len(copy_items), n_out_blocks
+        self.out_blocks = c.out_blocks
+        self.agents = agents_c
+        self._ref = C.addressof(c)
+        self._call = lib.vmas_b200_env_step
+        # everything the addresses above point into stays alive with the plan
+        self.keep = (dt, slab, st, agents_c, segs, blocks, bad_flag, steps, program, columns, obs_out,
+                     [src for src, _, _ in copy_items])
+
+    def run(self) -> int:
+        """(the caller has filled in ``agents[i].actions`` and ``out_blocks[j]``)"""
+        return _check(self.lib, self._call(self._ref, _stream(self.device)))
 
 
 def distance_shaping(lib, dt: DeviceTables, slab, pairs, factor: float, prev, dist, rew) -> int:

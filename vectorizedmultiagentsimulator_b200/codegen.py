@@ -110,7 +110,7 @@ def emit_world(desc: P.WorldDescription, label: str, tuning: Dict = None) -> Tup
         cols = [
             P.EF_D0, P.EF_D1, P.EF_MASS, P.EF_INERTIA, P.EF_DRAG_MULT, P.EF_LIN_FRIC, P.EF_ANG_FRIC, P.EF_GRAV_X,
             P.EF_GRAV_Y, P.EF_MAX_SPEED, P.EF_V_RANGE, P.EF_MAX_F, P.EF_F_RANGE, P.EF_MAX_T, P.EF_T_RANGE,
-            P.EF_CIRC_R,
+            P.EF_CIRC_R, P.EF_R_PLUS_LMD,
         ]
         vals = ", ".join(_f(r[c]) for c in cols)
         lines.append(f"      {{{int(ei[e, 0])}, {int(ei[e, 1])}, {int(ei[e, 2])}, {vals}}},  // {desc.entities[e]['name']}")
@@ -128,6 +128,46 @@ def emit_world(desc: P.WorldDescription, label: str, tuning: Dict = None) -> Tup
             f"      {{{int(ii[0])}, {int(ii[1])}, {int(ii[2])}, {flags}, {int(tables.mask_slot[k])}, {vals}}},"
             f"  // {P.KIND_NAMES[int(ii[0])]}"
         )
+    lines.append("  };")
+    lines.append("};")
+    return name, "\n".join(lines), h
+
+
+def post_hash(cols, instrs) -> int:
+    """FNV-1a 64 of a step epilogue: the observation plan's column table (int32 ``[rows, width, 4]`` or None)
+    and the step program's instructions ``[(op, dst, a, b, arg, imm)]`` with entity indices resolved."""
+    blob = json.dumps(
+        [None if cols is None else [list(cols.shape), [int(x) for x in cols.reshape(-1)]],
+         [[int(op), int(dst), int(a), int(b), int(arg), _f(imm)] for op, dst, a, b, arg, imm in instrs]]
+    ).encode()
+    h = 0xCBF29CE484222325
+    for byte in blob:
+        h ^= byte
+        h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def emit_post(cols, instrs) -> Tuple[str, str, int]:
+    """C++ text of one epilogue struct (``spec_epilogue`` in csrc/spec_kernel.cuh).  Returns (name, text, hash)."""
+    h = post_hash(cols, instrs)
+    name = f"Post_{h:016x}"
+    rows, width = (0, 0) if cols is None else (int(cols.shape[0]), int(cols.shape[1]))
+    lines = [f"struct {name} {{"]
+    lines.append(f"  static constexpr int N_PROG = {len(instrs)}, OBS_ROWS = {rows}, OBS_WIDTH = {width};")
+    lines.append(f"  static constexpr ProgC prog[{max(len(instrs), 1)}] = {{")
+    for op, dst, a, b, arg, imm in instrs:
+        lines.append(f"      {{{int(op)}, {int(dst)}, {int(a)}, {int(b)}, {int(arg)}, {_f(imm)}}},")
+    if not instrs:
+        lines.append("      {0, 0, 0, 0, 0, 0.f},")
+    lines.append("  };")
+    lines.append(f"  static constexpr ObsColC obs[{max(rows * width, 1)}] = {{")
+    if rows * width == 0:
+        lines.append("      {0, 0, 0, 0.f},")
+    else:
+        flat = cols.reshape(-1, 4)
+        for op, src, src2, par in flat:
+            par_f = float(np.array([par], dtype=np.int32).view(np.float32)[0])
+            lines.append(f"      {{{int(op)}, {int(src)}, {int(src2)}, {_f(par_f)}}},")
     lines.append("  };")
     lines.append("};")
     return name, "\n".join(lines), h

@@ -17,6 +17,7 @@
 #include <utility>
 
 #include "geometry.cuh"
+#include "query.cuh"
 #include "vmas_b200.h"
 
 namespace vmas {
@@ -24,7 +25,7 @@ namespace vmas {
 struct EntC {
   int shape, flags, agent;
   float d0, d1, mass, inertia, drag_mult, lin_fric, ang_fric, grav_x, grav_y, max_speed, v_range, max_f, f_range,
-      max_t, t_range, circ_r;
+      max_t, t_range, circ_r, r_plus_lmd;
 };
 struct ItemC {
   int kind, a, b, flags, mask_bit;
@@ -34,6 +35,21 @@ struct CfgC {
   int substeps, has_x_semidim, has_y_semidim, has_world_gravity;
   float sub_dt, x_semidim, y_semidim, collision_force, joint_force, torque_constraint_force, contact_margin,
       gravity_x, gravity_y;
+};
+
+// The whole-step kernel's epilogue (see spec_epilogue): the scenario's step program and observation rows,
+// compile-time data like the world itself
+struct ProgC {
+  int op, dst, a, b, arg;
+  float imm;
+};
+struct ObsColC {
+  int op, src, src2;  // as the observation gather's column codes: (field << 24) | element offset in the env's row
+  float par;
+};
+struct EpiArgs {
+  float* obs_out;  // [rows, B, width] or null
+  void* buffers[VMAS_PROG_MAX_BUFFERS];
 };
 
 struct SpecArgs {
@@ -514,9 +530,152 @@ struct SpecRows {
   }
 };
 
-// One env, all of `a.n_substeps` substeps, state in the calling thread's registers.
-template <class W, bool TRACK = false>
-DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask_words)[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1]) {
+// ---- the whole-step kernel's epilogue -----------------------------------------------------------------
+// What Environment.step does after World.step for a scenario written on a StepProgram and an ObservationPlan
+// (vmas_b200_post_step: the reward / done glue and the slab-derived observation columns), executed by the
+// thread that just stepped the env, on the registers that still hold its state: the program and the column
+// table are constexpr members of `P`, every query is resolved against compile-time shapes.  Same functions,
+// same arithmetic, same bits as post_step_kernel.
+
+// one element of an env's state after the step: from the registers where the kernel keeps it, else from the slab
+template <class W, int FIELD, int OFF>
+DEVI float epi_state(const EnvRegs<W::E>& r, const SpecArgs& a, const long env) {
+  constexpr int E = W::E;
+  if constexpr (FIELD == VMAS_OBS_POS) {
+    return (OFF & 1) ? r.py[OFF / 2] : r.px[OFF / 2];
+  } else if constexpr (FIELD == VMAS_OBS_VEL) {
+    if constexpr (W::ent[OFF / 2].flags & VMAS_F_MOVABLE)
+      return (OFF & 1) ? r.vy[OFF / 2] : r.vx[OFF / 2];
+    else
+      return a.st.vel[(size_t)env * 2 * E + OFF];
+  } else if constexpr (FIELD == VMAS_OBS_ROT) {
+    if constexpr (W::ent[OFF].flags & (VMAS_F_TRIG | VMAS_F_ROTATABLE))
+      return r.rot[OFF];
+    else
+      return a.st.rot[(size_t)env * E + OFF];
+  } else {
+    if constexpr (W::ent[OFF].flags & VMAS_F_ROTATABLE)
+      return r.w[OFF];
+    else
+      return a.st.ang_vel[(size_t)env * E + OFF];
+  }
+}
+
+template <class W, int EI>
+DEVI EntG epi_ent(const EnvRegs<W::E>& r, const SpecArgs& a, const long env) {
+  constexpr EntC en = W::ent[EI];
+  EntG g;
+  g.shape = en.shape;
+  g.p = mk(r.px[EI], r.py[EI]);
+  g.rot = epi_state<W, VMAS_OBS_ROT, EI>(r, a, env);
+  g.d0 = en.d0;
+  g.d1 = en.d1;
+  g.r_plus_lmd = en.r_plus_lmd;
+  return g;
+}
+
+template <class W, class P>
+DEVI void spec_epilogue(const EnvRegs<W::E>& r, const SpecArgs& a, const EpiArgs& e, const long env) {
+  // the step program (ref scenarios/balance.py:197-263 as a StepProgram; see vmas_b200_post_step)
+  float pr[VMAS_PROG_REGS];
+#pragma unroll
+  for (int i = 0; i < VMAS_PROG_REGS; ++i) pr[i] = 0.f;
+  static_for<P::N_PROG>([&](auto ii) {
+    constexpr ProgC in = P::prog[decltype(ii)::value];
+    constexpr int ia = in.arg & 0xFFFF, ib = (in.arg >> 16) & 0xFFFF;
+    if constexpr (in.op == VMAS_OP_OVERLAP) {
+      pr[in.dst] = pair_overlap(epi_ent<W, ia>(r, a, env), epi_ent<W, ib>(r, a, env)) ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_DISTANCE) {
+      pr[in.dst] = pair_distance(epi_ent<W, ia>(r, a, env), epi_ent<W, ib>(r, a, env));
+    } else if constexpr (in.op == VMAS_OP_CENTER_DISTANCE) {
+      pr[in.dst] = norm2(r.px[ia] - r.px[ib], r.py[ia] - r.py[ib]);
+    } else if constexpr (in.op == VMAS_OP_SHAPING) {
+      const float d = norm2(r.px[ia] - r.px[ib], r.py[ia] - r.py[ib]);
+      const float shaping = d * in.imm;
+      float* prev = static_cast<float*>(e.buffers[in.a]) + env;
+      pr[in.dst] = *prev - shaping;
+      pr[in.dst + 1] = d;
+      *prev = shaping;
+    } else if constexpr (in.op == VMAS_OP_LOAD_F32) {
+      pr[in.dst] = static_cast<const float*>(e.buffers[in.a])[env];
+    } else if constexpr (in.op == VMAS_OP_LOAD_BOOL) {
+      pr[in.dst] = static_cast<const uint8_t*>(e.buffers[in.a])[env] ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_CONST) {
+      pr[in.dst] = in.imm;
+    } else if constexpr (in.op == VMAS_OP_ADD) {
+      pr[in.dst] = pr[in.a] + pr[in.b];
+    } else if constexpr (in.op == VMAS_OP_SUB) {
+      pr[in.dst] = pr[in.a] - pr[in.b];
+    } else if constexpr (in.op == VMAS_OP_MUL) {
+      pr[in.dst] = pr[in.a] * pr[in.b];
+    } else if constexpr (in.op == VMAS_OP_MIN) {
+      pr[in.dst] = fminf(pr[in.a], pr[in.b]);
+    } else if constexpr (in.op == VMAS_OP_MAX) {
+      pr[in.dst] = fmaxf(pr[in.a], pr[in.b]);
+    } else if constexpr (in.op == VMAS_OP_NEG) {
+      pr[in.dst] = -pr[in.a];
+    } else if constexpr (in.op == VMAS_OP_OR) {
+      pr[in.dst] = (pr[in.a] != 0.f || pr[in.b] != 0.f) ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_AND) {
+      pr[in.dst] = (pr[in.a] != 0.f && pr[in.b] != 0.f) ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_NOT) {
+      pr[in.dst] = pr[in.a] != 0.f ? 0.f : 1.f;
+    } else if constexpr (in.op == VMAS_OP_LT) {
+      pr[in.dst] = pr[in.a] < pr[in.b] ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_LE) {
+      pr[in.dst] = pr[in.a] <= pr[in.b] ? 1.f : 0.f;
+    } else if constexpr (in.op == VMAS_OP_WHERE) {
+      pr[in.dst] = pr[in.a] != 0.f ? pr[in.b] : pr[in.arg & 0xFF];
+    } else if constexpr (in.op == VMAS_OP_STORE_F32) {
+      static_cast<float*>(e.buffers[in.b])[env] = pr[in.a];
+    } else if constexpr (in.op == VMAS_OP_STORE_BOOL) {
+      static_cast<uint8_t*>(e.buffers[in.b])[env] = pr[in.a] != 0.f ? 1 : 0;
+    }
+  });
+  // the observation rows (ref scenarios/balance.py:236-262 as an ObservationPlan): [rows, B, width]
+  if constexpr (P::OBS_ROWS > 0) {
+    constexpr int F = P::OBS_WIDTH;
+    constexpr int VEC = F % 4 == 0 ? 4 : 1;
+    static_for<P::OBS_ROWS>([&](auto ri) {
+      constexpr int row = decltype(ri)::value;
+      float* dst = e.obs_out + ((size_t)row * a.batch_dim + env) * F;
+      static_for<F / VEC>([&](auto gi) {
+        constexpr int c0 = decltype(gi)::value * VEC;
+        float v[VEC];
+        bool all = true;
+        static_for<VEC>([&](auto ki) {
+          constexpr int k = decltype(ki)::value;
+          constexpr ObsColC col = P::obs[row * F + c0 + k];
+          v[k] = 0.f;
+          if constexpr (col.op != VMAS_OBS_SKIP) {
+            v[k] = epi_state<W, (col.src >> 24) & 3, col.src & 0xFFFFFF>(r, a, env);
+            if constexpr (col.op == VMAS_OBS_DIFF)
+              v[k] = v[k] - epi_state<W, (col.src2 >> 24) & 3, col.src2 & 0xFFFFFF>(r, a, env);
+            if constexpr (col.op == VMAS_OBS_REMAINDER) v[k] = obs_remainder(v[k], col.par);
+          } else {
+            all = false;
+          }
+        });
+        if constexpr (VEC == 4) {
+          if (all) {
+            *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            return;
+          }
+        }
+        static_for<VEC>([&](auto ki) {
+          constexpr int k = decltype(ki)::value;
+          if constexpr (P::obs[row * F + c0 + k].op != VMAS_OBS_SKIP) dst[c0 + k] = v[k];
+        });
+      });
+    });
+  }
+}
+
+// One env, all of `a.n_substeps` substeps, state in the calling thread's registers.  `P` (not void): the
+// step's epilogue runs behind the last substep (the whole-step kernel).
+template <class W, bool TRACK = false, class P = void>
+DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask_words)[W::MASK_WORDS > 0 ? W::MASK_WORDS : 1],
+                        const EpiArgs* epi = nullptr) {
   constexpr int E = W::E, NA = W::A, NI = W::NI;
   if (env >= a.batch_dim) return;
   SpecRows<W> rows;
@@ -535,6 +694,9 @@ DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask
     spec_integrate<W>(r, sub);
   }
   rows.store(a, env, r, afx, afy, atq);
+  if constexpr (!std::is_void_v<P>) {
+    if (a.first_substep + a.n_substeps == W::cfg.substeps) spec_epilogue<W, P>(r, a, *epi, env);
+  }
   if constexpr (TRACK) {
     if (a.sig) a.sig[env] = (a.first_substep == 0 ? 0u : a.sig[env]) | sig;  // OR over the substeps of a step
   }
@@ -576,6 +738,40 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_spec_kernel(cons
   } else {
     spec_env_step<W, false>(a, tid, mask_words);
   }
+}
+
+// The whole-step kernel: step_spec_kernel with the epilogue P behind the last substep.
+template <class W, class P>
+__global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_fused_kernel(const SpecArgs a, const EpiArgs e) {
+  constexpr int MW = W::MASK_WORDS;
+  const long tid = (long)blockIdx.x * W::BLOCK + threadIdx.x;
+  uint32_t mask_words[MW > 0 ? MW : 1];
+  if constexpr (MW > 0) {
+    __shared__ uint32_t s_mask[MW];
+    if (a.use_mask) {
+      for (int w = threadIdx.x; w < MW; w += W::BLOCK) s_mask[w] = a.mask[w];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned done = atomicAdd(&a.mask[MW], 1u);
+        if (done == gridDim.x - 1) {
+          for (int w = 0; w < MW; ++w) a.mask[w] = 0u;
+          a.mask[MW] = 0u;
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
+    }
+  }
+  if (tid >= a.batch_dim) return;
+  spec_env_step<W, false, P>(a, tid, mask_words, &e);
+}
+
+template <class W, class P>
+static cudaError_t launch_fused(const SpecArgs& a, const EpiArgs& e, cudaStream_t stream) {
+  const long blocks = ((long)a.batch_dim + W::BLOCK - 1) / W::BLOCK;
+  step_fused_kernel<W, P><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a, e);
+  return cudaGetLastError();
 }
 
 // host-side launcher used by the registry in generated/specializations.cuh

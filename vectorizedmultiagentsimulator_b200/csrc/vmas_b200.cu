@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "geometry.cuh"
+#include "query.cuh"
 #include "generated/specializations.cuh"
 #include "vmas_b200.h"
 
@@ -1033,12 +1034,6 @@ struct QueryArgs {
   void* out;
 };
 
-struct EntG {
-  int shape;
-  V2 p;
-  float rot, d0, d1;
-};
-
 DEVI EntG load_ent(const QueryArgs& q, int e, size_t env_base) {
   EntG g;
   g.shape = __ldg(q.tb.ent_i32 + e * 4);
@@ -1047,112 +1042,8 @@ DEVI EntG load_ent(const QueryArgs& q, int e, size_t env_base) {
   g.rot = q.st.rot[env_base + e];
   g.d0 = __ldg(q.tb.ent_f32 + (size_t)e * VMAS_EF_COLS + VMAS_EF_D0);
   g.d1 = __ldg(q.tb.ent_f32 + (size_t)e * VMAS_EF_COLS + VMAS_EF_D1);
+  g.r_plus_lmd = __ldg(q.tb.ent_f32 + (size_t)e * VMAS_EF_COLS + VMAS_EF_R_PLUS_LMD);
   return g;
-}
-
-DEVI Seg seg_of(const EntG& g) {
-  float sn, cs;
-  sincosf(g.rot, &sn, &cs);
-  return mkseg(g.p, cs, sn, g.d0 / 2.f);
-}
-
-DEVI BoxG box_of(const EntG& g) {
-  BoxG b;
-  b.p = g.p;
-  sincosf(g.rot, &b.s, &b.c);
-  sincosf(g.rot + HALF_PI_F, &b.s2, &b.c2);
-  b.half_l = g.d0 / 2.f;
-  b.half_w = g.d1 / 2.f;
-  return b;
-}
-
-// ref core.py:1788-1820
-DEVI float dist_from_point(const EntG& g, V2 pt) {
-  if (g.shape == VMAS_SHAPE_SPHERE) return norm2(g.p - pt) - g.d0;
-  V2 cp = (g.shape == VMAS_SHAPE_BOX) ? closest_point_box(box_of(g), pt) : closest_point_seg(seg_of(g), pt);
-  return norm2(pt - cp) - LINE_MIN_DIST_F;
-}
-
-// ref core.py:1933-1964 (box / sphere overlap)
-DEVI bool box_sphere_overlap(const QueryArgs& q, const EntG& box, const EntG& sph, int sph_index) {
-  V2 cp = closest_point_box(box_of(box), sph.p);
-  float d_s_cp = norm2(sph.p - cp);
-  float d_s_b = norm2(sph.p - box.p);
-  float d_cp_b = norm2(box.p - cp);
-  // fp32(radius + LINE_MIN_DIST) with the sum taken in double, as the reference does
-  const float dist_min = __ldg(q.tb.ent_f32 + (size_t)sph_index * VMAS_EF_COLS + VMAS_EF_R_PLUS_LMD);
-  return (d_s_b < d_cp_b) || (d_s_cp < dist_min);
-}
-
-// Exact early-out for is_overlapping: true only if the two shapes are separated by clearly more
-// than the overlap threshold (sphere radii / LINE_MIN_DIST, ref core.py:1907-1969), so the answer
-// is "no" without any closest-point arithmetic.  Conservative tests (bounding circles; for boxes
-// the other shape's extent in the box frame) with a 1e-3 margin that dwarfs fp32 rounding.
-DEVI bool overlap_impossible(const EntG& ga, const EntG& gb) {
-  const float M = 1e-3f;
-  const int sa = ga.shape, sb = gb.shape;
-  if (sa == VMAS_SHAPE_SPHERE && sb == VMAS_SHAPE_SPHERE) return false;  // one norm: nothing to save
-  if (sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_BOX) {
-    const float ra = 0.5f * norm2(ga.d0, ga.d1), rb = 0.5f * norm2(gb.d0, gb.d1);
-    const float lim = ra + rb + LINE_MIN_DIST_F + M;
-    const V2 d = ga.p - gb.p;
-    return d.x * d.x + d.y * d.y > lim * lim;
-  }
-  if (sa == VMAS_SHAPE_BOX || sb == VMAS_SHAPE_BOX) {
-    const EntG& box = sa == VMAS_SHAPE_BOX ? ga : gb;
-    const EntG& other = sa == VMAS_SHAPE_BOX ? gb : ga;
-    float sn, cs;
-    sincosf(box.rot, &sn, &cs);
-    const V2 d = other.p - box.p;
-    const float lx = d.x * cs + d.y * sn, ly = d.y * cs - d.x * sn;  // other's centre in the box frame
-    float ex, ey, reach;
-    if (other.shape == VMAS_SHAPE_SPHERE) {
-      ex = ey = 0.f;
-      reach = other.d0 + LINE_MIN_DIST_F + M;
-    } else {  // line: half-length projected on the box axes
-      float so, co;
-      sincosf(other.rot, &so, &co);
-      const float half = other.d0 / 2.f;
-      ex = half * fabsf(co * cs + so * sn);
-      ey = half * fabsf(so * cs - co * sn);
-      reach = LINE_MIN_DIST_F + M;
-    }
-    return fabsf(lx) - ex > box.d0 / 2.f + reach || fabsf(ly) - ey > box.d1 / 2.f + reach;
-  }
-  // line - sphere, line - line: bounding circles
-  const float ra = sa == VMAS_SHAPE_LINE ? ga.d0 / 2.f : ga.d0, rb = sb == VMAS_SHAPE_LINE ? gb.d0 / 2.f : gb.d0;
-  const float lim = ra + rb + LINE_MIN_DIST_F + M;
-  const V2 d = ga.p - gb.p;
-  return d.x * d.x + d.y * d.y > lim * lim;
-}
-
-// ref core.py:1822-1905
-DEVI float pair_distance(const QueryArgs& q, const EntG& ga, const EntG& gb, int ia, int ib) {
-  const int sa = ga.shape, sb = gb.shape;
-  if (sa == VMAS_SHAPE_SPHERE && sb == VMAS_SHAPE_SPHERE) return dist_from_point(ga, gb.p) - gb.d0;
-  if ((sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_SPHERE) || (sb == VMAS_SHAPE_BOX && sa == VMAS_SHAPE_SPHERE)) {
-    const bool a_is_box = sa == VMAS_SHAPE_BOX;
-    const EntG& box = a_is_box ? ga : gb;
-    const EntG& sph = a_is_box ? gb : ga;
-    float d = dist_from_point(box, sph.p) - sph.d0;
-    return box_sphere_overlap(q, box, sph, a_is_box ? ib : ia) ? -1.f : d;
-  }
-  if ((sa == VMAS_SHAPE_LINE && sb == VMAS_SHAPE_SPHERE) || (sb == VMAS_SHAPE_LINE && sa == VMAS_SHAPE_SPHERE)) {
-    const EntG& line = sa == VMAS_SHAPE_LINE ? ga : gb;
-    const EntG& sph = sa == VMAS_SHAPE_LINE ? gb : ga;
-    return dist_from_point(line, sph.p) - sph.d0;
-  }
-  Pair c;
-  if (sa == VMAS_SHAPE_LINE && sb == VMAS_SHAPE_LINE) {
-    c = closest_seg_seg(seg_of(ga), seg_of(gb));
-  } else if (sa == VMAS_SHAPE_BOX && sb == VMAS_SHAPE_BOX) {
-    c = closest_box_box(box_of(ga), box_of(gb));
-  } else {
-    const EntG& box = sa == VMAS_SHAPE_BOX ? ga : gb;
-    const EntG& line = sa == VMAS_SHAPE_BOX ? gb : ga;
-    c = closest_box_seg(box_of(box), seg_of(line));
-  }
-  return norm2(c.a - c.b) - LINE_MIN_DIST_F;
 }
 
 __global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
@@ -1161,7 +1052,7 @@ __global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
   const size_t env_base = (size_t)env * q.cfg.n_entities;
   const EntG ga = load_ent(q, q.a, env_base), gb = load_ent(q, q.b, env_base);
   if (q.mode == 0) {
-    static_cast<float*>(q.out)[env] = pair_distance(q, ga, gb, q.a, q.b);
+    static_cast<float*>(q.out)[env] = pair_distance(ga, gb);
     return;
   }
   bool over = false;
@@ -1171,9 +1062,9 @@ __global__ void __launch_bounds__(256) pair_query_kernel(const QueryArgs q) {
     over = false;
   } else if (box_sphere) {
     const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
-    over = box_sphere_overlap(q, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? q.b : q.a);
+    over = box_sphere_overlap(a_is_box ? ga : gb, a_is_box ? gb : ga);
   } else {
-    over = pair_distance(q, ga, gb, q.a, q.b) < 0.f;
+    over = pair_distance(ga, gb) < 0.f;
   }
   static_cast<uint8_t*>(q.out)[env] = over ? 1 : 0;
 }
@@ -1226,18 +1117,6 @@ __global__ void __launch_bounds__(128) pair_query_spheres_kernel(const PairBatch
   }
 }
 
-// World.is_overlapping of one pair in one env (ref core.py:1907-1969)
-DEVI bool pair_overlap(const QueryArgs& q, const EntG& ga, const EntG& gb, int ia, int ib) {
-  const bool box_sphere = (ga.shape == VMAS_SHAPE_BOX && gb.shape == VMAS_SHAPE_SPHERE) ||
-                          (gb.shape == VMAS_SHAPE_BOX && ga.shape == VMAS_SHAPE_SPHERE);
-  if (overlap_impossible(ga, gb)) return false;
-  if (box_sphere) {
-    const bool a_is_box = ga.shape == VMAS_SHAPE_BOX;
-    return box_sphere_overlap(q, a_is_box ? ga : gb, a_is_box ? gb : ga, a_is_box ? ib : ia);
-  }
-  return pair_distance(q, ga, gb, ia, ib) < 0.f;
-}
-
 __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatchArgs a) {
   const long env = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long B = a.base.cfg.batch_dim;
@@ -1253,11 +1132,11 @@ __global__ void __launch_bounds__(128) pair_query_batched_kernel(const PairBatch
     const int ia = __ldg(a.pairs + 2 * k), ib = __ldg(a.pairs + 2 * k + 1);
     const EntG ga = load_ent(a.base, ia, env_base), gb = load_ent(a.base, ib, env_base);
     if (a.base.mode == 0) {
-      static_cast<float*>(a.base.out)[idx] = pair_distance(a.base, ga, gb, ia, ib);
+      static_cast<float*>(a.base.out)[idx] = pair_distance(ga, gb);
     } else if (a.base.mode == 2) {
       static_cast<float*>(a.base.out)[idx] = norm2(ga.p - gb.p);
     } else {
-      static_cast<uint8_t*>(a.base.out)[idx] = pair_overlap(a.base, ga, gb, ia, ib) ? 1 : 0;
+      static_cast<uint8_t*>(a.base.out)[idx] = pair_overlap(ga, gb) ? 1 : 0;
     }
   }
 }
@@ -1318,11 +1197,6 @@ struct ObsSrc {
   unsigned base, pitch;
 };
 
-__device__ __noinline__ float obs_remainder(float v, float m) {  // torch.remainder: sign follows the modulus
-  float r = fmodf(v, m);
-  if (r != 0.f && (signbit(m) != signbit(r))) r = r + m;
-  return r;
-}
 
 // blockIdx.y = observation row, blockIdx.x = a tile of `tile_envs` consecutive envs.
 // (1) The tile's slab rows (pos, vel, rot, ang_vel: four contiguous global ranges) are copied to
@@ -1458,11 +1332,11 @@ DEVI void post_step_program_body(const ProgArgs& p, const int tile_envs) {
       switch (in.op) {
         case VMAS_OP_OVERLAP: {
           const EntG ga = load_ent(p.base, ia, env_base), gb = load_ent(p.base, ib, env_base);
-          r[in.dst] = pair_overlap(p.base, ga, gb, ia, ib) ? 1.f : 0.f;
+          r[in.dst] = pair_overlap(ga, gb) ? 1.f : 0.f;
         } break;
         case VMAS_OP_DISTANCE: {
           const EntG ga = load_ent(p.base, ia, env_base), gb = load_ent(p.base, ib, env_base);
-          r[in.dst] = pair_distance(p.base, ga, gb, ia, ib);
+          r[in.dst] = pair_distance(ga, gb);
         } break;
         case VMAS_OP_CENTER_DISTANCE: {
           const float2 pa = row[ia], pb = row[ib];
@@ -1852,6 +1726,38 @@ static int g_num_dyn_specs = 0;
 static int num_specs() { return kNumSpecs + g_num_dyn_specs; }
 static const SpecEntry& spec_at(int index) { return index < kNumSpecs ? kSpecs[index] : g_dyn_specs[index - kNumSpecs]; }
 
+// whole-step kernels compiled at run time (vmas_b200_register_step_kernel): handles 1, 2, ...
+struct FusedEntry {
+  uint64_t key;
+  int n_entities, n_items;
+  cudaError_t (*launch)(const SpecArgs&, const EpiArgs&, cudaStream_t);
+};
+static FusedEntry g_fused[VMAS_MAX_RUNTIME_SPECS];
+static int g_num_fused = 0;
+
+static SpecArgs spec_args_of(const StepArgs& args) {
+  SpecArgs sa;
+  sa.st = args.st;
+  sa.joint_rot = args.tb.joint_rot;
+  sa.mask = args.mask;
+  sa.batch_dim = args.cfg.batch_dim;
+  sa.use_mask = args.use_mask;
+  sa.first_substep = args.first_substep;
+  sa.n_substeps = args.n_substeps;
+  sa.order = nullptr;
+  sa.sig = nullptr;
+  return sa;
+}
+
+static int dispatch_fused(const StepArgs& args, int handle, const EpiArgs& epi, cudaStream_t stream) {
+  if (handle < 1 || handle > g_num_fused) return fail("unknown whole-step kernel%s");
+  const FusedEntry& f = g_fused[handle - 1];
+  if (f.n_entities != args.cfg.n_entities || f.n_items != args.cfg.n_items)
+    return fail("whole-step kernel does not match the world (stale handle?)%s");
+  CUDA_OK(f.launch(spec_args_of(args), epi, stream));
+  return 1;
+}
+
 static int dispatch_spec(const StepArgs& args, cudaStream_t stream) {
   const SpecEntry& sp = spec_at(args.tb.specialization);
   if (sp.n_entities != args.cfg.n_entities || sp.n_items != args.cfg.n_items)
@@ -1991,6 +1897,22 @@ int vmas_b200_register_specialization(uint64_t world_hash, int32_t n_entities, i
   return kNumSpecs + g_num_dyn_specs++;
 }
 
+int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch,
+                                   int32_t spec_args_bytes, int32_t epi_args_bytes) {
+  if (!launch) return fail("null launch function%s");
+  if (spec_args_bytes != (int32_t)sizeof(SpecArgs) || epi_args_bytes != (int32_t)sizeof(EpiArgs))
+    return fail("SpecArgs / EpiArgs layout mismatch: rebuild the whole-step kernel%s");
+  for (int i = 0; i < g_num_fused; ++i)
+    if (g_fused[i].key == key) return i + 1;
+  if (g_num_fused >= VMAS_MAX_RUNTIME_SPECS) return fail("too many whole-step kernels%s");
+  FusedEntry& e = g_fused[g_num_fused];
+  e.key = key;
+  e.n_entities = n_entities;
+  e.n_items = n_items;
+  e.launch = reinterpret_cast<cudaError_t (*)(const SpecArgs&, const EpiArgs&, cudaStream_t)>(launch);
+  return ++g_num_fused;
+}
+
 int vmas_b200_specialization_has_tile(int index) {
   return (index >= 0 && index < num_specs() && spec_at(index).has_tile) ? 1 : 0;
 }
@@ -2001,9 +1923,11 @@ const char* vmas_b200_specialization_name(int index) {
 
 const char* vmas_b200_last_error(void) { return g_last_error; }
 
+// `fused` > 0: the launches go to that whole-step kernel (its epilogue `epi` runs behind the last substep)
 static int substeps_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, const VmasState* st,
                          uint32_t* mask, int exact_broad_phase, int first_substep, int n_substeps,
-                         void* cuda_stream, void* ev_begin, void* ev_end) {
+                         void* cuda_stream, void* ev_begin, void* ev_end, int fused = 0,
+                         const EpiArgs* epi = nullptr) {
   if (check_common(cfg, tb, st) < 0) return -1;
   if (cfg->n_agents > 0 && (!st->force || !st->torque)) return fail("null force/torque pointer%s");
   if (cfg->n_items > 0 && (!tb->item_f32 || !tb->item_i32 || !tb->sched || !tb->inc || !tb->inc_off))
@@ -2024,7 +1948,7 @@ static int substeps_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, c
     args.first_substep = first_substep;
     args.n_substeps = n_substeps;
     if (ev_begin) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), stream));
-    int r = dispatch_step(args, stream);
+    int r = fused > 0 ? dispatch_fused(args, fused, *epi, stream) : dispatch_step(args, stream);
     if (r < 0) return r;
     if (ev_end) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), stream));
     return r;
@@ -2040,7 +1964,7 @@ static int substeps_impl(const VmasWorldConfig* cfg, const VmasPlanTables* tb, c
       launches += r;
     }
     if (ev_begin && s == first_substep) CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), stream));
-    r = dispatch_step(args, stream);
+    r = fused > 0 ? dispatch_fused(args, fused, *epi, stream) : dispatch_step(args, stream);
     if (r < 0) return r;
     launches += r;
   }
@@ -2507,6 +2431,63 @@ int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cu
   copy_buffers_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a, n_segs);
   CUDA_OK(cudaGetLastError());
   return 1;
+}
+
+// Environment.step as one call: the host side of a step is otherwise three crossings of the FFI (ingest,
+// graph replay through torch, hand-out copy) with their marshalling — more host time than the kernels take.
+int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
+  if (!s || !s->cfg || !s->tb || !s->st) return fail("null argument%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  int launches = 0, r;
+  if (s->n_agents > 0) {
+    r = ingest_impl(s->cfg, s->tb, s->st, s->agents, s->n_agents, s->clamp, s->bad_flag, s->steps, s->ingest_mask,
+                    cuda_stream);
+    if (r < 0) return r;
+    launches += r;
+  }
+  if (s->graph_exec) {
+    CUDA_OK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s->graph_exec), stream));
+  } else {
+    const bool has_post = (s->program && s->program->n_instr > 0) || (s->columns && s->n_rows > 0);
+    if (s->fused_kernel > 0 && has_post) {
+      // the whole-step kernel: the program and the observation rows run in the substep kernel's epilogue
+      EpiArgs epi;
+      epi.obs_out = s->obs_out;
+      for (int i = 0; i < VMAS_PROG_MAX_BUFFERS; ++i) epi.buffers[i] = s->program ? s->program->buffers[i] : nullptr;
+      if (s->columns && s->n_rows > 0 && (!s->obs_out || ((uintptr_t)s->obs_out & 15u))) return fail("observation block missing or not 16-byte aligned%s");
+      r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream, nullptr,
+                        nullptr, s->fused_kernel, &epi);
+      if (r < 0) return r;
+      launches += r;
+    } else {
+    r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream, nullptr,
+                      nullptr);
+    if (r < 0) return r;
+    launches += r;
+    if (has_post) {
+      r = vmas_b200_post_step(s->cfg, s->tb, s->st, s->program, s->columns, s->n_rows, s->width, s->obs_out,
+                              cuda_stream);
+      if (r < 0) return r;
+      launches += r;
+    }
+    }
+  }
+  if (s->n_segs > 0) {
+    if (s->n_segs > VMAS_MAX_COPY_SEGMENTS || !s->segs || !s->seg_block) return fail("bad hand-out segments%s");
+    if (s->n_out_blocks < 0 || s->n_out_blocks > VMAS_MAX_OUT_BLOCKS) return fail("too many output blocks%s");
+    VmasCopySegment segs[VMAS_MAX_COPY_SEGMENTS];
+    for (int i = 0; i < s->n_segs; ++i) {
+      const int b = s->seg_block[i];
+      if (b < 0 || b >= s->n_out_blocks || !s->out_blocks[b]) return fail("hand-out segment without its block%s");
+      segs[i].src = s->segs[i].src;
+      segs[i].dst = static_cast<char*>(s->out_blocks[b]) + reinterpret_cast<uintptr_t>(s->segs[i].dst);
+      segs[i].bytes = s->segs[i].bytes;
+    }
+    r = vmas_b200_copy_buffers(segs, s->n_segs, cuda_stream);
+    if (r < 0) return r;
+    launches += r;
+  }
+  return launches;
 }
 
 }  // extern "C"

@@ -47,6 +47,29 @@ int vmas_jit_spec_args_bytes(void) {{ return (int)sizeof(vmas::SpecArgs); }}
 }}
 """
 
+_STEP_TEMPLATE = """// GENERATED at run time by vectorizedmultiagentsimulator_b200/jit.py — one whole-step kernel:
+// the world's specialised substep kernel with a scenario's step program + observation rows as its epilogue.
+#include "spec_kernel.cuh"
+
+namespace vmas {{
+
+{world}
+
+{post}
+
+}}  // namespace vmas
+
+using W = vmas::{name};
+using P = vmas::{post_name};
+extern "C" {{
+cudaError_t vmas_jit_launch_fused(const vmas::SpecArgs& a, const vmas::EpiArgs& e, cudaStream_t stream) {{
+  return vmas::launch_fused<W, P>(a, e, stream);
+}}
+int vmas_jit_spec_args_bytes(void) {{ return (int)sizeof(vmas::SpecArgs); }}
+int vmas_jit_epi_args_bytes(void) {{ return (int)sizeof(vmas::EpiArgs); }}
+}}
+"""
+
 _lock = threading.Lock()
 _jobs: Dict[int, "Job"] = {}
 _keepalive = []  # loaded objects must outlive the registry entries that point into them
@@ -55,7 +78,7 @@ _keepalive = []  # loaded objects must outlive the registry entries that point i
 def _source_stamp() -> str:
     """Hash of the headers the object is compiled from: a header edit invalidates the cache."""
     h = hashlib.sha1()
-    for name in ("geometry.cuh", "spec_kernel.cuh", "spec_tile_kernel.cuh"):
+    for name in ("geometry.cuh", "query.cuh", "spec_kernel.cuh", "spec_tile_kernel.cuh"):
         h.update(open(os.path.join(_native.CSRC, name), "rb").read())
     h.update(open(os.path.join(_native.INCLUDE, "vmas_b200.h"), "rb").read())
     return h.hexdigest()[:12]
@@ -140,6 +163,69 @@ def request(desc: P.WorldDescription) -> Optional[Job]:
                 start = thread.start
         else:
             start = None
+    if start is not None:
+        start()
+    return job
+
+
+class StepKernelJob(Job):
+    """The whole-step kernel of one (world, observation columns, step program): ``index`` is the handle for
+    ``VmasEnvStep.fused_kernel`` once ``done`` is set."""
+
+    def __init__(self, desc: P.WorldDescription, cols, instrs):
+        super().__init__(desc)
+        self.cols, self.instrs = cols, instrs
+        self.post_hash = codegen.post_hash(cols, instrs)
+        self.key = (self.hash ^ ((self.post_hash << 1) | (self.post_hash >> 63))) & 0xFFFFFFFFFFFFFFFF
+
+    def _compile_and_register(self) -> int:
+        desc = self.desc
+        name, text, h = codegen.emit_world(desc, "whole-step kernel")
+        post_name, post_text, _ = codegen.emit_post(self.cols, self.instrs)
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        stem = os.path.join(CACHE_DIR, f"step_{self.key:016x}_{_native.ARITH}_{_source_stamp()}")
+        so = stem + ".so"
+        if not os.path.exists(so):
+            with open(stem + ".cu", "w") as fh:
+                fh.write(_STEP_TEMPLATE.format(world=text, post=post_text, name=name, post_name=post_name))
+            flags = _native.NVCC_FLAGS + _native.ARITH_FLAGS[_native.ARITH]
+            tmp = f"{so}.{os.getpid()}.tmp"
+            cmd = [_native._nvcc()] + flags + ["-I", _native.INCLUDE, "-I", _native.CSRC, "-o", tmp, stem + ".cu"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                raise RuntimeError(f"nvcc failed: {proc.stderr[-600:]}")
+            os.replace(tmp, so)
+        obj = C.CDLL(so)
+        lib = _native.load()
+        with _lock:
+            handle = lib.vmas_b200_register_step_kernel(
+                C.c_uint64(self.key), desc.n_entities, len(desc.items), C.cast(obj.vmas_jit_launch_fused, C.c_void_p),
+                obj.vmas_jit_spec_args_bytes(), obj.vmas_jit_epi_args_bytes(),
+            )
+            if handle <= 0:
+                raise RuntimeError(lib.vmas_b200_last_error().decode())
+            _keepalive.append(obj)
+        return handle
+
+
+_step_jobs: Dict[int, StepKernelJob] = {}
+
+
+def request_step_kernel(desc: P.WorldDescription, cols, instrs, block: bool = False) -> Optional[StepKernelJob]:
+    """Starts (or finds) the compilation of the whole-step kernel; None if the world cannot be specialised."""
+    if not available() or not codegen.specializable(desc):
+        return None
+    job = StepKernelJob(desc, cols, instrs)
+    with _lock:
+        have = _step_jobs.get(job.key)
+        if have is None:
+            _step_jobs[job.key] = job
+            if MODE == "block" or block:
+                start = job.run
+            else:
+                start = threading.Thread(target=job.run, name=f"vmas-b200-jit-step-{job.key:016x}", daemon=True).start
+        else:
+            job, start = have, None
     if start is not None:
         start()
     return job

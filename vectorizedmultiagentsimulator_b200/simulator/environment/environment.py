@@ -38,6 +38,9 @@ from ..scenario import BaseScenario
 from ..utils import AGENT_OBS_TYPE, DEVICE_TYPING, TorchUtils
 from . import spaces
 
+#: a captured step runs through ONE call into the library (``vmas_b200_env_step``: ingest, graph launch, hand-out)
+_ONE_CALL_STEP = os.environ.get("VMAS_B200_ONE_CALL_STEP", "1") != "0"
+
 
 def _rebuild_outputs(node, fresh):
     """Output structure of a captured step with fresh leaves.  A module-level function: a
@@ -165,6 +168,8 @@ class Environment(TorchVectorizedObject):
             self._graph_outputs = None
             self._graph_plan_version = None
             self._graph_warmup_left = 2
+            self._one_call = None
+            self._one_call_state = "off"
             self.graph_replays = 0
 
             observations = self._reset(seed=seed)
@@ -579,6 +584,8 @@ class Environment(TorchVectorizedObject):
                 self._graph_warmup_left -= 1
                 return self._step_device([a.to(self.device) for a in actions])
             self._capture(actions)
+        if self._one_call_state == "on" and self._fused_ingest_applies(actions):
+            return self._step_one_call(actions)
         if self._graph_inputs is None:
             # the fused ingest kernel reads the caller's tensors directly (one eager launch in
             # front of the replay; no staging copy into graph-owned input buffers)
@@ -596,7 +603,15 @@ class Environment(TorchVectorizedObject):
         else:
             for static, a in zip(self._graph_inputs, actions):
                 static.copy_(a, non_blocking=True)
-        self._graph.replay()
+        if self._one_call_state == "probe":
+            # torch's replay advances the philox offset of a graph that draws random numbers; a raw
+            # cudaGraphLaunch would replay the same numbers, so such a graph stays on torch's replay
+            gen = torch.cuda.default_generators[self.device.index if self.device.index is not None else torch.cuda.current_device()]
+            before = gen.get_offset()
+            self._graph.replay()
+            self._one_call_state = "on" if gen.get_offset() == before else "off"
+        else:
+            self._graph.replay()
         self.graph_replays += 1
         backend = world._get_backend()
         backend.launches += self._graph_launches
@@ -690,8 +705,6 @@ class Environment(TorchVectorizedObject):
 
     def _unpack_graph_outputs(self):
         """Fresh output tensors: one clone per pack, then views (no further kernel launches)."""
-        fresh = [None] * len(self._graph_out_shapes)
-        packs = self._graph_out_packs
         copies = [torch.empty(n, dtype=dtype, device=self.device) for n, dtype in self._graph_out_blocks]
         # one kernel for every output block (an SM copy: a cudaMemcpy D2D would queue on a copy engine
         # behind a concurrent download of the previous step's results); sources and sizes were marshalled
@@ -700,6 +713,12 @@ class Environment(TorchVectorizedObject):
         bases = [c.data_ptr() for c in copies]
         for plan in self._graph_out_copy:
             backend.launches += plan.run(backend.lib, backend.device, bases)
+        return self._views_of_output_blocks(copies)
+
+    def _views_of_output_blocks(self, copies):
+        """The step's output structure over freshly filled blocks (views only: no launches)."""
+        fresh = [None] * len(self._graph_out_shapes)
+        packs = self._graph_out_packs
         # leaves of equal shape that sit next to each other come out of ONE view + unbind
         for flat, (_, ids), layout in zip(copies, packs, self._graph_out_layouts):
             pieces = [flat] if len(layout) == 1 else flat.split_with_sizes([n * numel for n, _, numel in layout])
@@ -737,6 +756,7 @@ class Environment(TorchVectorizedObject):
             if ingest_outside:
                 # (binds the action buffers; the replay that follows the capture ingests — and counts — again)
                 self._apply_actions([a.to(self._ingest_dtype()).contiguous() for a in dev_actions], count_step=False)
+            ingest_built_mask = bool(getattr(backend, "_mask_ready", False))
             before = backend.launches
             with torch.cuda.graph(graph):
                 # outputs stay un-cloned inside the graph; they are packed into flat buffers
@@ -757,6 +777,61 @@ class Environment(TorchVectorizedObject):
         self._graph = graph
         self._graph_outputs = outputs
         self._graph_plan_version = self.world._plan_version
+        self._one_call = None
+        self._one_call_state = "off"
+        if ingest_outside and _ONE_CALL_STEP:
+            self._one_call = self._build_one_call_step(graph, ingest_built_mask)
+            # the first replay goes through torch and tells whether the graph draws device random numbers
+            self._one_call_state = "probe" if self._one_call is not None else "off"
+
+    def _build_one_call_step(self, graph, ingest_built_mask: bool):
+        """Everything ``vmas_b200_env_step`` needs, marshalled once (None: this step does not fit the call)."""
+        backend = self.world._get_backend()
+        N = backend._native
+        specs = self._fused_ingest_specs()
+        live = [i for i, s in enumerate(specs) if s[0].action_size > 0]
+        arr = getattr(backend, "_ingest_arr", None)
+        if (
+            arr is None or len(arr) != len(live) or not live or len(live) > N.MAX_INGEST_AGENTS
+            or len(self._graph_out_copy) > 1 or len(self._graph_out_blocks) > N.MAX_OUT_BLOCKS
+            or not hasattr(graph, "raw_cuda_graph_exec")
+        ):
+            return None
+        counts = self.steps.dtype == torch.float32 and self.steps.is_contiguous()
+        copy = self._graph_out_copy[0] if self._graph_out_copy else None
+        items = [] if copy is None else [(src, block, offset) for src, (block, offset) in zip(copy.keep, copy.where)]
+        plan = N.EnvStepPlan(
+            backend.lib, backend._dev_tables, self.world.slab, arr, len(live), self.clamp_action,
+            self._bad_action_flag if self.action_checks == "deferred" else None, self.steps if counts else None,
+            ingest_built_mask, graph.raw_cuda_graph_exec(), items, len(self._graph_out_blocks),
+        )
+        plan.live = live
+        plan.counts = counts
+        plan.drones = list(getattr(backend, "_ingest_drones", []))
+        plan.launches = (1 if copy is not None else 0) + 1
+        return plan
+
+    def _step_one_call(self, actions: List[Tensor]):
+        """A captured step through ``vmas_b200_env_step``: action ingest, graph launch and the hand-out copy
+        in one crossing of the FFI."""
+        plan = self._one_call
+        agents = plan.agents
+        for k, i in enumerate(plan.live):
+            agents[k].actions = actions[i].data_ptr()
+        for c, model in plan.drones:  # a reset re-binds the drone's 12-state tensor
+            c.dyn_state = model.drone_state.data_ptr()
+        device = self.device
+        copies = [torch.empty(n, dtype=dtype, device=device) for n, dtype in self._graph_out_blocks]
+        blocks = plan.out_blocks
+        for j, c in enumerate(copies):
+            blocks[j] = c.data_ptr()
+        plan.run()
+        self.graph_replays += 1
+        backend = self.world._get_backend()
+        backend.launches += self._graph_launches + plan.launches
+        backend._mask_ready = False
+        backend.after_step()
+        return self._views_of_output_blocks(copies)
 
     def _done(self, clone=True):
         terminated = self.scenario.done()

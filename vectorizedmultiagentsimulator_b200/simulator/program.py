@@ -182,6 +182,16 @@ class StepProgram:
         self._finalized = True
         return self
 
+    def instructions(self, index_of) -> List[Tuple]:
+        """``[(op, dst, a, b, arg, imm)]`` with the entities of query instructions resolved to slab indices
+        (``arg = index_a | index_b << 16``), as ``VmasProgInstr`` holds them."""
+        out = []
+        for op, dst, a, b, arg, imm, entities in self.instr:
+            if entities is not None:
+                arg = index_of(entities[0]) | (index_of(entities[1]) << 16)
+            out.append((op, dst, a, b, arg, imm))
+        return out
+
     # -- running ---------------------------------------------------------------------------
     def resolve(self, buf) -> Tensor:
         if isinstance(buf, Output):
