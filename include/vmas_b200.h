@@ -108,7 +108,7 @@ typedef struct VmasCopySegment {
   void* dst;
   size_t bytes;
 } VmasCopySegment;
-#define VMAS_MAX_COPY_SEGMENTS 32
+#define VMAS_MAX_COPY_SEGMENTS 64
 
 int vmas_b200_abi_version(void);
 const char* vmas_b200_last_error(void);
@@ -238,7 +238,7 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
  * `columns`, `n_rows`, `width`, `obs_out`: as vmas_b200_gather_observations (or NULL / 0: program only).
  */
 #define VMAS_PROG_MAX_INSTR 64
-#define VMAS_PROG_MAX_BUFFERS 16
+#define VMAS_PROG_MAX_BUFFERS 32
 #define VMAS_PROG_REGS 32
 enum {
   VMAS_OP_OVERLAP = 1, VMAS_OP_DISTANCE, VMAS_OP_CENTER_DISTANCE, VMAS_OP_SHAPING, VMAS_OP_LOAD_F32, VMAS_OP_LOAD_BOOL,
@@ -403,7 +403,7 @@ int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasP
  *      `fused_kernel`, ONE launch doing both;
  *   3. vmas_b200_copy_buffers handing results out: segment i is copied to out_blocks[seg_block[i]] +
  *      (byte offset held in segs[i].dst), so that a caller allocating fresh result blocks every step only
- *      fills in `out_blocks`.
+ *      fills in `out_blocks` (n_segs may be 0: see `obs_block` / `mirror_*` below).
  * `ingest_mask` non-NULL: the ingest launch also builds the first substep's broad-phase mask (then
  * `exact_broad_phase` must be 2 in direct mode, and the captured graph must have been captured that way).
  * Returns the number of kernels this call launched itself (the graph's nodes are not counted).
@@ -417,6 +417,10 @@ int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasP
  */
 int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch,
                                    int32_t spec_args_bytes, int32_t epi_args_bytes);
+
+/* Number of nodes of a cudaGraph_t (a caller that captured a step checks whether the graph holds only
+ * this library's launches: then VmasEnvStep's direct mode can stand in for it). */
+int vmas_b200_graph_num_nodes(void* cuda_graph);
 
 #define VMAS_MAX_OUT_BLOCKS 8
 typedef struct VmasEnvStep {
@@ -443,6 +447,15 @@ typedef struct VmasEnvStep {
   const int32_t* seg_block;
   int32_t n_segs, n_out_blocks;
   void* out_blocks[VMAS_MAX_OUT_BLOCKS];
+  /* direct mode: results written straight into the caller's fresh blocks instead of being copied there.
+   * obs_block >= 0: the observation rows go to out_blocks[obs_block] + obs_offset (not to `obs_out`);
+   * mirror i: program buffer slot mirror_slot[i] (the target of a STORE instruction the caller appended for
+   * one of its result leaves) is out_blocks[mirror_block[i]] + mirror_offset[i] in this step. */
+  int32_t obs_block, n_mirrors;
+  size_t obs_offset;
+  int32_t mirror_slot[VMAS_PROG_MAX_BUFFERS];
+  int32_t mirror_block[VMAS_PROG_MAX_BUFFERS];
+  size_t mirror_offset[VMAS_PROG_MAX_BUFFERS];
 } VmasEnvStep;
 int vmas_b200_env_step(const VmasEnvStep* step, void* cuda_stream);
 

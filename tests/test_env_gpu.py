@@ -422,22 +422,63 @@ def test_a_graph_that_draws_device_random_numbers_stays_on_torchs_replay():
     assert quiet._one_call_state == "on"
 
 
-def test_one_call_step_can_be_switched_off_and_changes_no_bit(monkeypatch):
+def test_every_way_of_issuing_a_captured_step_gives_the_same_bits(monkeypatch):
+    """balance's captured step holds only library launches, so it runs as ONE whole-step kernel behind the
+    ingest launch (substeps + step program + observation rows, results written straight into the step's
+    fresh output tensors; vmas_b200_env_step, direct mode).  The same step with the results copied out of
+    static buffers, as two launches (no whole-step kernel), as a graph launch from the library, as torch's
+    replay with separate ingest / hand-out calls, and eagerly must all give the same bits."""
     from vectorizedmultiagentsimulator_b200.simulator.environment import environment as E
 
-    envs = []
-    for flag in (True, False):
-        monkeypatch.setattr(E, "_ONE_CALL_STEP", flag)
-        env = b200.make_env("balance", num_envs=96, device="cuda", seed=0, cuda_graph=True, n_agents=4)
-        env.reset()
-        envs.append(env)
+    variants = {
+        "whole-step kernel": dict(),
+        "copied results": dict(_WRITE_RESULTS_IN_PLACE=False),
+        "two launches": dict(_WHOLE_STEP_KERNEL=False),
+        "graph launch": dict(_DIRECT_STEP=False),
+        "torch replay": dict(_ONE_CALL_STEP=False),
+    }
+    envs = {}
+    for label, flags in variants.items():
+        with monkeypatch.context() as m:
+            for k, v in flags.items():
+                m.setattr(E, k, v)
+            env = b200.make_env("balance", num_envs=96, device="cuda", seed=0, cuda_graph=True, n_agents=4)
+            env.reset()
+            # (the flags are read when the step is captured: warm-up steps + capture happen here)
+            for _ in range(4):
+                env.step([torch.zeros(96, 2, device="cuda") for _ in range(4)])
+            envs[label] = env
+    eager = b200.make_env("balance", num_envs=96, device="cuda", seed=0, n_agents=4)
+    eager.reset()
+    for _ in range(4):
+        eager.step([torch.zeros(96, 2, device="cuda") for _ in range(4)])
+    for env in envs.values():
+        sync_env(eager, env)
     gen = torch.Generator().manual_seed(5)
-    for t in range(8):
+    for t in range(10):
         actions = [(torch.rand(96, 2, generator=gen) * 2 - 1).cuda() for _ in range(4)]
-        a = envs[0].step([x.clone() for x in actions])
-        monkeypatch.setattr(E, "_ONE_CALL_STEP", False)
-        b = envs[1].step([x.clone() for x in actions])
-        for g, w in zip(flatten(a), flatten(b)):
-            assert torch.equal(g, w)
-    assert envs[0]._one_call_state == "on" and envs[1]._one_call_state == "off"
-    assert float(envs[0].steps[0]) == float(envs[1].steps[0]) == 8.0
+        want = eager.step([x.clone() for x in actions])
+        for label, env in envs.items():
+            got = env.step([x.clone() for x in actions])
+            for i, (g, w) in enumerate(zip(flatten(got), flatten(want))):
+                assert torch.equal(g, w), f"{label}: step {t} output {i}"
+            for k in ("pos", "vel", "rot", "ang_vel"):
+                assert torch.equal(getattr(env.world.slab, k), getattr(eager.world.slab, k)), f"{label}: step {t} {k}"
+        if t == 5:  # a partial reset in between (the carried shaping term is rewritten in place)
+            eager.reset_at(7)
+            for env in envs.values():
+                env.reset_at(7)
+                sync_env(eager, env)
+    whole, copied, two, graph, replay = (envs[k] for k in variants)
+    assert whole._one_call_state == "on" and whole._one_call.direct and whole._one_call.c.fused_kernel > 0
+    assert whole._one_call.c.n_segs == 0 and whole._one_call.c.obs_block >= 0 and whole._one_call.c.n_mirrors == 13
+    assert copied._one_call.c.fused_kernel > 0 and copied._one_call.c.n_segs == 14 and copied._one_call.c.n_mirrors == 0
+    assert two._one_call_state == "on" and two._one_call.direct and two._one_call.c.fused_kernel == 0
+    assert graph._one_call_state == "on" and not graph._one_call.direct
+    assert replay._one_call_state == "off"
+    assert float(whole.steps[0]) == float(eager.steps[0])
+    # kernels per step: ingest (+ broad phase) and the whole-step kernel; with copied results the hand-out copy
+    for env, n in ((whole, 2), (copied, 3), (two, 3)):
+        before = env.world._get_backend().launches
+        env.step(actions)
+        assert env.world._get_backend().launches - before == n

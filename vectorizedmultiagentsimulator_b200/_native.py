@@ -255,6 +255,7 @@ EXPORTS = [
     "vmas_b200_copy_buffers",
     "vmas_b200_env_step",
     "vmas_b200_register_step_kernel",
+    "vmas_b200_graph_num_nodes",
     "vmas_b200_build_env_order",
     "vmas_b200_set_l2_fetch_granularity",
     "vmas_b200_reset_state",
@@ -327,6 +328,7 @@ def load():
         C.c_float, C.c_float, C.c_void_p,
     ]
     lib.vmas_b200_env_step.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vmas_b200_graph_num_nodes.argtypes = [C.c_void_p]
     lib.vmas_b200_register_step_kernel.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
     lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.vmas_b200_set_l2_fetch_granularity.argtypes = [C.c_int32]
@@ -657,7 +659,7 @@ def velocity_controller(lib, dt: DeviceTables, slab, entity: int, u, accum, prev
     return _check(lib, rc)
 
 
-PROG_MAX_INSTR, PROG_MAX_BUFFERS = 64, 16
+PROG_MAX_INSTR, PROG_MAX_BUFFERS = 64, 32
 
 
 class ProgInstrC(C.Structure):
@@ -688,7 +690,7 @@ class CopySegmentC(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_size_t)]
 
 
-MAX_COPY_SEGMENTS = 32
+MAX_COPY_SEGMENTS = 64
 
 
 def copy_buffers(lib, device, pairs) -> int:
@@ -744,6 +746,9 @@ class EnvStepC(C.Structure):
         ("obs_out", C.c_void_p),
         ("segs", C.c_void_p), ("seg_block", C.c_void_p), ("n_segs", C.c_int32), ("n_out_blocks", C.c_int32),
         ("out_blocks", C.c_void_p * MAX_OUT_BLOCKS),
+        ("obs_block", C.c_int32), ("n_mirrors", C.c_int32), ("obs_offset", C.c_size_t),
+        ("mirror_slot", C.c_int32 * PROG_MAX_BUFFERS), ("mirror_block", C.c_int32 * PROG_MAX_BUFFERS),
+        ("mirror_offset", C.c_size_t * PROG_MAX_BUFFERS),
     ]
 
 
@@ -755,7 +760,10 @@ class EnvStepPlan:
 
     def __init__(self, lib, dt: "DeviceTables", slab, agents_c, n_agents: int, clamp: bool, bad_flag, steps,
                  ingest_broad_phase: bool, graph_exec: int, copy_items, n_out_blocks: int,
-                 program=None, columns=None, n_rows: int = 0, width: int = 0, obs_out=None, exact_broad_phase: int = 1):
+                 program=None, columns=None, n_rows: int = 0, width: int = 0, obs_out=None, exact_broad_phase: int = 1,
+                 obs_to=None, mirrors=()):
+        """``obs_to``: (block, byte offset) the observation rows are written to directly (direct mode);
+        ``mirrors``: [(program buffer slot, block, byte offset)] stores that land in the fresh blocks."""
         assert len(copy_items) <= MAX_COPY_SEGMENTS and n_out_blocks <= MAX_OUT_BLOCKS and n_agents <= MAX_INGEST_AGENTS
         self.lib, self.device = lib, dt.device
         st = dt.state_struct(slab)
@@ -780,6 +788,13 @@ class EnvStepPlan:
         c.obs_out = None if obs_out is None else obs_out.data_ptr()
         c.segs, c.seg_block = C.addressof(segs), C.addressof(blocks)
         c.n_segs, c.n_out_blocks = len(copy_items), n_out_blocks
+        c.obs_block = -1
+        if obs_to is not None:
+            c.obs_block, c.obs_offset = obs_to
+        assert len(mirrors) <= PROG_MAX_BUFFERS
+        c.n_mirrors = len(mirrors)
+        for k, (slot, block, offset) in enumerate(mirrors):
+            c.mirror_slot[k], c.mirror_block[k], c.mirror_offset[k] = slot, block, offset
         self.out_blocks = c.out_blocks
         self.agents = agents_c
         self._ref = C.addressof(c)

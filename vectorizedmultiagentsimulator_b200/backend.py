@@ -121,6 +121,8 @@ class CudaBackend(PlanRuntime):
         #: when set to a list, every step() appends a (begin, end) event pair bracketing the
         #: substep kernel(s) (bench.py's roofline measurement)
         self.kernel_events = None
+        #: while a list: the library launches of a step being captured, in order (Environment._capture)
+        self.trace = None
 
     # -- tables ----------------------------------------------------------------------------
     def on_new_tables(self):
@@ -201,7 +203,10 @@ class CudaBackend(PlanRuntime):
         # 2: the fused ingest launch of this step already built the first substep's broad-phase mask
         mode = 2 if (getattr(self, "_mask_ready", False) and self.world.exact_broad_phase) else self.world.exact_broad_phase
         self._mask_ready = False
-        self.launches += self._native.world_step(self.lib, self._dev_tables, slab, exact_broad_phase=mode, events=events)
+        n = self._native.world_step(self.lib, self._dev_tables, slab, exact_broad_phase=mode, events=events)
+        self.launches += n
+        if self.trace is not None:
+            self.trace.append(("step", n, int(mode)))
         if not torch.cuda.is_current_stream_capturing():
             self.after_step()  # (a graph replay calls it itself: Environment._step_graphed)
 
@@ -322,9 +327,15 @@ class CudaBackend(PlanRuntime):
             assert t.dtype in (torch.float32, torch.bool, torch.uint8), "program buffers are fp32 or bool"
             c.buffers[slot] = t.data_ptr()
         if observe is not None:
-            return self.observe(observe, program=c)
+            before = self.launches
+            out = self.observe(observe, program=c)
+            if self.trace is not None:
+                self.trace.append(("post", self.launches - before, prog, observe, c, out))
+            return out
         self._native.post_step(self.lib, self._dev_tables, self.world.slab, c, None, 0, 0, None)
         self.launches += 1
+        if self.trace is not None:
+            self.trace.append(("post", 1, prog, None, c, None))
         return None
 
     def observe(self, plan, program=None) -> Tensor:

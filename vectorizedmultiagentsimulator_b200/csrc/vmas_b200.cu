@@ -2433,6 +2433,13 @@ int vmas_b200_copy_buffers(const VmasCopySegment* segs, int32_t n_segs, void* cu
   return 1;
 }
 
+int vmas_b200_graph_num_nodes(void* cuda_graph) {
+  if (!cuda_graph) return fail("null graph%s");
+  size_t n = 0;
+  CUDA_OK(cudaGraphGetNodes(static_cast<cudaGraph_t>(cuda_graph), nullptr, &n));
+  return (int)n;
+}
+
 // Environment.step as one call: the host side of a step is otherwise three crossings of the FFI (ingest,
 // graph replay through torch, hand-out copy) with their marshalling — more host time than the kernels take.
 int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
@@ -2445,16 +2452,36 @@ int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
     if (r < 0) return r;
     launches += r;
   }
+  if (s->n_out_blocks < 0 || s->n_out_blocks > VMAS_MAX_OUT_BLOCKS) return fail("too many output blocks%s");
   if (s->graph_exec) {
     CUDA_OK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s->graph_exec), stream));
   } else {
-    const bool has_post = (s->program && s->program->n_instr > 0) || (s->columns && s->n_rows > 0);
+    // results that go straight into this step's fresh blocks: the observation rows, mirrored program stores
+    float* obs_out = s->obs_out;
+    if (s->obs_block >= 0 && s->columns && s->n_rows > 0) {
+      if (s->obs_block >= s->n_out_blocks || !s->out_blocks[s->obs_block]) return fail("observation rows without their block%s");
+      obs_out = reinterpret_cast<float*>(static_cast<char*>(s->out_blocks[s->obs_block]) + s->obs_offset);
+    }
+    VmasStepProgram patched;
+    const VmasStepProgram* program = s->program;
+    if (s->n_mirrors > 0) {
+      if (!s->program || s->n_mirrors > VMAS_PROG_MAX_BUFFERS) return fail("mirrored stores without a program%s");
+      patched = *s->program;
+      for (int i = 0; i < s->n_mirrors; ++i) {
+        const int slot = s->mirror_slot[i], b = s->mirror_block[i];
+        if (slot < 0 || slot >= VMAS_PROG_MAX_BUFFERS || b < 0 || b >= s->n_out_blocks || !s->out_blocks[b])
+          return fail("bad mirrored store%s");
+        patched.buffers[slot] = static_cast<char*>(s->out_blocks[b]) + s->mirror_offset[i];
+      }
+      program = &patched;
+    }
+    const bool has_post = (program && program->n_instr > 0) || (s->columns && s->n_rows > 0);
     if (s->fused_kernel > 0 && has_post) {
       // the whole-step kernel: the program and the observation rows run in the substep kernel's epilogue
       EpiArgs epi;
-      epi.obs_out = s->obs_out;
-      for (int i = 0; i < VMAS_PROG_MAX_BUFFERS; ++i) epi.buffers[i] = s->program ? s->program->buffers[i] : nullptr;
-      if (s->columns && s->n_rows > 0 && (!s->obs_out || ((uintptr_t)s->obs_out & 15u))) return fail("observation block missing or not 16-byte aligned%s");
+      epi.obs_out = obs_out;
+      for (int i = 0; i < VMAS_PROG_MAX_BUFFERS; ++i) epi.buffers[i] = program ? program->buffers[i] : nullptr;
+      if (s->columns && s->n_rows > 0 && (!obs_out || ((uintptr_t)obs_out & 15u))) return fail("observation block missing or not 16-byte aligned%s");
       r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream, nullptr,
                         nullptr, s->fused_kernel, &epi);
       if (r < 0) return r;
@@ -2465,7 +2492,7 @@ int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
     if (r < 0) return r;
     launches += r;
     if (has_post) {
-      r = vmas_b200_post_step(s->cfg, s->tb, s->st, s->program, s->columns, s->n_rows, s->width, s->obs_out,
+      r = vmas_b200_post_step(s->cfg, s->tb, s->st, program, s->columns, s->n_rows, s->width, obs_out,
                               cuda_stream);
       if (r < 0) return r;
       launches += r;
@@ -2474,7 +2501,6 @@ int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
   }
   if (s->n_segs > 0) {
     if (s->n_segs > VMAS_MAX_COPY_SEGMENTS || !s->segs || !s->seg_block) return fail("bad hand-out segments%s");
-    if (s->n_out_blocks < 0 || s->n_out_blocks > VMAS_MAX_OUT_BLOCKS) return fail("too many output blocks%s");
     VmasCopySegment segs[VMAS_MAX_COPY_SEGMENTS];
     for (int i = 0; i < s->n_segs; ++i) {
       const int b = s->seg_block[i];

@@ -229,3 +229,41 @@ def request_step_kernel(desc: P.WorldDescription, cols, instrs, block: bool = Fa
     if start is not None:
         start()
     return job
+
+
+def prebuild_step_kernels(verbose: bool = False):
+    """Compiles the whole-step kernels of the preset worlds (``codegen.PRESETS``) whose scenario is written
+    on a step program, so that they are in the on-disk cache before the first capture (``__graft_entry__.build``).
+    Returns ``[(label, key)]``."""
+    import torch
+
+    from . import scenarios
+
+    built = []
+    stamp = f"_{_source_stamp()}."
+    if os.path.isdir(CACHE_DIR):  # objects compiled from older headers can never be loaded again
+        for name in os.listdir(CACHE_DIR):
+            if stamp not in name:
+                os.remove(os.path.join(CACHE_DIR, name))
+    for scenario, kwargs, *_ in codegen.PRESETS:
+        sc = scenarios.load(scenario + ".py").Scenario()
+        if not (hasattr(sc, "_step_program") and hasattr(sc, "_observation_plan")):
+            continue
+        world = sc.env_make_world(1, torch.device("cpu"), **dict(kwargs))
+        prog, plan = sc._step_program(), sc._observation_plan()
+        cols, lidars = plan.compile(world)
+        if lidars:
+            continue
+        index = {id(e): i for i, e in enumerate(world.entities)}
+        desc = P.describe_world(world)
+        if not codegen.specializable(desc):
+            continue
+        job = StepKernelJob(desc, cols if (cols[..., 0] != 0).any() else None, prog.instructions(lambda e: index[id(e)]))
+        job.run()
+        label = scenario + "(" + ", ".join(f"{k}={v}" for k, v in kwargs.items()) + ")"
+        if job.error:
+            raise RuntimeError(f"whole-step kernel of {label}: {job.error}")
+        if verbose:
+            print(f"whole-step kernel {job.key:016x}  {label}  ({job.seconds:.1f} s)")
+        built.append((label, job.key))
+    return built

@@ -24,6 +24,7 @@ with one ``[num_envs, ...]`` tensor per policy agent).  What differs is undernea
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import math
 import os
 import random
@@ -40,6 +41,14 @@ from . import spaces
 
 #: a captured step runs through ONE call into the library (``vmas_b200_env_step``: ingest, graph launch, hand-out)
 _ONE_CALL_STEP = os.environ.get("VMAS_B200_ONE_CALL_STEP", "1") != "0"
+#: ... which issues the step's launches itself when the captured graph holds nothing but library launches
+_DIRECT_STEP = os.environ.get("VMAS_B200_DIRECT_STEP", "1") != "0"
+#: ... as ONE whole-step kernel (substeps + the scenario's step program + observation rows) compiled for the
+#: (world, program, plan) at hand; the capture waits this long for the compiler before going on without it
+_WHOLE_STEP_KERNEL = os.environ.get("VMAS_B200_WHOLE_STEP_KERNEL", "1") != "0"
+#: ... and writes the step's results straight into the fresh output blocks (no hand-out copy)
+_WRITE_RESULTS_IN_PLACE = os.environ.get("VMAS_B200_RESULTS_IN_PLACE", "1") != "0"
+_WHOLE_STEP_KERNEL_WAIT_S = float(os.environ.get("VMAS_B200_WHOLE_STEP_KERNEL_WAIT_S", "60"))
 
 
 def _rebuild_outputs(node, fresh):
@@ -751,13 +760,17 @@ class Environment(TorchVectorizedObject):
         backend.refresh()
         backend.wait_for_jit()  # a run-time specialisation still compiling: capture the kernel that stays
         torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
+        try:
+            graph = torch.cuda.CUDAGraph(keep_graph=True)  # (the node count below needs the cudaGraph_t)
+        except TypeError:  # pragma: no cover
+            graph = torch.cuda.CUDAGraph()
         try:
             if ingest_outside:
                 # (binds the action buffers; the replay that follows the capture ingests — and counts — again)
                 self._apply_actions([a.to(self._ingest_dtype()).contiguous() for a in dev_actions], count_step=False)
             ingest_built_mask = bool(getattr(backend, "_mask_ready", False))
             before = backend.launches
+            backend.trace = []
             with torch.cuda.graph(graph):
                 # outputs stay un-cloned inside the graph; they are packed into flat buffers
                 # there, and each replay hands out clones of those buffers
@@ -767,6 +780,7 @@ class Environment(TorchVectorizedObject):
                     outputs = self._step_device(self._graph_inputs, clone_outputs=False)
                 self._pack_graph_outputs(outputs)
         except Exception as err:  # noqa: BLE001
+            backend.trace = None
             raise RuntimeError(
                 "cuda_graph=True: capturing Environment.step failed. The scenario (or a dynamics / "
                 "action script) is not graph-safe: it must not synchronise with the host inside "
@@ -774,17 +788,42 @@ class Environment(TorchVectorizedObject):
             ) from err
         self._graph_launches = backend.launches - before
         backend.launches = before
+        trace, backend.trace = backend.trace, None
+        if hasattr(graph, "instantiate"):
+            graph.instantiate()
         self._graph = graph
         self._graph_outputs = outputs
         self._graph_plan_version = self.world._plan_version
         self._one_call = None
         self._one_call_state = "off"
         if ingest_outside and _ONE_CALL_STEP:
-            self._one_call = self._build_one_call_step(graph, ingest_built_mask)
+            self._one_call = self._build_one_call_step(graph, ingest_built_mask, trace)
             # the first replay goes through torch and tells whether the graph draws device random numbers
             self._one_call_state = "probe" if self._one_call is not None else "off"
 
-    def _build_one_call_step(self, graph, ingest_built_mask: bool):
+    def _library_only_step(self, graph, trace):
+        """``(exact_broad_phase mode, program struct, StepProgram, plan, columns, obs block)`` if the captured
+        step consists of nothing but this library's ``World.step`` followed by one step program / observation
+        launch — the graph then holds no torch kernel, and ``vmas_b200_env_step`` can issue those launches
+        itself (direct mode), or one whole-step kernel.  None otherwise."""
+        if not _DIRECT_STEP or trace is None or [t[0] for t in trace] != ["step", "post"]:
+            return None
+        (_, n_step, mode), (_, n_post, prog, plan, c, out) = trace
+        if n_post != 1 or n_step + n_post != self._graph_launches:
+            return None  # (LIDAR columns ride in a second launch; anything else the backend launched)
+        backend = self.world._get_backend()
+        try:
+            nodes = backend.lib.vmas_b200_graph_num_nodes(graph.raw_cuda_graph())
+        except Exception:  # noqa: BLE001  (no access to the cudaGraph_t: stay on the graph)
+            return None
+        if nodes != self._graph_launches:
+            return None  # torch kernels / memsets in the graph: scenario code outside the program
+        cols = None
+        if plan is not None:
+            dev = plan.device_cache.get(id(backend))
+            cols = dev["cols"] if dev is not None and dev["any_state"] else None
+        return mode, c, prog, plan, cols, out
+    def _build_one_call_step(self, graph, ingest_built_mask: bool, trace=None):
         """Everything ``vmas_b200_env_step`` needs, marshalled once (None: this step does not fit the call)."""
         backend = self.world._get_backend()
         N = backend._native
@@ -800,21 +839,124 @@ class Environment(TorchVectorizedObject):
         counts = self.steps.dtype == torch.float32 and self.steps.is_contiguous()
         copy = self._graph_out_copy[0] if self._graph_out_copy else None
         items = [] if copy is None else [(src, block, offset) for src, (block, offset) in zip(copy.keep, copy.where)]
-        plan = N.EnvStepPlan(
-            backend.lib, backend._dev_tables, self.world.slab, arr, len(live), self.clamp_action,
-            self._bad_action_flag if self.action_checks == "deferred" else None, self.steps if counts else None,
-            ingest_built_mask, graph.raw_cuda_graph_exec(), items, len(self._graph_out_blocks),
-        )
+        direct = self._library_only_step(graph, trace)
+        job = None
+        if direct is None:
+            plan = N.EnvStepPlan(
+                backend.lib, backend._dev_tables, self.world.slab, arr, len(live), self.clamp_action,
+                self._bad_action_flag if self.action_checks == "deferred" else None, self.steps if counts else None,
+                ingest_built_mask, graph.raw_cuda_graph_exec(), items, len(self._graph_out_blocks),
+            )
+        else:
+            mode, c, prog, oplan, cols, out = direct
+            instrs = prog.instructions(backend.index_of)
+            obs_to, mirrors = None, []
+            if _WRITE_RESULTS_IN_PLACE:
+                # results the post stage can write straight into the step's fresh blocks instead of into static
+                # buffers that are then copied: the observation rows (if one leaf run covers the whole block),
+                # and every leaf that is an output of the program (one more STORE per leaf)
+                c, instrs, items, obs_to, mirrors = self._results_in_place(c, prog, instrs, items, cols, out)
+            plan = N.EnvStepPlan(
+                backend.lib, backend._dev_tables, self.world.slab, arr, len(live), self.clamp_action,
+                self._bad_action_flag if self.action_checks == "deferred" else None, self.steps if counts else None,
+                ingest_built_mask, 0, items, len(self._graph_out_blocks), program=c, columns=cols,
+                n_rows=0 if oplan is None else oplan.n_rows, width=0 if oplan is None else oplan.width, obs_out=out,
+                exact_broad_phase=mode, obs_to=obs_to, mirrors=mirrors,
+            )
+            plan.keep += (prog, oplan)
+            if _WHOLE_STEP_KERNEL and backend._dev_tables.tb.specialization >= 0:
+                # the whole-step kernel of this (world, program, observation plan): compiled once (seconds),
+                # cached on disk; until it is there the step runs as two launches — same bits
+                from ... import jit
+
+                cols_np = None if cols is None else oplan.compile(self.world)[0]
+                job = jit.request_step_kernel(backend.tables.desc, cols_np, instrs)
+                if job is not None:
+                    job.done.wait(timeout=_WHOLE_STEP_KERNEL_WAIT_S)
+        plan.direct = direct is not None
+        plan.job = job
         plan.live = live
         plan.counts = counts
         plan.drones = list(getattr(backend, "_ingest_drones", []))
-        plan.launches = (1 if copy is not None else 0) + 1
+        plan.launches = (1 if plan.c.n_segs > 0 else 0) + 1
+        self._adopt_whole_step_kernel(plan)
         return plan
+
+    def _results_in_place(self, c, prog, instrs, items, cols, out):
+        """Splits the hand-out copies ``items`` = [(source, block, byte offset)] into what the post stage can
+        write in place.  Returns ``(program struct with the extra stores, its instructions, the copies that
+        remain, (block, offset) of the observation rows or None, [(buffer slot, block, offset)])``."""
+        from ... import _native as N
+        from .. import program as SP
+
+        B = self.num_envs
+        by_ptr = {}
+        for o in prog.outputs:
+            by_ptr.setdefault((o.tensor.data_ptr(), o.tensor.dtype), o)
+        store_of = {}  # output slot -> register it stores
+        for op, dst, a, b, arg, imm in instrs:
+            if op in (SP.OP_STORE_F32, SP.OP_STORE_BOOL):
+                store_of[b] = (op, a)
+        rest, obs_to, mirrors, extra = [], None, [], []
+        n_slots = len(prog.buffers)
+        obs_pieces = set()
+        if cols is not None and out is not None:
+            # the copies that together move the observation block, piece after piece, to one place
+            lo, size = out.data_ptr(), out.numel() * out.element_size()
+            inside = [k for k, (src, _, _) in enumerate(items) if lo <= src.data_ptr() < lo + size]
+            if inside:
+                _, block0, offset0 = items[inside[0]]
+                at = 0
+                for k in inside:
+                    src, block, offset = items[k]
+                    if src.data_ptr() != lo + at or block != block0 or offset != offset0 + at:
+                        break
+                    at += src.numel() * src.element_size()
+                else:
+                    if at == size and offset0 % 16 == 0:
+                        obs_to, obs_pieces = (block0, offset0), set(inside)
+        for k, (src, block, offset) in enumerate(items):
+            if k in obs_pieces:
+                continue
+            o = by_ptr.get((src.data_ptr(), src.dtype))
+            if (
+                o is not None and src.numel() == B and o._slot in store_of
+                and n_slots + len(extra) < N.PROG_MAX_BUFFERS and len(instrs) + len(extra) < N.PROG_MAX_INSTR
+            ):
+                op, reg = store_of[o._slot]
+                slot = n_slots + len(extra)
+                extra.append((op, 0, reg, slot, 0, 0.0))
+                mirrors.append((slot, block, offset))
+                continue
+            rest.append((src, block, offset))
+        if not extra:
+            return c, instrs, rest, obs_to, mirrors
+        c2 = N.StepProgramC()
+        ctypes.memmove(ctypes.addressof(c2), ctypes.addressof(c), ctypes.sizeof(c2))
+        for k, (op, dst, a, b, arg, imm) in enumerate(extra):
+            ins = c2.instr[len(instrs) + k]
+            ins.op, ins.dst, ins.a, ins.b, ins.arg, ins.imm = op, dst, a, b, arg, imm
+        c2.n_instr = len(instrs) + len(extra)
+        return c2, instrs + extra, rest, obs_to, mirrors
+
+    def _adopt_whole_step_kernel(self, plan):
+        job = plan.job
+        if job is None or not job.done.is_set():
+            return
+        plan.job = None
+        if job.index > 0:
+            plan.c.fused_kernel = job.index
+        elif job.error:
+            import warnings
+
+            warnings.warn(f"vmas_b200: no whole-step kernel, staying on two launches per step ({job.error})")
 
     def _step_one_call(self, actions: List[Tensor]):
         """A captured step through ``vmas_b200_env_step``: action ingest, graph launch and the hand-out copy
         in one crossing of the FFI."""
         plan = self._one_call
+        if plan.job is not None:
+            self._adopt_whole_step_kernel(plan)
         agents = plan.agents
         for k, i in enumerate(plan.live):
             agents[k].actions = actions[i].data_ptr()
@@ -828,7 +970,7 @@ class Environment(TorchVectorizedObject):
         plan.run()
         self.graph_replays += 1
         backend = self.world._get_backend()
-        backend.launches += self._graph_launches + plan.launches
+        backend.launches += self._graph_launches + plan.launches - (1 if plan.c.fused_kernel > 0 else 0)
         backend._mask_ready = False
         backend.after_step()
         return self._views_of_output_blocks(copies)
