@@ -470,10 +470,19 @@ def main_b200(args):
     host_actions = pregenerate_actions(env, W + K, seed=101 + rank, device=device, pin=True)
     # one pinned block per step ([A, B, action_size] when the agents' actions have one size): one upload
     same_size = len({tuple(a.shape) for a in host_actions[0]}) == 1
+    # Environment.step is handed the pinned host tensors themselves: the step's kernel reads them over PCIe where
+    # they lie (no staging copy).  Measured against an explicit upload in front of the step: 187 vs 208 us per
+    # step (profiles/r2z_bench_pinned.json, r2z_bench.json).  VMAS_BENCH_PINNED_ACTIONS=0: the explicit upload.
+    pinned_actions = os.environ.get("VMAS_BENCH_PINNED_ACTIONS", "1") == "1" and env.continuous_actions
+    # one pinned block per step ([A, B, action_size] when the agents' actions have one size): one upload
+    same_size = len({tuple(a.shape) for a in host_actions[0]}) == 1
     if same_size:
         host_blocks = [torch.stack(step_actions).pin_memory() for step_actions in host_actions]
         dev_block = torch.empty_like(host_blocks[0], device=device)
     obs0, rew0, done0, _ = env.step(dev_actions[0])
+    # pinned host buffers for a step's results (observations and rewards stacked over the agents, dones), two
+    # sets.  Stacking costs a device copy per step, but every separate download costs ~8 us of the bracket
+    # (measured: one copy per result tensor 231 us per step, three stacked copies 205 us; profiles/r2y_bench.json)
     host_sets = [
         (
             torch.empty((len(obs0),) + tuple(obs0[0].shape), dtype=obs0[0].dtype).pin_memory(),
@@ -496,10 +505,12 @@ def main_b200(args):
 
     def e2e_step(i):
         main = torch.cuda.current_stream()
-        # this step's actions first (measured: a host->device copy issued while the 8 MB download is in
-        # flight crawls at ~5 GB/s and holds the step's first kernel back; profiles/r2f_e2e_timeline.txt),
-        # then the previous step's results start travelling while this step's kernels run
-        if same_size:
+        # this step's actions first (an explicit host->device copy issued while the 8 MB download is in flight
+        # crawls at ~5 GB/s and holds the step's first kernel back; profiles/r2f_e2e_timeline.txt), then the
+        # previous step's results start travelling while this step's kernels run
+        if pinned_actions:
+            actions = host_actions[(W + i) % len(host_actions)]  # (read by the step's kernel where they lie)
+        elif same_size:
             dev_block.copy_(host_blocks[(W + i) % len(host_blocks)], non_blocking=True)
             actions = list(dev_block.unbind(0))
         else:
@@ -690,9 +701,10 @@ def main_b200(args):
             "h2d_bytes_per_step": h2d_bytes,
             "d2h_bytes_per_step": d2h_bytes,
             "ms_per_step": ms_e2e / K,
-            "how": "per step: the actions are uploaded from a pinned host block, Environment.step runs, and the "
-            "observations, rewards, dones travel to pinned host buffers; the download of step t-1 overlaps the "
-            "kernels of step t on a copy stream, inside the brackets",
+            "how": ("per step: Environment.step is handed the actions as pinned HOST tensors (its kernel reads them "
+                    "over PCIe), " if pinned_actions else "per step: the actions are uploaded from a pinned host block, "
+                    "Environment.step runs, ") + "and the observations, rewards, dones travel to pinned host buffers; "
+            "the download of step t-1 overlaps the kernels of step t on a copy stream, inside the brackets",
             "bracket_ms_first5_last5": [round(x, 4) for x in e2e_brackets[:5] + e2e_brackets[-5:]],
             "pcie_roofline": "the download alone (8.4 MB at the measured 56 GB/s, profiles/r2b_pcie.txt) is 160 us per "
             "step of 32768 balance envs = 2.05e8 env-steps/s",

@@ -412,11 +412,13 @@ int vmas_b200_ingest_actions_broad_phase(const VmasWorldConfig* cfg, const VmasP
  * Registers a WHOLE-STEP kernel compiled at run time for one (world, step program, observation plan): the
  * specialised substep kernel with the program and the observation rows as its epilogue (csrc/spec_kernel.cuh,
  * step_fused_kernel; built by vectorizedmultiagentsimulator_b200/jit.py).  `launch`:
- * cudaError_t (*)(const SpecArgs&, const EpiArgs&, cudaStream_t).  Returns a handle > 0 for
+ * cudaError_t (*)(const SpecArgs&, const EpiArgs&, cudaStream_t); `launch_env` (or NULL): the same kernel with
+ * the action ingest and the broad phase as its prologue (step_env_kernel),
+ * cudaError_t (*)(const SpecArgs&, const EpiArgs&, const ActArgs&, cudaStream_t).  Returns a handle > 0 for
  * VmasEnvStep.fused_kernel (the same key returns the same handle).
  */
-int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch,
-                                   int32_t spec_args_bytes, int32_t epi_args_bytes);
+int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch, void* launch_env,
+                                   int32_t spec_args_bytes, int32_t epi_args_bytes, int32_t act_args_bytes);
 
 /* Number of nodes of a cudaGraph_t (a caller that captured a step checks whether the graph holds only
  * this library's launches: then VmasEnvStep's direct mode can stand in for it). */
@@ -453,6 +455,10 @@ typedef struct VmasEnvStep {
    * one of its result leaves) is out_blocks[mirror_block[i]] + mirror_offset[i] in this step. */
   int32_t obs_block, n_mirrors;
   size_t obs_offset;
+  /* != 0 (direct mode with `fused_kernel`): the whole step goes out as ONE launch if the kernel has the
+   * ingest prologue for these agents (continuous holonomic actions) and the batch fits the GPU at once (a
+   * masked world's broad phase needs a grid-wide barrier); otherwise the launches above are issued. */
+  int32_t ingest_in_kernel, reserved;
   int32_t mirror_slot[VMAS_PROG_MAX_BUFFERS];
   int32_t mirror_block[VMAS_PROG_MAX_BUFFERS];
   size_t mirror_offset[VMAS_PROG_MAX_BUFFERS];

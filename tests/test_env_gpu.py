@@ -291,7 +291,12 @@ def test_broad_phase_in_the_ingest_launch_changes_no_bit(graph):
         counts.append([e.world._get_backend().launches - b for e, b in zip((fused, plain), before)])
         for g, w in zip(flatten(got[:3]), flatten(want[:3])):
             assert torch.equal(g, w), f"step {t}"
-    assert all(c[1] == c[0] + 1 for c in counts[-3:]), counts  # the separate broad-phase launch
+    if graph:
+        # captured: the whole step is ONE kernel; with pre_step overridden the ingest and the broad phase stay
+        # launches of their own in front of the whole-step kernel
+        assert counts[-3:] == [[1, 3]] * 3, counts
+    else:
+        assert all(c[1] == c[0] + 1 for c in counts[-3:]), counts  # the separate broad-phase launch
 
 
 def test_reset_at_and_state_views_on_gpu():
@@ -423,15 +428,17 @@ def test_a_graph_that_draws_device_random_numbers_stays_on_torchs_replay():
 
 
 def test_every_way_of_issuing_a_captured_step_gives_the_same_bits(monkeypatch):
-    """balance's captured step holds only library launches, so it runs as ONE whole-step kernel behind the
-    ingest launch (substeps + step program + observation rows, results written straight into the step's
-    fresh output tensors; vmas_b200_env_step, direct mode).  The same step with the results copied out of
+    """balance's captured step holds only library launches, so it runs as ONE kernel (action ingest + broad
+    phase with a grid-wide barrier + substeps + step program + observation rows, results written straight
+    into the step's fresh output tensors; vmas_b200_env_step, direct mode).  The same step with the ingest as
+    a launch of its own,  The same step with the results copied out of
     static buffers, as two launches (no whole-step kernel), as a graph launch from the library, as torch's
     replay with separate ingest / hand-out calls, and eagerly must all give the same bits."""
     from vectorizedmultiagentsimulator_b200.simulator.environment import environment as E
 
     variants = {
-        "whole-step kernel": dict(),
+        "one kernel": dict(),
+        "whole-step kernel": dict(_INGEST_IN_KERNEL=False),
         "copied results": dict(_WRITE_RESULTS_IN_PLACE=False),
         "two launches": dict(_WHOLE_STEP_KERNEL=False),
         "graph launch": dict(_DIRECT_STEP=False),
@@ -469,16 +476,63 @@ def test_every_way_of_issuing_a_captured_step_gives_the_same_bits(monkeypatch):
             for env in envs.values():
                 env.reset_at(7)
                 sync_env(eager, env)
-    whole, copied, two, graph, replay = (envs[k] for k in variants)
+    one, whole, copied, two, graph, replay = (envs[k] for k in variants)
+    assert one._one_call.c.ingest_in_kernel == 1 and one._one_call.c.fused_kernel > 0 and one._one_call.c.n_segs == 0
+    assert whole._one_call.c.ingest_in_kernel == 0
     assert whole._one_call_state == "on" and whole._one_call.direct and whole._one_call.c.fused_kernel > 0
     assert whole._one_call.c.n_segs == 0 and whole._one_call.c.obs_block >= 0 and whole._one_call.c.n_mirrors == 13
-    assert copied._one_call.c.fused_kernel > 0 and copied._one_call.c.n_segs == 14 and copied._one_call.c.n_mirrors == 0
+    assert copied._one_call.c.fused_kernel > 0 and copied._one_call.c.n_segs >= 14 and copied._one_call.c.n_mirrors == 0
     assert two._one_call_state == "on" and two._one_call.direct and two._one_call.c.fused_kernel == 0
     assert graph._one_call_state == "on" and not graph._one_call.direct
     assert replay._one_call_state == "off"
     assert float(whole.steps[0]) == float(eager.steps[0])
     # kernels per step: ingest (+ broad phase) and the whole-step kernel; with copied results the hand-out copy
-    for env, n in ((whole, 2), (copied, 3), (two, 3)):
+    for env, n in ((one, 1), (whole, 2), (copied, 2), (two, 3)):
         before = env.world._get_backend().launches
         env.step(actions)
         assert env.world._get_backend().launches - before == n
+
+
+def test_one_kernel_step_falls_back_when_the_batch_does_not_fit_the_gpu_at_once():
+    """The one-kernel step's broad phase needs a grid-wide barrier, hence every block resident; beyond that
+    (here: more envs than 148 SMs x 8 blocks x 64 threads) the same call issues ingest + whole-step kernel."""
+    n_envs = 148 * 8 * 64 + 4096
+    big = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, cuda_graph=True, n_agents=4)
+    eager = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, n_agents=4)
+    big.reset()
+    eager.reset()
+    sync_env(eager, big)
+    gen = torch.Generator().manual_seed(11)
+    for t in range(7):
+        actions = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1).cuda() for _ in range(4)]
+        want = eager.step([x.clone() for x in actions])
+        got = big.step([x.clone() for x in actions])
+        for i, (g, w) in enumerate(zip(flatten(got), flatten(want))):
+            assert torch.equal(g, w), f"step {t} output {i}"
+    assert big._one_call_state == "on" and big._one_call.c.ingest_in_kernel == 1
+    before = big.world._get_backend().launches
+    big.step(actions)
+    assert big.world._get_backend().launches - before == 2
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pinned_host_actions_are_read_where_they_lie(graph):
+    """Continuous actions handed in as PINNED host tensors are not staged: the ingest (a launch of its own, or
+    the prologue of the one-kernel step) reads them over PCIe.  Same results as with device tensors."""
+    n_envs = 256
+    a = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, cuda_graph=graph, n_agents=4)
+    b = b200.make_env("balance", num_envs=n_envs, device="cuda", seed=0, cuda_graph=graph, n_agents=4)
+    sync_env(a, b)
+    gen = torch.Generator().manual_seed(23)
+    for t in range(7):
+        host = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
+        assert a._fused_ingest_applies(host)
+        got = a.step(host)
+        want = b.step([x.cuda() for x in host])
+        torch.cuda.synchronize()
+        for g, w in zip(flatten(got), flatten(want)):
+            assert torch.equal(g, w), f"step {t}"
+        for ag_a, ag_b in zip(a.agents, b.agents):
+            assert torch.equal(ag_a.action.u, ag_b.action.u)
+    if graph:
+        assert a._one_call_state == "on"

@@ -107,3 +107,31 @@ def test_device_tables_build_for_every_mapping_on_cpu():
             else:
                 with pytest.raises(RuntimeError):
                     _native.DeviceTables(tables, None, cpu, mapping=mapping)
+
+
+def test_ctypes_structs_have_the_layout_of_the_c_header(tmp_path):
+    """Every ctypes mirror of a C-ABI struct: same field names, offsets and total size as ``include/vmas_b200.h``
+    gives them (checked by compiling a few ``offsetof`` lines with gcc) — a field inserted on one side only
+    would otherwise shift pointers silently."""
+    import subprocess
+
+    pairs = [
+        (_native.WorldConfig, "VmasWorldConfig"), (_native.PlanTablesC, "VmasPlanTables"), (_native.StateC, "VmasState"),
+        (_native.AgentActionsC, "VmasAgentActions"), (_native.ProgInstrC, "VmasProgInstr"),
+        (_native.StepProgramC, "VmasStepProgram"), (_native.CopySegmentC, "VmasCopySegment"),
+        (_native.EnvStepC, "VmasEnvStep"),
+    ]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vmas_b200.h"', "int main(void) {"]
+    for cls, cname in pairs:
+        lines.append(f'  printf("%zu\\n", sizeof({cname}));')
+        for field, *_ in cls._fields_:
+            lines.append(f'  printf("%zu\\n", offsetof({cname}, {field}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-I", _native.INCLUDE, str(src), "-o", str(exe)], check=True)
+    got = iter(int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    for cls, cname in pairs:
+        assert ctypes.sizeof(cls) == next(got), f"sizeof({cname})"
+        for field, *_ in cls._fields_:
+            assert getattr(cls, field).offset == next(got), f"{cname}.{field}"

@@ -329,7 +329,7 @@ def load():
     ]
     lib.vmas_b200_env_step.argtypes = [C.c_void_p, C.c_void_p]
     lib.vmas_b200_graph_num_nodes.argtypes = [C.c_void_p]
-    lib.vmas_b200_register_step_kernel.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+    lib.vmas_b200_register_step_kernel.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.vmas_b200_build_env_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.vmas_b200_set_l2_fetch_granularity.argtypes = [C.c_int32]
     lib.vmas_b200_find_specialization.argtypes = [C.c_uint64]
@@ -487,7 +487,7 @@ class DeviceTables:
             else None
         )
         words = (tables.n_masked + 31) // 32
-        self.mask = torch.zeros(words + 1, dtype=torch.int32, device=self.device)
+        self.mask = torch.zeros(words + 2, dtype=torch.int32, device=self.device)  # + the kernels' two arrival counters
         self.n_rounds = int(sched.shape[0])
 
         self.cfg = make_config(tables, B)
@@ -747,6 +747,7 @@ class EnvStepC(C.Structure):
         ("segs", C.c_void_p), ("seg_block", C.c_void_p), ("n_segs", C.c_int32), ("n_out_blocks", C.c_int32),
         ("out_blocks", C.c_void_p * MAX_OUT_BLOCKS),
         ("obs_block", C.c_int32), ("n_mirrors", C.c_int32), ("obs_offset", C.c_size_t),
+        ("ingest_in_kernel", C.c_int32), ("reserved", C.c_int32),
         ("mirror_slot", C.c_int32 * PROG_MAX_BUFFERS), ("mirror_block", C.c_int32 * PROG_MAX_BUFFERS),
         ("mirror_offset", C.c_size_t * PROG_MAX_BUFFERS),
     ]

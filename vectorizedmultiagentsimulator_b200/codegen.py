@@ -117,12 +117,12 @@ def emit_world(desc: P.WorldDescription, label: str, tuning: Dict = None) -> Tup
     lines.append("  };")
     lines.append(f"  static constexpr ItemC item[{max(NI, 1)}] = {{")
     if NI == 0:
-        lines.append("      {0, 0, 0, 0, -1, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},")
+        lines.append("      {0, 0, 0, 0, -1, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},")
     for k in range(NI):
         ii, f32 = tables.item_i32[k], tables.item_f32[k]
         flags = int(ii[3]) & 0xFF
         vals = ", ".join(
-            _f(f32[c]) for c in (P.IF_DMIN_BASE, P.IF_AX, P.IF_AY, P.IF_BX, P.IF_BY, P.IF_DIST, P.IF_FIXED_ROT)
+            _f(f32[c]) for c in (P.IF_DMIN_BASE, P.IF_AX, P.IF_AY, P.IF_BX, P.IF_BY, P.IF_DIST, P.IF_FIXED_ROT, P.IF_BROAD_THR)
         )
         lines.append(
             f"      {{{int(ii[0])}, {int(ii[1])}, {int(ii[2])}, {flags}, {int(tables.mask_slot[k])}, {vals}}},"
@@ -133,12 +133,15 @@ def emit_world(desc: P.WorldDescription, label: str, tuning: Dict = None) -> Tup
     return name, "\n".join(lines), h
 
 
-def post_hash(cols, instrs) -> int:
-    """FNV-1a 64 of a step epilogue: the observation plan's column table (int32 ``[rows, width, 4]`` or None)
-    and the step program's instructions ``[(op, dst, a, b, arg, imm)]`` with entity indices resolved."""
+def post_hash(cols, instrs, acts=()) -> int:
+    """FNV-1a 64 of what a whole-step kernel does around the substeps: the observation plan's column table
+    (int32 ``[rows, width, 4]`` or None), the step program's instructions ``[(op, dst, a, b, arg, imm)]`` with
+    entity indices resolved, and the action ingest ``[(agent row, u_range x 2, u_multiplier x 2)]`` of the
+    policy agents (empty: actions are ingested by a launch of their own)."""
     blob = json.dumps(
         [None if cols is None else [list(cols.shape), [int(x) for x in cols.reshape(-1)]],
-         [[int(op), int(dst), int(a), int(b), int(arg), _f(imm)] for op, dst, a, b, arg, imm in instrs]]
+         [[int(op), int(dst), int(a), int(b), int(arg), _f(imm)] for op, dst, a, b, arg, imm in instrs],
+         [[int(agent)] + [_f(v) for v in rest] for agent, *rest in acts]]
     ).encode()
     h = 0xCBF29CE484222325
     for byte in blob:
@@ -147,13 +150,20 @@ def post_hash(cols, instrs) -> int:
     return h
 
 
-def emit_post(cols, instrs) -> Tuple[str, str, int]:
-    """C++ text of one epilogue struct (``spec_epilogue`` in csrc/spec_kernel.cuh).  Returns (name, text, hash)."""
-    h = post_hash(cols, instrs)
+def emit_post(cols, instrs, acts=()) -> Tuple[str, str, int]:
+    """C++ text of one epilogue (+ ingest prologue) struct (``spec_epilogue`` / ``spec_ingest`` in
+    csrc/spec_kernel.cuh).  Returns (name, text, hash)."""
+    h = post_hash(cols, instrs, acts)
     name = f"Post_{h:016x}"
     rows, width = (0, 0) if cols is None else (int(cols.shape[0]), int(cols.shape[1]))
     lines = [f"struct {name} {{"]
-    lines.append(f"  static constexpr int N_PROG = {len(instrs)}, OBS_ROWS = {rows}, OBS_WIDTH = {width};")
+    lines.append(f"  static constexpr int N_PROG = {len(instrs)}, OBS_ROWS = {rows}, OBS_WIDTH = {width}, N_ACT = {len(acts)};")
+    lines.append(f"  static constexpr ActC act[{max(len(acts), 1)}] = {{")
+    for agent, r0, r1, m0, m1 in acts:
+        lines.append(f"      {{{int(agent)}, {_f(r0)}, {_f(r1)}, {_f(m0)}, {_f(m1)}}},")
+    if not acts:
+        lines.append("      {0, 0.f, 0.f, 0.f, 0.f},")
+    lines.append("  };")
     lines.append(f"  static constexpr ProgC prog[{max(len(instrs), 1)}] = {{")
     for op, dst, a, b, arg, imm in instrs:
         lines.append(f"      {{{int(op)}, {int(dst)}, {int(a)}, {int(b)}, {int(arg)}, {_f(imm)}}},")

@@ -29,7 +29,7 @@ struct EntC {
 };
 struct ItemC {
   int kind, a, b, flags, mask_bit;
-  float dmin_base, ax, ay, bx, by, dist, fixed_rot;
+  float dmin_base, ax, ay, bx, by, dist, fixed_rot, broad_thr;
 };
 struct CfgC {
   int substeps, has_x_semidim, has_y_semidim, has_world_gravity;
@@ -50,6 +50,18 @@ struct ObsColC {
 struct EpiArgs {
   float* obs_out;  // [rows, B, width] or null
   void* buffers[VMAS_PROG_MAX_BUFFERS];
+};
+// ... and its prologue (see spec_ingest): the policy agents' continuous holonomic actions
+struct ActC {
+  int agent;  // row of the agent in the force / torque slab
+  float range0, range1, mult0, mult1;
+};
+struct ActArgs {
+  const float* actions[VMAS_MAX_INGEST_AGENTS];  // [B, 2] each, the caller's tensors
+  float* u[VMAS_MAX_INGEST_AGENTS];              // [B, 2] each: agent.action.u
+  uint8_t* bad_flag;
+  float* steps;  // [B] or null
+  int clamp;
 };
 
 struct SpecArgs {
@@ -434,13 +446,15 @@ DEVI void spec_integrate(EnvRegs<E>& r, const int sub) {
 
 // The rows of one env (pos, vel, rot, ang_vel, agent force, agent torque) and which vector chunks
 // of them are read / written: derived from the world's entity flags at compile time.
-template <class W>
+// ALL_FORCE: every movable agent's force columns are stored (the whole-step kernel ingests the actions itself)
+template <class W, bool ALL_FORCE = false>
 struct SpecRows {
   static constexpr int E = W::E, NA = W::A;
   static constexpr uint64_t ALL_POS = (2 * E >= 64) ? ~0ull : ((1ull << (2 * E)) - 1);
   static constexpr uint64_t MOV2 = ent_cols<W>(VMAS_F_MOVABLE, 2);
   static constexpr uint64_t ROT1 = ent_cols<W>(VMAS_F_ROTATABLE, 1);
-  static constexpr uint64_t F_DIRTY = agent_cols<W>(VMAS_F_MOVABLE, VMAS_F_MAX_F | VMAS_F_F_RANGE, 2);
+  static constexpr uint64_t F_DIRTY =
+      ALL_FORCE ? agent_cols<W>(VMAS_F_MOVABLE, 0, 2) : agent_cols<W>(VMAS_F_MOVABLE, VMAS_F_MAX_F | VMAS_F_F_RANGE, 2);
   static constexpr uint64_t T_DIRTY = agent_cols<W>(VMAS_F_ROTATABLE, VMAS_F_MAX_T | VMAS_F_T_RANGE, 1);
   // a vector chunk that will be stored must have been loaded whole (it carries unchanged columns)
   static constexpr uint64_t VEL_IO = chunk_closure(MOV2, 2 * E, RowVec<2 * E>::W);
@@ -513,7 +527,7 @@ struct SpecRows {
         w[e] = r.w[e];
       }
       if constexpr (en.flags & VMAS_F_AGENT) {
-        if constexpr ((en.flags & VMAS_F_MOVABLE) && (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE))) {
+        if constexpr ((en.flags & VMAS_F_MOVABLE) && (ALL_FORCE || (en.flags & (VMAS_F_MAX_F | VMAS_F_F_RANGE)))) {
           f[2 * en.agent] = afx[en.agent];
           f[2 * en.agent + 1] = afy[en.agent];
         }
@@ -765,6 +779,157 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_fused_kernel(con
   }
   if (tid >= a.batch_dim) return;
   spec_env_step<W, false, P>(a, tid, mask_words, &e);
+}
+
+// ---- the whole Environment.step as ONE kernel -----------------------------------------------------------
+// step_fused_kernel plus what the ingest launch in front of it does (vmas_b200_ingest_actions_broad_phase):
+// every thread decodes its env's actions (continuous, holonomic: ref environment.py:616-655, 707 and
+// dynamics/holonomic.py:14-15) straight into the force registers, counts the step, and tests its env's
+// masked pairs for the batch-wide broad phase (ref core.py:2797-2801); the mask is complete once every block
+// has contributed — a grid-wide barrier, which needs all blocks resident (cooperative launch; the launcher
+// says no for batches beyond that and the caller keeps the separate ingest launch).
+//   a.mask: [MASK_WORDS] bits, [MASK_WORDS] arrivals at the barrier, [MASK_WORDS + 1] blocks done with the mask
+template <class W>
+__host__ __device__ constexpr int spec_first_masked() {
+  for (int i = 0; i < W::NI; ++i)
+    if (W::item[i].mask_bit >= 0) return i;
+  return W::NI;
+}
+
+DEVI unsigned ld_acquire_u32(const uint32_t* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <class W, class P>
+__global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_env_kernel(const SpecArgs a, const EpiArgs e, const ActArgs act) {
+  constexpr int MW = W::MASK_WORDS, E = W::E, NA = W::A, NI = W::NI;
+  const long tid = (long)blockIdx.x * W::BLOCK + threadIdx.x;
+  const bool live = tid < a.batch_dim;
+  const long env = live ? tid : (long)a.batch_dim - 1;  // (the tail threads shadow the last env and store nothing)
+  SpecRows<W, true> rows;
+  rows.load_pos_rot(a, env);
+  rows.load_rest(a, env);
+  EnvRegs<E> r;
+  float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
+  rows.unpack_pos_rot(r);
+  rows.unpack_rest(r, afx, afy, atq);
+  // the actions
+  bool bad = false;
+  static_for<P::N_ACT>([&](auto ki) {
+    constexpr int k = decltype(ki)::value;
+    constexpr ActC ac = P::act[k];
+    float2 v = reinterpret_cast<const float2*>(act.actions[k])[env];
+    if (act.clamp) {  // torch.clamp keeps NaN
+      v.x = fminf(fmaxf(v.x, -ac.range0), ac.range0);
+      v.y = fminf(fmaxf(v.y, -ac.range1), ac.range1);
+    }
+    bad |= (v.x != v.x) || (fabsf(v.x) > ac.range0) || (v.y != v.y) || (fabsf(v.y) > ac.range1);
+    const float2 u = make_float2(v.x * ac.mult0, v.y * ac.mult1);
+    if (live) reinterpret_cast<float2*>(act.u[k])[env] = u;
+    afx[ac.agent] = u.x;
+    afy[ac.agent] = u.y;
+  });
+  if (live) {
+    if (bad && act.bad_flag) *act.bad_flag = 1;
+    if (act.steps) act.steps[env] = act.steps[env] + 1.f;
+  }
+  // The broad phase of this step's (only) substep.  ARRIVE here: the block's pairs-in-range bits go to the
+  // global mask and the block checks in at the barrier; WAIT (below) only where the first masked work item
+  // is due — the trigonometry, the per-entity forces and the unmasked items in front of it (sphere pairs)
+  // run while the other blocks arrive.
+  uint32_t mask_words[MW > 0 ? MW : 1];
+  [[maybe_unused]] __shared__ uint32_t s_mask[MW > 0 ? MW : 1];
+  if constexpr (MW > 0) {
+    if (a.use_mask) {
+      if (threadIdx.x < MW) s_mask[threadIdx.x] = 0u;
+      static_assert(MW <= W::BLOCK, "more mask words than threads in a block");
+      __syncthreads();
+      uint32_t bits[MW];
+#pragma unroll
+      for (int w = 0; w < MW; ++w) bits[w] = 0u;
+      static_for<NI>([&](auto ii) {
+        constexpr ItemC it = W::item[decltype(ii)::value];
+        if constexpr (it.mask_bit >= 0) {
+          const bool near = live && norm2(r.px[it.a] - r.px[it.b], r.py[it.a] - r.py[it.b]) <= it.broad_thr;
+          if (__any_sync(0xffffffffu, near)) bits[it.mask_bit >> 5] |= 1u << (it.mask_bit & 31);
+        }
+      });
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int w = 0; w < MW; ++w)
+          if (bits[w]) atomicOr(&s_mask[w], bits[w]);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 0; w < MW; ++w) {  // (bits only ever get set: a stale read costs one redundant atomic)
+          const uint32_t b = s_mask[w];
+          if (b && (ld_acquire_u32(&a.mask[w]) & b) != b) atomicOr(&a.mask[w], b);
+        }
+        __threadfence();
+        atomicAdd(&a.mask[MW], 1u);
+      }
+    }
+  }
+  uint32_t sig = 0;
+  for (int sub = 0; sub < W::cfg.substeps; ++sub) {
+    spec_trig<W>(r);
+    spec_entity_forces<W>(r, afx, afy, atq);
+    static_for<NI>([&](auto ii) {
+      constexpr int I = decltype(ii)::value;
+      if constexpr (MW > 0 && I == spec_first_masked<W>()) {
+        if (a.use_mask) {  // WAIT (masked worlds run one substep per launch: the launcher sees to it)
+          if (threadIdx.x == 0) {
+            while (ld_acquire_u32(&a.mask[MW]) < gridDim.x) __nanosleep(20);
+            for (int w = 0; w < MW; ++w) s_mask[w] = ld_acquire_u32(&a.mask[w]);
+            __threadfence();
+            const unsigned done = atomicAdd(&a.mask[MW + 1], 1u);
+            if (done == gridDim.x - 1) {  // every block has its copy: clear for the next step
+              for (int w = 0; w < MW + 2; ++w) a.mask[w] = 0u;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int w = 0; w < MW; ++w) mask_words[w] = s_mask[w];
+        }
+      }
+      spec_item<W, I, false>(r, a, env, mask_words, sig);
+    });
+    spec_integrate<W>(r, sub);
+  }
+  if (!live) return;
+  rows.store(a, env, r, afx, afy, atq);
+  spec_epilogue<W, P>(r, a, e, env);
+}
+
+// cudaErrorCooperativeLaunchTooLarge: the batch does not fit the GPU at once (masked worlds only)
+template <class W, class P>
+static cudaError_t launch_env(const SpecArgs& a, const EpiArgs& e, const ActArgs& act, cudaStream_t stream) {
+  const long blocks = ((long)a.batch_dim + W::BLOCK - 1) / W::BLOCK;
+  if (W::MASK_WORDS > 0 && a.use_mask) {
+    if (W::cfg.substeps != 1) return cudaErrorInvalidValue;
+    static long capacity[64] = {0};
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
+    if (err != cudaSuccess) return err;
+    long cap = device < 64 ? capacity[device] : 0;
+    if (cap == 0) {
+      int per_sm = 0, sms = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_env_kernel<W, P>, W::BLOCK, 0);
+      if (err != cudaSuccess) return err;
+      err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      if (err != cudaSuccess) return err;
+      cap = (long)per_sm * sms;
+      if (device < 64) capacity[device] = cap;
+    }
+    if (blocks > cap) return cudaErrorCooperativeLaunchTooLarge;
+    void* args[] = {const_cast<SpecArgs*>(&a), const_cast<EpiArgs*>(&e), const_cast<ActArgs*>(&act)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(step_env_kernel<W, P>), dim3((unsigned)blocks),
+                                       dim3(W::BLOCK), args, 0, stream);
+  }
+  step_env_kernel<W, P><<<(unsigned)blocks, W::BLOCK, 0, stream>>>(a, e, act);
+  return cudaGetLastError();
 }
 
 template <class W, class P>

@@ -1731,6 +1731,7 @@ struct FusedEntry {
   uint64_t key;
   int n_entities, n_items;
   cudaError_t (*launch)(const SpecArgs&, const EpiArgs&, cudaStream_t);
+  cudaError_t (*launch_env)(const SpecArgs&, const EpiArgs&, const ActArgs&, cudaStream_t);  // or null
 };
 static FusedEntry g_fused[VMAS_MAX_RUNTIME_SPECS];
 static int g_num_fused = 0;
@@ -1897,11 +1898,12 @@ int vmas_b200_register_specialization(uint64_t world_hash, int32_t n_entities, i
   return kNumSpecs + g_num_dyn_specs++;
 }
 
-int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch,
-                                   int32_t spec_args_bytes, int32_t epi_args_bytes) {
+int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_items, void* launch, void* launch_env,
+                                   int32_t spec_args_bytes, int32_t epi_args_bytes, int32_t act_args_bytes) {
   if (!launch) return fail("null launch function%s");
-  if (spec_args_bytes != (int32_t)sizeof(SpecArgs) || epi_args_bytes != (int32_t)sizeof(EpiArgs))
-    return fail("SpecArgs / EpiArgs layout mismatch: rebuild the whole-step kernel%s");
+  if (spec_args_bytes != (int32_t)sizeof(SpecArgs) || epi_args_bytes != (int32_t)sizeof(EpiArgs) ||
+      (launch_env && act_args_bytes != (int32_t)sizeof(ActArgs)))
+    return fail("SpecArgs / EpiArgs / ActArgs layout mismatch: rebuild the whole-step kernel%s");
   for (int i = 0; i < g_num_fused; ++i)
     if (g_fused[i].key == key) return i + 1;
   if (g_num_fused >= VMAS_MAX_RUNTIME_SPECS) return fail("too many whole-step kernels%s");
@@ -1910,6 +1912,8 @@ int vmas_b200_register_step_kernel(uint64_t key, int32_t n_entities, int32_t n_i
   e.n_entities = n_entities;
   e.n_items = n_items;
   e.launch = reinterpret_cast<cudaError_t (*)(const SpecArgs&, const EpiArgs&, cudaStream_t)>(launch);
+  e.launch_env =
+      reinterpret_cast<cudaError_t (*)(const SpecArgs&, const EpiArgs&, const ActArgs&, cudaStream_t)>(launch_env);
   return ++g_num_fused;
 }
 
@@ -2440,80 +2444,153 @@ int vmas_b200_graph_num_nodes(void* cuda_graph) {
   return (int)n;
 }
 
-// Environment.step as one call: the host side of a step is otherwise three crossings of the FFI (ingest,
-// graph replay through torch, hand-out copy) with their marshalling — more host time than the kernels take.
+// ---- Environment.step as one call ------------------------------------------------------------------------
+// The host side of a step is otherwise three crossings of the FFI (ingest, graph replay through torch,
+// hand-out copy) with their marshalling — more host time than the kernels take.
+
+// where this step's post stage writes: the caller's static buffers, or (direct mode) this step's fresh blocks
+struct StepTargets {
+  float* obs_out;
+  const VmasStepProgram* program;
+  VmasStepProgram patched;
+};
+
+static int env_step_targets(const VmasEnvStep* s, StepTargets& t) {
+  t.obs_out = s->obs_out;
+  t.program = s->program;
+  if (s->obs_block >= 0 && s->columns && s->n_rows > 0) {
+    if (s->obs_block >= s->n_out_blocks || !s->out_blocks[s->obs_block]) return fail("observation rows without their block%s");
+    t.obs_out = reinterpret_cast<float*>(static_cast<char*>(s->out_blocks[s->obs_block]) + s->obs_offset);
+  }
+  if (s->n_mirrors > 0) {
+    if (!s->program || s->n_mirrors > VMAS_PROG_MAX_BUFFERS) return fail("mirrored stores without a program%s");
+    t.patched = *s->program;
+    for (int i = 0; i < s->n_mirrors; ++i) {
+      const int slot = s->mirror_slot[i], b = s->mirror_block[i];
+      if (slot < 0 || slot >= VMAS_PROG_MAX_BUFFERS || b < 0 || b >= s->n_out_blocks || !s->out_blocks[b])
+        return fail("bad mirrored store%s");
+      t.patched.buffers[slot] = static_cast<char*>(s->out_blocks[b]) + s->mirror_offset[i];
+    }
+    t.program = &t.patched;
+  }
+  if (s->columns && s->n_rows > 0 && (!t.obs_out || ((uintptr_t)t.obs_out & 15u)))
+    return fail("observation block missing or not 16-byte aligned%s");
+  return 0;
+}
+
+static int env_step_hand_out(const VmasEnvStep* s, void* cuda_stream) {
+  if (s->n_segs <= 0) return 0;
+  if (s->n_segs > VMAS_MAX_COPY_SEGMENTS || !s->segs || !s->seg_block) return fail("bad hand-out segments%s");
+  VmasCopySegment segs[VMAS_MAX_COPY_SEGMENTS];
+  for (int i = 0; i < s->n_segs; ++i) {
+    const int b = s->seg_block[i];
+    if (b < 0 || b >= s->n_out_blocks || !s->out_blocks[b]) return fail("hand-out segment without its block%s");
+    segs[i].src = s->segs[i].src;
+    segs[i].dst = static_cast<char*>(s->out_blocks[b]) + reinterpret_cast<uintptr_t>(s->segs[i].dst);
+    segs[i].bytes = s->segs[i].bytes;
+  }
+  return vmas_b200_copy_buffers(segs, s->n_segs, cuda_stream);
+}
+
+static EpiArgs epi_args_of(const StepTargets& t) {
+  EpiArgs epi;
+  epi.obs_out = t.obs_out;
+  for (int i = 0; i < VMAS_PROG_MAX_BUFFERS; ++i) epi.buffers[i] = t.program ? t.program->buffers[i] : nullptr;
+  return epi;
+}
+
+// The whole step as ONE launch (step_env_kernel).  1: launched; 0: not applicable this time (the batch does
+// not fit the GPU at once, which the kernel's grid-wide barrier needs); < 0: error.
+static int env_step_one_kernel(const VmasEnvStep* s, const StepTargets& t, cudaStream_t stream) {
+  if (s->fused_kernel < 1 || s->fused_kernel > g_num_fused) return fail("unknown whole-step kernel%s");
+  const FusedEntry& f = g_fused[s->fused_kernel - 1];
+  if (!f.launch_env) return 0;
+  if (check_common(s->cfg, s->tb, s->st) < 0) return -1;
+  if (f.n_entities != s->cfg->n_entities || f.n_items != s->cfg->n_items)
+    return fail("whole-step kernel does not match the world (stale handle?)%s");
+  if (!s->st->force || !s->st->torque || !s->agents) return fail("null force/torque/agents pointer%s");
+  const bool masked = s->cfg->n_masked > 0 && s->exact_broad_phase;
+  if (masked && (!s->mask || s->cfg->substeps != 1)) return 0;
+  StepArgs args;
+  args.cfg = *s->cfg;
+  args.tb = *s->tb;
+  args.st = *s->st;
+  args.mask = s->mask;
+  args.mask_words = (s->cfg->n_masked + 31) / 32;
+  args.use_mask = masked ? 1 : 0;
+  args.first_substep = 0;
+  args.n_substeps = s->cfg->substeps;
+  ActArgs act;
+  if (s->n_agents > VMAS_MAX_INGEST_AGENTS) return 0;
+  for (int i = 0; i < s->n_agents; ++i) {
+    const VmasAgentActions& ag = s->agents[i];
+    if (!ag.actions || !ag.u) return fail("null action buffer%s");
+    if (ag.action_kind != VMAS_ACT_CONTINUOUS || ag.dynamics != VMAS_DYN_HOLONOMIC || ag.action_size != 2) return 0;
+    if (((uintptr_t)ag.actions | (uintptr_t)ag.u) & 7u) return 0;
+    act.actions[i] = ag.actions;
+    act.u[i] = ag.u;
+  }
+  act.bad_flag = s->bad_flag;
+  act.steps = s->steps;
+  act.clamp = s->clamp;
+  const cudaError_t err = f.launch_env(spec_args_of(args), epi_args_of(t), act, stream);
+  if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorInvalidValue) {
+    cudaGetLastError();  // (not an error of this call: the step goes out as separate launches)
+    return 0;
+  }
+  CUDA_OK(err);
+  return 1;
+}
+
 int vmas_b200_env_step(const VmasEnvStep* s, void* cuda_stream) {
   if (!s || !s->cfg || !s->tb || !s->st) return fail("null argument%s");
+  if (s->n_out_blocks < 0 || s->n_out_blocks > VMAS_MAX_OUT_BLOCKS) return fail("too many output blocks%s");
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   int launches = 0, r;
-  if (s->n_agents > 0) {
-    r = ingest_impl(s->cfg, s->tb, s->st, s->agents, s->n_agents, s->clamp, s->bad_flag, s->steps, s->ingest_mask,
-                    cuda_stream);
+  StepTargets t;
+  if (!s->graph_exec && env_step_targets(s, t) < 0) return -1;
+  bool stepped = false;
+  if (s->ingest_in_kernel && s->n_agents > 0 && s->fused_kernel > 0 && !s->graph_exec) {
+    r = env_step_one_kernel(s, t, stream);
     if (r < 0) return r;
     launches += r;
+    stepped = r > 0;
   }
-  if (s->n_out_blocks < 0 || s->n_out_blocks > VMAS_MAX_OUT_BLOCKS) return fail("too many output blocks%s");
-  if (s->graph_exec) {
-    CUDA_OK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s->graph_exec), stream));
-  } else {
-    // results that go straight into this step's fresh blocks: the observation rows, mirrored program stores
-    float* obs_out = s->obs_out;
-    if (s->obs_block >= 0 && s->columns && s->n_rows > 0) {
-      if (s->obs_block >= s->n_out_blocks || !s->out_blocks[s->obs_block]) return fail("observation rows without their block%s");
-      obs_out = reinterpret_cast<float*>(static_cast<char*>(s->out_blocks[s->obs_block]) + s->obs_offset);
-    }
-    VmasStepProgram patched;
-    const VmasStepProgram* program = s->program;
-    if (s->n_mirrors > 0) {
-      if (!s->program || s->n_mirrors > VMAS_PROG_MAX_BUFFERS) return fail("mirrored stores without a program%s");
-      patched = *s->program;
-      for (int i = 0; i < s->n_mirrors; ++i) {
-        const int slot = s->mirror_slot[i], b = s->mirror_block[i];
-        if (slot < 0 || slot >= VMAS_PROG_MAX_BUFFERS || b < 0 || b >= s->n_out_blocks || !s->out_blocks[b])
-          return fail("bad mirrored store%s");
-        patched.buffers[slot] = static_cast<char*>(s->out_blocks[b]) + s->mirror_offset[i];
-      }
-      program = &patched;
-    }
-    const bool has_post = (program && program->n_instr > 0) || (s->columns && s->n_rows > 0);
-    if (s->fused_kernel > 0 && has_post) {
-      // the whole-step kernel: the program and the observation rows run in the substep kernel's epilogue
-      EpiArgs epi;
-      epi.obs_out = obs_out;
-      for (int i = 0; i < VMAS_PROG_MAX_BUFFERS; ++i) epi.buffers[i] = program ? program->buffers[i] : nullptr;
-      if (s->columns && s->n_rows > 0 && (!obs_out || ((uintptr_t)obs_out & 15u))) return fail("observation block missing or not 16-byte aligned%s");
-      r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream, nullptr,
-                        nullptr, s->fused_kernel, &epi);
+  if (!stepped) {
+    if (s->n_agents > 0) {
+      r = ingest_impl(s->cfg, s->tb, s->st, s->agents, s->n_agents, s->clamp, s->bad_flag, s->steps, s->ingest_mask,
+                      cuda_stream);
       if (r < 0) return r;
       launches += r;
+    }
+    if (s->graph_exec) {
+      CUDA_OK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s->graph_exec), stream));
     } else {
-    r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream, nullptr,
-                      nullptr);
-    if (r < 0) return r;
-    launches += r;
-    if (has_post) {
-      r = vmas_b200_post_step(s->cfg, s->tb, s->st, program, s->columns, s->n_rows, s->width, obs_out,
-                              cuda_stream);
-      if (r < 0) return r;
-      launches += r;
-    }
+      const bool has_post = (t.program && t.program->n_instr > 0) || (s->columns && s->n_rows > 0);
+      if (s->fused_kernel > 0 && has_post) {
+        // the whole-step kernel: the program and the observation rows run in the substep kernel's epilogue
+        const EpiArgs epi = epi_args_of(t);
+        r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream,
+                          nullptr, nullptr, s->fused_kernel, &epi);
+        if (r < 0) return r;
+        launches += r;
+      } else {
+        r = substeps_impl(s->cfg, s->tb, s->st, s->mask, s->exact_broad_phase, 0, s->cfg->substeps, cuda_stream,
+                          nullptr, nullptr);
+        if (r < 0) return r;
+        launches += r;
+        if (has_post) {
+          r = vmas_b200_post_step(s->cfg, s->tb, s->st, t.program, s->columns, s->n_rows, s->width, t.obs_out,
+                                  cuda_stream);
+          if (r < 0) return r;
+          launches += r;
+        }
+      }
     }
   }
-  if (s->n_segs > 0) {
-    if (s->n_segs > VMAS_MAX_COPY_SEGMENTS || !s->segs || !s->seg_block) return fail("bad hand-out segments%s");
-    VmasCopySegment segs[VMAS_MAX_COPY_SEGMENTS];
-    for (int i = 0; i < s->n_segs; ++i) {
-      const int b = s->seg_block[i];
-      if (b < 0 || b >= s->n_out_blocks || !s->out_blocks[b]) return fail("hand-out segment without its block%s");
-      segs[i].src = s->segs[i].src;
-      segs[i].dst = static_cast<char*>(s->out_blocks[b]) + reinterpret_cast<uintptr_t>(s->segs[i].dst);
-      segs[i].bytes = s->segs[i].bytes;
-    }
-    r = vmas_b200_copy_buffers(segs, s->n_segs, cuda_stream);
-    if (r < 0) return r;
-    launches += r;
-  }
-  return launches;
+  r = env_step_hand_out(s, cuda_stream);
+  if (r < 0) return r;
+  return launches + r;
 }
 
 }  // extern "C"

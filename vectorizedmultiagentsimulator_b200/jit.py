@@ -65,8 +65,13 @@ extern "C" {{
 cudaError_t vmas_jit_launch_fused(const vmas::SpecArgs& a, const vmas::EpiArgs& e, cudaStream_t stream) {{
   return vmas::launch_fused<W, P>(a, e, stream);
 }}
+cudaError_t vmas_jit_launch_env(const vmas::SpecArgs& a, const vmas::EpiArgs& e, const vmas::ActArgs& act, cudaStream_t stream) {{
+  return vmas::launch_env<W, P>(a, e, act, stream);
+}}
+int vmas_jit_has_ingest(void) {{ return P::N_ACT > 0 ? 1 : 0; }}
 int vmas_jit_spec_args_bytes(void) {{ return (int)sizeof(vmas::SpecArgs); }}
 int vmas_jit_epi_args_bytes(void) {{ return (int)sizeof(vmas::EpiArgs); }}
+int vmas_jit_act_args_bytes(void) {{ return (int)sizeof(vmas::ActArgs); }}
 }}
 """
 
@@ -172,16 +177,16 @@ class StepKernelJob(Job):
     """The whole-step kernel of one (world, observation columns, step program): ``index`` is the handle for
     ``VmasEnvStep.fused_kernel`` once ``done`` is set."""
 
-    def __init__(self, desc: P.WorldDescription, cols, instrs):
+    def __init__(self, desc: P.WorldDescription, cols, instrs, acts=()):
         super().__init__(desc)
-        self.cols, self.instrs = cols, instrs
-        self.post_hash = codegen.post_hash(cols, instrs)
+        self.cols, self.instrs, self.acts = cols, instrs, tuple(acts)
+        self.post_hash = codegen.post_hash(cols, instrs, self.acts)
         self.key = (self.hash ^ ((self.post_hash << 1) | (self.post_hash >> 63))) & 0xFFFFFFFFFFFFFFFF
 
     def _compile_and_register(self) -> int:
         desc = self.desc
         name, text, h = codegen.emit_world(desc, "whole-step kernel")
-        post_name, post_text, _ = codegen.emit_post(self.cols, self.instrs)
+        post_name, post_text, _ = codegen.emit_post(self.cols, self.instrs, self.acts)
         os.makedirs(CACHE_DIR, exist_ok=True)
         stem = os.path.join(CACHE_DIR, f"step_{self.key:016x}_{_native.ARITH}_{_source_stamp()}")
         so = stem + ".so"
@@ -200,7 +205,8 @@ class StepKernelJob(Job):
         with _lock:
             handle = lib.vmas_b200_register_step_kernel(
                 C.c_uint64(self.key), desc.n_entities, len(desc.items), C.cast(obj.vmas_jit_launch_fused, C.c_void_p),
-                obj.vmas_jit_spec_args_bytes(), obj.vmas_jit_epi_args_bytes(),
+                C.cast(obj.vmas_jit_launch_env, C.c_void_p) if obj.vmas_jit_has_ingest() else None,
+                obj.vmas_jit_spec_args_bytes(), obj.vmas_jit_epi_args_bytes(), obj.vmas_jit_act_args_bytes(),
             )
             if handle <= 0:
                 raise RuntimeError(lib.vmas_b200_last_error().decode())
@@ -211,11 +217,13 @@ class StepKernelJob(Job):
 _step_jobs: Dict[int, StepKernelJob] = {}
 
 
-def request_step_kernel(desc: P.WorldDescription, cols, instrs, block: bool = False) -> Optional[StepKernelJob]:
-    """Starts (or finds) the compilation of the whole-step kernel; None if the world cannot be specialised."""
+def request_step_kernel(desc: P.WorldDescription, cols, instrs, acts=(), block: bool = False) -> Optional[StepKernelJob]:
+    """Starts (or finds) the compilation of the whole-step kernel; None if the world cannot be specialised.
+    ``acts``: [(agent row, u_range x 2, u_multiplier x 2)] of the policy agents if the kernel is to ingest
+    their (continuous, holonomic) actions itself."""
     if not available() or not codegen.specializable(desc):
         return None
-    job = StepKernelJob(desc, cols, instrs)
+    job = StepKernelJob(desc, cols, instrs, acts)
     with _lock:
         have = _step_jobs.get(job.key)
         if have is None:

@@ -48,6 +48,8 @@ _DIRECT_STEP = os.environ.get("VMAS_B200_DIRECT_STEP", "1") != "0"
 _WHOLE_STEP_KERNEL = os.environ.get("VMAS_B200_WHOLE_STEP_KERNEL", "1") != "0"
 #: ... and writes the step's results straight into the fresh output blocks (no hand-out copy)
 _WRITE_RESULTS_IN_PLACE = os.environ.get("VMAS_B200_RESULTS_IN_PLACE", "1") != "0"
+#: ... with the action ingest and the broad phase inside that kernel too (continuous holonomic agents)
+_INGEST_IN_KERNEL = os.environ.get("VMAS_B200_INGEST_IN_KERNEL", "1") != "0"
 _WHOLE_STEP_KERNEL_WAIT_S = float(os.environ.get("VMAS_B200_WHOLE_STEP_KERNEL_WAIT_S", "60"))
 
 
@@ -490,7 +492,13 @@ class Environment(TorchVectorizedObject):
             return False
         if self.continuous_actions:
             # (an agent without action components — Static dynamics — hands in a [B, 0] tensor)
-            return all(a.dtype == torch.float32 and a.is_contiguous() and a.device.type == "cuda" for a in actions)
+            # Pinned host tensors are read by the kernel where they lie (unified addressing: no staging copy, the
+            # step's first kernel pulls the actions over PCIe itself); as with any asynchronous copy the caller
+            # must leave them alone until the step has run.
+            return all(
+                a.dtype == torch.float32 and a.is_contiguous() and (a.device.type == "cuda" or a.is_pinned())
+                for a in actions
+            )
         # discrete spaces: int64 indices, [B, 1] (flat index of the product) or [B, action_size] (multi-discrete)
         return all(
             a.dtype == torch.int64 and a.is_contiguous() and a.device.type == "cuda" and a.dim() == 2
@@ -870,7 +878,22 @@ class Environment(TorchVectorizedObject):
                 from ... import jit
 
                 cols_np = None if cols is None else oplan.compile(self.world)[0]
-                job = jit.request_step_kernel(backend.tables.desc, cols_np, instrs)
+                # ... with the action ingest (and the broad phase) as its prologue where the agents allow it:
+                # the whole step is then ONE launch
+                acts = ()
+                if (
+                    _INGEST_IN_KERNEL and self.continuous_actions and len(live) == len(specs)
+                    and all(s[1] == N.DYN_HOLONOMIC and s[0].action_size == 2 for s in specs)
+                    and type(self.scenario).pre_step is BaseScenario.pre_step and not self.world.scripted_agents
+                    and (ingest_built_mask or backend.tables.n_masked == 0 or not self.world.exact_broad_phase)
+                ):
+                    acts = tuple(
+                        (int(c.agent_index), float(c.u_range[0]), float(c.u_range[1]), float(c.u_multiplier[0]),
+                         float(c.u_multiplier[1]))
+                        for c in arr
+                    )
+                    plan.c.ingest_in_kernel = 1
+                job = jit.request_step_kernel(backend.tables.desc, cols_np, instrs, acts)
                 if job is not None:
                     job.done.wait(timeout=_WHOLE_STEP_KERNEL_WAIT_S)
         plan.direct = direct is not None
@@ -878,7 +901,6 @@ class Environment(TorchVectorizedObject):
         plan.live = live
         plan.counts = counts
         plan.drones = list(getattr(backend, "_ingest_drones", []))
-        plan.launches = (1 if plan.c.n_segs > 0 else 0) + 1
         self._adopt_whole_step_kernel(plan)
         return plan
 
@@ -967,10 +989,10 @@ class Environment(TorchVectorizedObject):
         blocks = plan.out_blocks
         for j, c in enumerate(copies):
             blocks[j] = c.data_ptr()
-        plan.run()
+        launched = plan.run()  # (the kernels the call issued itself; a graph's nodes come on top)
         self.graph_replays += 1
         backend = self.world._get_backend()
-        backend.launches += self._graph_launches + plan.launches - (1 if plan.c.fused_kernel > 0 else 0)
+        backend.launches += launched + (0 if plan.direct else self._graph_launches)
         backend._mask_ready = False
         backend.after_step()
         return self._views_of_output_blocks(copies)
