@@ -266,12 +266,28 @@ def prebuild_step_kernels(verbose: bool = False):
         desc = P.describe_world(world)
         if not codegen.specializable(desc):
             continue
-        job = StepKernelJob(desc, cols if (cols[..., 0] != 0).any() else None, prog.instructions(lambda e: index[id(e)]))
-        job.run()
         label = scenario + "(" + ", ".join(f"{k}={v}" for k, v in kwargs.items()) + ")"
-        if job.error:
-            raise RuntimeError(f"whole-step kernel of {label}: {job.error}")
-        if verbose:
-            print(f"whole-step kernel {job.key:016x}  {label}  ({job.seconds:.1f} s)")
-        built.append((label, job.key))
+        columns = cols if (cols[..., 0] != 0).any() else None
+        instrs = prog.instructions(lambda e: index[id(e)])
+        # with and without the action ingest as the kernel's prologue (step_env_kernel / step_fused_kernel); an
+        # environment adds one STORE per result leaf to the program when it captures its step, so its own
+        # variant is compiled then (seconds) — these two make sure the templates build, and serve
+        # VMAS_B200_RESULTS_IN_PLACE=0
+        from .simulator.dynamics.basic import Holonomic
+
+        agents = world.policy_agents
+        holonomic = all(type(a.dynamics) is Holonomic and a.action_size == 2 for a in agents)
+        row = {id(a): j for j, a in enumerate(world.agents)}
+        acts = tuple(
+            (row[id(a)], *(float(v) for v in a.action.u_range_tensor.tolist()), *(float(v) for v in a.action.u_multiplier_tensor.tolist()))
+            for a in agents
+        ) if holonomic else ()
+        for variant in ((), acts) if acts else ((),):
+            job = StepKernelJob(desc, columns, instrs, variant)
+            job.run()
+            if job.error:
+                raise RuntimeError(f"whole-step kernel of {label}: {job.error}")
+            if verbose:
+                print(f"whole-step kernel {job.key:016x}  {label}  ({job.seconds:.1f} s)")
+            built.append((label, job.key))
     return built
