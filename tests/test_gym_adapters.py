@@ -62,3 +62,18 @@ def test_gymnasium_wrappers():
 def test_rllib_wrapper_fails_up_front_with_instructions():
     with use_oracle(), pytest.raises(ImportError, match="VectorEnvWrapper"):
         b200.make_env("balance", num_envs=2, device="cpu", seed=0, wrapper="rllib")
+
+
+def test_stack_views_is_a_view_when_the_slices_are_adjacent_and_a_copy_otherwise():
+    import vectorizedmultiagentsimulator_b200 as b200
+
+    block = torch.arange(4 * 6 * 3, dtype=torch.float32).reshape(4, 6, 3)
+    rows = list(block.unbind(0))
+    view = b200.stack_views(rows)
+    assert view.shape == (4, 6, 3) and view.data_ptr() == block.data_ptr() and torch.equal(view, block)
+    tail = b200.stack_views(rows[1:3])  # a run that starts inside the block
+    assert tail.data_ptr() == rows[1].data_ptr() and torch.equal(tail, block[1:3])
+    # not adjacent / not the same storage / strided: a plain stack
+    for parts in ([rows[0], rows[2]], [rows[0], rows[1].clone()], [block[:, 0], block[:, 1]]):
+        out = b200.stack_views(parts)
+        assert torch.equal(out, torch.stack(parts)) and out.data_ptr() not in {p.data_ptr() for p in parts}
