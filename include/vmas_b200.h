@@ -215,12 +215,23 @@ int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables
 #define VMAS_OBS_COPY 1
 #define VMAS_OBS_DIFF 2
 #define VMAS_OBS_REMAINDER 3
+/* a per-env fp32 value another producer holds (a flag the scenario's step program stored, say):
+ * source a = index into `buffers` (vmas_b200_gather_observations_buffers); the launch that wrote the buffer
+ * must precede this one in stream order */
+#define VMAS_OBS_BUFFER 4
+/* (whole-step kernels only: the column is register `source a` of the step program that ran in the same thread) */
+#define VMAS_OBS_REG 5
+#define VMAS_OBS_MAX_BUFFERS 8
 #define VMAS_OBS_POS 0
 #define VMAS_OBS_VEL 1
 #define VMAS_OBS_ROT 2
 #define VMAS_OBS_ANG_VEL 3
 int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
                                   int32_t n_rows, int32_t width, float* out, void* cuda_stream);
+/* The same with VMAS_OBS_BUFFER columns: `buffers` = n_buffers device pointers to fp32 [B] arrays. */
+int vmas_b200_gather_observations_buffers(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
+                                          int32_t n_rows, int32_t width, float* out, const float* const* buffers,
+                                          int32_t n_buffers, void* cuda_stream);
 
 /*
  * Post-step program: the scenario's reward / done glue (distance and overlap queries, the distance-shaping

@@ -79,6 +79,10 @@ class OracleBackend(PlanRuntime):
                 elif isinstance(t, O._Lidar):
                     reading = t.sensor.measure()
                     parts.append(t.sensor._max_range - reading if t.range_minus_distance else reading)
+                elif isinstance(t, O._Buffer):  # a per-env value another producer holds (ref transport.py:177-183)
+                    src = t.source
+                    held = src.tensor if hasattr(src, "_slot") else (src() if callable(src) else src)
+                    parts.append(held.to(torch.float32).unsqueeze(-1))
                 else:
                     parts.append(torch.zeros(self.world.batch_dim, t.width, device=self.world.device))
             rows.append(torch.cat(parts, dim=-1))

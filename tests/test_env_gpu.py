@@ -556,3 +556,51 @@ def test_pinned_host_actions_are_read_where_they_lie(graph):
             assert torch.equal(ag_a.action.u, ag_b.action.u)
     if graph:
         assert a._one_call_state == "on"
+
+
+@pytest.mark.parametrize(
+    "kwargs,launches",
+    [
+        (dict(n_agents=4), 1),  # one substep: the whole step is one kernel
+        # three substeps with a broad phase each: ingest (+ first mask), then per substep [mask] + kernel, the
+        # last of them with the program and the observation rows as its epilogue
+        (dict(n_agents=4, n_lines=2, substeps=3), 6),
+    ],
+)
+def test_transport_goal_flags_are_program_results_and_observation_columns(kwargs, launches):
+    """transport's ``on_goal`` flags are computed by the step program AND are columns of every agent's
+    observation (``observe.value``).  Eagerly that is a program launch followed by a gather launch; captured,
+    the whole-step kernel's epilogue reads the flag from the program's register."""
+    n_envs = 192
+    eager = b200.make_env("transport", num_envs=n_envs, device="cuda", seed=0, **kwargs)
+    graph = b200.make_env("transport", num_envs=n_envs, device="cuda", seed=0, cuda_graph=True, **kwargs)
+    with use_oracle():
+        cpu = b200.make_env("transport", num_envs=n_envs, device="cpu", seed=0, **kwargs)
+    # put a package on its goal in a few envs so that the flag is not constant
+    for env in (cpu, eager, graph):
+        package, goal = env.scenario.packages[0], env.world.landmarks[0]
+        sync_env(cpu, env) if env is not cpu else None
+    pos = cpu.scenario.packages[0].state.pos.clone()
+    pos[::5] = cpu.world.landmarks[0].state.pos[::5]
+    for env in (cpu, eager, graph):
+        env.scenario.packages[0].set_pos(pos.to(env.device), batch_index=None)
+    gen = torch.Generator().manual_seed(9)
+    for t in range(8):
+        actions = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1) for _ in cpu.agents]
+        want = eager.step([a.cuda() for a in actions])
+        got = graph.step([a.cuda() for a in actions])
+        ref = cpu.step([a.clone() for a in actions])
+        for i, (g, w) in enumerate(zip(flatten(got), flatten(want))):
+            assert same(g, w), f"step {t} output {i}"
+        _compare(want[0], ref[0], f"transport step {t} obs vs oracle", atol=1e-5)
+        _compare(want[2], ref[2], f"transport step {t} dones vs oracle", atol=0)
+        resync(eager, graph)
+        sync_env(cpu, eager)
+        sync_env(cpu, graph)
+    flag_column = want[0][0][:, 4 + 6]  # pos, vel, then per package: 2 + 2 + 2 columns and the flag
+    assert 0 < float(flag_column.sum()) < n_envs and set(flag_column.unique().tolist()) <= {0.0, 1.0}
+    plan = graph._one_call
+    assert graph._one_call_state == "on" and plan.direct and plan.c.fused_kernel > 0
+    before = graph.world._get_backend().launches
+    graph.step([a.cuda() for a in actions])
+    assert graph.world._get_backend().launches - before == launches

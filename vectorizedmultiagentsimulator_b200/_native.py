@@ -250,6 +250,7 @@ EXPORTS = [
     "vmas_b200_cast_rays_batched",
     "vmas_b200_pair_query_batched",
     "vmas_b200_gather_observations",
+    "vmas_b200_gather_observations_buffers",
     "vmas_b200_distance_shaping",
     "vmas_b200_post_step",
     "vmas_b200_copy_buffers",
@@ -304,6 +305,9 @@ def load():
     ]
     lib.vmas_b200_gather_observations.argtypes = [
         p_cfg, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p
+    ]
+    lib.vmas_b200_gather_observations_buffers.argtypes = [
+        p_cfg, p_st, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p
     ]
     lib.vmas_b200_distance_shaping.argtypes = [
         p_cfg, p_st, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
@@ -826,9 +830,17 @@ OBS_SKIP, OBS_COPY, OBS_DIFF, OBS_REMAINDER = 0, 1, 2, 3
 OBS_POS, OBS_VEL, OBS_ROT, OBS_ANG_VEL = 0, 1, 2, 3
 
 
-def gather_observations(lib, dt: DeviceTables, slab, columns, n_rows: int, width: int, out) -> int:
-    """``columns`` int32[R, F, 4] on the device, ``out`` fp32 [R, B, F] (see include/vmas_b200.h)."""
+def gather_observations(lib, dt: DeviceTables, slab, columns, n_rows: int, width: int, out, buffers=()) -> int:
+    """``columns`` int32[R, F, 4] on the device, ``out`` fp32 [R, B, F]; ``buffers``: the fp32 ``[B]`` tensors
+    VMAS_OBS_BUFFER columns read (see include/vmas_b200.h)."""
     st = dt.state_struct(slab)
+    if buffers:
+        ptrs = (C.c_void_p * len(buffers))(*[b.data_ptr() for b in buffers])
+        rc = lib.vmas_b200_gather_observations_buffers(
+            C.byref(dt.cfg), C.byref(st), columns.data_ptr(), int(n_rows), int(width), out.data_ptr(), ptrs,
+            len(buffers), _stream(dt.device),
+        )
+        return _check(lib, rc)
     rc = lib.vmas_b200_gather_observations(
         C.byref(dt.cfg), C.byref(st), columns.data_ptr(), int(n_rows), int(width), out.data_ptr(), _stream(dt.device)
     )

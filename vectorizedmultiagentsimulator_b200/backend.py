@@ -371,7 +371,19 @@ class CudaBackend(PlanRuntime):
                 )
             plan.device_cache[id(self)] = dev
         out = torch.empty(plan.n_rows, B, F, dtype=torch.float32, device=self.device)
-        if program is not None:
+        buffers = plan.resolve_buffers()
+        for t in buffers:
+            assert t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (B,), \
+                "observation value columns read contiguous fp32 [B] tensors on the world's device"
+        if program is not None and buffers:
+            # value columns read what the program stores: the program first, then the gather (in a captured
+            # step both run in the whole-step kernel's epilogue, in this order, in the thread of the env)
+            self._native.post_step(self.lib, self._dev_tables, self.world.slab, program, None, 0, 0, None)
+            self._native.gather_observations(
+                self.lib, self._dev_tables, self.world.slab, dev["cols"], plan.n_rows, F, out, buffers
+            )
+            self.launches += 2
+        elif program is not None:
             # the scenario's reward / done program rides in the same launch as the state-slab columns
             self._native.post_step(
                 self.lib, self._dev_tables, self.world.slab, program, dev["cols"] if dev["any_state"] else None,
@@ -380,7 +392,7 @@ class CudaBackend(PlanRuntime):
             self.launches += 1
         elif dev["any_state"]:
             self._native.gather_observations(
-                self.lib, self._dev_tables, self.world.slab, dev["cols"], plan.n_rows, F, out
+                self.lib, self._dev_tables, self.world.slab, dev["cols"], plan.n_rows, F, out, buffers
             )
             self.launches += 1
         if dev["rays"] is not None:

@@ -150,6 +150,21 @@ def post_hash(cols, instrs, acts=()) -> int:
     return h
 
 
+def fuse_value_columns(cols, buffer_sources, instrs):
+    """The column table of an observation plan for a whole-step kernel: value columns (``observe.value`` of a
+    program output; OP_BUFFER = 4, index into ``buffer_sources``) become reads of the program register that
+    output stores (OP_REG = 5) — program and observation rows run in one thread there."""
+    OP_BUFFER, OP_REG, STORES = 4, 5, (20, 21)
+    if cols is None or not buffer_sources:
+        return cols
+    reg_of = {b: a for op, _, a, b, _, _ in instrs if op in STORES}
+    cols = cols.copy()
+    for row in cols.reshape(-1, 4):
+        if row[0] == OP_BUFFER:
+            row[0], row[1] = OP_REG, reg_of[buffer_sources[int(row[1])]._slot]
+    return cols
+
+
 def emit_post(cols, instrs, acts=()) -> Tuple[str, str, int]:
     """C++ text of one epilogue (+ ingest prologue) struct (``spec_epilogue`` / ``spec_ingest`` in
     csrc/spec_kernel.cuh).  Returns (name, text, hash)."""

@@ -661,7 +661,9 @@ DEVI void spec_epilogue(const EnvRegs<W::E>& r, const SpecArgs& a, const EpiArgs
           constexpr int k = decltype(ki)::value;
           constexpr ObsColC col = P::obs[row * F + c0 + k];
           v[k] = 0.f;
-          if constexpr (col.op != VMAS_OBS_SKIP) {
+          if constexpr (col.op == VMAS_OBS_REG) {
+            v[k] = pr[col.src];  // a value the step program (above, same thread) computed
+          } else if constexpr (col.op != VMAS_OBS_SKIP) {
             v[k] = epi_state<W, (col.src >> 24) & 3, col.src & 0xFFFFFF>(r, a, env);
             if constexpr (col.op == VMAS_OBS_DIFF)
               v[k] = v[k] - epi_state<W, (col.src2 >> 24) & 3, col.src2 & 0xFFFFFF>(r, a, env);

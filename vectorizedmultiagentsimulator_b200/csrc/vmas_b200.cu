@@ -1189,6 +1189,7 @@ struct ObsArgs {
   const int32_t* cols;  // [rows * width * 4]
   float* out;           // [rows, B, width]
   int32_t rows, width, batch_dim, n_entities;
+  const float* buffers[VMAS_OBS_MAX_BUFFERS];  // VMAS_OBS_BUFFER columns: fp32 [B] each
 };
 
 // A source decoded once per thread: where the field's tile starts in shared memory, the element
@@ -1259,6 +1260,7 @@ DEVI void gather_observations_body(const ObsArgs& a, const int tile_envs, const 
     op[k] = c.x;
     sa[k] = decode(c.y);
     sb[k] = decode(c.z);
+    if (c.x == VMAS_OBS_BUFFER) sa[k].pitch = (unsigned)c.y & (VMAS_OBS_MAX_BUFFERS - 1);  // (which buffer)
     par[k] = __int_as_float(c.w);
     any |= c.x != VMAS_OBS_SKIP;
     all &= c.x != VMAS_OBS_SKIP;
@@ -1270,7 +1272,9 @@ DEVI void gather_observations_body(const ObsArgs& a, const int tile_envs, const 
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       v[k] = 0.f;
-      if (op[k] != VMAS_OBS_SKIP) {
+      if (op[k] == VMAS_OBS_BUFFER) {
+        v[k] = a.buffers[sa[k].pitch][env0 + e];
+      } else if (op[k] != VMAS_OBS_SKIP) {
         v[k] = s_state[sa[k].base + e * sa[k].pitch];
         if (op[k] == VMAS_OBS_DIFF) v[k] = v[k] - s_state[sb[k].base + e * sb[k].pitch];
         if (op[k] == VMAS_OBS_REMAINDER) v[k] = obs_remainder(v[k], par[k]);
@@ -2236,7 +2240,14 @@ int vmas_b200_cast_rays_batched(const VmasWorldConfig* cfg, const VmasPlanTables
 
 int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
                                   int32_t n_rows, int32_t width, float* out, void* cuda_stream) {
+  return vmas_b200_gather_observations_buffers(cfg, st, columns, n_rows, width, out, nullptr, 0, cuda_stream);
+}
+
+int vmas_b200_gather_observations_buffers(const VmasWorldConfig* cfg, const VmasState* st, const int32_t* columns,
+                                          int32_t n_rows, int32_t width, float* out, const float* const* buffers,
+                                          int32_t n_buffers, void* cuda_stream) {
   if (!cfg || !st || !columns || !out) return fail("null argument%s");
+  if (n_buffers < 0 || n_buffers > VMAS_OBS_MAX_BUFFERS || (n_buffers > 0 && !buffers)) return fail("0..8 observation buffers%s");
   if (!st->pos || !st->vel || !st->rot || !st->ang_vel) return fail("null state pointer%s");
   if (n_rows <= 0 || width <= 0 || cfg->batch_dim <= 0) return fail("empty observation block%s");
   ObsArgs a;
@@ -2247,6 +2258,9 @@ int vmas_b200_gather_observations(const VmasWorldConfig* cfg, const VmasState* s
   a.width = width;
   a.batch_dim = cfg->batch_dim;
   a.n_entities = cfg->n_entities;
+  for (int i = 0; i < VMAS_OBS_MAX_BUFFERS; ++i) a.buffers[i] = i < n_buffers ? buffers[i] : nullptr;
+  for (int i = 0; i < n_buffers; ++i)
+    if (!buffers[i]) return fail("null observation buffer%s");
   if (n_rows > 65535) return fail("more than 65535 observation rows%s");
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   // vector width: the widest that divides the row (and keeps every store aligned)
@@ -2306,6 +2320,7 @@ int vmas_b200_post_step(const VmasWorldConfig* cfg, const VmasPlanTables* tb, co
   oa.width = has_obs ? width : 4;
   oa.batch_dim = cfg->batch_dim;
   oa.n_entities = cfg->n_entities;
+  for (int i = 0; i < VMAS_OBS_MAX_BUFFERS; ++i) oa.buffers[i] = nullptr;  // (buffer columns need a launch of their own)
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   int vec = 4;
   if (has_obs) vec = (width % 4 == 0 && ((uintptr_t)obs_out % 16 == 0)) ? 4 : (width % 2 == 0 && ((uintptr_t)obs_out % 8 == 0)) ? 2 : 1;

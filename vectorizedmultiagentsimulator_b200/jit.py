@@ -267,8 +267,8 @@ def prebuild_step_kernels(verbose: bool = False):
         if not codegen.specializable(desc):
             continue
         label = scenario + "(" + ", ".join(f"{k}={v}" for k, v in kwargs.items()) + ")"
-        columns = cols if (cols[..., 0] != 0).any() else None
         instrs = prog.instructions(lambda e: index[id(e)])
+        columns = codegen.fuse_value_columns(cols, plan.buffer_sources, instrs) if (cols[..., 0] != 0).any() else None
         # with and without the action ingest as the kernel's prologue (step_env_kernel / step_fused_kernel); an
         # environment adds one STORE per result leaf to the program when it captures its step, so its own
         # variant is compiled then (seconds) — these two make sure the templates build, and serve

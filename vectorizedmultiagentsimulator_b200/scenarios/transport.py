@@ -14,11 +14,29 @@ from ..simulator.scenario import BaseScenario
 from ..simulator.utils import Color, ScenarioUtils
 
 
+class _Package(Landmark):
+    """A package shows red until it sits on its goal, then green (ref transport.py:157-161, set there by
+    every reward()); here the colour is derived from the goal flag when somebody asks for it."""
+
+    @property
+    def color(self):
+        on_goal = getattr(self, "on_goal", None)
+        if on_goal is None:
+            return Color.RED.value
+        red = torch.tensor(Color.RED.value, device=on_goal.device, dtype=torch.float32)
+        green = torch.tensor(Color.GREEN.value, device=on_goal.device, dtype=torch.float32)
+        return torch.where(on_goal.unsqueeze(-1), green, red)
+
+    @color.setter
+    def color(self, color):
+        self._color = color
+
+
 class Scenario(BaseScenario):
     supports_masked_reset = True  # reset_world_at(env_index): None, an int, or a [B] bool mask
 
     def make_world(self, batch_dim: int, device: torch.device, **kwargs):
-        self._obs_plan = self._obs_all = self._shaping_block = self._zero = None
+        self._obs_plan = self._obs_all = self._shaping_block = self._zero = self._program = None
         n_agents = kwargs.pop("n_agents", 4)
         self.n_packages = kwargs.pop("n_packages", 1)
         self.package_width = kwargs.pop("package_width", 0.15)
@@ -41,7 +59,7 @@ class Scenario(BaseScenario):
         world.add_landmark(goal)
         self.packages = []
         for i in range(self.n_packages):
-            package = Landmark(
+            package = _Package(
                 name=f"package {i}",
                 collide=True,
                 movable=True,
@@ -92,68 +110,95 @@ class Scenario(BaseScenario):
             y_bounds=bounds,
             occupied_positions=occupied,
         )
+        self._obs_all, self._obs_from_program, self._done_from_program = None, False, None
         for package in self.packages:
-            package.on_goal = world.is_overlapping(package, package.goal)
             dist = torch.linalg.vector_norm(package.state.pos - package.goal.state.pos, dim=1)
             self.keep(package, "global_shaping", dist * self.shaping_factor, env_index)
+        prog = self._step_program()
+        for k, package in enumerate(self.packages):
+            # the goal flags live in the program's outputs (written in place: a captured step keeps their address)
+            on_goal = world.is_overlapping(package, package.goal)
+            prog.out_on_goal[k].tensor.copy_(on_goal)
+            prog.out_on_goal_value[k].tensor.copy_(on_goal)
+            package.on_goal = prog.out_on_goal[k].tensor
+
+    def _step_program(self):
+        """reward() / done() / the ``on_goal`` observation columns as one step program (ref transport.py:129-194):
+        per package the distance-shaping term, the goal test, the reward contribution (0 once on the goal);
+        the episode ends when every package is on its goal."""
+        prog = getattr(self, "_program", None)
+        if prog is not None and prog.world is self.world:
+            return prog
+        from ..simulator.program import StepProgram
+
+        block = getattr(self, "_shaping_block", None)
+        if block is None:  # every package's carried shaping term as one [K, B] block
+            for package in self.packages:
+                if getattr(package, "global_shaping", None) is None:  # (no reset yet)
+                    package.global_shaping = torch.zeros(self.world.batch_dim, device=self.world.device)
+            block = self._shaping_block = torch.stack([p.global_shaping for p in self.packages])
+            for k, package in enumerate(self.packages):
+                package.global_shaping = block[k]
+        p = StepProgram(self.world)
+        rew, done = p.const(0.0), None
+        p.out_dist, p.out_on_goal, p.out_on_goal_value = [], [], []
+        for k, package in enumerate(self.packages):
+            shaped, dist = p.shaping(package, package.goal, self.shaping_factor, prev=lambda k=k: self._shaping_block[k])
+            on_goal = p.overlap(package, package.goal)
+            rew = p.add(rew, p.where(on_goal, p.const(0.0), shaped))
+            done = on_goal if done is None else p.logical_and(done, on_goal)
+            p.out_dist.append(p.store(dist))
+            p.out_on_goal.append(p.store(on_goal))
+            p.out_on_goal_value.append(p.store(on_goal, torch.float32))  # the observation column (0. / 1.)
+        p.out_rew, p.out_done = p.store(rew), p.store(done, torch.bool)
+        self._program = p.finalize()
+        return self._program
+
+    def _observation_plan(self):
+        plan = getattr(self, "_obs_plan", None)
+        if plan is None:
+            prog = self._step_program()
+            plan = self._obs_plan = O.ObservationPlan(
+                [
+                    [O.pos(a), O.vel(a)]
+                    + [
+                        t
+                        for package, flag in zip(self.packages, prog.out_on_goal_value)
+                        for t in (O.rel_pos(package, package.goal), O.rel_pos(package, a), O.vel(package), O.value(flag))
+                    ]
+                    for a in self.world.agents
+                ]
+            )
+        return plan
 
     def reward(self, agent: Agent):
         if agent is self.world.agents[0]:
-            rew = torch.zeros(self.world.batch_dim, device=self.world.device, dtype=torch.float32)
-            if getattr(self, "_colors", None) is None:  # constants: uploaded once, not every step
-                self._colors = (
-                    torch.tensor(Color.RED.value, device=self.world.device, dtype=torch.float32),
-                    torch.tensor(Color.GREEN.value, device=self.world.device, dtype=torch.float32),
-                )
-            red, green = self._colors
-            block = getattr(self, "_shaping_block", None)
-            if block is None:  # every package's carried shaping term as one [K, B] block
-                block = self._shaping_block = torch.stack([p.global_shaping for p in self.packages])
-                for k, package in enumerate(self.packages):
-                    package.global_shaping = block[k]
-            dist, shaped = self.world.distance_shaping(
-                [(p, p.goal) for p in self.packages], self.shaping_factor, block
-            )
-            zero = self._zero_reward()
+            prog = self._step_program()
+            # one launch (captured: the epilogue of the step's kernel) for the reward, the flags and the
+            # observations of the step; observation() hands the block out
+            self._obs_all = prog.run(observe=self._observation_plan())
+            self._obs_from_program = True
             for k, package in enumerate(self.packages):
-                package.dist_to_goal = dist[k]
-                package.on_goal = self.world.is_overlapping(package, package.goal)
-                package.color = torch.where(package.on_goal.unsqueeze(-1), green, red)
-                rew = rew + torch.where(package.on_goal, zero, shaped[k])
-            self.rew = rew
+                package.dist_to_goal = prog.out_dist[k].tensor
+                package.on_goal = prog.out_on_goal[k].tensor
+            self.rew = prog.out_rew.tensor
+            self._done_from_program = prog.out_done.tensor
         return self.rew
-
-    def _zero_reward(self):
-        zero = getattr(self, "_zero", None)
-        if zero is None or zero.device != self.world.slab.pos.device:
-            zero = self._zero = torch.tensor(0.0, dtype=torch.float32, device=self.world.slab.pos.device)
-        return zero
 
     def observation(self, agent: Agent):
         agents = self.world.agents
-        if agent is agents[0] or getattr(self, "_obs_all", None) is None:
-            plan = getattr(self, "_obs_plan", None)
-            if plan is None:
-                self._on_goal_terms = [O.blank(1) for _ in self.packages]
-                plan = self._obs_plan = O.ObservationPlan(
-                    [
-                        [O.pos(a), O.vel(a)]
-                        + [
-                            t
-                            for package, flag in zip(self.packages, self._on_goal_terms)
-                            for t in (O.rel_pos(package, package.goal), O.rel_pos(package, a), O.vel(package), flag)
-                        ]
-                        for a in agents
-                    ]
-                )
-            block = self.world.observe(plan)  # [A, B, 4 + 7 * n_packages], one launch
-            for package, flag in zip(self.packages, self._on_goal_terms):
-                block[:, :, plan.column_of(0, flag)] = package.on_goal  # bool -> 0. / 1., every agent
-            self._obs_all = block
+        fresh = getattr(self, "_obs_from_program", False)  # reward() of this step already produced the block
+        if (agent is agents[0] and not fresh) or getattr(self, "_obs_all", None) is None:
+            # (after a reset: the goal flags of the program's outputs were refreshed there)
+            self._obs_all = self.world.observe(self._observation_plan())
         row = self._obs_all[agents.index(agent)]
         if agent is agents[-1]:
             self._obs_all = None  # one sweep over the agents per block: a later call measures anew
+            self._obs_from_program = False
         return row
 
     def done(self):
+        from_program, self._done_from_program = getattr(self, "_done_from_program", None), None
+        if from_program is not None:  # reward() of this step computed it
+            return from_program
         return torch.stack([p.on_goal for p in self.packages], dim=1).all(dim=-1)

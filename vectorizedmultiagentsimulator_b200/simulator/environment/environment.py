@@ -817,8 +817,11 @@ class Environment(TorchVectorizedObject):
         if not _DIRECT_STEP or trace is None or [t[0] for t in trace] != ["step", "post"]:
             return None
         (_, n_step, mode), (_, n_post, prog, plan, c, out) = trace
-        if n_post != 1 or n_step + n_post != self._graph_launches:
-            return None  # (LIDAR columns ride in a second launch; anything else the backend launched)
+        values = plan is not None and bool(plan.buffer_sources)  # columns fed by the program: program, then gather
+        if n_post != (2 if values and prog is not None else 1) or n_step + n_post != self._graph_launches:
+            return None  # (LIDAR columns ride in a launch of their own; anything else the backend launched)
+        if values and any(not hasattr(src, "_slot") or src not in prog.outputs for src in plan.buffer_sources):
+            return None  # (value columns that are not outputs of this program)
         backend = self.world._get_backend()
         try:
             nodes = backend.lib.vmas_b200_graph_num_nodes(graph.raw_cuda_graph())
@@ -878,6 +881,10 @@ class Environment(TorchVectorizedObject):
                 from ... import jit
 
                 cols_np = None if cols is None else oplan.compile(self.world)[0]
+                if cols_np is not None:
+                    from ... import codegen
+
+                    cols_np = codegen.fuse_value_columns(cols_np, oplan.buffer_sources, instrs)
                 # ... with the action ingest (and the broad phase) as its prologue where the agents allow it:
                 # the whole step is then ONE launch
                 acts = ()
@@ -896,6 +903,12 @@ class Environment(TorchVectorizedObject):
                 job = jit.request_step_kernel(backend.tables.desc, cols_np, instrs, acts)
                 if job is not None:
                     job.done.wait(timeout=_WHOLE_STEP_KERNEL_WAIT_S)
+        if direct is not None and direct[3] is not None and direct[3].buffer_sources and not (
+            job is not None and job.done.is_set() and job.index > 0
+        ):
+            # value columns need the program and the gather in ONE thread: without the whole-step kernel the
+            # step stays a captured graph (program launch, then gather launch)
+            return self._build_one_call_step(graph, ingest_built_mask, None)
         plan.direct = direct is not None
         plan.job = job
         plan.live = live

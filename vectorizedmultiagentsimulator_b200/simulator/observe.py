@@ -19,7 +19,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-OP_SKIP, OP_COPY, OP_DIFF, OP_REMAINDER = 0, 1, 2, 3
+OP_SKIP, OP_COPY, OP_DIFF, OP_REMAINDER, OP_BUFFER, OP_REG = 0, 1, 2, 3, 4, 5
+MAX_BUFFERS = 8
 FIELD_POS, FIELD_VEL, FIELD_ROT, FIELD_ANG_VEL = 0, 1, 2, 3
 _FIELDS = {"pos": (FIELD_POS, 2), "vel": (FIELD_VEL, 2), "rot": (FIELD_ROT, 1), "ang_vel": (FIELD_ANG_VEL, 1)}
 
@@ -78,6 +79,21 @@ def rot_remainder(entity, modulus: float) -> Term:
     return _State("rot", entity, modulus=float(modulus))
 
 
+class _Buffer(Term):
+    width = 1
+
+    def __init__(self, source):
+        self.source = source
+
+
+def value(source) -> Term:
+    """One column holding a per-env fp32 value another producer computed: ``source`` is a ``[B]`` fp32 tensor, a
+    callable returning one, or a ``program.Output`` (fp32) — e.g. a flag of the scenario's step program that is
+    also part of the observation (ref scenarios/transport.py:177-183, ``package.on_goal``).  Read when the block
+    is assembled: the producer must have run before ``World.observe`` / within the same ``StepProgram.run``."""
+    return _Buffer(source)
+
+
 def lidar(sensor, range_minus_distance: bool = False) -> Term:
     """The readings of ``sensor`` (``sensor.measure()``), or ``max_range - readings``."""
     return _Lidar(sensor, range_minus_distance)
@@ -103,6 +119,7 @@ class ObservationPlan:
         self.width = widths.pop()
         self.n_rows = len(self.rows)
         self._compiled = None  # (plan version, columns, lidars)
+        self.buffer_sources = []
         self.device_cache = {}  # backend-owned device copies, keyed by the backend
 
     def column_of(self, row: int, term: Term) -> int:
@@ -122,6 +139,7 @@ class ObservationPlan:
         index = {id(e): i for i, e in enumerate(world.entities)}
         cols = np.zeros((self.n_rows, self.width, 4), dtype=np.int32)
         lidars = []
+        self.buffer_sources = []  # what OP_BUFFER columns read, in the order of their indices
         for r, row in enumerate(self.rows):
             c = 0
             for t in row:
@@ -137,6 +155,14 @@ class ObservationPlan:
                             cols[r, c + k] = (OP_COPY, src, 0, 0)
                 elif isinstance(t, _Lidar):
                     lidars.append((r, c, t.sensor, t.range_minus_distance))
+                elif isinstance(t, _Buffer):
+                    known = [k for k, src in enumerate(self.buffer_sources) if src is t.source]
+                    if not known:
+                        if len(self.buffer_sources) >= MAX_BUFFERS:
+                            raise ValueError(f"an observation plan reads at most {MAX_BUFFERS} value buffers")
+                        self.buffer_sources.append(t.source)
+                        known = [len(self.buffer_sources) - 1]
+                    cols[r, c] = (OP_BUFFER, known[0], 0, 0)
                 c += t.width
         flips = {f for _, _, _, f in lidars}
         if len(flips) > 1:
@@ -144,3 +170,11 @@ class ObservationPlan:
         self._compiled = (version, cols, lidars)
         self.device_cache.clear()
         return cols, lidars
+
+    def resolve_buffers(self):
+        """The ``[B]`` fp32 tensors the plan's value columns read, in column-index order."""
+        out = []
+        for src in self.buffer_sources:
+            t = src.tensor if hasattr(src, "tensor") and hasattr(src, "_slot") else (src() if callable(src) else src)
+            out.append(t)
+        return out
