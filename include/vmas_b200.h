@@ -468,7 +468,8 @@ typedef struct VmasEnvStep {
   size_t obs_offset;
   /* != 0 (direct mode with `fused_kernel`): the whole step goes out as ONE launch if the kernel has the
    * ingest prologue for these agents (continuous holonomic actions) and the batch fits the GPU at once (a
-   * masked world's broad phase needs a grid-wide barrier); otherwise the launches above are issued. */
+   * masked world's broad phase needs a grid-wide barrier per substep; `mask` must then hold
+   * substeps x ((n_masked + 31) / 32 + 2) zeroed words); otherwise the launches above are issued. */
   int32_t ingest_in_kernel, reserved;
   int32_t mirror_slot[VMAS_PROG_MAX_BUFFERS];
   int32_t mirror_block[VMAS_PROG_MAX_BUFFERS];

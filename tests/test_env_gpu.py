@@ -561,10 +561,8 @@ def test_pinned_host_actions_are_read_where_they_lie(graph):
 @pytest.mark.parametrize(
     "kwargs,launches",
     [
-        (dict(n_agents=4), 1),  # one substep: the whole step is one kernel
-        # three substeps with a broad phase each: ingest (+ first mask), then per substep [mask] + kernel, the
-        # last of them with the program and the observation rows as its epilogue
-        (dict(n_agents=4, n_lines=2, substeps=3), 6),
+        (dict(n_agents=4), 1),  # the whole step is one kernel
+        (dict(n_agents=4, n_lines=2, substeps=3), 1),  # ... with a grid-wide barrier per substep (batch-wide mask)
     ],
 )
 def test_transport_goal_flags_are_program_results_and_observation_columns(kwargs, launches):

@@ -491,7 +491,8 @@ class DeviceTables:
             else None
         )
         words = (tables.n_masked + 31) // 32
-        self.mask = torch.zeros(words + 2, dtype=torch.int32, device=self.device)  # + the kernels' two arrival counters
+        # (+ the kernels' arrival counters; the one-kernel step keeps a mask per substep)
+        self.mask = torch.zeros(max(1, int(tables.desc.substeps)) * (words + 2), dtype=torch.int32, device=self.device)
         self.n_rounds = int(sched.shape[0])
 
         self.cfg = make_config(tables, B)

@@ -790,7 +790,8 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_fused_kernel(con
 // masked pairs for the batch-wide broad phase (ref core.py:2797-2801); the mask is complete once every block
 // has contributed — a grid-wide barrier, which needs all blocks resident (cooperative launch; the launcher
 // says no for batches beyond that and the caller keeps the separate ingest launch).
-//   a.mask: [MASK_WORDS] bits, [MASK_WORDS] arrivals at the barrier, [MASK_WORDS + 1] blocks done with the mask
+//   a.mask: per substep [MASK_WORDS] bits, [MASK_WORDS] arrivals at the barrier, [MASK_WORDS + 1] blocks done
+//   with the mask (substeps x (MASK_WORDS + 2) words, zero between launches)
 template <class W>
 __host__ __device__ constexpr int spec_first_masked() {
   for (int i = 0; i < W::NI; ++i)
@@ -837,58 +838,61 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_env_kernel(const
     if (bad && act.bad_flag) *act.bad_flag = 1;
     if (act.steps) act.steps[env] = act.steps[env] + 1.f;
   }
-  // The broad phase of this step's (only) substep.  ARRIVE here: the block's pairs-in-range bits go to the
-  // global mask and the block checks in at the barrier; WAIT (below) only where the first masked work item
-  // is due — the trigonometry, the per-entity forces and the unmasked items in front of it (sphere pairs)
-  // run while the other blocks arrive.
+  // The batch-wide broad phase of every substep, inside the kernel.  ARRIVE: the block's pairs-in-range bits go
+  // to the global mask of the substep and the block checks in at its barrier; WAIT only where the first masked
+  // work item is due — the trigonometry, the per-entity forces and the unmasked items in front of it (sphere
+  // pairs) run while the other blocks arrive.  Substep s uses a.mask + s * (MW + 2): [MW] bits, arrivals, blocks
+  // done with the mask (the last of them clears the region for the next step).
   uint32_t mask_words[MW > 0 ? MW : 1];
   [[maybe_unused]] __shared__ uint32_t s_mask[MW > 0 ? MW : 1];
-  if constexpr (MW > 0) {
-    if (a.use_mask) {
-      if (threadIdx.x < MW) s_mask[threadIdx.x] = 0u;
-      static_assert(MW <= W::BLOCK, "more mask words than threads in a block");
-      __syncthreads();
-      uint32_t bits[MW];
-#pragma unroll
-      for (int w = 0; w < MW; ++w) bits[w] = 0u;
-      static_for<NI>([&](auto ii) {
-        constexpr ItemC it = W::item[decltype(ii)::value];
-        if constexpr (it.mask_bit >= 0) {
-          const bool near = live && norm2(r.px[it.a] - r.px[it.b], r.py[it.a] - r.py[it.b]) <= it.broad_thr;
-          if (__any_sync(0xffffffffu, near)) bits[it.mask_bit >> 5] |= 1u << (it.mask_bit & 31);
-        }
-      });
-      if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int w = 0; w < MW; ++w)
-          if (bits[w]) atomicOr(&s_mask[w], bits[w]);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int w = 0; w < MW; ++w) {  // (bits only ever get set: a stale read costs one redundant atomic)
-          const uint32_t b = s_mask[w];
-          if (b && (ld_acquire_u32(&a.mask[w]) & b) != b) atomicOr(&a.mask[w], b);
-        }
-        __threadfence();
-        atomicAdd(&a.mask[MW], 1u);
-      }
-    }
-  }
+  static_assert(MW <= W::BLOCK, "more mask words than threads in a block");
   uint32_t sig = 0;
   for (int sub = 0; sub < W::cfg.substeps; ++sub) {
+    [[maybe_unused]] uint32_t* gmask = a.mask + sub * (MW + 2);
+    if constexpr (MW > 0) {
+      if (a.use_mask) {
+        if (sub > 0) __syncthreads();  // (every thread has taken the previous substep's mask out of s_mask)
+        if (threadIdx.x < MW) s_mask[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t bits[MW];
+#pragma unroll
+        for (int w = 0; w < MW; ++w) bits[w] = 0u;
+        static_for<NI>([&](auto ii) {
+          constexpr ItemC it = W::item[decltype(ii)::value];
+          if constexpr (it.mask_bit >= 0) {
+            const bool near = live && norm2(r.px[it.a] - r.px[it.b], r.py[it.a] - r.py[it.b]) <= it.broad_thr;
+            if (__any_sync(0xffffffffu, near)) bits[it.mask_bit >> 5] |= 1u << (it.mask_bit & 31);
+          }
+        });
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+          for (int w = 0; w < MW; ++w)
+            if (bits[w]) atomicOr(&s_mask[w], bits[w]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          for (int w = 0; w < MW; ++w) {  // (bits only ever get set: a stale read costs one redundant atomic)
+            const uint32_t b = s_mask[w];
+            if (b && (ld_acquire_u32(&gmask[w]) & b) != b) atomicOr(&gmask[w], b);
+          }
+          __threadfence();
+          atomicAdd(&gmask[MW], 1u);
+        }
+      }
+    }
     spec_trig<W>(r);
     spec_entity_forces<W>(r, afx, afy, atq);
     static_for<NI>([&](auto ii) {
       constexpr int I = decltype(ii)::value;
       if constexpr (MW > 0 && I == spec_first_masked<W>()) {
-        if (a.use_mask) {  // WAIT (masked worlds run one substep per launch: the launcher sees to it)
+        if (a.use_mask) {  // WAIT
           if (threadIdx.x == 0) {
-            while (ld_acquire_u32(&a.mask[MW]) < gridDim.x) __nanosleep(20);
-            for (int w = 0; w < MW; ++w) s_mask[w] = ld_acquire_u32(&a.mask[w]);
+            while (ld_acquire_u32(&gmask[MW]) < gridDim.x) __nanosleep(20);
+            for (int w = 0; w < MW; ++w) s_mask[w] = ld_acquire_u32(&gmask[w]);
             __threadfence();
-            const unsigned done = atomicAdd(&a.mask[MW + 1], 1u);
+            const unsigned done = atomicAdd(&gmask[MW + 1], 1u);
             if (done == gridDim.x - 1) {  // every block has its copy: clear for the next step
-              for (int w = 0; w < MW + 2; ++w) a.mask[w] = 0u;
+              for (int w = 0; w < MW + 2; ++w) gmask[w] = 0u;
             }
           }
           __syncthreads();
@@ -910,7 +914,6 @@ template <class W, class P>
 static cudaError_t launch_env(const SpecArgs& a, const EpiArgs& e, const ActArgs& act, cudaStream_t stream) {
   const long blocks = ((long)a.batch_dim + W::BLOCK - 1) / W::BLOCK;
   if (W::MASK_WORDS > 0 && a.use_mask) {
-    if (W::cfg.substeps != 1) return cudaErrorInvalidValue;
     static long capacity[64] = {0};
     int device = 0;
     cudaError_t err = cudaGetDevice(&device);

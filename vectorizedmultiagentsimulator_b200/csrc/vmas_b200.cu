@@ -2525,7 +2525,7 @@ static int env_step_one_kernel(const VmasEnvStep* s, const StepTargets& t, cudaS
     return fail("whole-step kernel does not match the world (stale handle?)%s");
   if (!s->st->force || !s->st->torque || !s->agents) return fail("null force/torque/agents pointer%s");
   const bool masked = s->cfg->n_masked > 0 && s->exact_broad_phase;
-  if (masked && (!s->mask || s->cfg->substeps != 1)) return 0;
+  if (masked && !s->mask) return 0;  // (mask scratch: substeps x (mask words + 2) uint32, see VmasEnvStep)
   StepArgs args;
   args.cfg = *s->cfg;
   args.tb = *s->tb;

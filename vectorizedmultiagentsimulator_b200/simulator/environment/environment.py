@@ -426,6 +426,22 @@ class Environment(TorchVectorizedObject):
             )
         return sizes[1]
 
+    def _hold_host_actions(self, actions: List[Tensor]):
+        """Pinned host action tensors are read by a kernel where they lie (no staging copy): they must not go
+        back to torch's pinned-memory pool — and from there into another tensor — before that kernel has run.
+        They are kept referenced until an event recorded behind the step has completed."""
+        held = getattr(self, "_held_host_actions", None)
+        if held is None:
+            import collections
+
+            held = self._held_host_actions = collections.deque()
+        while held and held[0][0].query():
+            held.popleft()
+        if any(a.device.type == "cpu" for a in actions):
+            event = torch.cuda.Event()
+            event.record()
+            held.append((event, list(actions)))
+
     def _step(self, actions):
         self._raise_deferred_action_errors()
         actions = self._normalize_actions(actions)
@@ -433,6 +449,10 @@ class Environment(TorchVectorizedObject):
             result = self._step_graphed(actions)
         else:
             result = self._step_device(actions)
+        if self.device.type == "cuda" and (
+            getattr(self, "_held_host_actions", None) or any(a.device.type == "cpu" for a in actions)
+        ):
+            self._hold_host_actions(actions)
         self._launch_deferred_action_readback()
         return result
 
