@@ -602,3 +602,25 @@ def test_transport_goal_flags_are_program_results_and_observation_columns(kwargs
     before = graph.world._get_backend().launches
     graph.step([a.cuda() for a in actions])
     assert graph.world._get_backend().launches - before == launches
+
+
+def test_value_columns_without_a_whole_step_kernel_keep_the_captured_graph(monkeypatch):
+    """Observation columns fed by the step program need program and gather in one thread (the whole-step
+    kernel) or in two launches; without the kernel (no compiler on the box, or switched off) the captured
+    step must stay a graph holding the two launches — never the single fused launch, which would race."""
+    from vectorizedmultiagentsimulator_b200.simulator.environment import environment as E
+
+    monkeypatch.setattr(E, "_WHOLE_STEP_KERNEL", False)
+    n_envs = 128
+    eager = b200.make_env("transport", num_envs=n_envs, device="cuda", seed=0, n_agents=3)
+    graph = b200.make_env("transport", num_envs=n_envs, device="cuda", seed=0, n_agents=3, cuda_graph=True)
+    sync_env(eager, graph)
+    gen = torch.Generator().manual_seed(2)
+    for t in range(7):
+        actions = [(torch.rand(n_envs, 2, generator=gen) * 2 - 1).cuda() for _ in eager.agents]
+        want = eager.step([a.clone() for a in actions])
+        got = graph.step([a.clone() for a in actions])
+        for i, (g, w) in enumerate(zip(flatten(got), flatten(want))):
+            assert same(g, w), f"step {t} output {i}"
+        resync(eager, graph)
+    assert graph._one_call_state == "on" and not graph._one_call.direct and graph._one_call.c.fused_kernel == 0

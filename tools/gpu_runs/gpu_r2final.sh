@@ -24,6 +24,9 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:step
 stamp "ncu --set full rc=$?"
 python tools/ncu_summary.py gpurun_out/r2final_step_env_kernel.ncu-rep > gpurun_out/r2final_step_env_kernel_ncu_full.txt 2>&1
 python tools/ncu_regions.py gpurun_out/r2final_step_env_kernel.ncu-rep 0x1000 >> gpurun_out/r2final_step_env_kernel_ncu_full.txt 2>&1
+# the whole-step kernels compiled on this box: back into the snapshot's JIT cache (same toolchain, same source stamp)
+mkdir -p gpurun_out/jit && cp vectorizedmultiagentsimulator_b200/csrc/generated/jit/*.so gpurun_out/jit/ 2>/dev/null
+ls gpurun_out/jit | wc -l
 python - <<'PY'
 import json
 for f in ("r2final_bench_driver", "r2final_bench", "r2final_bench_reference"):
