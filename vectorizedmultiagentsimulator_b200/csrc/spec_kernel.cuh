@@ -588,6 +588,29 @@ DEVI EntG epi_ent(const EnvRegs<W::E>& r, const SpecArgs& a, const long env) {
   return g;
 }
 
+// The epilogue's per-env inputs (carried shaping terms, loaded flags) are first touched at the very end of the
+// thread's instruction chain; requested when the thread starts, their DRAM round trip is over by then.
+DEVI void spec_prefetch(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+template <class P>
+DEVI void spec_epilogue_prefetch(const EpiArgs& e, const long env) {
+#ifdef __CUDA_ARCH__
+  static_for<P::N_PROG>([&](auto ii) {
+    constexpr ProgC in = P::prog[decltype(ii)::value];
+    if constexpr (in.op == VMAS_OP_SHAPING || in.op == VMAS_OP_LOAD_F32)
+      spec_prefetch(static_cast<const float*>(e.buffers[in.a]) + env);
+    else if constexpr (in.op == VMAS_OP_LOAD_BOOL)
+      spec_prefetch(static_cast<const uint8_t*>(e.buffers[in.a]) + env);
+  });
+#endif
+}
+
 template <class W, class P>
 DEVI void spec_epilogue(const EnvRegs<W::E>& r, const SpecArgs& a, const EpiArgs& e, const long env) {
   // the step program (ref scenarios/balance.py:197-263 as a StepProgram; see vmas_b200_post_step)
@@ -697,6 +720,9 @@ DEVI void spec_env_step(const SpecArgs& a, const long env, const uint32_t (&mask
   SpecRows<W> rows;
   rows.load_pos_rot(a, env);
   rows.load_rest(a, env);
+  if constexpr (!std::is_void_v<P>) {
+    if (a.first_substep + a.n_substeps == W::cfg.substeps) spec_epilogue_prefetch<P>(*epi, env);
+  }
   EnvRegs<E> r;
   float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
   rows.unpack_pos_rot(r);
@@ -814,6 +840,10 @@ __global__ void __launch_bounds__(W::BLOCK, W::MIN_BLOCKS) step_env_kernel(const
   SpecRows<W, true> rows;
   rows.load_pos_rot(a, env);
   rows.load_rest(a, env);
+  spec_epilogue_prefetch<P>(e, env);
+#ifdef __CUDA_ARCH__
+  if (act.steps) spec_prefetch(act.steps + env);
+#endif
   EnvRegs<E> r;
   float afx[NA > 0 ? NA : 1], afy[NA > 0 ? NA : 1], atq[NA > 0 ? NA : 1];
   rows.unpack_pos_rot(r);
